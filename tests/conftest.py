@@ -1,0 +1,55 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), '..'))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, 'tests', 'golden')
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+    config.addinivalue_line('markers', 'reference: needs /root/reference (build container only)')
+
+
+def pytest_collection_modifyitems(config, items):
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    skip_gpu = pytest.mark.skip(reason='no CUDA device')
+    for item in items:
+        if 'gpu' in item.keywords and not has_gpu:
+            item.add_marker(skip_gpu)
+
+
+class Golden(object):
+    """Lazy npz reader with dotted-prefix helpers."""
+    def __init__(self, name):
+        self._z = np.load(os.path.join(GOLDEN_DIR, name + '.npz'))
+
+    def __getitem__(self, key):
+        return self._z[key]
+
+    def __contains__(self, key):
+        return key in self._z.files
+
+    def sub(self, prefix):
+        n = len(prefix)
+        return {k[n:]: self._z[k] for k in self._z.files if k.startswith(prefix)}
+
+
+@pytest.fixture(scope='session')
+def golden():
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            cache[name] = Golden(name)
+        return cache[name]
+    return get

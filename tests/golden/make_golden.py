@@ -1,0 +1,321 @@
+"""Generate the committed golden vectors from the LIVE reference.
+
+Run inside the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+Imports the unmodified reference through oracle/load_reference.py (signatory /
+ghalton supplied by oracle/refshim), drives it on small seeded inputs, records
+every random draw it consumes (torch.rand_like noise, numpy minibatch indices,
+numpy uniforms / normals) and writes inputs + outputs to tests/golden/*.npz.
+The GPU box has no /root/reference: tests there read these files only.
+"""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.abspath(os.path.join(HERE, '..', '..')))
+
+from oracle import load_reference  # noqa: E402
+
+ref_bs = load_reference.load('bayes_sim')
+ref_mdnn = load_reference.load('models.mdnn')
+ref_mdrff = load_reference.load('models.mdrff')
+ref_sum = load_reference.load('utils.summarizers')
+ref_pdf = load_reference.load('utils.pdf')
+
+
+def quiet():
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+class RecordRandLike(object):
+    """Patch torch.rand_like so that every draw is recorded."""
+    def __init__(self):
+        self.draws = []
+
+    def __enter__(self):
+        self._orig = torch.rand_like
+
+        def rec(t, *a, **k):
+            out = self._orig(t, *a, **k)
+            self.draws.append(out.detach().cpu().numpy().copy())
+            return out
+        torch.rand_like = rec
+        return self
+
+    def __exit__(self, *exc):
+        torch.rand_like = self._orig
+
+
+class RecordRandint(object):
+    def __init__(self):
+        self.draws = []
+
+    def __enter__(self):
+        self._orig = np.random.randint
+
+        def rec(*a, **k):
+            out = self._orig(*a, **k)
+            self.draws.append(np.array(out).copy())
+            return out
+        np.random.randint = rec
+        return self
+
+    def __exit__(self, *exc):
+        np.random.randint = self._orig
+
+
+def synth(seed, n, t1, d, a):
+    g = torch.Generator('cpu').manual_seed(seed)
+    states = torch.randn(n, t1, d, generator=g).clamp_(-100, 100)
+    actions = torch.rand(n, t1, a, generator=g)
+    return states, actions
+
+
+def golden_summarizers():
+    out = {}
+    cases = {  # name: (seed, N, T1, D, A)
+        'pendulum': (11, 7, 21, 3, 1),
+        'cartpole': (12, 5, 21, 4, 1),
+        'ant': (13, 3, 51, 60, 8),
+        'humanoid': (14, 2, 11, 108, 21),
+        'exact10': (15, 4, 10, 3, 2),
+        'short6': (16, 3, 6, 4, 2),      # T1 < W: corr uses all 6 steps
+        'single_pad': (17, 1, 6, 3, 1),  # N == 1: summary_start pads to 10
+    }
+    for name, (seed, n, t1, d, a) in cases.items():
+        s, ac = synth(seed, n, t1, d, a)
+        out[name + '.states'] = s.numpy()
+        out[name + '.actions'] = ac.numpy()
+        with quiet():
+            if t1 >= 10 or n == 1:
+                out[name + '.summary_start'] = ref_sum.summary_start(s, ac).numpy()
+                out[name + '.summary_waypts'] = ref_sum.summary_waypts(s, ac).numpy()
+            out[name + '.summary_corr'] = ref_sum.summary_corr(s, ac).numpy()
+            out[name + '.summary_corrdiff'] = ref_sum.summary_corrdiff(s, ac).numpy()
+        assert torch.equal(ref_sum.summary_start(s, ac) if (t1 >= 10 or n == 1)
+                           else torch.zeros(1),
+                           ref_sum.summary_waypts(s, ac) if (t1 >= 10 or n == 1)
+                           else torch.zeros(1))
+    out['signature_depth.in'] = np.array([1, 5, 6, 22, 23, 69, 110, 111, 130, 232])
+    out['signature_depth.out'] = np.array(
+        [ref_sum.signature_depth(int(c)) for c in out['signature_depth.in']])
+    np.savez_compressed(os.path.join(HERE, 'summarizers.npz'), **out)
+    print('summarizers.npz', len(out), 'arrays')
+
+
+def state_to_np(model):
+    return {k: v.detach().cpu().numpy().copy() for k, v in model.state_dict().items()}
+
+
+def golden_mdn():
+    out = {}
+    cases = {
+        # name: (cls, input_dim, P, K, full_cov, hidden, B)
+        'diag': ('MDNN', 12, 3, 4, False, (16, 16), 9),
+        'full': ('MDNN', 6, 4, 3, True, (8,), 7),
+        'full_big': ('MDNN', 10, 13, 10, True, (32, 32), 12),
+        'p1': ('MDNN', 5, 1, 2, True, (8, 8), 6),
+        'rff': ('MDRFF', 7, 3, 5, False, (), 10),
+        'rff_full': ('MDRFF', 150, 2, 3, True, (), 8),
+    }
+    for name, (cls, din, p, k, full, hidden, b) in cases.items():
+        torch.manual_seed(100 + len(name))
+        np.random.seed(200 + len(name))
+        lows = np.linspace(0.1, 0.5, p)
+        highs = lows + np.linspace(1.0, 3.0, p)
+        kwargs = dict(input_dim=din, output_dim=p, output_lows=lows,
+                      output_highs=highs, n_gaussians=k, full_covariance=full,
+                      hidden_layers=hidden, activation=torch.nn.Tanh, lr=1e-3,
+                      device='cpu')
+        with quiet():
+            if cls == 'MDNN':
+                model = ref_mdnn.MDNN(**kwargs)
+            else:
+                model = ref_mdrff.MDRFF(n_feat=20, sigma=4.0, kernel='RBF', **kwargs)
+        x = torch.randn(b, din)
+        y_raw = torch.from_numpy(lows + (highs - lows) * np.random.rand(b, p)).float()
+        y = model.normalize_samples(y_raw)
+        out[name + '.meta'] = np.array([din, p, k, int(full), b] + list(hidden))
+        out[name + '.lows'] = lows
+        out[name + '.highs'] = highs
+        out[name + '.x'] = x.numpy()
+        out[name + '.y'] = y.numpy()
+        out[name + '.y_raw'] = y_raw.numpy()
+        if cls == 'MDRFF':
+            out[name + '.rff.freqs'] = model.rff.freqs.numpy()
+            out[name + '.rff.sigma'] = model.rff.sigma.numpy()
+            out[name + '.rff.features'] = model.rff.to_features(x).numpy()
+        for key, val in state_to_np(model).items():
+            out[name + '.init.' + key] = val
+        # three Adam steps on the same batch with fresh noise each step
+        opt = torch.optim.Adam(model.parameters(), lr=model.lr)
+        for step in range(3):
+            with RecordRandLike() as rec:
+                opt.zero_grad()
+                w, mu, ld, low = model(x)
+                loss = model.mdn_loss_fn(w, mu, ld, low, y)
+                loss.backward()
+            assert len(rec.draws) == 1
+            tag = '%s.step%d.' % (name, step)
+            out[tag + 'noise'] = rec.draws[0]
+            out[tag + 'weights'] = w.detach().numpy().copy()
+            out[tag + 'mu'] = mu.detach().numpy().copy()
+            out[tag + 'L_d'] = ld.detach().numpy().copy()
+            if low is not None:
+                out[tag + 'L'] = low.detach().numpy().copy()
+            out[tag + 'loss'] = np.array(loss.item())
+            for key, prm in model.named_parameters():
+                out[tag + 'grad.' + key] = prm.grad.detach().numpy().copy()
+            opt.step()
+            for key, val in state_to_np(model).items():
+                out[tag + 'after.' + key] = val
+        # predict_MoGs at R = 1 (the only R the reference supports with full cov)
+        xs = x[:1] if full else x[:3]
+        with RecordRandLike() as rec:
+            mogs = model.predict_MoGs(xs)
+        out[name + '.predict.noise'] = rec.draws[0]
+        out[name + '.predict.xs'] = xs.numpy()
+        out[name + '.predict.a'] = np.stack([m.a for m in mogs])
+        for fld in ('m', 'C', 'S', 'P', 'Pm'):
+            out[name + '.predict.' + fld] = np.stack(
+                [np.stack([getattr(g, fld) for g in m.xs]) for m in mogs])
+        out[name + '.predict.logdetP'] = np.stack(
+            [np.array([g.logdetP for g in m.xs]) for m in mogs])
+    np.savez_compressed(os.path.join(HERE, 'mdn.npz'), **out)
+    print('mdn.npz', len(out), 'arrays')
+
+
+def golden_pdf():
+    out = {}
+    rs = np.random.RandomState(7)
+    for name, p, k, dt in (('f32', 3, 4, np.float32), ('f64', 5, 6, np.float64),
+                           ('p1', 1, 3, np.float32), ('p13', 13, 10, np.float32)):
+        a = rs.rand(k) + 0.05
+        a = (a / a.sum()).astype(dt)
+        ms = [rs.randn(p).astype(dt) for _ in range(k)]
+        nl = p * (p - 1) // 2
+        ls = [np.concatenate([0.3 + rs.rand(p), 0.2 * rs.randn(nl)]).astype(dt)
+              for _ in range(k)]
+        mog = ref_pdf.MoG(a=a, ms=ms, Ls=ls)
+        out[name + '.a'] = a
+        out[name + '.ms'] = np.stack(ms)
+        out[name + '.Ls'] = np.stack(ls)
+        for fld in ('C', 'S', 'P', 'Pm'):
+            out[name + '.' + fld] = np.stack([getattr(g, fld) for g in mog.xs])
+        out[name + '.logdetP'] = np.array([g.logdetP for g in mog.xs])
+        n = 257
+        np.random.seed(31)
+        smp = mog.gen(n_samples=n)
+        np.random.seed(31)
+        u = np.random.rand(n, 1)
+        z = np.random.randn(n, p)     # == concatenated per-component randn blocks
+        out[name + '.gen.u'] = u
+        out[name + '.gen.z'] = z
+        out[name + '.gen.samples'] = smp
+        np.random.seed(32)
+        out[name + '.discrete.idx'] = ref_pdf.discrete_sample(a, 100)
+        np.random.seed(32)
+        out[name + '.discrete.u'] = np.random.rand(100, 1)
+        xq = (rs.randn(33, p) * 1.5)
+        out[name + '.eval.x64'] = xq
+        out[name + '.eval.log64'] = mog.eval(xq, log=True)
+        out[name + '.eval.lin64'] = mog.eval(xq, log=False)
+        out[name + '.eval.log32'] = mog.eval(xq.astype(np.float32), log=True)
+        one = mog.gen(n_samples=1)
+        assert one.shape == (1, p)
+    # pruning (pdf.py:562-570)
+    a = np.array([0.001, 0.5, 0.002, 0.497])
+    mog = ref_pdf.MoG(a=a, ms=[np.zeros(2)] * 4, Ls=[np.ones(2)] * 4)
+    mog.prune_negligible_components(threshold=0.005)
+    out['prune.a_in'] = a
+    out['prune.a_out'] = mog.a
+    np.savez_compressed(os.path.join(HERE, 'pdf.npz'), **out)
+    print('pdf.npz', len(out), 'arrays')
+
+
+def load_pendulum(fnm, limit=None):
+    loaded = np.load(fnm)
+    params = loaded['params']
+    data = loaded['data']
+    if params.ndim == 1:
+        params, data = params.reshape(1, -1), data.reshape(1, -1)
+    if limit:
+        params, data = params[:limit], data[:limit]
+    return params, data
+
+
+def golden_bayessim():
+    """End-to-end BayesSim.run_training + predict on a slice of the reference's
+    own Pendulum fixture (tests/data/*.npz), all random draws recorded."""
+    out = {}
+    data_dir = os.path.join(load_reference.REFERENCE_ROOT, 'bayes_sim_ig', 'tests', 'data')
+    params, data = load_pendulum(
+        os.path.join(data_dir, 'pendulum_train_data_ones_policy_nornd.npz'), 250)
+    tparams, tdata = load_pendulum(
+        os.path.join(data_dir, 'pendulum_true_data_ones_policy_nornd.npz'))
+    out['pendulum.params'] = params.astype(np.float32)
+    out['pendulum.data'] = data.astype(np.float32)
+    out['pendulum.true_params'] = tparams.astype(np.float32)
+    out['pendulum.true_data'] = tdata.astype(np.float32)
+    lows, highs = np.array([0.01] * 2), np.array([2.0] * 2)
+    cls = ref_bs.BayesSim
+    saved = (cls.NUM_GRAD_UPDATES, cls.MINIBATCH_SIZE)
+    cls.NUM_GRAD_UPDATES, cls.MINIBATCH_SIZE = 20, 32
+    try:
+        for name, model_class, summ in (('mdnn_start', 'MDNN', 'summary_start'),
+                                        ('mdrff_corrdiff', 'MDRFF', 'summary_corrdiff')):
+            torch.manual_seed(2)
+            np.random.seed(2)
+            cfg = {'modelClass': model_class, 'summarizerFxn': summ,
+                   'trainTrajLen': 10, 'components': 10,
+                   'hiddenLayers': (24, 24), 'lr': 5e-4}
+            with quiet():
+                bsim = cls(model_cfg=cfg, obs_dim=3, act_dim=1, params_dim=2,
+                           params_lows=lows, params_highs=highs, prior=None,
+                           proposal=None, device='cpu')
+            sa = torch.from_numpy(data).float().reshape(params.shape[0], -1, 4)
+            st, ac = sa[:, :, :3], sa[:, :, 3:]
+            prm = torch.from_numpy(params).float()
+            for key, val in state_to_np(bsim.model).items():
+                out[name + '.init.' + key] = val
+            if model_class == 'MDRFF':
+                out[name + '.rff.freqs'] = bsim.model.rff.freqs.numpy()
+                out[name + '.rff.sigma'] = bsim.model.rff.sigma.numpy()
+            with quiet(), RecordRandLike() as rl, RecordRandint() as ri:
+                logs = bsim.run_training(prm, st, ac)
+            out[name + '.train.idx'] = np.stack(ri.draws)
+            # 20 training forwards + 6 test forwards (epochs 0,4,8,12,16,19)
+            out[name + '.train.n_noise'] = np.array(len(rl.draws))
+            for i, dr in enumerate(rl.draws):
+                out[name + '.train.noise%02d' % i] = dr
+            out[name + '.train.train_loss'] = np.array(logs['train_loss'])
+            out[name + '.train.test_loss'] = np.array(logs['test_loss'])
+            for key, val in state_to_np(bsim.model).items():
+                out[name + '.after.' + key] = val
+            tsa = torch.from_numpy(tdata).float().reshape(1, -1, 4)
+            with quiet(), RecordRandLike() as rl:
+                post = bsim.predict(tsa[:, :, :3], tsa[:, :, 3:])
+            out[name + '.predict.noise'] = rl.draws[0]
+            out[name + '.predict.a'] = post.a
+            out[name + '.predict.m'] = np.stack([g.m for g in post.xs])
+            out[name + '.predict.S'] = np.stack([g.S for g in post.xs])
+            out[name + '.predict.nll_true'] = -post.eval(tparams.astype(np.float32))
+    finally:
+        cls.NUM_GRAD_UPDATES, cls.MINIBATCH_SIZE = saved
+    np.savez_compressed(os.path.join(HERE, 'bayessim.npz'), **out)
+    print('bayessim.npz', len(out), 'arrays')
+
+
+if __name__ == '__main__':
+    torch.set_num_threads(1)   # reproducible reduction order
+    golden_summarizers()
+    golden_mdn()
+    golden_pdf()
+    golden_bayessim()

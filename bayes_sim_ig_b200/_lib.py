@@ -1,0 +1,123 @@
+"""ctypes binding of libbsig_b200.so (the C ABI declared in include/bsig.h).
+
+There is no CPU fallback anywhere in this package: if the shared library is
+missing the import fails loudly, and every kernel entry point refuses tensors
+that are not fp32/contiguous/on a CUDA device.
+"""
+import ctypes
+import os
+
+import torch
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, 'libbsig_b200.so')
+
+_c_ptr = ctypes.c_void_p
+_i64 = ctypes.c_int64
+_int = ctypes.c_int
+_f32 = ctypes.c_float
+_u64 = ctypes.c_uint64
+
+# name -> (restype, argtypes); must list every symbol of include/bsig.h
+SIGNATURES = {
+    'bsig_last_error': (ctypes.c_char_p, []),
+    'bsig_version': (_int, []),
+    'bsig_launch_count': (_i64, []),
+    'bsig_device_info': (_int, [ctypes.POINTER(_int)] * 3),
+    'bsig_summary_start': (_int, [_c_ptr, _c_ptr, _c_ptr] + [_i64] * 6 + [_c_ptr]),
+    'bsig_summary_crosscorr': (_int, [_c_ptr, _c_ptr, _c_ptr] + [_i64] * 6 + [_int, _c_ptr, _c_ptr]),
+    'bsig_signature_fwd': (_int, [_c_ptr, _c_ptr, _c_ptr] + [_i64] * 6 + [_int, _c_ptr]),
+    'bsig_linear_ws_bytes': (_i64, [_i64] * 3),
+    'bsig_linear_fwd': (_int, [_c_ptr, _i64, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _i64, _i64, _i64,
+                               _int, _int, _c_ptr, _i64, _c_ptr]),
+    'bsig_linear_dgrad': (_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _i64, _i64, _i64, _int, _int,
+                                 _c_ptr, _i64, _c_ptr]),
+    'bsig_linear_wgrad': (_int, [_c_ptr, _c_ptr, _i64, _c_ptr, _c_ptr, _c_ptr, _i64, _i64, _i64,
+                                 _int, _c_ptr, _i64, _c_ptr]),
+    'bsig_tanh_bwd': (_int, [_c_ptr, _c_ptr, _c_ptr, _i64, _c_ptr]),
+    'bsig_rff_features': (_int, [_c_ptr, _i64, _c_ptr, _c_ptr, _c_ptr, _i64, _i64, _i64, _f32,
+                                 _int, _c_ptr, _i64, _c_ptr]),
+    'bsig_mdn_ws_bytes': (_i64, [_i64]),
+    'bsig_mdn_head_fwd': (_int, [_c_ptr] * 4 + [_i64] * 3 + [_int, _c_ptr, _i64, _c_ptr, _c_ptr]),
+    'bsig_mdn_head_bwd': (_int, [_c_ptr] * 8 + [_i64] * 3 + [_int, _c_ptr, _i64, _c_ptr]),
+    'bsig_mog_nll_fwd': (_int, [_c_ptr, _c_ptr, _i64, _c_ptr, _i64, _c_ptr, _i64, _c_ptr, _c_ptr,
+                                _c_ptr, _i64, _i64, _i64, _c_ptr, _i64, _c_ptr, _c_ptr]),
+    'bsig_mog_nll_bwd': (_int, [_c_ptr, _c_ptr, _i64, _c_ptr, _i64, _c_ptr, _i64, _c_ptr, _c_ptr,
+                                _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _i64, _i64, _i64,
+                                _c_ptr, _i64, _c_ptr]),
+    'bsig_mdn_nll_fused': (_int, [_c_ptr] * 6 + [_i64] * 3 + [_int, _c_ptr, _i64, _c_ptr, _c_ptr]),
+    'bsig_adam_step': (_int, [_c_ptr] * 4 + [_i64, _i64, _f32, _f32, _f32, _f32, _f32, _c_ptr]),
+    'bsig_gather_rows': (_int, [_c_ptr, _i64, _c_ptr, _c_ptr, _i64, _i64, _c_ptr]),
+    'bsig_finite_flag': (_int, [_c_ptr, _i64, _c_ptr, _c_ptr]),
+    'bsig_normalize_rows': (_int, [_c_ptr] * 4 + [_i64, _i64, _c_ptr]),
+    'bsig_mog_denorm': (_int, [_c_ptr, _c_ptr, _i64, _c_ptr, _i64, _c_ptr, _i64, _c_ptr, _c_ptr,
+                               _c_ptr, _c_ptr, _c_ptr, _i64, _i64, _i64, _c_ptr]),
+    'bsig_mog_sample': (_int, [_c_ptr, _int] + [_c_ptr] * 7 + [_i64] * 3 + [_c_ptr]),
+    'bsig_mog_sample_philox': (_int, [_c_ptr] * 5 + [_u64, _i64, _i64, _i64, _c_ptr]),
+    'bsig_mog_logpdf': (_int, [_c_ptr, _int] + [_c_ptr] * 5 + [_i64] * 3 + [_int, _c_ptr]),
+}
+
+_lib = None
+
+
+class BsigError(RuntimeError):
+    pass
+
+
+def load():
+    """Load (once) and return the ctypes handle; raises if the .so is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            'libbsig_b200.so is not built (%s). Run `python -m bayes_sim_ig_b200.build` '
+            '(needs nvcc); this package has no CPU fallback.' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)     # AttributeError if the symbol is missing
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load().bsig_last_error().decode('utf-8', 'replace')
+
+
+def call(name, *args):
+    """Invoke an int-returning entry point and raise on a non-zero status."""
+    rc = getattr(load(), name)(*args)
+    if rc != 0:
+        raise BsigError('%s failed (%d): %s' % (name, rc, last_error()))
+
+
+def stream_ptr(device=None):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr(t, dtype=torch.float32, allow_none=False):
+    """Device pointer of a tensor after checking what the kernels assume."""
+    if t is None:
+        if allow_none:
+            return None
+        raise BsigError('missing tensor argument')
+    if not t.is_cuda:
+        raise BsigError('bsig kernels need CUDA tensors (got %s); there is no CPU fallback'
+                        % t.device)
+    if t.dtype != dtype:
+        raise BsigError('expected dtype %s, got %s' % (dtype, t.dtype))
+    if not t.is_contiguous():
+        raise BsigError('expected a contiguous tensor')
+    return t.data_ptr()
+
+
+def require_cuda(device):
+    dev = torch.device(device)
+    if dev.type != 'cuda':
+        raise BsigError("bayes_sim_ig_b200 runs on CUDA devices only (device=%r): the hot path "
+                        "is hand-written sm_100a kernels with no CPU fallback" % (device,))
+    if not torch.cuda.is_available():
+        raise BsigError('CUDA is not available in this process')
+    return dev

@@ -1,0 +1,128 @@
+"""The BayesSim facade on the B200 kernels (reference bayes_sim_ig/bayes_sim.py).
+
+Same constructor, class constants, ``run_training`` and ``predict`` as the
+reference; the summarizer and model named in ``model_cfg`` are looked up by name
+among this package's implementations.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .models.mdnn import MDNN
+from .models.mdrff import MDRFF
+from .utils import pdf
+from .utils import summarizers as _summarizers
+from .utils.summarizers import *  # noqa: F401,F403  (same names as the reference exposes)
+
+_MODEL_CLASSES = {'MDNN': MDNN, 'MDRFF': MDRFF}
+
+
+class BayesSim(object):
+    NUM_TRAIN_TRAJ_PER_BATCH = 1000  # num trajs for each training batch
+    NUM_TRAIN_EPOCHS = 10            # num times to go over the batch
+    MINIBATCH_SIZE = 100             # minibatch size for NN training
+    NUM_GRAD_UPDATES = NUM_TRAIN_EPOCHS*NUM_TRAIN_TRAJ_PER_BATCH//MINIBATCH_SIZE
+    TEST_FRACTION = 0.2              # fraction of dataset to use as test
+
+    def __init__(self, model_cfg, obs_dim, act_dim, params_dim, params_lows, params_highs,
+                 prior, proposal=None, device='cuda'):
+        """Reference bayes_sim.py:27-82."""
+        _lib.require_cuda(device)
+        self.prior = prior
+        self.proposal = proposal
+        model_class = model_cfg['modelClass']
+        name = model_cfg['summarizerFxn']
+        if name not in _summarizers.__all__ or not name.startswith(('summary_', 'cross_')):
+            raise NameError("name '%s' is not defined" % name)
+        self.summarizer_fxn = getattr(_summarizers, name)
+        # the reference sizes the model by running the summarizer on zeros of
+        # length trainTrajLen (bayes_sim.py:57-60); the width is known in closed form
+        traj_summaries_dim = _summarizers.summary_width(
+            name, model_cfg['trainTrajLen'], obs_dim, act_dim)
+        full_covariance = False
+        if 'fullCovariance' in model_cfg:
+            full_covariance = model_cfg['fullCovariance']
+        kwargs = {'input_dim': traj_summaries_dim, 'output_dim': params_dim,
+                  'output_lows': params_lows, 'output_highs': params_highs,
+                  'n_gaussians': model_cfg['components'],
+                  'hidden_layers': model_cfg['hiddenLayers'],
+                  'lr': model_cfg['lr'],
+                  'activation': torch.nn.Tanh,
+                  'full_covariance': full_covariance,
+                  'device': device}
+        if model_class.startswith('MDRFF'):
+            kernel = 'RBF'
+            sigma = 4.0
+            if '_' in model_class:
+                model_params = model_class.split('_')
+                model_class = model_params[0]
+                kernel = model_params[1]
+                if len(model_params) > 2:
+                    sigma = float(model_params[2])
+            kwargs.update({'n_feat': 200, 'sigma': sigma, 'kernel': kernel})
+        if model_class not in _MODEL_CLASSES:
+            raise NameError("name '%s' is not defined" % model_class)
+        self.model = _MODEL_CLASSES[model_class](**kwargs)
+
+    @staticmethod
+    def get_n_trajs_per_batch(n_train_trajs, n_train_trajs_done):
+        n_trajs_per_batch = BayesSim.NUM_TRAIN_TRAJ_PER_BATCH
+        if n_train_trajs_done + n_trajs_per_batch > n_train_trajs:
+            n_trajs_per_batch = n_train_trajs - n_train_trajs_done
+        return n_trajs_per_batch
+
+    def run_training(self, params, traj_states, traj_actions):
+        """Reference bayes_sim.py:91-114: summarize, then NUM_GRAD_UPDATES Adam
+        steps of MINIBATCH_SIZE on the summaries."""
+        dev = self.model.flat_params.device
+        traj_summaries = self.summarizer_fxn(traj_states.to(dev), traj_actions.to(dev))
+        log_dict = self.model.run_training(
+            x_data=traj_summaries, y_data=params,
+            n_updates=BayesSim.NUM_GRAD_UPDATES,
+            batch_size=BayesSim.MINIBATCH_SIZE,
+            test_frac=BayesSim.TEST_FRACTION)
+        return log_dict
+
+    def predict(self, states, actions, threshold=0.005):
+        """Reference bayes_sim.py:116-179 -> host ``pdf.MoG`` posterior."""
+        dev = self.model.flat_params.device
+        xs = self.summarizer_fxn(states.to(dev), actions.to(dev))
+        mogs = self.model.predict_MoGs(xs)
+        if self.proposal is not None:
+            for tmp_i, mog in enumerate(mogs):
+                mog.prune_negligible_components(threshold=threshold)
+                if isinstance(self.prior, pdf.Uniform):
+                    post = mog / self.proposal
+                elif isinstance(self.prior, pdf.Gaussian):
+                    post = (mog * self.prior) / self.proposal
+                else:
+                    raise NotImplementedError
+                mogs[tmp_i] = post
+        if len(mogs) == 1:
+            return mogs[0]
+        # Several real trajectories: resample the per-trajectory mixtures and fit
+        # one unconditional mixture to the pooled samples (bayes_sim.py:148-179).
+        kwargs = {'input_dim': 1,
+                  'output_dim': self.model.output_dim,
+                  'output_lows': self.model.output_lows.detach().cpu().numpy(),
+                  'output_highs': self.model.output_highs.detach().cpu().numpy(),
+                  'n_gaussians': self.model.n_gaussians,
+                  'hidden_layers': (128, 128),
+                  'lr': self.model.lr,
+                  'activation': self.model.activation,
+                  'full_covariance': self.model.L_size > 0,
+                  'device': self.model.device}
+        mog_model = MDNN(**kwargs)
+        tot_smpls = int(1e4)
+        n_smpls_per_mog = int(tot_smpls/xs.shape[0])
+        mog_smpls = np.concatenate(
+            [mogs[tmp_i].gen(n_samples=n_smpls_per_mog) for tmp_i in range(xs.shape[0])], axis=0)
+        mog_smpls = torch.from_numpy(mog_smpls).float().to(dev)
+        print(f'Fitting posterior from {len(mogs):d} mogs')
+        batch_size = 100
+        n_updates = 5*tot_smpls//batch_size
+        input = torch.zeros(mog_smpls.shape[0], 1).to(dev)
+        mog_model.run_training(input, mog_smpls, n_updates, batch_size)
+        fitted_mogs = mog_model.predict_MoGs(input[0:1, :])
+        assert (len(fitted_mogs) == 1)
+        return fitted_mogs[0]

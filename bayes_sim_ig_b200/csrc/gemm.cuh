@@ -1,0 +1,48 @@
+// Internal GEMM plumbing shared by the SIMT and tcgen05 engines.
+#pragma once
+#include "common.cuh"
+
+namespace bsig {
+
+enum Epilogue {
+  EPI_STORE = 0,      // C = acc
+  EPI_BIAS = 1,       // C = acc + bias[j]
+  EPI_BIAS_TANH = 2,  // C = tanh(acc + bias[j])
+  EPI_MUL_DTANH = 3,  // C = acc * (1 - aux[i,j]^2)
+  EPI_SINCOS = 4      // C[i,j] = scale*cos(acc), C[i,N+j] = scale*sin(acc)
+};
+
+struct GemmArgs {
+  const float* A;
+  const float* B;
+  float* C;
+  int M, N, K;
+  int64_t a_si, a_sr;        // A(i,r) strides
+  int64_t b_sr, b_sj;        // B(r,j) strides
+  int64_t ldc;
+  const int64_t* a_rows;     // optional gather of A's i index
+  const int64_t* b_rows;     // optional gather of B's r index
+  int epi;
+  const float* bias;
+  const float* aux;
+  int64_t ld_aux;
+  float scale;
+  // filled by the launcher
+  int k_per_split;
+  float* partial;
+};
+
+inline GemmArgs gemm_args_zero() {
+  GemmArgs g;
+  g.A = g.B = nullptr; g.C = nullptr; g.M = g.N = g.K = 0;
+  g.a_si = g.a_sr = g.b_sr = g.b_sj = g.ldc = 0;
+  g.a_rows = g.b_rows = nullptr; g.epi = EPI_STORE; g.bias = g.aux = nullptr;
+  g.ld_aux = 0; g.scale = 1.f; g.k_per_split = 0; g.partial = nullptr;
+  return g;
+}
+
+int gemm_simt(GemmArgs g, void* ws, int64_t ws_bytes, cudaStream_t st);
+int64_t gemm_simt_ws_bytes(int64_t M, int64_t N, int64_t K);
+int colsum(const float* dy, float* db, int64_t M, int64_t N, cudaStream_t st);
+
+}  // namespace bsig

@@ -1,0 +1,77 @@
+// bsig_linear_* / bsig_rff_features: shape the three layer GEMMs (forward,
+// dgrad, wgrad) and the RFF projection and hand them to a GEMM engine.
+#include "common.cuh"
+#include "gemm.cuh"
+
+using namespace bsig;
+
+static int run_gemm(const GemmArgs& g, int engine, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  (void)engine;  // BSIG_GEMM_TC_* engines are wired in gemm_tc.cu
+  return gemm_simt(g, ws, ws_bytes, st);
+}
+
+extern "C" int64_t bsig_linear_ws_bytes(int64_t m, int64_t n, int64_t k) {
+  // the same scratch serves forward (m,n,k), dgrad (m,k,n) and wgrad (n,k,m)
+  int64_t a = gemm_simt_ws_bytes(m, n, k);
+  int64_t b = gemm_simt_ws_bytes(m, k, n);
+  int64_t c = gemm_simt_ws_bytes(n, k, m);
+  int64_t r = a > b ? a : b;
+  r = r > c ? r : c;
+  return r + 256;
+}
+
+extern "C" int bsig_linear_fwd(const float* x, int64_t ldx, const int64_t* x_rows, const float* w,
+                               const float* b, float* y, int64_t m, int64_t n, int64_t k, int act,
+                               int engine, void* ws, int64_t ws_bytes, void* stream) {
+  BSIG_REQUIRE(m >= 1 && n >= 1 && k >= 1, "linear_fwd: empty problem");
+  BSIG_REQUIRE(act == BSIG_ACT_NONE || act == BSIG_ACT_TANH, "linear_fwd: unknown activation");
+  GemmArgs g = gemm_args_zero();
+  g.A = x; g.a_si = ldx; g.a_sr = 1; g.a_rows = x_rows;
+  g.B = w; g.b_sr = 1; g.b_sj = k;          // B(r,j) = w[j,r]
+  g.C = y; g.ldc = n; g.M = (int)m; g.N = (int)n; g.K = (int)k;
+  g.bias = b;
+  g.epi = b == nullptr ? EPI_STORE : (act == BSIG_ACT_TANH ? EPI_BIAS_TANH : EPI_BIAS);
+  BSIG_REQUIRE(!(b == nullptr && act == BSIG_ACT_TANH), "linear_fwd: tanh needs a bias");
+  return run_gemm(g, engine, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int bsig_linear_dgrad(const float* dy, const float* w, const float* h_prev, float* dx,
+                                 int64_t m, int64_t n, int64_t k, int act_prev, int engine,
+                                 void* ws, int64_t ws_bytes, void* stream) {
+  BSIG_REQUIRE(m >= 1 && n >= 1 && k >= 1, "linear_dgrad: empty problem");
+  GemmArgs g = gemm_args_zero();
+  g.A = dy; g.a_si = n; g.a_sr = 1;         // A(i,r) = dy[i,r], r over n
+  g.B = w; g.b_sr = k; g.b_sj = 1;          // B(r,j) = w[r,j]
+  g.C = dx; g.ldc = k; g.M = (int)m; g.N = (int)k; g.K = (int)n;
+  if (act_prev == BSIG_ACT_TANH) {
+    BSIG_REQUIRE(h_prev != nullptr, "linear_dgrad: h_prev required for tanh");
+    g.epi = EPI_MUL_DTANH; g.aux = h_prev; g.ld_aux = k;
+  }
+  return run_gemm(g, engine, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int bsig_linear_wgrad(const float* dy, const float* x, int64_t ldx,
+                                 const int64_t* x_rows, float* dw, float* db, int64_t m, int64_t n,
+                                 int64_t k, int engine, void* ws, int64_t ws_bytes, void* stream) {
+  BSIG_REQUIRE(m >= 1 && n >= 1 && k >= 1, "linear_wgrad: empty problem");
+  GemmArgs g = gemm_args_zero();
+  g.A = dy; g.a_si = 1; g.a_sr = n;         // A(i,r) = dy[r,i]
+  g.B = x; g.b_sr = ldx; g.b_sj = 1; g.b_rows = x_rows;   // B(r,j) = x[rows[r], j]
+  g.C = dw; g.ldc = k; g.M = (int)n; g.N = (int)k; g.K = (int)m;
+  if (run_gemm(g, engine, ws, ws_bytes, (cudaStream_t)stream)) return 1;
+  if (db != nullptr) return colsum(dy, db, m, n, (cudaStream_t)stream);
+  return 0;
+}
+
+extern "C" int bsig_rff_features(const float* x, int64_t ldx, const int64_t* x_rows,
+                                 const float* coeff, float* out, int64_t m, int64_t d,
+                                 int64_t nf_half, float scale, int engine, void* ws,
+                                 int64_t ws_bytes, void* stream) {
+  BSIG_REQUIRE(m >= 1 && d >= 1 && nf_half >= 1, "rff_features: empty problem");
+  GemmArgs g = gemm_args_zero();
+  g.A = x; g.a_si = ldx; g.a_sr = 1; g.a_rows = x_rows;
+  g.B = coeff; g.b_sr = 1; g.b_sj = d;
+  g.C = out; g.ldc = 2 * nf_half; g.M = (int)m; g.N = (int)nf_half; g.K = (int)d;
+  g.epi = EPI_SINCOS; g.scale = scale;
+  return run_gemm(g, engine, ws, ws_bytes, (cudaStream_t)stream);
+}

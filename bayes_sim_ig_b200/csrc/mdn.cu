@@ -1,0 +1,673 @@
+// Mixture-density head epilogue and mixture-of-Gaussians negative log-likelihood
+// (reference bayes_sim_ig/models/mdnn.py:109-119 and 127-178), forward and
+// backward, as explicit kernels.
+//
+// Layout of the concatenated head output z [B, NH]:
+//   [0,K) pi logits | [K,K+PK) mu, col p*K+k | [K+PK,K+2PK) log-diag |
+//   [K+2PK, K+2PK+LK) strict-lower entries, col l*K+k (np.tril_indices order)
+//
+// Work decomposition of the NLL kernels: a sub-warp group of GW lanes (GW =
+// pow2 >= min(K,32)) owns one sample; lane g handles components g, g+GW, ...
+// Per component the Cholesky-parameterised log-density needs a forward
+// substitution (z = L^-1 (y-mu)), the backward pass a back substitution
+// (v = L^-T z); the logsumexp over components is a shuffle reduction inside
+// the group.  All of it is HBM/L2-bound streaming over z: each entry of z is
+// read twice (forward, backward) and each entry of dz written once.
+//
+// Every cross-sample reduction (mean of exp(z_d) for the eps-noise term, the
+// loss, the eps-term gradient) is two-stage and fixed-order => deterministic.
+#include "common.cuh"
+
+namespace bsig {
+
+constexpr float kLLLimit = 1.0e5f;     // MDNN.LL_LIMIT   mdnn.py:22
+constexpr float kMinWeight = 1.0e-5f;  // MDNN.MIN_WEIGHT mdnn.py:23
+constexpr float kEpsNoise = 1.0e-5f;   // MDNN.EPS_NOISE  mdnn.py:24
+constexpr float kLog2Pi = 1.8378770664093453f;
+
+constexpr int kMaxParts = 1024;  // per-block partial slots
+// workspace layout (floats): [0,kMaxParts) exp-sum partials, then loss
+// partials, then eps-gradient partials, then 4 counters/scalars.
+constexpr int kWsFloats = 3 * kMaxParts + 8;
+
+struct NllArgs {
+  // forward inputs (row strides in floats)
+  const float* z_pi;   int64_t ld_pi;    // FUSED: logits; else weights [b,K]
+  const float* mu;     int64_t ld_mu;
+  const float* zd;     int64_t ld_zd;    // FUSED: log-diag; else l_d
+  const float* low;    int64_t ld_low;   // nullable
+  const float* noise;                    // FUSED only, [b,P,K]
+  const float* y;      const int64_t* y_rows;
+  const float* grad_scale;               // nullable device scalar (non-fused bwd)
+  // outputs
+  float* loss;
+  float* d_pi;   int64_t ldo_pi;         // FUSED: d logits; else d weights
+  float* d_mu;   int64_t ldo_mu;
+  float* d_zd;   int64_t ldo_zd;
+  float* d_low;  int64_t ldo_low;
+  float* ws;
+  int* flag;
+  int B, P, K, L;
+  int nparts_e;                          // number of valid exp-sum partials
+};
+
+// ---------------------------------------------------------------- exp-sum (eps)
+__global__ void __launch_bounds__(256)
+exp_sum_kernel(const float* __restrict__ zd, int64_t ld_zd, int B, int PK, float* ws) {
+  __shared__ float scratch[33];
+  const int64_t total = (int64_t)B * PK;
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / PK;
+    const int c = (int)(i - b * PK);
+    acc += expf(__ldg(zd + b * ld_zd + c));
+  }
+  acc = block_sum(acc, scratch);
+  if (threadIdx.x == 0) ws[blockIdx.x] = acc;
+}
+
+__device__ __forceinline__ float sum_parts(const float* parts, int n, float* scratch) {
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += parts[i];
+  return block_sum(acc, scratch);
+}
+
+template <int GW>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = GW / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int GW>
+__device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+  for (int o = GW / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// --------------------------------------------------------------------- NLL core
+// FUSED: inputs are raw head outputs (softmax / exp+noise applied here, and the
+//        gradients are taken back through them to the logits).
+// FULL : full covariance (strict-lower block present).
+// BWD  : also write gradients.
+template <int GW, int KPL, bool FUSED, bool FULL, bool BWD>
+__global__ void __launch_bounds__(128) nll_kernel(NllArgs a) {
+  extern __shared__ float dyn[];           // FULL: zs[P][128], vs[P][128]
+  __shared__ float scratch[33];
+  const int tid = threadIdx.x;
+  const int lane_g = tid & (GW - 1);
+  const int gid = tid / GW;
+  constexpr int GPB = 128 / GW;
+  const int B = a.B, P = a.P, K = a.K;
+  float* zs = dyn + tid;                   // element p at zs[p*128]
+  float* vs = dyn + (size_t)P * 128 + tid;
+
+  float eps = 0.f;
+  if (FUSED) {
+    const float esum = sum_parts(a.ws, a.nparts_e, scratch);
+    eps = kEpsNoise * (esum / (float)((int64_t)B * P * K));
+  }
+  float gscale = 1.f;
+  if (BWD && a.grad_scale != nullptr) gscale = __ldg(a.grad_scale);
+  const float coef_scale = gscale / (float)B;
+
+  float loss_acc = 0.f, s_acc = 0.f;
+  bool bad = false;
+
+  for (int base = blockIdx.x * GPB; base < B; base += gridDim.x * GPB) {
+    const int b = base + gid;
+    const bool row_ok = b < B;
+    const int64_t bb = row_ok ? b : 0;
+    const float* yrow = a.y + (a.y_rows ? __ldg(a.y_rows + bb) : bb) * P;
+    const float* mu_r = a.mu + bb * a.ld_mu;
+    const float* zd_r = a.zd + bb * a.ld_zd;
+    const float* low_r = FULL ? a.low + bb * a.ld_low : nullptr;
+    const float* nz_r = FUSED ? a.noise + bb * (int64_t)P * K : nullptr;
+
+    // ---- mixture weights
+    float w[KPL], soft[KPL], csum = 1.f;
+    if (FUSED) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < KPL; ++j) {
+        const int k = lane_g + j * GW;
+        soft[j] = (row_ok && k < K) ? __ldg(a.z_pi + bb * a.ld_pi + k) : -INFINITY;
+        mx = fmaxf(mx, soft[j]);
+      }
+      mx = group_max<GW>(mx);
+      float sm = 0.f;
+#pragma unroll
+      for (int j = 0; j < KPL; ++j) {
+        soft[j] = (soft[j] == -INFINITY) ? 0.f : expf(soft[j] - mx);
+        sm += soft[j];
+      }
+      sm = group_sum<GW>(sm);
+      float cs = 0.f;
+#pragma unroll
+      for (int j = 0; j < KPL; ++j) {
+        const int k = lane_g + j * GW;
+        soft[j] = soft[j] / sm;
+        w[j] = (k < K) ? fminf(fmaxf(soft[j], kMinWeight), 1.0f) : 0.f;  // clamped
+        cs += w[j];
+      }
+      csum = group_sum<GW>(cs);
+#pragma unroll
+      for (int j = 0; j < KPL; ++j) w[j] = w[j] / csum;
+    } else {
+#pragma unroll
+      for (int j = 0; j < KPL; ++j) {
+        const int k = lane_g + j * GW;
+        w[j] = (row_ok && k < K) ? __ldg(a.z_pi + bb * a.ld_pi + k) : 0.f;
+        soft[j] = 0.f;
+      }
+    }
+
+    // ---- per-component log density
+    float r[KPL], g[KPL];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) {
+      const int k = lane_g + j * GW;
+      r[j] = -INFINITY;
+      g[j] = 0.f;
+      if (row_ok && k < K) {
+        float quad = 0.f, logdet = 0.f;
+        for (int i = 0; i < P; ++i) {
+          float ldv = __ldg(zd_r + i * K + k);
+          if (FUSED) ldv = expf(ldv) + __ldg(nz_r + i * K + k) * eps;
+          const float m = __ldg(mu_r + i * K + k);
+          float acc = __ldg(yrow + i) - m;
+          if (FULL) {
+            const float* lrow = low_r + (int64_t)(i * (i - 1) / 2) * K + k;
+            for (int c = 0; c < i; ++c) acc -= __ldg(lrow + c * K) * zs[c * 128];
+          }
+          const float zi = acc / ldv;
+          if (FULL) zs[i * 128] = zi;
+          quad += zi * zi;
+          logdet += logf(ldv);
+          bad |= !(finite_f(ldv) && finite_f(m));
+        }
+        const float gj = -0.5f * ((float)P * kLog2Pi + quad) - logdet;
+        bad |= !(finite_f(gj) && finite_f(w[j]));
+        g[j] = gj;
+        const float gc = fminf(fmaxf(gj, -kLLLimit), kLLLimit);
+        const float wc = fminf(fmaxf(w[j], kMinWeight), 1.0f);
+        r[j] = gc + logf(wc);
+        mx = fmaxf(mx, r[j]);
+      }
+    }
+    mx = group_max<GW>(mx);
+    float se = 0.f;
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) se += (r[j] == -INFINITY) ? 0.f : expf(r[j] - mx);
+    se = group_sum<GW>(se);
+    const float lse = mx + logf(se);
+    if (row_ok && lane_g == 0) loss_acc -= lse;
+
+    if (BWD) {
+      // ---- gradient wrt weights (and back through clamp/renorm/softmax if FUSED)
+      float dw[KPL], coef[KPL];
+      float t1 = 0.f;
+#pragma unroll
+      for (int j = 0; j < KPL; ++j) {
+        const int k = lane_g + j * GW;
+        dw[j] = 0.f;
+        coef[j] = 0.f;
+        if (row_ok && k < K) {
+          const float rho = expf(r[j] - lse);
+          coef[j] = -rho * coef_scale;                // d loss / d r_k
+          const float wc = fminf(fmaxf(w[j], kMinWeight), 1.0f);
+          const bool in_w = (w[j] >= kMinWeight) && (w[j] <= 1.0f);
+          dw[j] = in_w ? coef[j] / wc : 0.f;
+          t1 += dw[j] * w[j];
+        }
+      }
+      if (FUSED) {
+        t1 = group_sum<GW>(t1);
+        float dp[KPL], t2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) {
+          const float dc = (dw[j] - t1) / csum;
+          const bool in_c = (soft[j] >= kMinWeight) && (soft[j] <= 1.0f);
+          dp[j] = in_c ? dc : 0.f;
+          t2 += dp[j] * soft[j];
+        }
+        t2 = group_sum<GW>(t2);
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) {
+          const int k = lane_g + j * GW;
+          if (row_ok && k < K) a.d_pi[bb * a.ldo_pi + k] = soft[j] * (dp[j] - t2);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) {
+          const int k = lane_g + j * GW;
+          if (row_ok && k < K) a.d_pi[bb * a.ldo_pi + k] = dw[j];
+        }
+      }
+
+      // ---- gradient wrt mu, l_d, low
+#pragma unroll
+      for (int j = 0; j < KPL; ++j) {
+        const int k = lane_g + j * GW;
+        if (!(row_ok && k < K)) continue;
+        const bool in_g = (g[j] >= -kLLLimit) && (g[j] <= kLLLimit);
+        const float cg = in_g ? coef[j] : 0.f;
+        float* dmu_r = a.d_mu + bb * a.ldo_mu;
+        float* dzd_r = a.d_zd + bb * a.ldo_zd;
+        if (!FULL) {
+          for (int i = 0; i < P; ++i) {
+            const float raw = __ldg(zd_r + i * K + k);
+            float e = raw, ldv = raw, nz = 0.f;
+            if (FUSED) {
+              e = expf(raw);
+              nz = __ldg(nz_r + i * K + k);
+              ldv = e + nz * eps;
+            }
+            const float zi = (__ldg(yrow + i) - __ldg(mu_r + i * K + k)) / ldv;
+            const float vi = zi / ldv;
+            const float dld = cg * (vi * zi - 1.0f / ldv);
+            dmu_r[i * K + k] = cg * vi;
+            if (FUSED) {
+              s_acc += dld * nz;
+              dzd_r[i * K + k] = e * dld;
+            } else {
+              dzd_r[i * K + k] = dld;
+            }
+          }
+        } else {
+          float* dlow_r = a.d_low + bb * a.ldo_low;
+          if (KPL > 1) {
+            // zs holds the LAST component's solve: redo the forward substitution
+            for (int i = 0; i < P; ++i) {
+              float ldv = __ldg(zd_r + i * K + k);
+              if (FUSED) ldv = expf(ldv) + __ldg(nz_r + i * K + k) * eps;
+              float acc = __ldg(yrow + i) - __ldg(mu_r + i * K + k);
+              const float* lrow = low_r + (int64_t)(i * (i - 1) / 2) * K + k;
+              for (int c = 0; c < i; ++c) acc -= __ldg(lrow + c * K) * zs[c * 128];
+              zs[i * 128] = acc / ldv;
+            }
+          }
+          // back substitution v = L^-T z, rows descending
+          for (int i = P - 1; i >= 0; --i) {
+            const float raw = __ldg(zd_r + i * K + k);
+            float e = raw, ldv = raw, nz = 0.f;
+            if (FUSED) {
+              e = expf(raw);
+              nz = __ldg(nz_r + i * K + k);
+              ldv = e + nz * eps;
+            }
+            float acc = zs[i * 128];
+            for (int c = i + 1; c < P; ++c)
+              acc -= __ldg(low_r + (int64_t)(c * (c - 1) / 2 + i) * K + k) * vs[c * 128];
+            const float vi = acc / ldv;
+            vs[i * 128] = vi;
+            const float zi = zs[i * 128];
+            const float dld = cg * (vi * zi - 1.0f / ldv);
+            dmu_r[i * K + k] = cg * vi;
+            if (FUSED) {
+              s_acc += dld * nz;
+              dzd_r[i * K + k] = e * dld;
+            } else {
+              dzd_r[i * K + k] = dld;
+            }
+            // d L[i][c] = cg * v_i * z_c for c < i
+            float* drow = dlow_r + (int64_t)(i * (i - 1) / 2) * K + k;
+            const float cv = cg * vi;
+            for (int c = 0; c < i; ++c) drow[c * K] = cv * zs[c * 128];
+          }
+        }
+      }
+    }
+  }
+
+  if (bad) atomicOr(a.flag, 1);
+
+  // ---- deterministic cross-block reductions
+  float* loss_parts = a.ws + kMaxParts;
+  float* s_parts = a.ws + 2 * kMaxParts;
+  unsigned int* counter = reinterpret_cast<unsigned int*>(a.ws + 3 * kMaxParts);
+  const float lsum = block_sum(loss_acc, scratch);
+  float ssum = 0.f;
+  if (FUSED && BWD) ssum = block_sum(s_acc, scratch);
+  __shared__ bool is_last;
+  if (tid == 0) {
+    loss_parts[blockIdx.x] = lsum;
+    if (FUSED && BWD) s_parts[blockIdx.x] = ssum;
+    __threadfence();
+    const unsigned int done = atomicAdd(counter, 1u);
+    is_last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    float acc = 0.f;
+    for (int i = tid; i < (int)gridDim.x; i += blockDim.x) acc += __ldcg(loss_parts + i);
+    acc = block_sum(acc, scratch);
+    if (tid == 0) {
+      a.loss[0] = acc / (float)B;
+      *counter = 0u;   // ready for the next launch
+    }
+  }
+}
+
+// eps-term fix-up of the fused backward: dzd += exp(zd) * (1e-5/M) * S
+__global__ void __launch_bounds__(256)
+eps_fixup_kernel(const float* __restrict__ zd, int64_t ld_zd, float* dzd, int64_t ldo_zd,
+                 int B, int PK, const float* s_parts, int nparts) {
+  __shared__ float scratch[33];
+  const float S = sum_parts(s_parts, nparts, scratch);
+  const int64_t total = (int64_t)B * PK;
+  const float c = kEpsNoise * S / (float)total;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / PK;
+    const int col = (int)(i - b * PK);
+    dzd[b * ldo_zd + col] += expf(__ldg(zd + b * ld_zd + col)) * c;
+  }
+}
+
+// --------------------------------------------------------- head epilogue (API path)
+__global__ void __launch_bounds__(256)
+head_fwd_kernel(const float* __restrict__ z, const float* __restrict__ noise,
+                float* __restrict__ weights, float* __restrict__ l_d,
+                int B, int P, int K, int NH, const float* ws, int nparts, int* flag) {
+  __shared__ float scratch[33];
+  const float esum = sum_parts(ws, nparts, scratch);
+  const int PK = P * K;
+  const float eps = kEpsNoise * (esum / (float)((int64_t)B * PK));
+  bool bad = false;
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t b = gtid; b < B; b += gstride) {
+    const float* zr = z + b * NH;
+    float mx = -INFINITY;
+    for (int k = 0; k < K; ++k) mx = fmaxf(mx, __ldg(zr + k));
+    float sm = 0.f;
+    for (int k = 0; k < K; ++k) sm += expf(__ldg(zr + k) - mx);
+    float cs = 0.f;
+    for (int k = 0; k < K; ++k)
+      cs += fminf(fmaxf(expf(__ldg(zr + k) - mx) / sm, kMinWeight), 1.0f);
+    for (int k = 0; k < K; ++k) {
+      const float wv = fminf(fmaxf(expf(__ldg(zr + k) - mx) / sm, kMinWeight), 1.0f) / cs;
+      weights[b * K + k] = wv;
+      bad |= !finite_f(wv);
+    }
+  }
+  const int64_t total = (int64_t)B * PK;
+  for (int64_t i = gtid; i < total; i += gstride) {
+    const int64_t b = i / PK;
+    const int c = (int)(i - b * PK);
+    const float v = expf(__ldg(z + b * NH + K + PK + c)) + __ldg(noise + i) * eps;
+    l_d[i] = v;
+    bad |= !finite_f(v) || !finite_f(__ldg(z + b * NH + K + c));
+  }
+  const int LK = NH - K - 2 * PK;
+  const int64_t total_l = (int64_t)B * LK;
+  for (int64_t i = gtid; i < total_l; i += gstride) {
+    const int64_t b = i / LK;
+    const int c = (int)(i - b * LK);
+    bad |= !finite_f(__ldg(z + b * NH + K + 2 * PK + c));
+  }
+  if (bad) atomicOr(flag, 1);
+}
+
+// S = sum d_ld * noise (partials)
+__global__ void __launch_bounds__(256)
+dot_parts_kernel(const float* __restrict__ x, const float* __restrict__ y, int64_t total,
+                 float* parts) {
+  __shared__ float scratch[33];
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x)
+    acc += __ldg(x + i) * __ldg(y + i);
+  acc = block_sum(acc, scratch);
+  if (threadIdx.x == 0) parts[blockIdx.x] = acc;
+}
+
+__global__ void __launch_bounds__(256)
+head_bwd_kernel(const float* __restrict__ z, const float* __restrict__ weights,
+                const float* __restrict__ d_weights, const float* __restrict__ d_mu,
+                const float* __restrict__ d_ld, const float* __restrict__ d_low,
+                float* __restrict__ dz, int B, int P, int K, int NH,
+                const float* s_parts, int nparts) {
+  __shared__ float scratch[33];
+  const float S = sum_parts(s_parts, nparts, scratch);
+  const int PK = P * K;
+  const float c_eps = kEpsNoise * S / (float)((int64_t)B * PK);
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t b = gtid; b < B; b += gstride) {
+    const float* zr = z + b * NH;
+    float mx = -INFINITY;
+    for (int k = 0; k < K; ++k) mx = fmaxf(mx, __ldg(zr + k));
+    float sm = 0.f;
+    for (int k = 0; k < K; ++k) sm += expf(__ldg(zr + k) - mx);
+    float cs = 0.f, t1 = 0.f;
+    for (int k = 0; k < K; ++k) {
+      cs += fminf(fmaxf(expf(__ldg(zr + k) - mx) / sm, kMinWeight), 1.0f);
+      t1 += __ldg(d_weights + b * K + k) * __ldg(weights + b * K + k);
+    }
+    float t2 = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const float p = expf(__ldg(zr + k) - mx) / sm;
+      const float dc = (__ldg(d_weights + b * K + k) - t1) / cs;
+      const float dp = (p >= kMinWeight && p <= 1.0f) ? dc : 0.f;
+      t2 += dp * p;
+    }
+    for (int k = 0; k < K; ++k) {
+      const float p = expf(__ldg(zr + k) - mx) / sm;
+      const float dc = (__ldg(d_weights + b * K + k) - t1) / cs;
+      const float dp = (p >= kMinWeight && p <= 1.0f) ? dc : 0.f;
+      dz[b * NH + k] = p * (dp - t2);
+    }
+  }
+  const int64_t total = (int64_t)B * PK;
+  for (int64_t i = gtid; i < total; i += gstride) {
+    const int64_t b = i / PK;
+    const int c = (int)(i - b * PK);
+    dz[b * NH + K + c] = __ldg(d_mu + i);
+    dz[b * NH + K + PK + c] = expf(__ldg(z + b * NH + K + PK + c)) * (__ldg(d_ld + i) + c_eps);
+  }
+  const int LK = NH - K - 2 * PK;
+  const int64_t total_l = (int64_t)B * LK;
+  for (int64_t i = gtid; i < total_l; i += gstride) {
+    const int64_t b = i / LK;
+    const int c = (int)(i - b * LK);
+    dz[b * NH + K + 2 * PK + c] = d_low ? __ldg(d_low + i) : 0.f;
+  }
+}
+
+// ------------------------------------------------------------------ host dispatch
+template <int GW, int KPL, bool FUSED, bool FULL>
+static int launch_nll_bwd_sel(const NllArgs& a, bool bwd, int grid, size_t smem, cudaStream_t st) {
+  if (bwd) {
+    if (smem > 48 * 1024)
+      BSIG_CUDA(cudaFuncSetAttribute(nll_kernel<GW, KPL, FUSED, FULL, true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nll_kernel<GW, KPL, FUSED, FULL, true><<<grid, 128, smem, st>>>(a);
+  } else {
+    if (smem > 48 * 1024)
+      BSIG_CUDA(cudaFuncSetAttribute(nll_kernel<GW, KPL, FUSED, FULL, false>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nll_kernel<GW, KPL, FUSED, FULL, false><<<grid, 128, smem, st>>>(a);
+  }
+  BSIG_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int GW, int KPL>
+static int launch_nll_gw(const NllArgs& a, bool fused, bool full, bool bwd, int grid, size_t smem,
+                         cudaStream_t st) {
+  if (fused) {
+    return full ? launch_nll_bwd_sel<GW, KPL, true, true>(a, bwd, grid, smem, st)
+                : launch_nll_bwd_sel<GW, KPL, true, false>(a, bwd, grid, smem, st);
+  }
+  return full ? launch_nll_bwd_sel<GW, KPL, false, true>(a, bwd, grid, smem, st)
+              : launch_nll_bwd_sel<GW, KPL, false, false>(a, bwd, grid, smem, st);
+}
+
+static int launch_nll(NllArgs& a, bool fused, bool bwd, cudaStream_t st) {
+  const int K = a.K;
+  BSIG_REQUIRE(K >= 1 && K <= 128, "mixture NLL: 1 <= n_gaussians <= 128 supported (got %d)", K);
+  BSIG_REQUIRE(a.P >= 1 && a.P <= 192, "mixture NLL: output_dim <= 192 supported (got %d)", a.P);
+  const bool full = a.L > 0;
+  int gw = 1;
+  while (gw < K && gw < 32) gw <<= 1;
+  const int gpb = 128 / gw;
+  const int grid = (int)std::min<int64_t>(ceil_div(a.B, gpb), kMaxParts);
+  const size_t smem = full ? (size_t)2 * a.P * 128 * sizeof(float) : 0;
+  switch (gw) {
+    case 1: return launch_nll_gw<1, 1>(a, fused, full, bwd, grid, smem, st);
+    case 2: return launch_nll_gw<2, 1>(a, fused, full, bwd, grid, smem, st);
+    case 4: return launch_nll_gw<4, 1>(a, fused, full, bwd, grid, smem, st);
+    case 8: return launch_nll_gw<8, 1>(a, fused, full, bwd, grid, smem, st);
+    case 16: return launch_nll_gw<16, 1>(a, fused, full, bwd, grid, smem, st);
+    default:
+      if (K <= 32) return launch_nll_gw<32, 1>(a, fused, full, bwd, grid, smem, st);
+      if (K <= 64) return launch_nll_gw<32, 2>(a, fused, full, bwd, grid, smem, st);
+      return launch_nll_gw<32, 4>(a, fused, full, bwd, grid, smem, st);
+  }
+}
+
+static int launch_exp_sum(const float* zd, int64_t ld_zd, int B, int PK, float* ws,
+                          cudaStream_t st, int* nparts) {
+  const int64_t total = (int64_t)B * PK;
+  const int grid = (int)std::min<int64_t>(ceil_div(total, 256 * 4), 256);
+  exp_sum_kernel<<<grid, 256, 0, st>>>(zd, ld_zd, B, PK, ws);
+  BSIG_LAUNCH_CHECK();
+  *nparts = grid;
+  return 0;
+}
+
+}  // namespace bsig
+
+using namespace bsig;
+
+extern "C" int64_t bsig_mdn_ws_bytes(int64_t b) {
+  (void)b;
+  return (int64_t)kWsFloats * sizeof(float);
+}
+
+extern "C" int bsig_mdn_head_fwd(const float* z, const float* noise, float* weights, float* l_d,
+                                 int64_t b, int64_t p, int64_t k, int full_cov, void* ws,
+                                 int64_t ws_bytes, int* flag, void* stream) {
+  BSIG_REQUIRE(ws_bytes >= bsig_mdn_ws_bytes(b), "mdn_head_fwd: workspace too small");
+  BSIG_REQUIRE(b >= 1 && p >= 1 && k >= 1, "mdn_head_fwd: bad sizes");
+  const int L = (full_cov && p > 1) ? (int)(p * (p - 1) / 2) : 0;
+  const int NH = (int)(k + 2 * p * k + (int64_t)L * k);
+  cudaStream_t st = (cudaStream_t)stream;
+  int nparts = 0;
+  if (launch_exp_sum(z + k + p * k, NH, (int)b, (int)(p * k), (float*)ws, st, &nparts)) return 1;
+  const int64_t work = b * (int64_t)NH;
+  const int grid = (int)std::min<int64_t>(ceil_div(work, 256), (int64_t)sm_count() * 8);
+  head_fwd_kernel<<<grid, 256, 0, st>>>(z, noise, weights, l_d, (int)b, (int)p, (int)k, NH,
+                                        (const float*)ws, nparts, flag);
+  BSIG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int bsig_mdn_head_bwd(const float* z, const float* noise, const float* weights,
+                                 const float* d_weights, const float* d_mu, const float* d_ld,
+                                 const float* d_low, float* dz, int64_t b, int64_t p, int64_t k,
+                                 int full_cov, void* ws, int64_t ws_bytes, void* stream) {
+  BSIG_REQUIRE(ws_bytes >= bsig_mdn_ws_bytes(b), "mdn_head_bwd: workspace too small");
+  const int L = (full_cov && p > 1) ? (int)(p * (p - 1) / 2) : 0;
+  const int NH = (int)(k + 2 * p * k + (int64_t)L * k);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = b * p * k;
+  float* s_parts = (float*)ws + 2 * kMaxParts;
+  const int gparts = (int)std::min<int64_t>(ceil_div(total, 1024), 256);
+  dot_parts_kernel<<<gparts, 256, 0, st>>>(d_ld, noise, total, s_parts);
+  BSIG_LAUNCH_CHECK();
+  const int grid = (int)std::min<int64_t>(ceil_div(b * (int64_t)NH, 256), (int64_t)sm_count() * 8);
+  head_bwd_kernel<<<grid, 256, 0, st>>>(z, weights, d_weights, d_mu, d_ld, d_low, dz, (int)b,
+                                        (int)p, (int)k, NH, s_parts, gparts);
+  BSIG_LAUNCH_CHECK();
+  return 0;
+}
+
+static void fill_common(NllArgs& a, const float* y, const int64_t* y_rows, float* loss, void* ws,
+                        int* flag, int64_t b, int64_t p, int64_t k, int L) {
+  a.y = y; a.y_rows = y_rows; a.loss = loss; a.ws = (float*)ws; a.flag = flag;
+  a.B = (int)b; a.P = (int)p; a.K = (int)k; a.L = L;
+  a.grad_scale = nullptr; a.noise = nullptr; a.nparts_e = 0;
+  a.d_pi = a.d_mu = a.d_zd = a.d_low = nullptr;
+  a.ldo_pi = a.ldo_mu = a.ldo_zd = a.ldo_low = 0;
+}
+
+extern "C" int bsig_mog_nll_fwd(const float* weights, const float* mu, int64_t ld_mu,
+                                const float* l_d, int64_t ld_ld, const float* low, int64_t ld_low,
+                                const float* y, const int64_t* y_rows, float* loss, int64_t b,
+                                int64_t p, int64_t k, void* ws, int64_t ws_bytes, int* flag,
+                                void* stream) {
+  BSIG_REQUIRE(ws_bytes >= bsig_mdn_ws_bytes(b), "mog_nll_fwd: workspace too small");
+  BSIG_REQUIRE(b >= 1, "mog_nll_fwd: empty batch");
+  NllArgs a;
+  fill_common(a, y, y_rows, loss, ws, flag, b, p, k, low ? (int)(p * (p - 1) / 2) : 0);
+  a.z_pi = weights; a.ld_pi = k; a.mu = mu; a.ld_mu = ld_mu; a.zd = l_d; a.ld_zd = ld_ld;
+  a.low = low; a.ld_low = ld_low;
+  return launch_nll(a, false, false, (cudaStream_t)stream);
+}
+
+extern "C" int bsig_mog_nll_bwd(const float* weights, const float* mu, int64_t ld_mu,
+                                const float* l_d, int64_t ld_ld, const float* low, int64_t ld_low,
+                                const float* y, const int64_t* y_rows, const float* grad_scale,
+                                float* d_weights, float* d_mu, float* d_ld, float* d_low,
+                                int64_t b, int64_t p, int64_t k, void* ws, int64_t ws_bytes,
+                                void* stream) {
+  BSIG_REQUIRE(ws_bytes >= bsig_mdn_ws_bytes(b), "mog_nll_bwd: workspace too small");
+  BSIG_REQUIRE(b >= 1, "mog_nll_bwd: empty batch");
+  NllArgs a;
+  // the (re-computed) loss and the finite flag of the backward launch are
+  // discarded into two spare workspace slots
+  float* wsf = (float*)ws;
+  fill_common(a, y, y_rows, wsf + 3 * kMaxParts + 4, ws, (int*)(wsf + 3 * kMaxParts + 5), b, p,
+              k, low ? (int)(p * (p - 1) / 2) : 0);
+  a.z_pi = weights; a.ld_pi = k; a.mu = mu; a.ld_mu = ld_mu; a.zd = l_d; a.ld_zd = ld_ld;
+  a.low = low; a.ld_low = ld_low; a.grad_scale = grad_scale;
+  a.d_pi = d_weights; a.ldo_pi = k;
+  a.d_mu = d_mu; a.ldo_mu = p * k;
+  a.d_zd = d_ld; a.ldo_zd = p * k;
+  a.d_low = d_low; a.ldo_low = low ? (p * (p - 1) / 2) * k : 0;
+  return launch_nll(a, false, true, (cudaStream_t)stream);
+}
+
+extern "C" int bsig_mdn_nll_fused(const float* z, const float* noise, const float* y,
+                                  const int64_t* y_rows, float* loss, float* dz, int64_t b,
+                                  int64_t p, int64_t k, int full_cov, void* ws, int64_t ws_bytes,
+                                  int* flag, void* stream) {
+  BSIG_REQUIRE(ws_bytes >= bsig_mdn_ws_bytes(b), "mdn_nll_fused: workspace too small");
+  BSIG_REQUIRE(b >= 1 && p >= 1 && k >= 1, "mdn_nll_fused: bad sizes");
+  const int L = (full_cov && p > 1) ? (int)(p * (p - 1) / 2) : 0;
+  const int64_t PK = p * k;
+  const int64_t NH = k + 2 * PK + (int64_t)L * k;
+  cudaStream_t st = (cudaStream_t)stream;
+  NllArgs a;
+  fill_common(a, y, y_rows, loss, ws, flag, b, p, k, L);
+  a.z_pi = z; a.ld_pi = NH;
+  a.mu = z + k; a.ld_mu = NH;
+  a.zd = z + k + PK; a.ld_zd = NH;
+  a.low = L ? z + k + 2 * PK : nullptr; a.ld_low = NH;
+  a.noise = noise;
+  if (launch_exp_sum(a.zd, NH, (int)b, (int)PK, (float*)ws, st, &a.nparts_e)) return 1;
+  const bool bwd = dz != nullptr;
+  if (bwd) {
+    a.d_pi = dz; a.ldo_pi = NH;
+    a.d_mu = dz + k; a.ldo_mu = NH;
+    a.d_zd = dz + k + PK; a.ldo_zd = NH;
+    a.d_low = L ? dz + k + 2 * PK : nullptr; a.ldo_low = NH;
+  }
+  if (launch_nll(a, true, bwd, st)) return 1;
+  if (bwd) {
+    int gw = 1;
+    while (gw < k && gw < 32) gw <<= 1;
+    const int nparts = (int)std::min<int64_t>(ceil_div(b, 128 / gw), kMaxParts);
+    const int grid = (int)std::min<int64_t>(ceil_div(b * PK, 256), (int64_t)sm_count() * 8);
+    eps_fixup_kernel<<<grid, 256, 0, st>>>(a.zd, NH, a.d_zd, NH, (int)b, (int)PK,
+                                           (float*)ws + 2 * kMaxParts, nparts);
+    BSIG_LAUNCH_CHECK();
+  }
+  return 0;
+}

@@ -1,0 +1,268 @@
+"""CUDA-graph training engine behind ``MDNN.run_training``.
+
+Restates the reference loop (models/mdnn.py:180-243) as one recorded stream of
+kernels per call:
+
+    for step in range(n_updates):
+        rows = idx[step]                         # np.random.randint, host (mdnn.py:221)
+        [MDRFF: feat = rff(x_train[rows])]       # fused gather + GEMM + sincos
+        h_l = tanh(h_{l-1} W_l^T + b_l)          # gather fused into layer 0
+        z   = h W_heads^T + b_heads              # the 3-4 heads as ONE GEMM
+        loss, dz = fused head epilogue + mixture NLL forward/backward
+        dW_heads, db_heads, dh, dW_l, db_l ...   # wgrad / dgrad (+ fused dtanh)
+        Adam over the flat parameter buffer      # fresh moments every call (Q9)
+        every n_updates//5 steps: test loss on the held-out 20 % (forward only)
+
+Random inputs (minibatch rows, eps-noise uniforms) are generated up front for
+the whole call; the 2 x n_log losses and the finiteness flag are read back with
+one device->host copy when the graph has finished.
+"""
+import numpy as np
+import torch
+
+from .. import _lib
+
+ACT_NONE, ACT_TANH = 0, 1
+
+
+def log_steps(n_updates):
+    every = max(n_updates // 5, 1)
+    return [e for e in range(n_updates) if e % every == 0 or e + 1 == n_updates]
+
+
+class TrainPlan(object):
+    """Persistent buffers + the captured graph for one problem shape."""
+
+    def __init__(self, model, n_train, n_test, n_updates, batch, in_dim):
+        self.model = model
+        dev = model.flat_params.device
+        self.dev = dev
+        self.n_train, self.n_test, self.n_updates, self.batch = n_train, n_test, n_updates, batch
+        self.in_dim = in_dim
+        p, k = model.output_dim, model.n_gaussians
+        self.p, self.k = p, k
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.logs = log_steps(n_updates)
+        n_log = len(self.logs)
+        self.x_train = torch.empty((n_train, in_dim), **f32)
+        self.y_train = torch.empty((n_train, p), **f32)
+        self.x_test = torch.empty((max(n_test, 1), in_dim), **f32)
+        self.y_test = torch.empty((max(n_test, 1), p), **f32)
+        self.y_stage = torch.empty((n_train + n_test, p), **f32)
+        self.idx = torch.empty((n_updates, batch), dtype=torch.int64, device=dev)
+        self.noise_train = torch.empty((n_updates, batch, p, k), **f32)
+        self.noise_test = torch.empty((n_log, max(n_test, 1), p, k), **f32)
+        trunk = model._trunk_layers()
+        self.rff = getattr(model, 'rff', None)
+        widths = [lin.weight.shape[0] for lin in trunk]
+        feat_dim = model.head_in if not trunk else trunk[0].weight.shape[1]
+        self.feat_dim = feat_dim
+        nh = model.n_head
+
+        def act_set(rows):
+            d = {}
+            d['feat'] = torch.empty((rows, feat_dim), **f32) if self.rff is not None else None
+            d['h'] = [torch.empty((rows, w), **f32) for w in widths]
+            d['z'] = torch.empty((rows, nh), **f32)
+            return d
+        self.tr = act_set(batch)
+        self.te = act_set(max(n_test, 1))
+        self.dz = torch.empty((batch, nh), **f32)
+        self.dh = [torch.empty((batch, w), **f32) for w in widths]
+        self.grads = torch.zeros_like(model.flat_params)
+        self.exp_avg = torch.zeros_like(model.flat_params)
+        self.exp_avg_sq = torch.zeros_like(model.flat_params)
+        lib = _lib.load()
+        rows_max = max(batch, n_test, 1)
+        shapes = [(nh, model.head_in)] + list(zip(widths, [feat_dim] + widths[:-1]))
+        if self.rff is not None:
+            shapes.append((self.rff.freqs.shape[0], in_dim))
+        ws_bytes = max(lib.bsig_linear_ws_bytes(rows, n_out, k_in)
+                       for rows in (batch, rows_max) for n_out, k_in in shapes)
+        self.ws_gemm = torch.empty(int(ws_bytes) + 256, dtype=torch.uint8, device=dev)
+        self.ws_mdn = torch.zeros(lib.bsig_mdn_ws_bytes(rows_max), dtype=torch.uint8, device=dev)
+        self.loss_buf = torch.zeros(2 * n_log + 1, **f32)   # [train..., test..., scratch]
+        self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.graph = None
+
+    # ------------------------------------------------------------- kernel sequence
+    def _views(self):
+        m = self.model
+        flat, g = m.flat_params, self.grads
+        out, off = [], 0
+        for lin in m._trunk_layers():
+            nw, nb = lin.weight.numel(), lin.bias.numel()
+            out.append(dict(w=flat[off:off + nw], b=flat[off + nw:off + nw + nb],
+                            dw=g[off:off + nw], db=g[off + nw:off + nw + nb],
+                            n=lin.weight.shape[0], k=lin.weight.shape[1]))
+            off += nw + nb
+        nhw = m.n_head * m.head_in
+        head = dict(w=flat[m._head_w_off:m._head_w_off + nhw],
+                    b=flat[m._head_b_off:m._head_b_off + m.n_head],
+                    dw=g[m._head_w_off:m._head_w_off + nhw],
+                    db=g[m._head_b_off:m._head_b_off + m.n_head],
+                    n=m.n_head, k=m.head_in)
+        return out, head
+
+    def _forward(self, acts, x, rows, n_rows, st):
+        """x (optionally row-gathered) -> acts['z']; returns the head input."""
+        m = self.model
+        eng = int(m.gemm_engine)
+        wsp, wsn = self.ws_gemm.data_ptr(), self.ws_gemm.numel()
+        rows_p = None if rows is None else rows.data_ptr()
+        layers, head = self._views()
+        cur, ld = x, x.shape[1]
+        if self.rff is not None:
+            coeff = self.rff.coeff()
+            _lib.call('bsig_rff_features', cur.data_ptr(), ld, rows_p, coeff.data_ptr(),
+                      acts['feat'].data_ptr(), n_rows, self.rff.d, coeff.shape[0],
+                      float(self.rff.a), int(self.rff.gemm_engine), wsp, wsn, st)
+            cur, ld, rows_p = acts['feat'], acts['feat'].shape[1], None
+        for li, lay in enumerate(layers):
+            _lib.call('bsig_linear_fwd', cur.data_ptr(), ld, rows_p, lay['w'].data_ptr(),
+                      lay['b'].data_ptr(), acts['h'][li].data_ptr(), n_rows, lay['n'], lay['k'],
+                      ACT_TANH, eng, wsp, wsn, st)
+            cur, ld, rows_p = acts['h'][li], lay['n'], None
+        _lib.call('bsig_linear_fwd', cur.data_ptr(), ld, rows_p, head['w'].data_ptr(),
+                  head['b'].data_ptr(), acts['z'].data_ptr(), n_rows, head['n'], head['k'],
+                  ACT_NONE, eng, wsp, wsn, st)
+        return cur, ld, rows_p
+
+    def _enqueue_step(self, step, st):
+        m = self.model
+        eng = int(m.gemm_engine)
+        wsp, wsn = self.ws_gemm.data_ptr(), self.ws_gemm.numel()
+        b, p, k = self.batch, self.p, self.k
+        rows = self.idx[step]
+        layers, head = self._views()
+        slot = self.logs.index(step) if step in self.logs else None
+        n_log = len(self.logs)
+        loss_ptr = self.loss_buf.data_ptr() + 4 * (slot if slot is not None else 2 * n_log)
+        hin, hin_ld, hin_rows = self._forward(self.tr, self.x_train, rows, b, st)
+        _lib.call('bsig_mdn_nll_fused', self.tr['z'].data_ptr(), self.noise_train[step].data_ptr(),
+                  self.y_train.data_ptr(), rows.data_ptr(), loss_ptr, self.dz.data_ptr(),
+                  b, p, k, 1 if m.full_covariance else 0, self.ws_mdn.data_ptr(),
+                  self.ws_mdn.numel(), self.flag.data_ptr(), st)
+        # heads: wgrad (+bias), then dgrad into the last hidden layer
+        _lib.call('bsig_linear_wgrad', self.dz.data_ptr(), hin.data_ptr(), hin_ld, hin_rows,
+                  head['dw'].data_ptr(), head['db'].data_ptr(), b, head['n'], head['k'], eng,
+                  wsp, wsn, st)
+        dcur = self.dz
+        nxt = head
+        for li in reversed(range(len(layers))):
+            lay = layers[li]
+            # d pre-activation of layer li = (dcur @ W_next) * (1 - h_li^2)
+            _lib.call('bsig_linear_dgrad', dcur.data_ptr(), nxt['w'].data_ptr(),
+                      self.tr['h'][li].data_ptr(), self.dh[li].data_ptr(), b, nxt['n'], nxt['k'],
+                      ACT_TANH, eng, wsp, wsn, st)
+            if li > 0:
+                xin, xld, xrows = self.tr['h'][li - 1], layers[li - 1]['n'], None
+            elif self.rff is not None:
+                xin, xld, xrows = self.tr['feat'], self.feat_dim, None
+            else:
+                xin, xld, xrows = self.x_train, self.in_dim, rows.data_ptr()
+            _lib.call('bsig_linear_wgrad', self.dh[li].data_ptr(), xin.data_ptr(), xld, xrows,
+                      lay['dw'].data_ptr(), lay['db'].data_ptr(), b, lay['n'], lay['k'], eng,
+                      wsp, wsn, st)
+            dcur, nxt = self.dh[li], lay
+        _lib.call('bsig_adam_step', m.flat_params.data_ptr(), self.grads.data_ptr(),
+                  self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), m.flat_params.numel(),
+                  step + 1, float(m.lr), 0.9, 0.999, 1e-8, 1.0, st)
+        if slot is not None and self.n_test > 0:
+            self._forward(self.te, self.x_test, None, self.n_test, st)
+            _lib.call('bsig_mdn_nll_fused', self.te['z'].data_ptr(),
+                      self.noise_test[slot].data_ptr(), self.y_test.data_ptr(), None,
+                      self.loss_buf.data_ptr() + 4 * (n_log + slot), None, self.n_test, p, k,
+                      1 if m.full_covariance else 0, self.ws_mdn.data_ptr(), self.ws_mdn.numel(),
+                      self.flag.data_ptr(), st)
+
+    def enqueue_all(self):
+        st = _lib.stream_ptr(self.dev)
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        for step in range(self.n_updates):
+            self._enqueue_step(step, st)
+
+    def capture(self):
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.enqueue_all()
+        self.graph = graph
+
+
+def _stage_inputs(plan, model, x_data, y_data):
+    n_train, n_test = plan.n_train, plan.n_test
+    dev = plan.dev
+    x_data = x_data.detach()
+    y_data = y_data.detach()
+    plan.x_train.copy_(x_data[:n_train], non_blocking=True)
+    if n_test > 0:
+        plan.x_test[:n_test].copy_(x_data[n_train:], non_blocking=True)
+    y_dev = y_data.to(device=dev, dtype=torch.float32).contiguous()
+    st = _lib.stream_ptr(dev)
+    if model.output_lows is not None:
+        _lib.call('bsig_normalize_rows', y_dev.data_ptr(), model.output_lows.data_ptr(),
+                  model.output_highs.data_ptr(), plan.y_stage.data_ptr(), y_dev.shape[0],
+                  y_dev.shape[1], st)
+    else:
+        plan.y_stage.copy_(y_dev)
+    plan.y_train.copy_(plan.y_stage[:n_train])
+    if n_test > 0:
+        plan.y_test[:n_test].copy_(plan.y_stage[n_train:])
+
+
+def run_training_captured(model, x_data, y_data, n_updates, batch_size, test_frac=0.2,
+                          use_graph=True, injected=None):
+    """See MDNN.run_training.  ``injected`` (tests only) = dict(idx=[n_updates,B]
+    int64, noise_train=[n_updates,B,P,K], noise_test=[n_log,n_test,P,K]) replaces
+    the generated random inputs so that runs can be compared draw for draw."""
+    assert (x_data.shape[0] == y_data.shape[0])
+    model._ensure_flat()
+    model.train()
+    dev = model.flat_params.device
+    n_tot = x_data.shape[0]
+    n_train = max(int(n_tot * (1.0 - test_frac)), 1)
+    n_test = n_tot - n_train
+    in_dim = x_data.shape[1]
+    key = (n_train, n_test, n_updates, batch_size, in_dim, bool(use_graph))
+    with torch.cuda.device(dev):
+        plan = model._plans.get(key)
+        if plan is None:
+            plan = TrainPlan(model, n_train, n_test, n_updates, batch_size, in_dim)
+            model._plans[key] = plan
+        _stage_inputs(plan, model, x_data, y_data)
+        if injected is None:
+            # same generator and call pattern as the reference: numpy's global RNG,
+            # one randint(0, n_train, batch) per update (mdnn.py:221)
+            ids = np.stack([np.random.randint(0, n_train, batch_size)
+                            for _ in range(n_updates)]) if n_updates > 0 else \
+                np.zeros((0, batch_size), dtype=np.int64)
+            plan.idx.copy_(torch.from_numpy(ids.astype(np.int64)), non_blocking=False)
+            plan.noise_train.uniform_(0.0, 1.0)
+            plan.noise_test.uniform_(0.0, 1.0)
+        else:
+            plan.idx.copy_(torch.as_tensor(injected['idx'], dtype=torch.int64))
+            plan.noise_train.copy_(torch.as_tensor(injected['noise_train']).reshape(
+                plan.noise_train.shape))
+            if n_test > 0:
+                plan.noise_test.copy_(torch.as_tensor(injected['noise_test']).reshape(
+                    plan.noise_test.shape))
+        plan.flag.zero_()
+        if n_test == 0:
+            plan.loss_buf.fill_(float('nan'))
+        if use_graph:
+            if plan.graph is None:
+                before = _lib.load().bsig_launch_count()
+                plan.capture()
+                plan.launches_per_replay = _lib.load().bsig_launch_count() - before
+            plan.graph.replay()
+        else:
+            plan.enqueue_all()
+        n_log = len(plan.logs)
+        host = torch.cat([plan.loss_buf[:2 * n_log], plan.flag.float()]).cpu().numpy()
+    assert (host[-1] == 0), 'non-finite value in MDNN training (forward / log-likelihood)'
+    train_loss = [float(v) for v in host[:n_log]]
+    test_loss = [float(v) for v in host[n_log:2 * n_log]]
+    for tr, te in zip(train_loss, test_loss):
+        print(f'loss: train {tr:0.4f} test {te:0.4f}')
+    return {'train_loss': train_loss, 'test_loss': test_loss}

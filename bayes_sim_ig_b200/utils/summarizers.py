@@ -1,0 +1,162 @@
+"""Trajectory summarizers on sm_100a kernels.
+
+Mirror of the reference module ``bayes_sim_ig/utils/summarizers.py`` (same
+function names, arguments, return shapes and assertion behaviour):
+
+    f(states [N, T, D], actions [N, T, A]) -> feats [N, F]     (fp32, CUDA)
+
+``summary_start`` / ``summary_waypts`` / ``summary_corr`` / ``summary_corrdiff``
+run the streaming kernels in csrc/summarizers.cu; ``summary_signatory`` runs
+the Chen-recursion kernel in csrc/signature.cu (no ``signatory`` dependency,
+SURVEY Q4).  Inputs must live on a CUDA device: there is no CPU path.
+
+Documented divergences from the reference:
+  * ``summary_signatory`` never drops rows (the reference's N > 10000 chunking
+    loses the last N mod 10 trajectories, summarizers.py:159-168);
+  * non-fp32 inputs are converted to fp32 (the reference already returns fp32
+    from ``summary_waypts`` whatever the input dtype, summarizers.py:81).
+"""
+import torch
+
+from .. import _lib
+
+__all__ = ['pad_states_actions', 'summary_start', 'summary_waypts', 'cross_correlation',
+           'summary_corrdiff', 'summary_corr', 'signature_depth', 'summary_signatory',
+           'summary_width']
+
+
+def _as_kernel_input(t):
+    if not t.is_cuda:
+        raise _lib.BsigError('summarizers need CUDA tensors (got %s); no CPU fallback' % t.device)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def pad_states_actions(states, actions, tgt_actions_len=None):
+    """Reference summarizers.py:20-62.  Chop (a view) or pad by repeating the
+    last step; like the reference, padding only concatenates for ntraj == 1."""
+    assert (len(states.shape) == 3), 'Need states: ntraj x n_steps x state_dim'
+    assert (len(actions.shape) == 3), 'Need actions: ntraj x n_steps x state_dim'
+    if tgt_actions_len is None:
+        tgt_actions_len = states.shape[1]
+
+    def fit(x):
+        npad = tgt_actions_len - x.shape[1]
+        if npad > 0:
+            last = x[:, -1, :].clone()
+            # same construction as the reference: a [1, N*npad, dim] block,
+            # which torch.cat only accepts when N == 1
+            return torch.cat([x, last.repeat(1, npad, 1)], dim=1)
+        return x[:, :tgt_actions_len, :]
+
+    states, actions = fit(states), fit(actions)
+    assert (states.shape[1] == actions.shape[1])
+    return states, actions
+
+
+def _leading_steps(states, actions, n_steps):
+    """Tensors whose first n_steps steps are valid + their stored lengths."""
+    if states.shape[1] < n_steps or actions.shape[1] < n_steps:
+        states, actions = pad_states_actions(states, actions, n_steps)
+    states, actions = _as_kernel_input(states), _as_kernel_input(actions)
+    return states, actions
+
+
+def summary_start(states, actions, max_t=10):
+    """Reference summarizers.py:65-70: first max_t steps, [s_t | a_t] per step."""
+    assert (len(states.shape) == 3), 'Need states: ntraj x n_steps x state_dim'
+    assert (len(actions.shape) == 3), 'Need actions: ntraj x n_steps x state_dim'
+    assert states.shape[0] == actions.shape[0]
+    states, actions = _leading_steps(states, actions, max_t)
+    n, ts, d = states.shape
+    ta, a = actions.shape[1], actions.shape[2]
+    out = torch.empty((n, max_t * (d + a)), dtype=torch.float32, device=states.device)
+    with torch.cuda.device(states.device):
+        _lib.call('bsig_summary_start', _lib.ptr(states), _lib.ptr(actions), _lib.ptr(out),
+                  n, ts, ta, d, a, max_t, _lib.stream_ptr(states.device))
+    return out
+
+
+def summary_waypts(states, actions, n_waypts=10):
+    """Reference summarizers.py:73-87.  The reference chops to n_waypts steps
+    before computing its stride, so the stride is always 1 and the result is
+    summary_start(max_t=n_waypts)."""
+    return summary_start(states, actions, max_t=n_waypts)
+
+
+def cross_correlation(states, actions, use_state_diff=False):
+    """Reference summarizers.py:90-122."""
+    assert (len(states.shape) == 3), 'Need states: ntraj x n_steps x state_dim'
+    assert (len(actions.shape) == 3), 'Need actions: ntraj x n_steps x state_dim'
+    ntraj, traj_len, state_dim = states.shape
+    if actions.shape[1] < traj_len:      # reference pads actions up to the states' length
+        states, actions = pad_states_actions(states, actions)
+    assert (traj_len > 1)  # empty episodes are problematic
+    max_traj_len = 5 if state_dim > 50 else 10
+    w = min(traj_len, max_traj_len)
+    states, actions = _as_kernel_input(states), _as_kernel_input(actions)
+    act_dim = actions.shape[2]
+    width = w * (state_dim - 1) * w * act_dim + 2
+    feats = torch.empty((ntraj, width), dtype=torch.float32, device=states.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=states.device)
+    with torch.cuda.device(states.device):
+        _lib.call('bsig_summary_crosscorr', _lib.ptr(states), _lib.ptr(actions), _lib.ptr(feats),
+                  ntraj, states.shape[1], actions.shape[1], state_dim, act_dim, w,
+                  1 if use_state_diff else 0, _lib.ptr(flag, torch.int32),
+                  _lib.stream_ptr(states.device))
+    assert (int(flag.item()) == 0)       # torch.isfinite(feats).all() in the reference
+    print('cross_corr feats', feats.shape, feats.device)
+    return feats
+
+
+def summary_corrdiff(states, actions):
+    return cross_correlation(states, actions, use_state_diff=True)
+
+
+def summary_corr(states, actions):
+    return cross_correlation(states, actions, use_state_diff=False)
+
+
+def signature_depth(ndim):
+    """Reference summarizers.py:133-141."""
+    max_output_dim = 110**2
+    for depth in reversed(range(4)):
+        if ndim**depth <= max_output_dim:
+            return depth
+    return 1
+
+
+def summary_signatory(states, actions):
+    """Reference summarizers.py:144-168: signature of the time-augmented path
+    [t | s_t | a_t] truncated at signature_depth(1 + D + A)."""
+    assert (len(states.shape) == 3), 'states should be batch x time x state_dim'
+    bsz, path_len, state_dim = states.shape
+    assert actions.shape[0] == bsz and actions.shape[1] >= path_len
+    states, actions = _as_kernel_input(states), _as_kernel_input(actions)
+    act_dim = actions.shape[2]
+    c = 1 + state_dim + act_dim
+    depth = signature_depth(c)
+    if depth == 0:
+        return torch.zeros((bsz, 0), dtype=torch.float32, device=states.device)
+    width = sum(c ** k for k in range(1, depth + 1))
+    out = torch.empty((bsz, width), dtype=torch.float32, device=states.device)
+    with torch.cuda.device(states.device):
+        _lib.call('bsig_signature_fwd', _lib.ptr(states), _lib.ptr(actions), _lib.ptr(out),
+                  bsz, path_len, states.shape[1], actions.shape[1], state_dim, act_dim, depth,
+                  _lib.stream_ptr(states.device))
+    return out
+
+
+def summary_width(name, traj_len, obs_dim, act_dim):
+    """Feature width of summarizer ``name`` for rollouts of ``traj_len`` steps
+    (what BayesSim.__init__ obtains by probing, bayes_sim.py:57-60)."""
+    if name in ('summary_start', 'summary_waypts'):
+        return 10 * (obs_dim + act_dim)
+    if name in ('summary_corr', 'summary_corrdiff', 'cross_correlation'):
+        w = min(traj_len, 5 if obs_dim > 50 else 10)
+        return w * (obs_dim - 1) * w * act_dim + 2
+    if name == 'summary_signatory':
+        c = 1 + obs_dim + act_dim
+        return sum(c ** k for k in range(1, signature_depth(c) + 1))
+    raise ValueError('unknown summarizer ' + str(name))

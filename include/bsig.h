@@ -1,0 +1,214 @@
+/*
+ * bsig.h -- C ABI of libbsig_b200.so: the B200 (sm_100a) kernels behind the
+ * BayesSimIG inference hot path (trajectory summarizers -> MDNN / MDRFF
+ * mixture-density training -> mixture-of-Gaussians posterior).
+ *
+ * The reference (NVlabs/bayes-sim-ig) is pure Python and has no FFI; its
+ * boundary for this path is the Python API resolved by name at
+ * bayes_sim_ig/bayes_sim.py:56,82.  Each entry point below therefore cites the
+ * reference torch / numpy call site it replaces; the Python mirror of the
+ * reference API (bayes_sim_ig_b200/) reaches these functions through ctypes.
+ * INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless it is
+ *     documented as host; tensors are dense row-major fp32 unless stated;
+ *   - sizes are int64_t; `stream` is a cudaStream_t passed as void*;
+ *   - functions only enqueue work on `stream` (they never synchronise and
+ *     are CUDA-graph capturable) unless documented otherwise;
+ *   - return value 0 = ok, non-zero = error; text via bsig_last_error();
+ *   - no function allocates device memory: scratch comes in as `ws`.
+ */
+#ifndef BSIG_H_
+#define BSIG_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSIG_VERSION 100
+
+/* activation / epilogue selectors for bsig_linear_* */
+#define BSIG_ACT_NONE 0
+#define BSIG_ACT_TANH 1
+
+/* GEMM engines: SIMT fp32 FFMA tiles, or tcgen05 tensor cores (tf32 operands,
+ * fp32 accumulate in TMEM; TF32X3 = error-compensated 3-pass split that keeps
+ * fp32-level accuracy). */
+#define BSIG_GEMM_SIMT 0
+#define BSIG_GEMM_TC_TF32 1
+#define BSIG_GEMM_TC_TF32X3 2
+
+const char* bsig_last_error(void);
+int bsig_version(void);
+/* number of kernel launches this library has enqueued in this process (host counter;
+ * launches recorded into a CUDA graph are counted once, at capture time) */
+int64_t bsig_launch_count(void);
+/* host query: SM count and compute capability of the current device */
+int bsig_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------ summarizers
+ * states [n, t_states, d], actions [n, t_actions, a]; only the leading steps
+ * are read. */
+
+/* summary_start / summary_waypts (utils/summarizers.py:65-70, 73-87):
+ * out [n, max_t*(d+a)], out[i, t*(d+a)+j] = j<d ? states[i,t,j] : actions[i,t,j-d].
+ * Requires t_states >= max_t and t_actions >= max_t. */
+int bsig_summary_start(const float* states, const float* actions, float* out,
+                       int64_t n, int64_t t_states, int64_t t_actions,
+                       int64_t d, int64_t a, int64_t max_t, void* stream);
+
+/* cross_correlation / summary_corr / summary_corrdiff (summarizers.py:90-130):
+ * w leading steps; sf = adjacent state-dimension differences (use_state_diff)
+ * or the first d-1 dims, flattened [w*(d-1)]; af [w*a];
+ * out [n, w*(d-1)*w*a + 2] = [ sf (x) af | mean(sf) | unbiased std(sf) ].
+ * *nonfinite_flag (int32, device) is OR-ed with 1 if any output is not finite
+ * (the reference asserts isfinite at summarizers.py:120). */
+int bsig_summary_crosscorr(const float* states, const float* actions, float* out,
+                           int64_t n, int64_t t_states, int64_t t_actions,
+                           int64_t d, int64_t a, int64_t w, int use_state_diff,
+                           int* nonfinite_flag, void* stream);
+
+/* summary_signatory (summarizers.py:144-168; arithmetic = signatory.signature):
+ * path_t = [t+1 | states[i,t,:] | actions[i,t,:]], t < len; depth in {1,2,3};
+ * out [n, sum_{k<=depth} c^k], c = 1+d+a, levels concatenated, each C-order.
+ * depth 3 requires c <= 24. */
+int bsig_signature_fwd(const float* states, const float* actions, float* out,
+                       int64_t n, int64_t len, int64_t t_states, int64_t t_actions,
+                       int64_t d, int64_t a, int depth, void* stream);
+/* ---------------------------------------------------------------- dense layers
+ * Replaces nn.Linear (+Tanh) at models/mdnn.py:68-87,108-119 and the RFF
+ * projection at models/rff.py:128-132 (cuBLAS sgemm + pointwise in the
+ * reference).  x [m, k] (row stride ldx), w [n, k], b [n], y [m, n].
+ * x_rows (int64, device, nullable): gather, row i of the operand is
+ * x[x_rows[i]] -- fuses the minibatch gather of mdnn.py:221-222.
+ * ws: scratch for split-K partials, ws_bytes >= bsig_linear_ws_bytes(). */
+int64_t bsig_linear_ws_bytes(int64_t m, int64_t n, int64_t k);
+int bsig_linear_fwd(const float* x, int64_t ldx, const int64_t* x_rows,
+                    const float* w, const float* b, float* y,
+                    int64_t m, int64_t n, int64_t k, int act, int engine,
+                    void* ws, int64_t ws_bytes, void* stream);
+/* dx [m,k] = (dy [m,n]) @ w [n,k]; if act_prev == BSIG_ACT_TANH the result is
+ * multiplied by (1 - h_prev^2) where h_prev [m,k] is the previous layer's
+ * tanh output (fused dtanh). */
+int bsig_linear_dgrad(const float* dy, const float* w, const float* h_prev, float* dx,
+                      int64_t m, int64_t n, int64_t k, int act_prev, int engine,
+                      void* ws, int64_t ws_bytes, void* stream);
+/* dw [n,k] = dy^T [n,m] @ x [m,k] (x optionally row-gathered); db [n] = colsum(dy). */
+int bsig_linear_wgrad(const float* dy, const float* x, int64_t ldx, const int64_t* x_rows,
+                      float* dw, float* db, int64_t m, int64_t n, int64_t k, int engine,
+                      void* ws, int64_t ws_bytes, void* stream);
+/* dpre = dy * (1 - y^2) elementwise (tanh backward, used by the autograd path) */
+int bsig_tanh_bwd(const float* dy, const float* y, float* dpre, int64_t count, void* stream);
+
+/* RFF._to_cos_sin_features (rff.py:128-132): coeff [nf_half, d] = freqs/sigma;
+ * out [m, 2*nf_half] = scale * [cos(x coeff^T) | sin(x coeff^T)]. */
+int bsig_rff_features(const float* x, int64_t ldx, const int64_t* x_rows,
+                      const float* coeff, float* out,
+                      int64_t m, int64_t d, int64_t nf_half, float scale, int engine,
+                      void* ws, int64_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------ mixture-density head + NLL
+ * z [b, n_head] is the concatenated head output, columns
+ *   [0,K) pi logits | [K, K+PK) mu (col p*K+k) | [K+PK, K+2PK) log-diag |
+ *   [K+2PK, K+2PK+LK) strict-lower entries (col l*K+k, np.tril_indices order)
+ * with L = P(P-1)/2 if full covariance else 0 (mdnn.py:109-119).
+ * noise [b, P, K]: the uniforms of torch.rand_like at mdnn.py:116. */
+
+/* MDNN.forward epilogue (mdnn.py:109-119): weights [b,K] = renorm(clamp(softmax)),
+ * l_d [b,P,K] = exp(z_d) + noise * 1e-5 * mean(exp(z_d)).  mu and L are views of z.
+ * ws >= bsig_mdn_ws_bytes(b). flag |= 1 if any of weights/mu/l_d/L is non-finite. */
+int64_t bsig_mdn_ws_bytes(int64_t b);
+int bsig_mdn_head_fwd(const float* z, const float* noise, float* weights, float* l_d,
+                      int64_t b, int64_t p, int64_t k, int full_cov,
+                      void* ws, int64_t ws_bytes, int* flag, void* stream);
+/* backward of the epilogue: given d_weights [b,K], d_mu [b,P,K], d_ld [b,P,K],
+ * d_low [b,L,K] (nullable) -> dz [b, n_head]; includes the non-detached eps term. */
+int bsig_mdn_head_bwd(const float* z, const float* noise, const float* weights,
+                      const float* d_weights, const float* d_mu, const float* d_ld,
+                      const float* d_low, float* dz,
+                      int64_t b, int64_t p, int64_t k, int full_cov,
+                      void* ws, int64_t ws_bytes, void* stream);
+
+/* MDNN.mdn_loss_fn (mdnn.py:127-178) on explicit (weights, mu, l_d, low):
+ * loss[0] = -mean_b logsumexp_k( clamp(log N(y; mu_k, L_k L_k^T), +-1e5)
+ *                                + log clamp(w_k, 1e-5, 1) ).
+ * y_rows (nullable) gathers target rows.  mu/l_d/low are addressed with an
+ * explicit row stride so that they may alias columns of z. */
+int bsig_mog_nll_fwd(const float* weights, const float* mu, int64_t ld_mu,
+                     const float* l_d, int64_t ld_ld, const float* low, int64_t ld_low,
+                     const float* y, const int64_t* y_rows, float* loss,
+                     int64_t b, int64_t p, int64_t k,
+                     void* ws, int64_t ws_bytes, int* flag, void* stream);
+/* gradients of grad_scale[0] * loss wrt weights, mu, l_d, low (dense outputs
+ * [b,K], [b,P,K], [b,P,K], [b,L,K]); grad_scale is a device scalar. */
+int bsig_mog_nll_bwd(const float* weights, const float* mu, int64_t ld_mu,
+                     const float* l_d, int64_t ld_ld, const float* low, int64_t ld_low,
+                     const float* y, const int64_t* y_rows, const float* grad_scale,
+                     float* d_weights, float* d_mu, float* d_ld, float* d_low,
+                     int64_t b, int64_t p, int64_t k,
+                     void* ws, int64_t ws_bytes, void* stream);
+
+/* Fused training form: head epilogue + NLL forward + full backward in one pass
+ * over z: loss[0] and dz [b, n_head] = d loss / d z (dz nullable: loss only).
+ * This is what MDNN.run_training's captured step uses. */
+int bsig_mdn_nll_fused(const float* z, const float* noise, const float* y,
+                       const int64_t* y_rows, float* loss, float* dz,
+                       int64_t b, int64_t p, int64_t k, int full_cov,
+                       void* ws, int64_t ws_bytes, int* flag, void* stream);
+
+/* ------------------------------------------------------------------- optimiser
+ * torch.optim.Adam defaults (mdnn.py:203,234) over one flat fp32 buffer. */
+int bsig_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                   int64_t count, int64_t step, float lr, float beta1, float beta2,
+                   float eps, float grad_scale, void* stream);
+/* out[i,:] = src[rows[i],:]  (x_train[ids], mdnn.py:222) */
+int bsig_gather_rows(const float* src, int64_t ld_src, const int64_t* rows, float* out,
+                     int64_t n_rows, int64_t width, void* stream);
+/* flag |= 1 if any of x[0..count) is not finite (torch.isfinite(..).all() asserts) */
+int bsig_finite_flag(const float* x, int64_t count, int* flag, void* stream);
+/* y = (x - lows) / (highs - lows) row-wise (MDNN.normalize_samples, mdnn.py:245-248) */
+int bsig_normalize_rows(const float* x, const float* lows, const float* highs, float* y,
+                        int64_t n_rows, int64_t width, void* stream);
+
+/* --------------------------------------------------------------------- posterior
+ * MDNN.predict_MoGs de-normalisation (mdnn.py:264-288, with L[pt,:,k]):
+ * a [r,K] ; means [r,K,P] = mu*rng + lows ; packed [r,K,P+L] =
+ * [ rng*l_d | rng[row(l)]*low ] -- the `Ls` argument of pdf.MoG. lows/highs nullable. */
+int bsig_mog_denorm(const float* weights, const float* mu, int64_t ld_mu,
+                    const float* l_d, int64_t ld_ld, const float* low, int64_t ld_low,
+                    const float* lows, const float* highs,
+                    float* a_out, float* means_out, float* packed_out,
+                    int64_t r, int64_t p, int64_t k, void* stream);
+
+/* pdf.discrete_sample + MoG.gen + Gaussian.gen (utils/pdf.py:61-76,465-472,296-300).
+ * a [K] mixture weights (float32 if a_is_f32 else float64, the dtype the
+ * reference compares in), u [n] float64 uniforms, z [n,P] float64 normals,
+ * means [K,P] and cmats [K,P,P] float64 (C = L^T).  comp_idx [n] int32 =
+ * #{j: u > cumsum(a[:-1])_j} (bit exact); counts [K] int32 (must be zeroed
+ * by the caller); samples [n,P] float64 GROUPED BY COMPONENT: block k holds
+ * z_rows(block k) @ C_k + m_k. */
+int bsig_mog_sample(const void* a, int a_is_f32, const double* u, const double* z,
+                    const double* means, const double* cmats,
+                    int32_t* comp_idx, int32_t* counts, double* samples,
+                    int64_t n, int64_t p, int64_t k, void* stream);
+/* Device-RNG variant for throughput (no host draws): Philox4x32-10 keyed by
+ * (seed, row); fp32 parameters and fp32 output in DRAW order. */
+int bsig_mog_sample_philox(const float* a, const float* means, const float* cmats,
+                           int32_t* comp_idx, float* samples, uint64_t seed,
+                           int64_t n, int64_t p, int64_t k, void* stream);
+
+/* MoG.eval, joint density (utils/pdf.py:474-491, 328-332):
+ * x [m,P] (float32 if x_is_f32 else float64); a [K], means [K,P], precs [K,P,P],
+ * logdet_p [K] float64; out [m] float64 = logsumexp_k(lp_k + log a_k) if
+ * log_space else sum_k a_k exp(lp_k). */
+int bsig_mog_logpdf(const void* x, int x_is_f32, const double* a, const double* means,
+                    const double* precs, const double* logdet_p, double* out,
+                    int64_t m, int64_t p, int64_t k, int log_space, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* BSIG_H_ */

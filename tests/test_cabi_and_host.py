@@ -1,0 +1,139 @@
+"""CPU-side checks: the C ABI library loads and exports every symbol declared in
+include/bsig.h, and the host-side logic (no kernel calls) matches the oracle."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import summarizers_np as osum
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), '..'))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, 'include', 'bsig.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(bsig_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from bayes_sim_ig_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), 'run python -m bayes_sim_ig_b200.build'
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), name
+    # and the ctypes table covers exactly the header
+    assert sorted(_lib.SIGNATURES) == declared
+    assert _lib.load().bsig_version() == 100
+
+
+def test_no_cpu_fallback():
+    import torch
+    from bayes_sim_ig_b200 import _lib
+    from bayes_sim_ig_b200.utils import summarizers
+    with pytest.raises(_lib.BsigError):
+        summarizers.summary_start(torch.zeros(2, 12, 3), torch.zeros(2, 12, 1))
+    with pytest.raises(_lib.BsigError):
+        _lib.require_cuda('cpu')
+
+
+def test_drop_in_import_paths():
+    import bayes_sim_ig.bayes_sim as bs
+    import bayes_sim_ig.models.mdnn as mdnn
+    import bayes_sim_ig.models.mdrff as mdrff
+    import bayes_sim_ig.models.rff as rff
+    import bayes_sim_ig.utils.pdf as pdf
+    import bayes_sim_ig.utils.summarizers as summ
+    assert bs.BayesSim.NUM_GRAD_UPDATES == 100 and bs.BayesSim.MINIBATCH_SIZE == 100
+    assert bs.BayesSim.TEST_FRACTION == 0.2 and bs.BayesSim.NUM_TRAIN_TRAJ_PER_BATCH == 1000
+    assert mdnn.MDNN.LL_LIMIT == 1e5 and mdnn.MDNN.MIN_WEIGHT == 1e-5 and mdnn.MDNN.EPS_NOISE == 1e-5
+    assert issubclass(mdrff.MDRFF, mdnn.MDNN)
+    for name in ('pad_states_actions', 'summary_start', 'summary_waypts', 'cross_correlation',
+                 'summary_corr', 'summary_corrdiff', 'signature_depth', 'summary_signatory'):
+        assert callable(getattr(summ, name)) and callable(getattr(bs, name))
+    for name in ('MoG', 'Gaussian', 'Uniform', 'discrete_sample', 'fit_mog'):
+        assert hasattr(pdf, name)
+    for name in ('RFF', 'RFFKernelRBF', 'RFFKernelMatern12', 'RFFKernelMatern32', 'RFFKernelMatern52'):
+        assert hasattr(rff, name)
+
+
+def test_summary_width_matches_oracle(golden):
+    from bayes_sim_ig_b200.utils.summarizers import signature_depth, summary_width
+    g = golden('summarizers')
+    for case in ('pendulum', 'cartpole', 'ant', 'humanoid', 'exact10'):
+        s, a = g[case + '.states'], g[case + '.actions']
+        t, d, ad = s.shape[1], s.shape[2], a.shape[2]
+        assert summary_width('summary_start', t, d, ad) == g[case + '.summary_start'].shape[1]
+        assert summary_width('summary_corrdiff', t, d, ad) == g[case + '.summary_corrdiff'].shape[1]
+        assert summary_width('summary_signatory', t, d, ad) == osum.summary_signatory(s[:1], a[:1]).shape[1]
+    assert [signature_depth(int(c)) for c in g['signature_depth.in']] == list(g['signature_depth.out'])
+
+
+def test_log_steps_match_reference_rule():
+    from bayes_sim_ig_b200.models.train_engine import log_steps
+    assert log_steps(100) == [0, 20, 40, 60, 80, 99]
+    assert log_steps(20) == [0, 4, 8, 12, 16, 19]
+    assert log_steps(500) == [0, 100, 200, 300, 400, 499]
+    assert log_steps(3) == [0, 1, 2]
+    assert log_steps(1) == [0]
+
+
+def test_minibatch_index_stream_matches_reference_pattern():
+    # one randint(0, n, B) per update == the reference's generator (mdnn.py:221)
+    np.random.seed(3)
+    a = np.stack([np.random.randint(0, 800, 100) for _ in range(7)])
+    np.random.seed(3)
+    b = np.stack([np.random.randint(0, len(range(800)), 100) for _ in range(7)])
+    np.testing.assert_array_equal(a, b)
+
+
+PDF_CASES = ['f32', 'f64', 'p1', 'p13']
+
+
+@pytest.mark.parametrize('case', PDF_CASES)
+def test_pdf_host_algebra_matches_reference(golden, case):
+    """Gaussian(m, L=) / MoG construction is host numpy: bit-exact vs the reference."""
+    from bayes_sim_ig_b200.utils import pdf
+    g = golden('pdf')
+    mog = pdf.MoG(a=g[case + '.a'], ms=list(g[case + '.ms']), Ls=list(g[case + '.Ls']))
+    assert mog.n_components == len(g[case + '.a']) and mog.ndim == g[case + '.ms'].shape[1]
+    for fld in ('C', 'S', 'P', 'Pm'):
+        got = np.stack([getattr(x, fld) for x in mog.xs])
+        assert got.dtype == g[case + '.' + fld].dtype
+        np.testing.assert_array_equal(got, g[case + '.' + fld])
+    np.testing.assert_array_equal(np.array([x.logdetP for x in mog.xs]), g[case + '.logdetP'])
+
+
+def test_pdf_prune_and_algebra(golden):
+    from bayes_sim_ig_b200.utils import pdf
+    g = golden('pdf')
+    mog = pdf.MoG(a=g['prune.a_in'], ms=[np.zeros(2)] * 4, Ls=[np.ones(2)] * 4)
+    mog.prune_negligible_components(threshold=0.005)
+    np.testing.assert_array_equal(mog.a, g['prune.a_out'])
+    assert mog.n_components == 2 and len(mog.xs) == 2
+    # product / quotient round trip (the reference's py2-only __div__, fixed here)
+    ga = pdf.Gaussian(m=np.array([0.3, -0.2]), S=np.array([[0.5, 0.1], [0.1, 0.4]]))
+    gb = pdf.Gaussian(m=np.array([0.1, 0.4]), S=np.array([[2.0, 0.0], [0.0, 3.0]]))
+    back = (ga * gb) / gb
+    np.testing.assert_allclose(back.m, ga.m, atol=1e-12)
+    np.testing.assert_allclose(back.S, ga.S, atol=1e-12)
+    assert ga.kl(ga) == pytest.approx(0.0, abs=1e-12)
+    with pytest.raises(ValueError):
+        pdf.Gaussian(P=np.eye(2))
+    with pytest.raises(ValueError):
+        pdf.MoG(a=[1.0])
+    u = pdf.Uniform(np.array([0.0, 1.0]), np.array([1.0, 3.0]))
+    assert np.allclose(u.eval(np.array([[0.5, 2.0]]), log=False), 0.5)
+    with pytest.raises(ValueError):
+        u.eval(np.array([[5.0, 5.0]]))
+
+
+def test_halton_points_in_open_unit_cube():
+    from bayes_sim_ig_b200.utils.halton import halton_points
+    pts = halton_points(100, 50)
+    assert pts.shape == (100, 50) and (pts > 0).all() and (pts < 1).all()
+    assert abs(pts.mean() - 0.5) < 0.05

@@ -1,0 +1,77 @@
+"""GPU parity: mixture sampling / component selection / log-density."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+CASES = ['f32', 'f64', 'p1', 'p13']
+
+
+def _mog(g, case):
+    from bayes_sim_ig.utils import pdf
+    return pdf.MoG(a=g[case + '.a'], ms=list(g[case + '.ms']), Ls=list(g[case + '.Ls']))
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_component_selection_bit_exact(golden, case):
+    from bayes_sim_ig.utils import pdf
+    g = golden('pdf')
+    np.random.seed(32)                      # the seed the golden indices were drawn with
+    idx = pdf.discrete_sample(g[case + '.a'], 100)
+    np.testing.assert_array_equal(idx, g[case + '.discrete.idx'])
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_gen_matches_reference_stream(golden, case):
+    g = golden('pdf')
+    mog = _mog(g, case)
+    np.random.seed(31)
+    smp = mog.gen(n_samples=257)
+    ref = g[case + '.gen.samples']
+    assert smp.shape == ref.shape and smp.dtype == np.float64
+    # float64 affine map: only the summation order of the dot product differs
+    np.testing.assert_allclose(smp, ref, rtol=1e-12, atol=1e-12)
+    assert mog.gen(n_samples=1).shape == (1, mog.ndim)
+    assert mog.gen(n_samples=0).shape == (0, mog.ndim)
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_eval_matches_reference(golden, case):
+    g = golden('pdf')
+    mog = _mog(g, case)
+    x64 = g[case + '.eval.x64']
+    np.testing.assert_allclose(mog.eval(x64, log=True), g[case + '.eval.log64'], rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(mog.eval(x64, log=False), g[case + '.eval.lin64'], rtol=1e-9, atol=1e-300)
+    got32 = mog.eval(x64.astype(np.float32), log=True)
+    assert got32.dtype == g[case + '.eval.log32'].dtype
+    np.testing.assert_allclose(got32, g[case + '.eval.log32'], rtol=2e-4, atol=2e-4)
+    # single Gaussian == one-component mixture
+    one = mog.xs[0].eval(x64)
+    from bayes_sim_ig.utils import pdf
+    solo = pdf.MoG(a=np.ones(1), xs=[mog.xs[0]])
+    np.testing.assert_allclose(one, solo.eval(x64), rtol=1e-12)
+
+
+def test_sampling_moments_large_n(golden):
+    """Size-independent property: 200k samples reproduce mixture mean/cov."""
+    g = golden('pdf')
+    mog = _mog(g, 'f64')
+    np.random.seed(5)
+    smp = mog.gen(n_samples=200000)
+    mean, cov = mog.calc_mean_and_cov()
+    np.testing.assert_allclose(smp.mean(0), mean, atol=0.02)
+    np.testing.assert_allclose(np.cov(smp.T), cov, atol=0.05)
+    dev = mog.gen(n_samples=200000, method='philox')
+    assert dev.dtype == np.float32
+    np.testing.assert_allclose(dev.mean(0), mean, atol=0.02)
+    np.testing.assert_allclose(np.cov(dev.T), cov, atol=0.05)
+
+
+def test_marginal_eval_close_to_joint_marginalisation(golden):
+    g = golden('pdf')
+    mog = _mog(g, 'f64')
+    x = np.random.RandomState(1).randn(50, 2)
+    np.random.seed(0)
+    lp = mog.eval(x, ii=[0, 2], log=True)
+    from scipy.stats import multivariate_normal as mvn
+    ref = np.log(sum(a * mvn.pdf(x, c.m[[0, 2]], c.S[[0, 2]][:, [0, 2]]) for a, c in zip(mog.a, mog.xs)))
+    np.testing.assert_allclose(lp, ref, rtol=1e-3, atol=1e-3)   # reference adds 1e-5 jitter

@@ -46,12 +46,13 @@ class _LinearFn(torch.autograd.Function):
     def forward(ctx, x, w, b, act, engine):
         x = x.contiguous()
         w = w.contiguous()
+        b = b.contiguous()
         m, k = x.shape
         n = w.shape[0]
         y = torch.empty((m, n), dtype=torch.float32, device=x.device)
         ws = _ws(_lib.load().bsig_linear_ws_bytes(m, n, k), x.device)
         with torch.cuda.device(x.device):
-            _lib.call('bsig_linear_fwd', _lib.ptr(x), k, None, _lib.ptr(w), _lib.ptr(b.contiguous()),
+            _lib.call('bsig_linear_fwd', _lib.ptr(x), k, None, _lib.ptr(w), _lib.ptr(b),
                       _lib.ptr(y), m, n, k, act, engine, ws.data_ptr(), ws.numel(),
                       _lib.stream_ptr(x.device))
         ctx.save_for_backward(x, w, y)
@@ -91,6 +92,7 @@ class _HeadEpilogueFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z, noise, p, k, full_cov):
         z = z.contiguous()
+        noise = noise.contiguous()
         b, nh = z.shape
         dev = z.device
         pk = p * k
@@ -99,7 +101,7 @@ class _HeadEpilogueFn(torch.autograd.Function):
         ws = torch.zeros(_lib.load().bsig_mdn_ws_bytes(b), dtype=torch.uint8, device=dev)
         flag = torch.zeros(1, dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
-            _lib.call('bsig_mdn_head_fwd', _lib.ptr(z), _lib.ptr(noise.contiguous()),
+            _lib.call('bsig_mdn_head_fwd', _lib.ptr(z), _lib.ptr(noise),
                       _lib.ptr(weights), _lib.ptr(l_d), b, p, k, 1 if full_cov else 0,
                       ws.data_ptr(), ws.numel(), _lib.ptr(flag, torch.int32), _lib.stream_ptr(dev))
         mu = z[:, k:k + pk].reshape(b, p, k).clone()
@@ -131,7 +133,7 @@ class _HeadEpilogueFn(torch.autograd.Function):
         dz = torch.empty_like(z)
         ws = torch.zeros(_lib.load().bsig_mdn_ws_bytes(b), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
-            _lib.call('bsig_mdn_head_bwd', _lib.ptr(z), _lib.ptr(noise.contiguous()),
+            _lib.call('bsig_mdn_head_bwd', _lib.ptr(z), _lib.ptr(noise),
                       _lib.ptr(weights), _lib.ptr(d_w), _lib.ptr(d_mu), _lib.ptr(d_ld),
                       _lib.ptr(d_low) if has_low else None, _lib.ptr(dz), b, p, k,
                       1 if full_cov else 0, ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
@@ -340,6 +342,8 @@ class MDNN(nn.Module):
         ntest, dim = xs.size()
         with torch.no_grad():
             pi, mu, L_d, L = self(xs)
+        pi, mu, L_d = pi.contiguous(), mu.contiguous(), L_d.contiguous()
+        L = None if L is None else L.contiguous()
         dev = mu.device
         p, k = self.output_dim, self.n_gaussians
         lsz = 0 if L is None else L.shape[1]
@@ -348,9 +352,8 @@ class MDNN(nn.Module):
         packed = torch.empty((ntest, k, p + lsz), dtype=torch.float32, device=dev)
         normalize = self.output_lows is not None
         with torch.cuda.device(dev):
-            _lib.call('bsig_mog_denorm', _lib.ptr(pi.contiguous()), _lib.ptr(mu.contiguous()),
-                      p * k, _lib.ptr(L_d.contiguous()), p * k,
-                      None if L is None else _lib.ptr(L.contiguous()), lsz * k,
+            _lib.call('bsig_mog_denorm', _lib.ptr(pi), _lib.ptr(mu), p * k, _lib.ptr(L_d), p * k,
+                      None if L is None else _lib.ptr(L), lsz * k,
                       _lib.ptr(self.output_lows) if normalize else None,
                       _lib.ptr(self.output_highs) if normalize else None,
                       _lib.ptr(a_out), _lib.ptr(means), _lib.ptr(packed), ntest, p, k,

@@ -25,6 +25,14 @@ from .. import _lib
 ACT_NONE, ACT_TANH = 0, 1
 
 
+_REPLAYED = [0]
+
+
+def replayed_launches():
+    """Kernel launches executed through graph replays so far (bench accounting)."""
+    return _REPLAYED[0]
+
+
 def log_steps(n_updates):
     every = max(n_updates // 5, 1)
     return [e for e in range(n_updates) if e % every == 0 or e + 1 == n_updates]
@@ -256,6 +264,7 @@ def run_training_captured(model, x_data, y_data, n_updates, batch_size, test_fra
                 plan.capture()
                 plan.launches_per_replay = _lib.load().bsig_launch_count() - before
             plan.graph.replay()
+            _REPLAYED[0] += int(getattr(plan, 'launches_per_replay', 0))
         else:
             plan.enqueue_all()
         n_log = len(plan.logs)

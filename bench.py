@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""Benchmark of the BayesSimIG hot path on B200 (contract: see DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One "step" = one pass of the hot path over one batch of synthetic rollouts of
+BASELINE.json configs[1]: 4096 Cartpole-shaped trajectories per GPU ->
+summary_corrdiff -> MDNN fit (reference constants: chunks of <= 1000
+trajectories, 100 Adam updates of minibatch 100 and 6 held-out evaluations per
+chunk) -> posterior for one held-out trajectory -> 10 000 posterior samples.
+metric = fit trajectories/sec (whole job, all GPUs).  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# ------------------------------------------------------------------ workload (configs[1])
+TASK = dict(name='cartpole', D=4, A=1, T1=21, P=13, K=10)
+N_TRAJ = 4096
+CHUNK = 1000
+HIDDEN = (128, 128)
+LR = 1e-4
+SUMMARIZER = 'summary_corrdiff'
+N_POSTERIOR_SAMPLES = 10000
+METRIC = 'mdnn_fit_trajectories_per_sec'
+UNIT = 'trajectories/s'
+
+
+def synth(seed, n, task, pin=False):
+    """Seeded synthetic rollouts shared by both implementations."""
+    g = torch.Generator('cpu').manual_seed(seed)
+    states = torch.randn(n, task['T1'], task['D'], generator=g).clamp_(-100, 100)
+    actions = torch.rand(n, task['T1'], task['A'], generator=g)
+    lows = np.full(task['P'], 0.1)
+    highs = np.full(task['P'], 2.0)
+    params = torch.from_numpy(lows).float() + torch.rand(n, task['P'], generator=g) * \
+        torch.from_numpy(highs - lows).float()
+    if pin and torch.cuda.is_available():
+        states, actions, params = states.pin_memory(), actions.pin_memory(), params.pin_memory()
+    return states, actions, params, lows, highs
+
+
+def workload_config(n_gpus):
+    return {'workload': 'configs[1]: Cartpole-shaped %d trajectories/GPU [T1=21,D=4,A=1,P=13], '
+                        'summary_corrdiff(F=302) + MDNN[128,128] K=10 fit (chunks of 1000: 100 Adam '
+                        'updates x minibatch 100 + 6 test evals) + predict + 10000 posterior samples'
+                        % N_TRAJ,
+            'trajectories_per_gpu': N_TRAJ, 'chunk': CHUNK, 'n_updates_per_chunk': 100,
+            'minibatch': 100, 'posterior_samples': N_POSTERIOR_SAMPLES,
+            'parallelism': 'dp%d' % n_gpus,
+            'l2_policy': 'L2 flushed (256 MiB write) between timed steps'}
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+             'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix='.csv')
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.gpu_index), '--query-gpu=' + self.QUERY,
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        try:
+            for line in open(self.path):
+                f = [c.strip() for c in line.split(',')]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, f[5:9]):
+                    if val.lower().startswith('active'):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm))
+        out['reasons'] = sorted(reasons)
+        return out
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# --------------------------------------------------------------------------- reference arm
+def cpu_pipeline_rate(n_traj, threads, seed=0):
+    """Time the torch-CPU port of the reference pipeline on n_traj trajectories."""
+    import contextlib
+    import io
+    from oracle import torch_port
+    torch.set_num_threads(threads)
+    states, actions, params, lows, highs = synth(seed, n_traj, TASK)
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    width = 10 * (TASK['D'] - 1) * 10 * TASK['A'] + 2
+    model = torch_port.PortModel(width, TASK['P'], lows, highs, TASK['K'], False, HIDDEN, LR)
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        torch_port.fit_pipeline(states, actions, params, model, SUMMARIZER, chunk=CHUNK,
+                                n_posterior_samples=N_POSTERIOR_SAMPLES)
+    dt = time.perf_counter() - t0
+    return n_traj / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    # bounded sample: one 1000-trajectory chunk per step (about 1.5-6 s of CPU work)
+    sample = 1000
+    for _ in range(args.warmup):
+        cpu_pipeline_rate(200, threads)
+    rates, times = [], []
+    for s in range(args.steps):
+        r, dt = cpu_pipeline_rate(sample, threads, seed=s)
+        rates.append(r)
+        times.append(dt)
+    value = sample * len(times) / sum(times)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT,
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': 1e3 * float(np.mean(times)), 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(args.gpus),
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                             'sample': 'oracle/torch_port.py (same torch ops as the reference CPU '
+                                       'path); %d Cartpole trajectories per step = 1 chunk of the '
+                                       'workload: corrdiff + 100 Adam updates + predict + 10000 '
+                                       'samples' % sample},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0,
+                    'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------- B200 arm
+def flush_l2(buf):
+    buf.add_(1.0)
+
+
+def time_kernel(fn, flush, reps=20, warm=3):
+    """Average device time of fn() in ms, CUDA events on the current stream, L2
+    flushed before every timed launch."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(reps):
+        flush()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / reps
+
+
+def kernel_rooflines(dev, flush, peak_gbs, peak_src):
+    """Stand-alone CUDA-event timings of the streaming kernels at sizes that
+    exceed L2, as achieved algorithmic GB/s against the measured HBM peak."""
+    from bayes_sim_ig_b200 import _lib
+    from bayes_sim_ig.utils import summarizers as S
+    import contextlib
+    import io
+    out = {}
+    st = lambda: _lib.stream_ptr(dev)
+
+    def entry(name, algo_bytes, ms, note):
+        ach = algo_bytes / (ms * 1e-3) / 1e9
+        out[name] = {'bound': 'hbm', 'achieved': round(ach, 1), 'peak': peak_gbs, 'unit': 'GB/s',
+                     'frac': round(ach / peak_gbs, 4), 'ms': round(ms, 4), 'traffic': None,
+                     'algorithmic_bytes': int(algo_bytes), 'shape': note, 'peak_source': peak_src}
+
+    # summary_corrdiff, ShadowHand-shaped (F = 105002): 4*[W(D+A) + F] B/traj
+    n, t1, d, a = 1024, 51, 211, 20
+    s = torch.randn(n, t1, d, device=dev)
+    ac = torch.rand(n, t1, a, device=dev)
+    width = 5 * (d - 1) * 5 * a + 2
+    feats = torch.empty((n, width), device=dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def cross():
+        _lib.call('bsig_summary_crosscorr', s.data_ptr(), ac.data_ptr(), feats.data_ptr(), n, t1, t1,
+                  d, a, 5, 1, flag.data_ptr(), st())
+    entry('summary_corrdiff_shadowhand', n * 4 * (5 * (d + a) + width), time_kernel(cross, flush),
+          'N=%d T1=51 D=211 A=20 -> F=%d' % (n, width))
+    del feats
+    # summary_corrdiff, Cartpole-shaped at 1M trajectories (F = 302)
+    n, t1, d, a = 1 << 20, 21, 4, 1
+    s = torch.randn(n, t1, d, device=dev)
+    ac = torch.rand(n, t1, a, device=dev)
+    feats = torch.empty((n, 302), device=dev)
+
+    def cross2():
+        _lib.call('bsig_summary_crosscorr', s.data_ptr(), ac.data_ptr(), feats.data_ptr(), n, t1, t1,
+                  d, a, 10, 1, flag.data_ptr(), st())
+    entry('summary_corrdiff_cartpole_1M', n * 4 * (10 * (d + a) + 302), time_kernel(cross2, flush),
+          'N=%d T1=21 D=4 A=1 -> F=302' % n)
+    # summary_start, Humanoid-shaped
+    n2, t2, d2, a2 = 1 << 16, 11, 108, 21
+    s2 = torch.randn(n2, t2, d2, device=dev)
+    ac2 = torch.rand(n2, t2, a2, device=dev)
+    o2 = torch.empty((n2, 10 * (d2 + a2)), device=dev)
+
+    def start():
+        _lib.call('bsig_summary_start', s2.data_ptr(), ac2.data_ptr(), o2.data_ptr(), n2, t2, t2, d2,
+                  a2, 10, st())
+    entry('summary_start_humanoid', n2 * 2 * 4 * 10 * (d2 + a2), time_kernel(start, flush),
+          'N=%d T1=11 D=108 A=21 -> F=1290' % n2)
+    # path signature depth 3, Cartpole-shaped (C = 6 -> 258)
+    sig = torch.empty((n, 258), device=dev)
+
+    def sigk():
+        _lib.call('bsig_signature_fwd', s.data_ptr(), ac.data_ptr(), sig.data_ptr(), n, t1, t1, t1,
+                  d, a, 3, st())
+    entry('signature_depth3_cartpole_1M', n * 4 * (t1 * (d + a) + 258), time_kernel(sigk, flush),
+          'N=%d L=21 C=6 depth 3 -> 258' % n)
+    del s, ac, feats, sig
+    # fused head + mixture NLL forward/backward, B = 262144, P = 13, K = 10 (diag)
+    b, p, k = 1 << 18, 13, 10
+    nh = k * (1 + 2 * p)
+    z = torch.randn(b, nh, device=dev) * 0.3
+    dz = torch.empty_like(z)
+    noise = torch.rand(b, p, k, device=dev)
+    y = torch.rand(b, p, device=dev)
+    loss = torch.zeros(1, device=dev)
+    ws = torch.zeros(_lib.load().bsig_mdn_ws_bytes(b), dtype=torch.uint8, device=dev)
+
+    def nll():
+        _lib.call('bsig_mdn_nll_fused', z.data_ptr(), noise.data_ptr(), y.data_ptr(), None,
+                  loss.data_ptr(), dz.data_ptr(), b, p, k, 0, ws.data_ptr(), ws.numel(),
+                  flag.data_ptr(), st())
+    # algorithmic: read z + noise + y, write dz  (3 launches: exp-sum, nll, eps fix-up)
+    entry('mdn_nll_fused_fwd_bwd', 4 * b * (2 * nh + p * k + p), time_kernel(nll, flush),
+          'B=%d P=13 K=10 diag, fwd+bwd (3 launches)' % b)
+    # Adam over 13.5 M parameters (ShadowHand MDNN): 28 B/param
+    cnt = 13540748
+    pr, g, m, v = (torch.zeros(cnt, device=dev) for _ in range(4))
+
+    def adam():
+        _lib.call('bsig_adam_step', pr.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), cnt, 1,
+                  1e-4, 0.9, 0.999, 1e-8, 1.0, st())
+    entry('adam_13.5M', 28 * cnt, time_kernel(adam, flush), 'flat fp32 buffer of %d params' % cnt)
+    return out
+
+
+def run_b200(args):
+    import contextlib
+    import io
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py (impl b200) needs a CUDA device'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    from bayes_sim_ig_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        from bayes_sim_ig_b200 import build as _b
+        _b.build()
+    from bayes_sim_ig.bayes_sim import BayesSim
+    from bayes_sim_ig_b200.models import train_engine
+
+    states_h, actions_h, params_h, lows, highs = synth(1000 + rank, N_TRAJ, TASK, pin=True)
+    states_d, actions_d, params_d = states_h.to(dev), actions_h.to(dev), params_h.to(dev)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    cfg = {'modelClass': 'MDNN', 'summarizerFxn': SUMMARIZER, 'trainTrajLen': TASK['T1'] - 1,
+           'components': TASK['K'], 'hiddenLayers': list(HIDDEN), 'lr': LR}
+    bsim = BayesSim(cfg, TASK['D'], TASK['A'], TASK['P'], lows, highs, prior=None, proposal=None,
+                    device=str(dev))
+    if world > 1:
+        from bayes_sim_ig_b200 import data_parallel
+        data_parallel.enable(bsim.model)
+    sink = io.StringIO()
+
+    def step(states, actions, params):
+        """The public-API pass: BayesSim.run_training per chunk, predict, MoG.gen."""
+        with contextlib.redirect_stdout(sink):
+            for lo in range(0, N_TRAJ, CHUNK):
+                logs = bsim.run_training(params[lo:lo + CHUNK], states[lo:lo + CHUNK],
+                                         actions[lo:lo + CHUNK])
+            post = bsim.predict(states[:1], actions[:1])
+            smp = post.gen(N_POSTERIOR_SAMPLES)
+        return logs, smp
+
+    flush_buf = torch.zeros(64 * 1024 * 1024, device=dev)     # 256 MiB > 126 MB L2
+    flush = lambda: flush_l2(flush_buf)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        tot = 0.0
+        for _ in range(k):
+            flush()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            tot += e0.elapsed_time(e1)
+        t = torch.tensor([tot], device=dev, dtype=torch.float64)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step(states_d, actions_d, params_d)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = _lib.load().bsig_launch_count() + train_engine.replayed_launches()
+    ms_res = timed(lambda: step(states_d, actions_d, params_d), args.steps)
+    launches = _lib.load().bsig_launch_count() + train_engine.replayed_launches() - launches0
+    ms_e2e = timed(lambda: step(states_h, actions_h, params_h), args.steps)
+    clocks = sampler.stop()
+    value = world * N_TRAJ * args.steps / (ms_res * 1e-3)
+    e2e_value = world * N_TRAJ * args.steps / (ms_e2e * 1e-3)
+    h2d = int(states_h.numel() + actions_h.numel() + params_h.numel()) * 4 + \
+        2 * (N_TRAJ // CHUNK + 1) * 100 * 100 * 8
+    d2h = (N_TRAJ // CHUNK + 1) * 13 * 4 + N_POSTERIOR_SAMPLES * TASK['P'] * 8 + \
+        TASK['K'] * (1 + 2 * TASK['P']) * 4
+
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms_res / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic', 'config': workload_config(world), 'clocks': clocks,
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+                    'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e / args.steps},
+            'gpu_launches': int(launches)}
+    if rank == 0 and world == 1:
+        peak, src = measured_peaks()
+        roofs = kernel_rooflines(dev, flush, peak, src)
+        line['roofline'] = roofs['summary_corrdiff_shadowhand']
+        line['roofline']['kernel'] = 'crosscorr_kernel'
+        line['rooflines'] = roofs
+        threads = os.cpu_count() or 1
+        rate, dt = cpu_pipeline_rate(1000, threads)
+        line['cpu_baseline'] = {
+            'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+            'sample': 'oracle/torch_port.py (same torch ops as the reference CPU path) on 1000 of '
+                      'the 4096 trajectories: corrdiff + 100 Adam updates + 6 test evals + predict '
+                      '+ 10000 samples; %.2f s' % dt}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -147,7 +147,7 @@ def test_nll_edge_values_and_nonfinite_assert(golden):
     far = y + 1e4
     tiny = ld * 1e-3
     loss = model.mdn_loss_fn(w, mu, tiny, low, far).item()
-    ref = mdn_np.mdn_loss(w.cpu().numpy().astype(np.float64), mu.detach().cpu().numpy().astype(np.float64),
+    ref = mdn_np.mdn_loss(w.detach().cpu().numpy().astype(np.float64), mu.detach().cpu().numpy().astype(np.float64),
                           tiny.detach().cpu().numpy().astype(np.float64), None, far.cpu().numpy())
     assert np.isfinite(loss) and abs(loss - ref) <= 1e-5 * abs(ref)
 

@@ -162,3 +162,45 @@ def test_pdf_ctor_gen_eval(golden, case):
                                g[case + '.eval.log64'], rtol=1e-12, atol=1e-12)
     np.testing.assert_allclose(pdf_np.mog_logpdf(x64, a, ms, precs, lds, log=False),
                                g[case + '.eval.lin64'], rtol=1e-10, atol=1e-300)
+
+
+@pytest.mark.parametrize('case', ['diag', 'full_big', 'rff'])
+def test_torch_port_matches_reference(golden, case):
+    """oracle/torch_port.py (the CPU timing baseline) issues the reference's torch
+    ops: with the recorded noise it must reproduce losses, grads and Adam steps."""
+    import torch
+    from helpers import injected_rand_like
+    from oracle import torch_port
+    torch.set_num_threads(1)
+    g = golden('mdn')
+    din, p, k, full, b, rff = _mdn_case(g, case)
+    hidden = tuple(int(v) for v in g[case + '.meta'][5:])
+    rff_t = None if rff is None else (torch.from_numpy(rff[0]), torch.from_numpy(rff[1]))
+    model = torch_port.PortModel(din, p, g[case + '.lows'], g[case + '.highs'], k, full, hidden,
+                                 1e-3, rff=rff_t)
+    model.load_state_dict({key: torch.from_numpy(v) for key, v in g.sub(case + '.init.').items()})
+    x, y = torch.from_numpy(g[case + '.x']), torch.from_numpy(g[case + '.y'])
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    for step in range(3):
+        tag = '%s.step%d.' % (case, step)
+        with injected_rand_like([g[tag + 'noise']], 'cpu'):
+            opt.zero_grad()
+            loss = model.loss(*model(x), y)
+            loss.backward()
+        np.testing.assert_allclose(loss.item(), g[tag + 'loss'], rtol=1e-6)
+        for name, prm in model.named_parameters():
+            np.testing.assert_allclose(prm.grad.numpy(), g[tag + 'grad.' + name], rtol=1e-4, atol=1e-7)
+        opt.step()
+    for name, ref in g.sub(case + '.step2.after.').items():
+        np.testing.assert_allclose(model.state_dict()[name].numpy(), ref, rtol=1e-5, atol=1e-6)
+
+
+def test_torch_port_summarizers_match_reference(golden):
+    import torch
+    from oracle import torch_port
+    g = golden('summarizers')
+    for case in ('pendulum', 'cartpole', 'ant'):
+        s, a = torch.from_numpy(g[case + '.states']), torch.from_numpy(g[case + '.actions'])
+        assert np.array_equal(torch_port.summary_start(s, a).numpy(), g[case + '.summary_start'])
+        assert np.array_equal(torch_port.summary_corrdiff(s, a).numpy(), g[case + '.summary_corrdiff'])
+        assert np.array_equal(torch_port.summary_corr(s, a).numpy(), g[case + '.summary_corr'])

@@ -54,7 +54,7 @@ SIGNATURES = {
                                _c_ptr, _c_ptr, _c_ptr, _i64, _i64, _i64, _c_ptr]),
     'bsig_mog_sample': (_int, [_c_ptr, _int] + [_c_ptr] * 7 + [_i64] * 3 + [_c_ptr]),
     'bsig_mog_sample_philox': (_int, [_c_ptr] * 5 + [_u64, _i64, _i64, _i64, _c_ptr]),
-    'bsig_mog_logpdf': (_int, [_c_ptr, _int] + [_c_ptr] * 5 + [_i64] * 3 + [_int, _c_ptr]),
+    'bsig_mog_logpdf': (_int, [_c_ptr, _int] + [_c_ptr] * 6 + [_i64] * 3 + [_int, _c_ptr]),
 }
 
 _lib = None

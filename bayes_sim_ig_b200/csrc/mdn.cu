@@ -51,18 +51,38 @@ struct NllArgs {
   int nparts_e;                          // number of valid exp-sum partials
 };
 
+// Flat index -> (row, column) walker for grid-stride loops over a [rows, width]
+// block: one division at start, none per iteration.
+struct RowCol {
+  int64_t row;
+  int col;
+  int64_t d_row;
+  int d_col;
+  int width;
+  __device__ __forceinline__ RowCol(int64_t start, int64_t stride, int w) : width(w) {
+    row = start / w;
+    col = (int)(start - row * w);
+    d_row = stride / w;
+    d_col = (int)(stride - d_row * w);
+  }
+  __device__ __forceinline__ void next() {
+    row += d_row;
+    col += d_col;
+    if (col >= width) { col -= width; ++row; }
+  }
+};
+
 // ---------------------------------------------------------------- exp-sum (eps)
 __global__ void __launch_bounds__(256)
 exp_sum_kernel(const float* __restrict__ zd, int64_t ld_zd, int B, int PK, float* ws) {
   __shared__ float scratch[33];
   const int64_t total = (int64_t)B * PK;
   float acc = 0.f;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t b = i / PK;
-    const int c = (int)(i - b * PK);
-    acc += expf(__ldg(zd + b * ld_zd + c));
-  }
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t start = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  RowCol rc(start, stride, PK);
+  for (int64_t i = start; i < total; i += stride, rc.next())
+    acc += expf(__ldg(zd + rc.row * ld_zd + rc.col));
   acc = block_sum(acc, scratch);
   if (threadIdx.x == 0) ws[blockIdx.x] = acc;
 }
@@ -360,12 +380,11 @@ eps_fixup_kernel(const float* __restrict__ zd, int64_t ld_zd, float* dzd, int64_
   const float S = sum_parts(s_parts, nparts, scratch);
   const int64_t total = (int64_t)B * PK;
   const float c = kEpsNoise * S / (float)total;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t b = i / PK;
-    const int col = (int)(i - b * PK);
-    dzd[b * ldo_zd + col] += expf(__ldg(zd + b * ld_zd + col)) * c;
-  }
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t start = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  RowCol rc(start, stride, PK);
+  for (int64_t i = start; i < total; i += stride, rc.next())
+    dzd[rc.row * ldo_zd + rc.col] += expf(__ldg(zd + rc.row * ld_zd + rc.col)) * c;
 }
 
 // --------------------------------------------------------- head epilogue (API path)
@@ -396,19 +415,18 @@ head_fwd_kernel(const float* __restrict__ z, const float* __restrict__ noise,
     }
   }
   const int64_t total = (int64_t)B * PK;
-  for (int64_t i = gtid; i < total; i += gstride) {
-    const int64_t b = i / PK;
-    const int c = (int)(i - b * PK);
-    const float v = expf(__ldg(z + b * NH + K + PK + c)) + __ldg(noise + i) * eps;
+  RowCol rc(gtid, gstride, PK);
+  for (int64_t i = gtid; i < total; i += gstride, rc.next()) {
+    const float v = expf(__ldg(z + rc.row * NH + K + PK + rc.col)) + __ldg(noise + i) * eps;
     l_d[i] = v;
-    bad |= !finite_f(v) || !finite_f(__ldg(z + b * NH + K + c));
+    bad |= !finite_f(v) || !finite_f(__ldg(z + rc.row * NH + K + rc.col));
   }
   const int LK = NH - K - 2 * PK;
-  const int64_t total_l = (int64_t)B * LK;
-  for (int64_t i = gtid; i < total_l; i += gstride) {
-    const int64_t b = i / LK;
-    const int c = (int)(i - b * LK);
-    bad |= !finite_f(__ldg(z + b * NH + K + 2 * PK + c));
+  if (LK > 0) {
+    const int64_t total_l = (int64_t)B * LK;
+    RowCol rl(gtid, gstride, LK);
+    for (int64_t i = gtid; i < total_l; i += gstride, rl.next())
+      bad |= !finite_f(__ldg(z + rl.row * NH + K + 2 * PK + rl.col));
   }
   if (bad) atomicOr(flag, 1);
 }
@@ -464,18 +482,18 @@ head_bwd_kernel(const float* __restrict__ z, const float* __restrict__ weights,
     }
   }
   const int64_t total = (int64_t)B * PK;
-  for (int64_t i = gtid; i < total; i += gstride) {
-    const int64_t b = i / PK;
-    const int c = (int)(i - b * PK);
-    dz[b * NH + K + c] = __ldg(d_mu + i);
-    dz[b * NH + K + PK + c] = expf(__ldg(z + b * NH + K + PK + c)) * (__ldg(d_ld + i) + c_eps);
+  RowCol rc(gtid, gstride, PK);
+  for (int64_t i = gtid; i < total; i += gstride, rc.next()) {
+    const int64_t o = rc.row * NH + K + rc.col;
+    dz[o] = __ldg(d_mu + i);
+    dz[o + PK] = expf(__ldg(z + o + PK)) * (__ldg(d_ld + i) + c_eps);
   }
   const int LK = NH - K - 2 * PK;
-  const int64_t total_l = (int64_t)B * LK;
-  for (int64_t i = gtid; i < total_l; i += gstride) {
-    const int64_t b = i / LK;
-    const int c = (int)(i - b * LK);
-    dz[b * NH + K + 2 * PK + c] = d_low ? __ldg(d_low + i) : 0.f;
+  if (LK > 0) {
+    const int64_t total_l = (int64_t)B * LK;
+    RowCol rl(gtid, gstride, LK);
+    for (int64_t i = gtid; i < total_l; i += gstride, rl.next())
+      dz[rl.row * NH + K + 2 * PK + rl.col] = d_low ? __ldg(d_low + i) : 0.f;
   }
 }
 

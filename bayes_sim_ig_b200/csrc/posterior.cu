@@ -156,7 +156,7 @@ mog_sample_philox_kernel(const float* __restrict__ a, const float* __restrict__ 
 template <typename X_T>
 __global__ void __launch_bounds__(128)
 mog_logpdf_kernel(const X_T* __restrict__ x, const double* __restrict__ a,
-                  const double* __restrict__ means, const double* __restrict__ precs,
+                  const double* __restrict__ log_a, const double* __restrict__ means, const double* __restrict__ precs,
                   const double* __restrict__ logdet, double* __restrict__ out, int64_t m, int P,
                   int K, int log_space) {
   const double log2pi = 1.8378770664093454835606594728112;
@@ -175,7 +175,7 @@ mog_logpdf_kernel(const X_T* __restrict__ x, const double* __restrict__ a,
       }
       const double lp = 0.5 * (-q + __ldg(logdet + k) - (double)P * log2pi);
       if (log_space) {
-        const double t = lp + log(__ldg(a + k));
+        const double t = lp + __ldg(log_a + k);
         if (t > run_max) {
           run_sum = run_sum * exp(run_max - t) + 1.0;
           run_max = t;
@@ -246,18 +246,18 @@ extern "C" int bsig_mog_sample_philox(const float* a, const float* means, const 
   return 0;
 }
 
-extern "C" int bsig_mog_logpdf(const void* x, int x_is_f32, const double* a, const double* means,
-                               const double* precs, const double* logdet_p, double* out,
+extern "C" int bsig_mog_logpdf(const void* x, int x_is_f32, const double* a, const double* log_a,
+                               const double* means, const double* precs, const double* logdet_p, double* out,
                                int64_t m, int64_t p, int64_t k, int log_space, void* stream) {
   BSIG_REQUIRE(m >= 0 && p >= 1 && k >= 1, "mog_logpdf: bad sizes");
   if (m == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = grid_for(m, 128);
   if (x_is_f32)
-    mog_logpdf_kernel<float><<<grid, 128, 0, st>>>((const float*)x, a, means, precs, logdet_p, out,
+    mog_logpdf_kernel<float><<<grid, 128, 0, st>>>((const float*)x, a, log_a, means, precs, logdet_p, out,
                                                    m, (int)p, (int)k, log_space);
   else
-    mog_logpdf_kernel<double><<<grid, 128, 0, st>>>((const double*)x, a, means, precs, logdet_p,
+    mog_logpdf_kernel<double><<<grid, 128, 0, st>>>((const double*)x, a, log_a, means, precs, logdet_p,
                                                     out, m, (int)p, (int)k, log_space);
   BSIG_LAUNCH_CHECK();
   return 0;

@@ -65,6 +65,10 @@ struct CrossArgs {
   int use_diff;
 };
 
+// TW = threads that cooperate on one row: a warp for short rows (many rows per
+// CTA in flight), the whole CTA for long rows.  No divisions in the store loop:
+// (p, q) advance incrementally by the per-iteration stride.
+template <int TW>
 __global__ void __launch_bounds__(256) crosscorr_kernel(CrossArgs p) {
   extern __shared__ float smem[];
   float* sf = smem;                         // [G][Pn]
@@ -82,19 +86,19 @@ __global__ void __launch_bounds__(256) crosscorr_kernel(CrossArgs p) {
   const int g_lo = (int)(c0 / p.F);
   const int g_hi = (int)((c1 - 1) / p.F);
   const int Dm1 = p.D - 1;
+  const int nrows = g_hi - g_lo + 1;
 
-  for (int g = g_lo; g <= g_hi; ++g) {
-    const float* s = p.states + (traj0 + g) * p.s_stride;
-    const float* a = p.actions + (traj0 + g) * p.a_stride;
-    for (int i = threadIdx.x; i < p.Pn; i += blockDim.x) {
-      const int t = i / Dm1, j = i - t * Dm1;
-      const float lo = __ldg(s + t * p.D + j);
-      sf[g * p.Pn + i] = p.use_diff ? (__ldg(s + t * p.D + j + 1) - lo) : lo;
-    }
-    for (int i = threadIdx.x; i < p.Qn; i += blockDim.x) {
-      // actions of the first W steps are contiguous: [t*A + k]
-      af[g * p.Qn + i] = __ldg(a + i);
-    }
+  for (int i = threadIdx.x; i < nrows * p.Pn; i += blockDim.x) {
+    const int g = g_lo + i / p.Pn, e = i % p.Pn;
+    const int t = e / Dm1, j = e - t * Dm1;
+    const float* s = p.states + (traj0 + g) * p.s_stride + t * p.D + j;
+    const float lo = __ldg(s);
+    sf[g * p.Pn + e] = p.use_diff ? (__ldg(s + 1) - lo) : lo;
+  }
+  for (int i = threadIdx.x; i < nrows * p.Qn; i += blockDim.x) {
+    const int g = g_lo + i / p.Qn, e = i % p.Qn;
+    // actions of the first W steps are contiguous: [t*A + k]
+    af[g * p.Qn + e] = __ldg(p.actions + (traj0 + g) * p.a_stride + e);
   }
   __syncthreads();
 
@@ -126,34 +130,53 @@ __global__ void __launch_bounds__(256) crosscorr_kernel(CrossArgs p) {
   float* out = p.out + traj0 * p.F;
   bool bad = false;
   const uint32_t Qn = (uint32_t)p.Qn;
-  for (int64_t e0 = c0 + (int64_t)threadIdx.x * 4; e0 < c1; e0 += (int64_t)blockDim.x * 4) {
-    int g = (int)(e0 / p.F);
-    int64_t r = e0 - (int64_t)g * p.F;
-    uint32_t pi = 0, qi = 0;
-    if (r < PQ) {
-      pi = (uint32_t)r / Qn;  // PQ < 2^31 is checked on the host
-      qi = (uint32_t)r - pi * Qn;
-    }
-    float v[4];
+  const int lt = threadIdx.x % TW, wk = threadIdx.x / TW;
+  constexpr int NWORK = 256 / TW;
+  constexpr uint32_t STEP = 4u * TW;
+  const uint32_t dP = STEP / Qn, dQ = STEP - dP * Qn;
+  for (int g = g_lo + wk; g <= g_hi; g += NWORK) {
+    const int64_t row0 = (int64_t)g * p.F;
+    const int64_t lo = max(c0, row0), hi = min(c1, row0 + p.F);
+    const int64_t pq_hi = min(hi, row0 + PQ);
+    const int64_t ea = (lo + 3) & ~3ll;                       // first aligned float4
+    const int64_t nb = pq_hi > ea ? (pq_hi - ea) >> 2 : 0;    // float4s fully inside products
+    const float* sfg = sf + g * p.Pn;
+    const float* afg = af + g * p.Qn;
+    uint32_t r = (uint32_t)(ea - row0) + 4u * lt;
+    uint32_t pi = r / Qn, qi = r - pi * Qn;
+    float* o = out + ea + 4 * lt;
+    for (int64_t i = lt; i < nb; i += TW) {
+      uint32_t pp = pi, qq = qi;
+      float v[4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      if (e0 + c < c1) {
-        if (r < PQ) {
-          v[c] = sf[g * p.Pn + pi] * af[g * p.Qn + qi];
-          if (++qi == Qn) { qi = 0; ++pi; }
-        } else {
-          v[c] = st[g * 2 + (int)(r - PQ)];
-        }
+      for (int c = 0; c < 4; ++c) {
+        v[c] = sfg[pp] * afg[qq];
+        if (++qq == Qn) { qq = 0; ++pp; }
         bad |= !finite_f(v[c]);
-        if (++r == p.F) { r = 0; pi = 0; qi = 0; ++g; }
-      } else {
-        v[c] = 0.f;
       }
+      st_stream_f4(o, make_float4(v[0], v[1], v[2], v[3]));
+      o += STEP;
+      qi += dQ;
+      pi += dP;
+      if (qi >= Qn) { qi -= Qn; ++pi; }
     }
-    if (e0 + 3 < c1) {
-      st_stream_f4(out + e0, make_float4(v[0], v[1], v[2], v[3]));
-    } else {
-      for (int c = 0; c < 4 && e0 + c < c1; ++c) out[e0 + c] = v[c];
+    // row boundaries: unaligned head, and the tail (last products + the two stats)
+    const int64_t head_end = min(ea, hi);
+    const int64_t body_end = max(head_end, ea + 4 * nb);
+    int64_t e = -1;
+    if (lt < 8) { if (lo + lt < head_end) e = lo + lt; }
+    else if (lt < 16) { if (body_end + (lt - 8) < hi) e = body_end + (lt - 8); }
+    if (e >= 0) {
+      const int64_t rr = e - row0;
+      float v;
+      if (rr < PQ) {
+        const uint32_t pp = (uint32_t)rr / Qn;
+        v = sfg[pp] * afg[(uint32_t)rr - pp * Qn];
+      } else {
+        v = st[g * 2 + (int)(rr - PQ)];
+      }
+      bad |= !finite_f(v);
+      out[e] = v;
     }
   }
   if (bad) atomicOr(p.flag, 1);
@@ -209,29 +232,38 @@ extern "C" int bsig_summary_crosscorr(const float* states, const float* actions,
   BSIG_REQUIRE(PQ < (1ll << 31), "crosscorr: feature row too wide");
   p.F = PQ + 2;
   p.use_diff = use_state_diff;
-  // group size: ~32 KB of output per group, a multiple that keeps 16B alignment,
-  // bounded by the shared-memory staging budget (40 KB).
+  // group size: >= 64 KB of output per CTA where the batch allows it, a multiple
+  // that keeps group bases 16B aligned, bounded by the staging budget (64 KB).
   const int galign = 4 / gcd_i((int)(p.F % 4 == 0 ? 4 : p.F % 4), 4);
-  int64_t G = ceil_div(8192, p.F);
+  int64_t G = ceil_div(16384, p.F);
   const int64_t per_traj_smem = (int64_t)(p.Pn + p.Qn + 2) * 4;
-  const int64_t gmax = std::max<int64_t>(1, (40 * 1024) / per_traj_smem);
+  const int64_t gmax = std::max<int64_t>(1, (64 * 1024) / per_traj_smem);
   G = std::min(G, gmax);
-  G = std::max<int64_t>(galign, (G / galign) * galign);
+  G = std::max<int64_t>(galign, ceil_div(G, galign) * galign);
   // do not starve the machine when n is small
   while (G > galign && ceil_div(n, G) < 2 * sm_count()) G -= galign;
   p.G = (int)G;
   const size_t smem = (size_t)G * per_traj_smem;
   BSIG_REQUIRE(smem <= 200 * 1024, "crosscorr: window too large for shared memory");
   const int64_t group_floats = G * p.F;
-  p.chunk = 8192;
+  p.chunk = group_floats <= 49152 ? ceil_div(group_floats, 4) * 4 : 32768;
   const int64_t nchunk = ceil_div(group_floats, p.chunk);
   const int64_t ngroup = ceil_div(n, G);
   BSIG_REQUIRE(ngroup < (1ll << 31) && nchunk <= 65535, "crosscorr: grid too large");
-  if (smem > 48 * 1024)
-    BSIG_CUDA(cudaFuncSetAttribute(crosscorr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)smem));
   dim3 grid((unsigned)ngroup, (unsigned)nchunk);
-  crosscorr_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+  const bool short_rows = p.F <= 4096;
+  if (smem > 48 * 1024) {
+    if (short_rows)
+      BSIG_CUDA(cudaFuncSetAttribute(crosscorr_kernel<32>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
+      BSIG_CUDA(cudaFuncSetAttribute(crosscorr_kernel<256>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  if (short_rows)
+    crosscorr_kernel<32><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+  else
+    crosscorr_kernel<256><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
   BSIG_LAUNCH_CHECK();
   return 0;
 }

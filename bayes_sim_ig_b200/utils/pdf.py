@@ -73,9 +73,12 @@ def _mixture_logpdf_device(x, a, means, precs, logdets, log):
     x_d = torch.from_numpy(x).to(dev)
     out = torch.empty(m, dtype=torch.float64, device=dev)
     # keep the staged parameter tensors alive until the result has been read back
-    a_d, m_d, p_d, l_d = (_dev64(t, dev) for t in (a, means, precs, logdets))
+    a = np.asarray(a)
+    with np.errstate(divide='ignore'):
+        log_a = np.log(a)               # in a's own dtype, like np.log(self.a) at pdf.py:486
+    a_d, la_d, m_d, p_d, l_d = (_dev64(t, dev) for t in (a, log_a, means, precs, logdets))
     _lib.call('bsig_mog_logpdf', x_d.data_ptr(), 1 if x_is_f32 else 0, a_d.data_ptr(),
-              m_d.data_ptr(), p_d.data_ptr(), l_d.data_ptr(), out.data_ptr(), m, p, k,
+              la_d.data_ptr(), m_d.data_ptr(), p_d.data_ptr(), l_d.data_ptr(), out.data_ptr(), m, p, k,
               1 if log else 0, _lib.stream_ptr(dev))
     return out.cpu().numpy()
 

@@ -201,11 +201,12 @@ int bsig_mog_sample_philox(const float* a, const float* means, const float* cmat
                            int64_t n, int64_t p, int64_t k, void* stream);
 
 /* MoG.eval, joint density (utils/pdf.py:474-491, 328-332):
- * x [m,P] (float32 if x_is_f32 else float64); a [K], means [K,P], precs [K,P,P],
- * logdet_p [K] float64; out [m] float64 = logsumexp_k(lp_k + log a_k) if
- * log_space else sum_k a_k exp(lp_k). */
-int bsig_mog_logpdf(const void* x, int x_is_f32, const double* a, const double* means,
-                    const double* precs, const double* logdet_p, double* out,
+ * x [m,P] (float32 if x_is_f32 else float64); a [K], log_a [K] (np.log(a) taken in
+ * a's own dtype, as the reference does), means [K,P], precs [K,P,P], logdet_p [K]
+ * float64; out [m] float64 = logsumexp_k(lp_k + log_a_k) if log_space else
+ * sum_k a_k exp(lp_k). */
+int bsig_mog_logpdf(const void* x, int x_is_f32, const double* a, const double* log_a,
+                    const double* means, const double* precs, const double* logdet_p, double* out,
                     int64_t m, int64_t p, int64_t k, int log_space, void* stream);
 
 #ifdef __cplusplus

@@ -27,6 +27,7 @@ struct GemmArgs {
   const float* aux;
   int64_t ld_aux;
   float scale;
+  float* rowsum;             // optional: rowsum[i] = sum_r A(i,r) (small engine only)
   // filled by the launcher
   int k_per_split;
   float* partial;
@@ -37,12 +38,14 @@ inline GemmArgs gemm_args_zero() {
   g.A = g.B = nullptr; g.C = nullptr; g.M = g.N = g.K = 0;
   g.a_si = g.a_sr = g.b_sr = g.b_sj = g.ldc = 0;
   g.a_rows = g.b_rows = nullptr; g.epi = EPI_STORE; g.bias = g.aux = nullptr;
-  g.ld_aux = 0; g.scale = 1.f; g.k_per_split = 0; g.partial = nullptr;
+  g.ld_aux = 0; g.scale = 1.f; g.rowsum = nullptr; g.k_per_split = 0; g.partial = nullptr;
   return g;
 }
 
 int gemm_simt(GemmArgs g, void* ws, int64_t ws_bytes, cudaStream_t st);
 int64_t gemm_simt_ws_bytes(int64_t M, int64_t N, int64_t K);
 int colsum(const float* dy, float* db, int64_t M, int64_t N, cudaStream_t st);
+bool gemm_small_applicable(const GemmArgs& g);
+int gemm_small(GemmArgs g, cudaStream_t st);
 
 }  // namespace bsig

@@ -7,6 +7,7 @@ using namespace bsig;
 
 static int run_gemm(const GemmArgs& g, int engine, void* ws, int64_t ws_bytes, cudaStream_t st) {
   (void)engine;  // BSIG_GEMM_TC_* engines are wired in gemm_tc.cu
+  if (gemm_small_applicable(g)) return gemm_small(g, st);
   return gemm_simt(g, ws, ws_bytes, st);
 }
 
@@ -58,8 +59,10 @@ extern "C" int bsig_linear_wgrad(const float* dy, const float* x, int64_t ldx,
   g.A = dy; g.a_si = 1; g.a_sr = n;         // A(i,r) = dy[r,i]
   g.B = x; g.b_sr = ldx; g.b_sj = 1; g.b_rows = x_rows;   // B(r,j) = x[rows[r], j]
   g.C = dw; g.ldc = k; g.M = (int)n; g.N = (int)k; g.K = (int)m;
+  const bool fused_bias = db != nullptr && gemm_small_applicable(g);
+  if (fused_bias) g.rowsum = db;            // db[i] = sum_r dy[r,i] rides along in the GEMM
   if (run_gemm(g, engine, ws, ws_bytes, (cudaStream_t)stream)) return 1;
-  if (db != nullptr) return colsum(dy, db, m, n, (cudaStream_t)stream);
+  if (db != nullptr && !fused_bias) return colsum(dy, db, m, n, (cudaStream_t)stream);
   return 0;
 }
 

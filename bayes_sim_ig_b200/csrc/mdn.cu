@@ -16,7 +16,11 @@
 //
 // Every cross-sample reduction (mean of exp(z_d) for the eps-noise term, the
 // loss, the eps-term gradient) is two-stage and fixed-order => deterministic.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace bsig {
 
@@ -111,31 +115,20 @@ __device__ __forceinline__ float group_max(float v) {
 //        gradients are taken back through them to the logits).
 // FULL : full covariance (strict-lower block present).
 // BWD  : also write gradients.
+// Per-sample work shared by the grid-wide and the single-cluster kernels.
+// Groups of GW lanes own samples base+gid for base = first, first+stride, ...
+// TS = threads per CTA (stride of the per-thread z/v vectors in shared memory).
 template <int GW, int KPL, bool FUSED, bool FULL, bool BWD>
-__global__ void __launch_bounds__(128) nll_kernel(NllArgs a) {
-  extern __shared__ float dyn[];           // FULL: zs[P][128], vs[P][128]
-  __shared__ float scratch[33];
+__device__ __forceinline__ void nll_samples(const NllArgs& a, const float eps,
+                                            const float coef_scale, const int first,
+                                            const int stride, const int TS, float* zs, float* vs,
+                                            float& loss_acc, float& s_acc, bool& bad) {
   const int tid = threadIdx.x;
   const int lane_g = tid & (GW - 1);
   const int gid = tid / GW;
-  constexpr int GPB = 128 / GW;
   const int B = a.B, P = a.P, K = a.K;
-  float* zs = dyn + tid;                   // element p at zs[p*128]
-  float* vs = dyn + (size_t)P * 128 + tid;
 
-  float eps = 0.f;
-  if (FUSED) {
-    const float esum = sum_parts(a.ws, a.nparts_e, scratch);
-    eps = kEpsNoise * (esum / (float)((int64_t)B * P * K));
-  }
-  float gscale = 1.f;
-  if (BWD && a.grad_scale != nullptr) gscale = __ldg(a.grad_scale);
-  const float coef_scale = gscale / (float)B;
-
-  float loss_acc = 0.f, s_acc = 0.f;
-  bool bad = false;
-
-  for (int base = blockIdx.x * GPB; base < B; base += gridDim.x * GPB) {
+  for (int base = first; base < B; base += stride) {
     const int b = base + gid;
     const bool row_ok = b < B;
     const int64_t bb = row_ok ? b : 0;
@@ -193,20 +186,44 @@ __global__ void __launch_bounds__(128) nll_kernel(NllArgs a) {
       g[j] = 0.f;
       if (row_ok && k < K) {
         float quad = 0.f, logdet = 0.f;
-        for (int i = 0; i < P; ++i) {
-          float ldv = __ldg(zd_r + i * K + k);
-          if (FUSED) ldv = expf(ldv) + __ldg(nz_r + i * K + k) * eps;
-          const float m = __ldg(mu_r + i * K + k);
-          float acc = __ldg(yrow + i) - m;
-          if (FULL) {
-            const float* lrow = low_r + (int64_t)(i * (i - 1) / 2) * K + k;
-            for (int c = 0; c < i; ++c) acc -= __ldg(lrow + c * K) * zs[c * 128];
+        if (!FULL) {
+          // diagonal covariance: no dependence between rows -> issue the loads of
+          // four rows together (memory-level parallelism; the batch is latency-bound)
+          for (int i0 = 0; i0 < P; i0 += 4) {
+            float zv[4], mv[4], nv[4], yv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int i = min(i0 + u, P - 1);
+              zv[u] = __ldg(zd_r + i * K + k);
+              mv[u] = __ldg(mu_r + i * K + k);
+              nv[u] = FUSED ? __ldg(nz_r + i * K + k) : 0.f;
+              yv[u] = __ldg(yrow + i);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (i0 + u < P) {
+                const float ldv = FUSED ? expf(zv[u]) + nv[u] * eps : zv[u];
+                const float zi = (yv[u] - mv[u]) / ldv;
+                quad += zi * zi;
+                logdet += logf(ldv);
+                bad |= !(finite_f(ldv) && finite_f(mv[u]));
+              }
+            }
           }
-          const float zi = acc / ldv;
-          if (FULL) zs[i * 128] = zi;
-          quad += zi * zi;
-          logdet += logf(ldv);
-          bad |= !(finite_f(ldv) && finite_f(m));
+        } else {
+          for (int i = 0; i < P; ++i) {
+            float ldv = __ldg(zd_r + i * K + k);
+            if (FUSED) ldv = expf(ldv) + __ldg(nz_r + i * K + k) * eps;
+            const float m = __ldg(mu_r + i * K + k);
+            float acc = __ldg(yrow + i) - m;
+            const float* lrow = low_r + (int64_t)(i * (i - 1) / 2) * K + k;
+            for (int c = 0; c < i; ++c) acc -= __ldg(lrow + c * K) * zs[c * TS];
+            const float zi = acc / ldv;
+            zs[i * TS] = zi;
+            quad += zi * zi;
+            logdet += logf(ldv);
+            bad |= !(finite_f(ldv) && finite_f(m));
+          }
         }
         const float gj = -0.5f * ((float)P * kLog2Pi + quad) - logdet;
         bad |= !(finite_f(gj) && finite_f(w[j]));
@@ -277,23 +294,34 @@ __global__ void __launch_bounds__(128) nll_kernel(NllArgs a) {
         float* dmu_r = a.d_mu + bb * a.ldo_mu;
         float* dzd_r = a.d_zd + bb * a.ldo_zd;
         if (!FULL) {
-          for (int i = 0; i < P; ++i) {
-            const float raw = __ldg(zd_r + i * K + k);
-            float e = raw, ldv = raw, nz = 0.f;
-            if (FUSED) {
-              e = expf(raw);
-              nz = __ldg(nz_r + i * K + k);
-              ldv = e + nz * eps;
+          for (int i0 = 0; i0 < P; i0 += 4) {
+            float zv[4], mv[4], nv[4], yv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int i = min(i0 + u, P - 1);
+              zv[u] = __ldg(zd_r + i * K + k);
+              mv[u] = __ldg(mu_r + i * K + k);
+              nv[u] = FUSED ? __ldg(nz_r + i * K + k) : 0.f;
+              yv[u] = __ldg(yrow + i);
             }
-            const float zi = (__ldg(yrow + i) - __ldg(mu_r + i * K + k)) / ldv;
-            const float vi = zi / ldv;
-            const float dld = cg * (vi * zi - 1.0f / ldv);
-            dmu_r[i * K + k] = cg * vi;
-            if (FUSED) {
-              s_acc += dld * nz;
-              dzd_r[i * K + k] = e * dld;
-            } else {
-              dzd_r[i * K + k] = dld;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int i = i0 + u;
+              if (i < P) {
+                const float e = FUSED ? expf(zv[u]) : zv[u];
+                const float ldv = FUSED ? e + nv[u] * eps : zv[u];
+                const float inv = 1.0f / ldv;
+                const float zi = (yv[u] - mv[u]) * inv;
+                const float vi = zi * inv;
+                const float dld = cg * (vi * zi - inv);
+                dmu_r[i * K + k] = cg * vi;
+                if (FUSED) {
+                  s_acc += dld * nv[u];
+                  dzd_r[i * K + k] = e * dld;
+                } else {
+                  dzd_r[i * K + k] = dld;
+                }
+              }
             }
           }
         } else {
@@ -305,8 +333,8 @@ __global__ void __launch_bounds__(128) nll_kernel(NllArgs a) {
               if (FUSED) ldv = expf(ldv) + __ldg(nz_r + i * K + k) * eps;
               float acc = __ldg(yrow + i) - __ldg(mu_r + i * K + k);
               const float* lrow = low_r + (int64_t)(i * (i - 1) / 2) * K + k;
-              for (int c = 0; c < i; ++c) acc -= __ldg(lrow + c * K) * zs[c * 128];
-              zs[i * 128] = acc / ldv;
+              for (int c = 0; c < i; ++c) acc -= __ldg(lrow + c * K) * zs[c * TS];
+              zs[i * TS] = acc / ldv;
             }
           }
           // back substitution v = L^-T z, rows descending
@@ -318,12 +346,12 @@ __global__ void __launch_bounds__(128) nll_kernel(NllArgs a) {
               nz = __ldg(nz_r + i * K + k);
               ldv = e + nz * eps;
             }
-            float acc = zs[i * 128];
+            float acc = zs[i * TS];
             for (int c = i + 1; c < P; ++c)
-              acc -= __ldg(low_r + (int64_t)(c * (c - 1) / 2 + i) * K + k) * vs[c * 128];
+              acc -= __ldg(low_r + (int64_t)(c * (c - 1) / 2 + i) * K + k) * vs[c * TS];
             const float vi = acc / ldv;
-            vs[i * 128] = vi;
-            const float zi = zs[i * 128];
+            vs[i * TS] = vi;
+            const float zi = zs[i * TS];
             const float dld = cg * (vi * zi - 1.0f / ldv);
             dmu_r[i * K + k] = cg * vi;
             if (FUSED) {
@@ -335,12 +363,38 @@ __global__ void __launch_bounds__(128) nll_kernel(NllArgs a) {
             // d L[i][c] = cg * v_i * z_c for c < i
             float* drow = dlow_r + (int64_t)(i * (i - 1) / 2) * K + k;
             const float cv = cg * vi;
-            for (int c = 0; c < i; ++c) drow[c * K] = cv * zs[c * 128];
+            for (int c = 0; c < i; ++c) drow[c * K] = cv * zs[c * TS];
           }
         }
       }
     }
   }
+
+}
+
+template <int GW, int KPL, bool FUSED, bool FULL, bool BWD>
+__global__ void __launch_bounds__(128) nll_kernel(NllArgs a) {
+  extern __shared__ float dyn[];           // FULL: zs[P][128], vs[P][128]
+  __shared__ float scratch[33];
+  const int tid = threadIdx.x;
+  constexpr int GPB = 128 / GW;
+  const int B = a.B, P = a.P, K = a.K;
+  float* zs = dyn + tid;                   // element p at zs[p*128]
+  float* vs = dyn + (size_t)P * 128 + tid;
+
+  float eps = 0.f;
+  if (FUSED) {
+    const float esum = sum_parts(a.ws, a.nparts_e, scratch);
+    eps = kEpsNoise * (esum / (float)((int64_t)B * P * K));
+  }
+  float gscale = 1.f;
+  if (BWD && a.grad_scale != nullptr) gscale = __ldg(a.grad_scale);
+  const float coef_scale = gscale / (float)B;
+
+  float loss_acc = 0.f, s_acc = 0.f;
+  bool bad = false;
+  nll_samples<GW, KPL, FUSED, FULL, BWD>(a, eps, coef_scale, blockIdx.x * GPB, gridDim.x * GPB,
+                                         128, zs, vs, loss_acc, s_acc, bad);
 
   if (bad) atomicOr(a.flag, 1);
 
@@ -370,6 +424,71 @@ __global__ void __launch_bounds__(128) nll_kernel(NllArgs a) {
       *counter = 0u;   // ready for the next launch
     }
   }
+}
+
+// Small-batch form (B*GW <= 8*512 lanes, i.e. the reference's minibatch of 100
+// and its 200-row test split): exp-sum, NLL forward/backward, eps-term fix-up and
+// the loss in ONE launch.  The CTAs form a single thread-block cluster; the three
+// batch-wide reductions go through distributed shared memory in rank order.
+template <int GW, int KPL, bool FULL, bool BWD>
+__global__ void __launch_bounds__(512) nll_cluster_kernel(NllArgs a) {
+  extern __shared__ float dyn[];           // FULL: zs[P][TS], vs[P][TS]
+  __shared__ float scratch[33];
+  __shared__ float red[3];                 // this CTA's exp-sum, loss, eps-gradient partials
+  cg::cluster_group cluster = cg::this_cluster();
+  const int tid = threadIdx.x, TS = blockDim.x;
+  const int NC = gridDim.x, rank = blockIdx.x;
+  const int GPB = TS / GW;
+  const int B = a.B, P = a.P, K = a.K, PK = P * K;
+  float* zs = dyn + tid;
+  float* vs = dyn + (size_t)P * TS + tid;
+
+  // phase 0: sum of exp(z_d) over the whole batch
+  {
+    const int64_t total = (int64_t)B * PK;
+    const int64_t stride = (int64_t)NC * TS, start = (int64_t)rank * TS + tid;
+    RowCol rc(start, stride, PK);
+    float acc = 0.f;
+    for (int64_t i = start; i < total; i += stride, rc.next())
+      acc += expf(__ldg(a.zd + rc.row * a.ld_zd + rc.col));
+    acc = block_sum(acc, scratch);
+    if (tid == 0) red[0] = acc;
+  }
+  cluster.sync();
+  float esum = 0.f;
+  for (int r = 0; r < NC; ++r) esum += *cluster.map_shared_rank(&red[0], r);
+  const float eps = kEpsNoise * (esum / (float)((int64_t)B * PK));
+  const float coef_scale = 1.0f / (float)B;
+
+  // phase 1: per-sample forward (+ backward)
+  float loss_acc = 0.f, s_acc = 0.f;
+  bool bad = false;
+  nll_samples<GW, KPL, true, FULL, BWD>(a, eps, coef_scale, rank * GPB, NC * GPB, TS, zs, vs,
+                                        loss_acc, s_acc, bad);
+  if (bad) atomicOr(a.flag, 1);
+  const float lsum = block_sum(loss_acc, scratch);
+  const float ssum = BWD ? block_sum(s_acc, scratch) : 0.f;
+  if (tid == 0) { red[1] = lsum; red[2] = ssum; }
+  cluster.sync();
+  if (rank == 0 && tid == 0) {
+    float acc = 0.f;
+    for (int r = 0; r < NC; ++r) acc += *cluster.map_shared_rank(&red[1], r);
+    a.loss[0] = acc / (float)B;
+  }
+  if (BWD) {
+    // phase 2: eps-term fix-up of the samples this CTA owns
+    float S = 0.f;
+    for (int r = 0; r < NC; ++r) S += *cluster.map_shared_rank(&red[2], r);
+    const float c = kEpsNoise * S / (float)((int64_t)B * PK);
+    for (int base = rank * GPB; base < B; base += NC * GPB) {
+      for (int e = tid; e < GPB * PK; e += TS) {
+        const int b = base + e / PK, col = e % PK;
+        if (b < B)
+          a.d_zd[(int64_t)b * a.ldo_zd + col] += expf(__ldg(a.zd + (int64_t)b * a.ld_zd + col)) * c;
+      }
+    }
+  }
+  cluster.sync();       // keep red[] alive until every CTA has read it
 }
 
 // eps-term fix-up of the fused backward: dzd += exp(zd) * (1e-5/M) * S
@@ -549,10 +668,58 @@ static int launch_nll(NllArgs& a, bool fused, bool bwd, cudaStream_t st) {
   }
 }
 
+template <int GW, int KPL, bool FULL, bool BWD>
+static int launch_nll_cluster_t(const NllArgs& a, int nc, int tpb, size_t smem, cudaStream_t st) {
+  if (smem > 48 * 1024)
+    BSIG_CUDA(cudaFuncSetAttribute(nll_cluster_kernel<GW, KPL, FULL, BWD>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)nc);
+  cfg.blockDim = dim3((unsigned)tpb);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)nc;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  BSIG_CUDA(cudaLaunchKernelEx(&cfg, nll_cluster_kernel<GW, KPL, FULL, BWD>, a));
+  BSIG_LAUNCH_CHECK();
+  return 0;
+}
+
+// Returns 0 if launched, -1 if the problem does not fit one cluster, >0 on error.
+static int launch_nll_cluster(const NllArgs& a, bool bwd, cudaStream_t st) {
+  const int K = a.K;
+  if (K > 32) return -1;
+  int gw = 1;
+  while (gw < K) gw <<= 1;
+  const int64_t lanes = (int64_t)a.B * gw;
+  if (lanes > 8 * 512) return -1;
+  const int tpb = lanes <= 8 * 128 ? 128 : (lanes <= 8 * 256 ? 256 : 512);
+  const int nc = (int)ceil_div(lanes, tpb);
+  const bool full = a.L > 0;
+  const size_t smem = full ? (size_t)2 * a.P * tpb * sizeof(float) : 0;
+  if (smem > 160 * 1024) return -1;
+#define BSIG_CL(GWV)                                                                        \
+  case GWV:                                                                                 \
+    if (full) return bwd ? launch_nll_cluster_t<GWV, 1, true, true>(a, nc, tpb, smem, st)   \
+                         : launch_nll_cluster_t<GWV, 1, true, false>(a, nc, tpb, smem, st); \
+    return bwd ? launch_nll_cluster_t<GWV, 1, false, true>(a, nc, tpb, smem, st)            \
+               : launch_nll_cluster_t<GWV, 1, false, false>(a, nc, tpb, smem, st);
+  switch (gw) {
+    BSIG_CL(1) BSIG_CL(2) BSIG_CL(4) BSIG_CL(8) BSIG_CL(16) BSIG_CL(32)
+  }
+#undef BSIG_CL
+  return -1;
+}
+
 static int launch_exp_sum(const float* zd, int64_t ld_zd, int B, int PK, float* ws,
                           cudaStream_t st, int* nparts) {
   const int64_t total = (int64_t)B * PK;
-  const int grid = (int)std::min<int64_t>(ceil_div(total, 256 * 4), 256);
+  const int grid = (int)std::min<int64_t>(ceil_div(total, 256 * 4), kMaxParts);
   exp_sum_kernel<<<grid, 256, 0, st>>>(zd, ld_zd, B, PK, ws);
   BSIG_LAUNCH_CHECK();
   *nparts = grid;
@@ -669,7 +836,6 @@ extern "C" int bsig_mdn_nll_fused(const float* z, const float* noise, const floa
   a.zd = z + k + PK; a.ld_zd = NH;
   a.low = L ? z + k + 2 * PK : nullptr; a.ld_low = NH;
   a.noise = noise;
-  if (launch_exp_sum(a.zd, NH, (int)b, (int)PK, (float*)ws, st, &a.nparts_e)) return 1;
   const bool bwd = dz != nullptr;
   if (bwd) {
     a.d_pi = dz; a.ldo_pi = NH;
@@ -677,6 +843,11 @@ extern "C" int bsig_mdn_nll_fused(const float* z, const float* noise, const floa
     a.d_zd = dz + k + PK; a.ldo_zd = NH;
     a.d_low = L ? dz + k + 2 * PK : nullptr; a.ldo_low = NH;
   }
+  {
+    const int rc = launch_nll_cluster(a, bwd, st);   // one launch when the batch fits a cluster
+    if (rc >= 0) return rc;
+  }
+  if (launch_exp_sum(a.zd, NH, (int)b, (int)PK, (float*)ws, st, &a.nparts_e)) return 1;
   if (launch_nll(a, true, bwd, st)) return 1;
   if (bwd) {
     int gw = 1;

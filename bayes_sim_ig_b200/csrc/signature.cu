@@ -44,48 +44,146 @@ __device__ __forceinline__ void load_paths(const SigArgs& p, float* xs, int64_t 
   }
 }
 
-template <int CP>
-__global__ void __launch_bounds__(512) signature3_kernel(SigArgs p) {
-  extern __shared__ float smem[];
-  const int C = p.C, L = p.L, CC = C * C;
-  float* xs = smem;                                   // [tpb][L][C]
-  float* stage = smem + (size_t)p.tpb * L * C;        // [tpb][siglen]
+// Increments d[traj][t][0..CPAD) (zero beyond C) in shared memory; rows of CPAD
+// floats are 16B aligned so that a step's increment is read with LDS.128.
+template <int CPAD>
+__device__ __forceinline__ void load_increments(const SigArgs& p, float* ds, int traj_stride,
+                                                int64_t traj0, int ntraj) {
+  const int steps = p.L - 1;
+  const int per = steps * CPAD;
+  for (int e = threadIdx.x; e < ntraj * per; e += blockDim.x) {
+    const int tl = e / per, r = e - tl * per;
+    const int t = r / CPAD, c = r - t * CPAD;
+    float v = 0.f;
+    if (c == 0) {
+      v = 1.0f;                                         // time channel t+1 -> t+2
+    } else if (c <= p.D) {
+      const float* s = p.states + (traj0 + tl) * p.s_stride + (int64_t)t * p.D + (c - 1);
+      v = __ldg(s + p.D) - __ldg(s);
+    } else if (c < p.C) {
+      const float* a = p.actions + (traj0 + tl) * p.a_stride + (int64_t)t * p.A + (c - 1 - p.D);
+      v = __ldg(a + p.A) - __ldg(a);
+    }
+    ds[tl * traj_stride + r] = v;
+  }
+}
+
+__device__ __forceinline__ void store_staged(const SigArgs& p, const float* stage, int64_t traj0,
+                                             int ntraj) {
+  float* out = p.out + traj0 * p.siglen;
+  const int64_t total = (int64_t)ntraj * p.siglen;
+  if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    const int64_t n4 = total >> 2;
+    for (int64_t e = threadIdx.x; e < n4; e += blockDim.x)
+      st_stream_f4(out + 4 * e, *reinterpret_cast<const float4*>(stage + 4 * e));
+    for (int64_t e = 4 * n4 + threadIdx.x; e < total; e += blockDim.x) out[e] = stage[e];
+  } else {
+    for (int64_t e = threadIdx.x; e < total; e += blockDim.x) out[e] = stage[e];
+  }
+}
+
+// Small channel counts (C <= 8; Pendulum C=5, Cartpole C=6): one thread owns row i
+// of every level -- S1[i], S2[i,:], S3[i,:,:] (C*C registers) -- so a step is
+// C*C + 2C FFMAs against three shared-memory loads.
+template <int C>
+__global__ void __launch_bounds__(256) signature3_small_kernel(SigArgs p) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int CPAD = 8;
+  const int steps = p.L - 1;
+  const int tstride = steps * CPAD + 8;                 // +8: spreads trajectories over banks
+  float* ds = smem;                                     // [tpb][tstride]
+  float* stage = smem + (size_t)p.tpb * tstride;        // [tpb][siglen]
   const int64_t traj0 = (int64_t)blockIdx.x * p.tpb;
   const int ntraj = (int)min((int64_t)p.tpb, p.n - traj0);
-  load_paths(p, xs, traj0, ntraj);
+  load_increments<CPAD>(p, ds, tstride, traj0, ntraj);
+  __syncthreads();
+  const int tl = threadIdx.x / C, i = threadIdx.x - tl * C;
+  if (tl < ntraj) {
+    const float* d = ds + tl * tstride;
+    float s1 = 0.f, s2[C], s3[C][C];
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      s2[j] = 0.f;
+#pragma unroll
+      for (int k = 0; k < C; ++k) s3[j][k] = 0.f;
+    }
+    for (int t = 0; t < steps; ++t) {
+      const float4 lo = *reinterpret_cast<const float4*>(d + t * CPAD);
+      const float4 hi = *reinterpret_cast<const float4*>(d + t * CPAD + 4);
+      const float dv[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+      const float di = d[t * CPAD + i];
+      const float a3 = (s1 + di * (1.0f / 3.0f)) * 0.5f;
+      const float a2 = s1 + di * 0.5f;
+#pragma unroll
+      for (int j = 0; j < C; ++j) {
+        const float t2 = fmaf(a3, dv[j], s2[j]);
+#pragma unroll
+        for (int k = 0; k < C; ++k) s3[j][k] = fmaf(t2, dv[k], s3[j][k]);
+        s2[j] = fmaf(a2, dv[j], s2[j]);
+      }
+      s1 += di;
+    }
+    float* o = stage + (size_t)tl * p.siglen;
+    o[i] = s1;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      o[C + i * C + j] = s2[j];
+#pragma unroll
+      for (int k = 0; k < C; ++k) o[C + C * C + (i * C + j) * C + k] = s3[j][k];
+    }
+  }
+  __syncthreads();
+  store_staged(p, stage, traj0, ntraj);
+}
+
+// 9 <= C <= 22 (depth 3 stops at C = 22): one thread owns one (i,j) pair --
+// S2[i,j] and the vector S3[i,j,:] in registers.
+template <int CPAD>
+__global__ void __launch_bounds__(512) signature3_kernel(SigArgs p) {
+  extern __shared__ __align__(16) float smem[];
+  const int C = p.C, CC = C * C;
+  const int steps = p.L - 1;
+  const int tstride = steps * CPAD;
+  float* ds = smem;                                     // [tpb][steps][CPAD]
+  float* stage = smem + (size_t)p.tpb * tstride;        // [tpb][siglen]
+  const int64_t traj0 = (int64_t)blockIdx.x * p.tpb;
+  const int ntraj = (int)min((int64_t)p.tpb, p.n - traj0);
+  load_increments<CPAD>(p, ds, tstride, traj0, ntraj);
   __syncthreads();
 
   const int tl = threadIdx.x / CC;
   const int ij = threadIdx.x - tl * CC;
   const int i = ij / C, j = ij - i * C;
   if (tl < ntraj) {
-    const float* x = xs + (size_t)tl * L * C;
-    float s2 = 0.f;
-    float s3[CP];
+    const float* d = ds + tl * tstride;
+    float s1 = 0.f, s2 = 0.f;
+    float s3[CPAD];
 #pragma unroll
-    for (int k = 0; k < CP; ++k) s3[k] = 0.f;
-    for (int t = 0; t + 1 < L; ++t) {
-      const float* x0 = x + t * C;
-      const float* x1 = x0 + C;
-      const float di = x1[i] - x0[i], dj = x1[j] - x0[j];
-      const float s1i = x0[i] - x[i];
-      const float t2 = s2 + (s1i + di * (1.0f / 3.0f)) * dj * 0.5f;
+    for (int k = 0; k < CPAD; ++k) s3[k] = 0.f;
+    for (int t = 0; t < steps; ++t) {
+      const float* dt = d + t * CPAD;
+      const float di = dt[i], dj = dt[j];
+      const float t2 = fmaf((s1 + di * (1.0f / 3.0f)) * 0.5f, dj, s2);
 #pragma unroll
-      for (int k = 0; k < CP; ++k)
-        if (k < C) s3[k] = fmaf(t2, x1[k] - x0[k], s3[k]);
-      s2 = fmaf(s1i + di * 0.5f, dj, s2);
+      for (int k4 = 0; k4 < CPAD / 4; ++k4) {
+        const float4 dk = *reinterpret_cast<const float4*>(dt + 4 * k4);
+        s3[4 * k4 + 0] = fmaf(t2, dk.x, s3[4 * k4 + 0]);
+        s3[4 * k4 + 1] = fmaf(t2, dk.y, s3[4 * k4 + 1]);
+        s3[4 * k4 + 2] = fmaf(t2, dk.z, s3[4 * k4 + 2]);
+        s3[4 * k4 + 3] = fmaf(t2, dk.w, s3[4 * k4 + 3]);
+      }
+      s2 = fmaf(s1 + di * 0.5f, dj, s2);
+      s1 += di;
     }
     float* o = stage + (size_t)tl * p.siglen;
-    if (i == 0) o[j] = x[(L - 1) * C + j] - x[j];
+    if (j == 0) o[i] = s1;
     o[C + ij] = s2;
 #pragma unroll
-    for (int k = 0; k < CP; ++k)
+    for (int k = 0; k < CPAD; ++k)
       if (k < C) o[C + CC + ij * C + k] = s3[k];
   }
   __syncthreads();
-  float* out = p.out + traj0 * p.siglen;
-  const int64_t total = (int64_t)ntraj * p.siglen;
-  for (int64_t e = threadIdx.x; e < total; e += blockDim.x) out[e] = stage[e];
+  store_staged(p, stage, traj0, ntraj);
 }
 
 // depth 2: one CTA per trajectory, threads stride over (i,j); depth 1: differences.
@@ -134,26 +232,49 @@ extern "C" int bsig_signature_fwd(const float* states, const float* actions, flo
   cudaStream_t st = (cudaStream_t)stream;
   if (depth == 3) {
     BSIG_REQUIRE(C <= 22, "signature: depth 3 supports at most 22 channels (got %d)", (int)C);
-    const int cc = (int)(C * C);
-    int tpb = std::max(1, 256 / cc);
-    // keep shared memory under ~100 KB so that two CTAs fit per SM
-    const int64_t per_traj = (len * C + p.siglen) * 4;
-    tpb = (int)std::max<int64_t>(1, std::min<int64_t>(tpb, (100 * 1024) / per_traj));
-    p.tpb = tpb;
-    const int threads = (int)(ceil_div((int64_t)tpb * cc, 32) * 32);
-    const size_t smem = (size_t)tpb * per_traj;
-    const unsigned grid = (unsigned)ceil_div(n, tpb);
-#define BSIG_SIG3(CPV)                                                                     \
-  do {                                                                                     \
-    if (smem > 48 * 1024)                                                                  \
-      BSIG_CUDA(cudaFuncSetAttribute(signature3_kernel<CPV>,                               \
+    const int64_t steps = len - 1;
+    if (C <= 8) {
+      int tpb = 256 / (int)C;
+      const int64_t per_traj = (steps * 8 + 8 + p.siglen) * 4;
+      tpb = (int)std::max<int64_t>(1, std::min<int64_t>(tpb, (100 * 1024) / per_traj));
+      if (tpb > 1) tpb &= ~1;               // even -> CTA bases stay 16B aligned (siglen even)
+      p.tpb = tpb;
+      const size_t smem = (size_t)tpb * per_traj;
+      const unsigned grid = (unsigned)ceil_div(n, tpb);
+#define BSIG_SIGS(CV)                                                                        \
+  case CV:                                                                                   \
+    if (smem > 48 * 1024)                                                                    \
+      BSIG_CUDA(cudaFuncSetAttribute(signature3_small_kernel<CV>,                            \
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    signature3_kernel<CPV><<<grid, threads, smem, st>>>(p);                                \
-  } while (0)
-    if (C <= 8) BSIG_SIG3(8);
-    else if (C <= 16) BSIG_SIG3(16);
-    else BSIG_SIG3(22);
-#undef BSIG_SIG3
+    signature3_small_kernel<CV><<<grid, 256, smem, st>>>(p);                                 \
+    break;
+      switch ((int)C) {
+        BSIG_SIGS(2) BSIG_SIGS(3) BSIG_SIGS(4) BSIG_SIGS(5) BSIG_SIGS(6) BSIG_SIGS(7) BSIG_SIGS(8)
+      }
+#undef BSIG_SIGS
+    } else {
+      const int cc = (int)(C * C);
+      const int cpad = C <= 16 ? 16 : 24;
+      int tpb = std::max(1, 256 / cc);
+      const int64_t per_traj = (steps * cpad + p.siglen) * 4;
+      tpb = (int)std::max<int64_t>(1, std::min<int64_t>(tpb, (100 * 1024) / per_traj));
+      p.tpb = tpb;
+      const int threads = (int)(ceil_div((int64_t)tpb * cc, 32) * 32);
+      const size_t smem = (size_t)tpb * per_traj;
+      BSIG_REQUIRE(smem <= 200 * 1024, "signature: path too long for shared memory");
+      const unsigned grid = (unsigned)ceil_div(n, tpb);
+      if (cpad == 16) {
+        if (smem > 48 * 1024)
+          BSIG_CUDA(cudaFuncSetAttribute(signature3_kernel<16>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        signature3_kernel<16><<<grid, threads, smem, st>>>(p);
+      } else {
+        if (smem > 48 * 1024)
+          BSIG_CUDA(cudaFuncSetAttribute(signature3_kernel<24>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        signature3_kernel<24><<<grid, threads, smem, st>>>(p);
+      }
+    }
   } else {
     p.tpb = 1;
     const size_t smem = (size_t)len * C * 4;

@@ -65,49 +65,66 @@ struct CrossArgs {
   int use_diff;
 };
 
-// TW = threads that cooperate on one row: a warp for short rows (many rows per
-// CTA in flight), the whole CTA for long rows.  No divisions in the store loop:
-// (p, q) advance incrementally by the per-iteration stride.
-template <int TW>
-__global__ void __launch_bounds__(256) crosscorr_kernel(CrossArgs p) {
+// Exact n / d for n*ceil(2^40/d) < 2^64 and n*d < 2^40 (checked on the host).
+struct FastDiv {
+  uint32_t d;
+  uint64_t m;
+};
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+  return (uint32_t)(((uint64_t)n * f.m) >> 40);
+}
+
+// Every thread owns aligned float4s of the CTA's flat range; (row, p, q) come
+// from two multiply-shift divisions, the four products of a float4 share at
+// most two state features (s0, s1) and read their action features from a
+// wrap-extended copy, so the common case has no per-element branches.
+// Finiteness: inputs are checked while staging; with finite inputs a product
+// can only be non-finite by overflow, tracked with one max per element.
+__global__ void __launch_bounds__(256) crosscorr_kernel(CrossArgs p, FastDiv divF, FastDiv divQ) {
   extern __shared__ float smem[];
+  const int Qx = p.Qn + 3;                  // action features + 3 wrap-around copies
   float* sf = smem;                         // [G][Pn]
-  float* af = sf + (size_t)p.G * p.Pn;      // [G][Qn]
-  float* st = af + (size_t)p.G * p.Qn;      // [G][2] mean, std
+  float* af = sf + (size_t)p.G * p.Pn;      // [G][Qn+3]
+  float* st = af + (size_t)p.G * Qx;        // [G][2] mean, std
 
   const int64_t traj0 = (int64_t)blockIdx.x * p.G;
   const int gcnt = (int)min((int64_t)p.G, p.n - traj0);
-  const int64_t group_floats = (int64_t)gcnt * p.F;
-  const int64_t c0 = (int64_t)blockIdx.y * p.chunk;
+  const uint32_t group_floats = (uint32_t)gcnt * (uint32_t)p.F;
+  const uint32_t c0 = blockIdx.y * (uint32_t)p.chunk;
   if (c0 >= group_floats) return;
-  const int64_t c1 = min(c0 + p.chunk, group_floats);
+  const uint32_t c1 = min(c0 + (uint32_t)p.chunk, group_floats);
+  const uint32_t F = (uint32_t)p.F, Qn = (uint32_t)p.Qn;
+  const uint32_t PQ = F - 2;
 
-  // trajectories whose data this chunk touches
-  const int g_lo = (int)(c0 / p.F);
-  const int g_hi = (int)((c1 - 1) / p.F);
+  const int g_lo = (int)(c0 / F);
+  const int g_hi = (int)((c1 - 1) / F);
   const int Dm1 = p.D - 1;
   const int nrows = g_hi - g_lo + 1;
+  bool bad = false;
 
   for (int i = threadIdx.x; i < nrows * p.Pn; i += blockDim.x) {
     const int g = g_lo + i / p.Pn, e = i % p.Pn;
     const int t = e / Dm1, j = e - t * Dm1;
     const float* s = p.states + (traj0 + g) * p.s_stride + t * p.D + j;
     const float lo = __ldg(s);
-    sf[g * p.Pn + e] = p.use_diff ? (__ldg(s + 1) - lo) : lo;
+    const float v = p.use_diff ? (__ldg(s + 1) - lo) : lo;
+    bad |= !finite_f(v);
+    sf[g * p.Pn + e] = v;
   }
-  for (int i = threadIdx.x; i < nrows * p.Qn; i += blockDim.x) {
-    const int g = g_lo + i / p.Qn, e = i % p.Qn;
-    // actions of the first W steps are contiguous: [t*A + k]
-    af[g * p.Qn + e] = __ldg(p.actions + (traj0 + g) * p.a_stride + e);
+  for (int i = threadIdx.x; i < nrows * Qx; i += blockDim.x) {
+    const int g = g_lo + i / Qx, e = i % Qx;
+    // actions of the first W steps are contiguous: [t*A + k]; entries >= Qn wrap
+    const float v = __ldg(p.actions + (traj0 + g) * p.a_stride + (e % p.Qn));
+    bad |= !finite_f(v);
+    af[g * Qx + e] = v;
   }
   __syncthreads();
 
   // mean / unbiased std of sf for trajectories whose stat slots are in range:
   // one warp per trajectory, float64 accumulation, two passes.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-  const int64_t PQ = (int64_t)p.Pn * p.Qn;
   for (int g = g_lo + warp; g <= g_hi; g += nwarp) {
-    const int64_t slot = (int64_t)g * p.F + PQ;
+    const uint32_t slot = (uint32_t)g * F + PQ;
     if (slot + 1 < c0 || slot >= c1) continue;
     const float* v = sf + g * p.Pn;
     double acc = 0.0;
@@ -121,65 +138,62 @@ __global__ void __launch_bounds__(256) crosscorr_kernel(CrossArgs p) {
     }
     sq = warp_sum(sq);
     if (lane == 0) {
+      const float sd = p.Pn < 2 ? 0.f : (float)sqrt(sq / (double)(p.Pn - 1));
       st[g * 2 + 0] = (float)mean;
-      st[g * 2 + 1] = p.Pn < 2 ? 0.f : (float)sqrt(sq / (double)(p.Pn - 1));
+      st[g * 2 + 1] = sd;
+      bad |= !finite_f(sd);
     }
   }
   __syncthreads();
 
   float* out = p.out + traj0 * p.F;
-  bool bad = false;
-  const uint32_t Qn = (uint32_t)p.Qn;
-  const int lt = threadIdx.x % TW, wk = threadIdx.x / TW;
-  constexpr int NWORK = 256 / TW;
-  constexpr uint32_t STEP = 4u * TW;
-  const uint32_t dP = STEP / Qn, dQ = STEP - dP * Qn;
-  for (int g = g_lo + wk; g <= g_hi; g += NWORK) {
-    const int64_t row0 = (int64_t)g * p.F;
-    const int64_t lo = max(c0, row0), hi = min(c1, row0 + p.F);
-    const int64_t pq_hi = min(hi, row0 + PQ);
-    const int64_t ea = (lo + 3) & ~3ll;                       // first aligned float4
-    const int64_t nb = pq_hi > ea ? (pq_hi - ea) >> 2 : 0;    // float4s fully inside products
-    const float* sfg = sf + g * p.Pn;
-    const float* afg = af + g * p.Qn;
-    uint32_t r = (uint32_t)(ea - row0) + 4u * lt;
-    uint32_t pi = r / Qn, qi = r - pi * Qn;
-    float* o = out + ea + 4 * lt;
-    for (int64_t i = lt; i < nb; i += TW) {
-      uint32_t pp = pi, qq = qi;
-      float v[4];
+  float vmax = 0.f;
+  for (uint32_t e0 = c0 + 4u * threadIdx.x; e0 < c1; e0 += 4u * 256u) {
+    const uint32_t g = fdiv(e0, divF);
+    const uint32_t r = e0 - g * F;
+    float4 v;
+    if (r + 3 < PQ && Qn >= 4) {
+      const uint32_t pi = fdiv(r, divQ);
+      const uint32_t qi = r - pi * Qn;
+      const float* sfg = sf + g * p.Pn;
+      const float* afg = af + g * Qx + qi;
+      const float s0 = sfg[pi];
+      const float s1 = sfg[min(pi + 1, (uint32_t)p.Pn - 1)];
+      const uint32_t nfirst = Qn - qi;       // elements still in feature row pi
+      v.x = s0 * afg[0];
+      v.y = (nfirst > 1 ? s0 : s1) * afg[1];
+      v.z = (nfirst > 2 ? s0 : s1) * afg[2];
+      v.w = (nfirst > 3 ? s0 : s1) * afg[3];
+      vmax = fmaxf(fmaxf(vmax, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+      st_stream_f4(out + e0, v);
+    } else {
+      // row boundary (last products, the two statistics, next row's head) or the
+      // ragged end of the chunk: element by element
+      float t[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        v[c] = sfg[pp] * afg[qq];
-        if (++qq == Qn) { qq = 0; ++pp; }
-        bad |= !finite_f(v[c]);
+        const uint32_t e = e0 + c;
+        t[c] = 0.f;
+        if (e < c1) {
+          const uint32_t gg = fdiv(e, divF);
+          const uint32_t rr = e - gg * F;
+          if (rr < PQ) {
+            const uint32_t pp = fdiv(rr, divQ);
+            t[c] = sf[gg * p.Pn + pp] * af[gg * Qx + (rr - pp * Qn)];
+          } else {
+            t[c] = st[gg * 2 + (rr - PQ)];
+          }
+          vmax = fmaxf(vmax, fabsf(t[c]));
+        }
       }
-      st_stream_f4(o, make_float4(v[0], v[1], v[2], v[3]));
-      o += STEP;
-      qi += dQ;
-      pi += dP;
-      if (qi >= Qn) { qi -= Qn; ++pi; }
-    }
-    // row boundaries: unaligned head, and the tail (last products + the two stats)
-    const int64_t head_end = min(ea, hi);
-    const int64_t body_end = max(head_end, ea + 4 * nb);
-    int64_t e = -1;
-    if (lt < 8) { if (lo + lt < head_end) e = lo + lt; }
-    else if (lt < 16) { if (body_end + (lt - 8) < hi) e = body_end + (lt - 8); }
-    if (e >= 0) {
-      const int64_t rr = e - row0;
-      float v;
-      if (rr < PQ) {
-        const uint32_t pp = (uint32_t)rr / Qn;
-        v = sfg[pp] * afg[(uint32_t)rr - pp * Qn];
+      if (e0 + 3 < c1) {
+        st_stream_f4(out + e0, make_float4(t[0], t[1], t[2], t[3]));
       } else {
-        v = st[g * 2 + (int)(rr - PQ)];
+        for (int c = 0; c < 4 && e0 + c < c1; ++c) out[e0 + c] = t[c];
       }
-      bad |= !finite_f(v);
-      out[e] = v;
     }
   }
-  if (bad) atomicOr(p.flag, 1);
+  if (bad || !(vmax <= 3.402823466e38f)) atomicOr(p.flag, 1);
 }
 
 static int gcd_i(int a, int b) { return b == 0 ? a : gcd_i(b, a % b); }
@@ -236,7 +250,7 @@ extern "C" int bsig_summary_crosscorr(const float* states, const float* actions,
   // that keeps group bases 16B aligned, bounded by the staging budget (64 KB).
   const int galign = 4 / gcd_i((int)(p.F % 4 == 0 ? 4 : p.F % 4), 4);
   int64_t G = ceil_div(16384, p.F);
-  const int64_t per_traj_smem = (int64_t)(p.Pn + p.Qn + 2) * 4;
+  const int64_t per_traj_smem = (int64_t)(p.Pn + p.Qn + 3 + 2) * 4;
   const int64_t gmax = std::max<int64_t>(1, (64 * 1024) / per_traj_smem);
   G = std::min(G, gmax);
   G = std::max<int64_t>(galign, ceil_div(G, galign) * galign);
@@ -246,24 +260,23 @@ extern "C" int bsig_summary_crosscorr(const float* states, const float* actions,
   const size_t smem = (size_t)G * per_traj_smem;
   BSIG_REQUIRE(smem <= 200 * 1024, "crosscorr: window too large for shared memory");
   const int64_t group_floats = G * p.F;
+  // multiply-shift division bounds (FastDiv): n*d < 2^40
+  BSIG_REQUIRE(group_floats < (1ll << 31) && group_floats * p.F < (1ll << 40) &&
+               PQ * p.Qn < (1ll << 40), "crosscorr: feature row too wide for this kernel");
   p.chunk = group_floats <= 49152 ? ceil_div(group_floats, 4) * 4 : 32768;
   const int64_t nchunk = ceil_div(group_floats, p.chunk);
   const int64_t ngroup = ceil_div(n, G);
   BSIG_REQUIRE(ngroup < (1ll << 31) && nchunk <= 65535, "crosscorr: grid too large");
   dim3 grid((unsigned)ngroup, (unsigned)nchunk);
-  const bool short_rows = p.F <= 4096;
-  if (smem > 48 * 1024) {
-    if (short_rows)
-      BSIG_CUDA(cudaFuncSetAttribute(crosscorr_kernel<32>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else
-      BSIG_CUDA(cudaFuncSetAttribute(crosscorr_kernel<256>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
-  if (short_rows)
-    crosscorr_kernel<32><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
-  else
-    crosscorr_kernel<256><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+  FastDiv divF, divQ;
+  divF.d = (uint32_t)p.F;
+  divF.m = ((1ull << 40) + (uint64_t)p.F - 1) / (uint64_t)p.F;
+  divQ.d = (uint32_t)p.Qn;
+  divQ.m = ((1ull << 40) + (uint64_t)p.Qn - 1) / (uint64_t)p.Qn;
+  if (smem > 48 * 1024)
+    BSIG_CUDA(cudaFuncSetAttribute(crosscorr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+  crosscorr_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p, divF, divQ);
   BSIG_LAUNCH_CHECK();
   return 0;
 }

@@ -21,6 +21,7 @@ import numpy as np
 import torch
 
 from .. import _lib
+from .. import data_parallel
 
 ACT_NONE, ACT_TANH = 0, 1
 
@@ -173,9 +174,12 @@ class TrainPlan(object):
                       lay['dw'].data_ptr(), lay['db'].data_ptr(), b, lay['n'], lay['k'], eng,
                       wsp, wsn, st)
             dcur, nxt = self.dh[li], lay
+        # data parallel: one NCCL sum of the flat gradient buffer, mean taken in Adam
+        world = data_parallel.world_of(m)
+        data_parallel.allreduce_gradients(m, self.grads)
         _lib.call('bsig_adam_step', m.flat_params.data_ptr(), self.grads.data_ptr(),
                   self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), m.flat_params.numel(),
-                  step + 1, float(m.lr), 0.9, 0.999, 1e-8, 1.0, st)
+                  step + 1, float(m.lr), 0.9, 0.999, 1e-8, 1.0 / world, st)
         if slot is not None and self.n_test > 0:
             self._forward(self.te, self.x_test, None, self.n_test, st)
             _lib.call('bsig_mdn_nll_fused', self.te['z'].data_ptr(),

@@ -1,0 +1,59 @@
+"""World-size-2 gloo checks of the data-parallel host logic (CPU only): row
+sharding, and that averaging per-rank gradients of equal shards reproduces the
+gradient of the concatenated batch (the exchange step of SURVEY 8.e)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), '..'))
+
+
+def test_shard_rows_partition():
+    from bayes_sim_ig_b200.data_parallel import shard_rows
+    for n, world in ((4096, 8), (1000, 3), (7, 8), (1 << 20, 4)):
+        spans = [shard_rows(n, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        for (a0, a1), (b0, b1) in zip(spans[:-1], spans[1:]):
+            assert a1 == b0 and a1 - a0 >= b1 - b0 >= 0
+        assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+
+
+def _worker(rank, world, port, tmpdir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from bayes_sim_ig_b200.data_parallel import shard_rows
+    from oracle import mdn_np
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'mdn.npz'))
+    case = 'diag'
+    p, k = 3, 4
+    params = {key[len(case + '.init.'):]: g[key].astype(np.float64)
+              for key in g.files if key.startswith(case + '.init.')}
+    x, y = g[case + '.x'][:8], g[case + '.y'][:8]
+    noise = np.full((8, p, k), 0.5)   # constant noise: the eps term is shard-independent
+    lo, hi = shard_rows(8, rank, world)
+    # local gradient on this rank's shard; the eps mean is local (documented)
+    _, grads = mdn_np.mdnn_loss_and_grads(params, x[lo:hi], y[lo:hi], noise[lo:hi], p, k)
+    flat = torch.from_numpy(np.concatenate([grads[key].ravel() for key in sorted(grads)]))
+    dist.all_reduce(flat)             # the one exchange step
+    flat /= world
+    _, full = mdn_np.mdnn_loss_and_grads(params, x, y, noise, p, k)
+    ref = np.concatenate([full[key].ravel() for key in sorted(full)])
+    err = np.abs(flat.numpy() - ref).max() / np.abs(ref).max()
+    torch.save(torch.tensor(err), os.path.join(tmpdir, 'err%d.pt' % rank))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_average_equals_full_batch(tmp_path):
+    world = 2
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        err = float(torch.load(os.path.join(str(tmp_path), 'err%d.pt' % r)))
+        # the only difference is the local-vs-global eps mean: O(1e-5) relative
+        assert err < 5e-5, err

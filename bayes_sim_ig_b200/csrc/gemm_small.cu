@@ -9,6 +9,7 @@
 // split-K of gemm_simt.cu and turns 4-16 CTAs into 32-128 busy SMs.
 // Optional fused row sums of A (the bias gradient of a wgrad GEMM) ride along.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "gemm.cuh"
@@ -162,7 +163,12 @@ bool gemm_small_applicable(const GemmArgs& g) {
 int gemm_small(GemmArgs g, cudaStream_t st) {
   BSIG_REQUIRE(g.M >= 1 && g.N >= 1 && g.K >= 1, "gemm: empty problem");
   const int64_t tiles = ceil_div(g.M, SBM) * ceil_div(g.N, SBN);
-  int S = (int)std::min<int64_t>(8, std::max<int64_t>(1, (2 * (int64_t)sm_count()) / tiles));
+  static const int max_split = [] {
+    const char* e = getenv("BSIG_SMALL_GEMM_MAXSPLIT");   // tuning / experiments only
+    const int v = e ? atoi(e) : 8;
+    return v < 1 ? 1 : (v > 8 ? 8 : v);
+  }();
+  int S = (int)std::min<int64_t>(max_split, std::max<int64_t>(1, (2 * (int64_t)sm_count()) / tiles));
   S = (int)std::min<int64_t>(S, std::max<int64_t>(1, g.K / SBK));
   int kps = (int)ceil_div(g.K, S);
   kps = (int)(ceil_div(kps, SBK) * SBK);

@@ -46,9 +46,38 @@ __device__ __forceinline__ void load_paths(const SigArgs& p, float* xs, int64_t 
 
 // Increments d[traj][t][0..CPAD) (zero beyond C) in shared memory; rows of CPAD
 // floats are 16B aligned so that a step's increment is read with LDS.128.
+// Two passes: (1) coalesced, independent loads of the raw rollouts into `raw`
+// (memory-level parallelism: nothing depends on a previous load), (2) the
+// differences from shared memory.  `raw` may alias the output staging buffer.
 template <int CPAD>
 __device__ __forceinline__ void load_increments(const SigArgs& p, float* ds, int traj_stride,
-                                                int64_t traj0, int ntraj) {
+                                                float* raw, int64_t traj0, int ntraj) {
+  const int LD = p.L * p.D, LA = p.L * p.A;
+  float* raw_s = raw;                       // [ntraj][L*D]
+  float* raw_a = raw + (size_t)p.tpb * LD;  // [ntraj][L*A]
+  const float* gs = p.states + traj0 * p.s_stride;
+  const float* ga = p.actions + traj0 * p.a_stride;
+  if (p.s_stride == LD) {
+#pragma unroll 4
+    for (int e = threadIdx.x; e < ntraj * LD; e += blockDim.x) raw_s[e] = __ldg(gs + e);
+  } else {
+#pragma unroll 4
+    for (int e = threadIdx.x; e < ntraj * LD; e += blockDim.x) {
+      const int tl = e / LD, r = e - tl * LD;
+      raw_s[e] = __ldg(gs + tl * p.s_stride + r);
+    }
+  }
+  if (p.a_stride == LA) {
+#pragma unroll 4
+    for (int e = threadIdx.x; e < ntraj * LA; e += blockDim.x) raw_a[e] = __ldg(ga + e);
+  } else {
+#pragma unroll 4
+    for (int e = threadIdx.x; e < ntraj * LA; e += blockDim.x) {
+      const int tl = e / LA, r = e - tl * LA;
+      raw_a[e] = __ldg(ga + tl * p.a_stride + r);
+    }
+  }
+  __syncthreads();
   const int steps = p.L - 1;
   const int per = steps * CPAD;
   for (int e = threadIdx.x; e < ntraj * per; e += blockDim.x) {
@@ -58,11 +87,11 @@ __device__ __forceinline__ void load_increments(const SigArgs& p, float* ds, int
     if (c == 0) {
       v = 1.0f;                                         // time channel t+1 -> t+2
     } else if (c <= p.D) {
-      const float* s = p.states + (traj0 + tl) * p.s_stride + (int64_t)t * p.D + (c - 1);
-      v = __ldg(s + p.D) - __ldg(s);
+      const float* s = raw_s + tl * LD + t * p.D + (c - 1);
+      v = s[p.D] - s[0];
     } else if (c < p.C) {
-      const float* a = p.actions + (traj0 + tl) * p.a_stride + (int64_t)t * p.A + (c - 1 - p.D);
-      v = __ldg(a + p.A) - __ldg(a);
+      const float* a = raw_a + tl * LA + t * p.A + (c - 1 - p.D);
+      v = a[p.A] - a[0];
     }
     ds[tl * traj_stride + r] = v;
   }
@@ -95,7 +124,7 @@ __global__ void __launch_bounds__(256) signature3_small_kernel(SigArgs p) {
   float* stage = smem + (size_t)p.tpb * tstride;        // [tpb][siglen]
   const int64_t traj0 = (int64_t)blockIdx.x * p.tpb;
   const int ntraj = (int)min((int64_t)p.tpb, p.n - traj0);
-  load_increments<CPAD>(p, ds, tstride, traj0, ntraj);
+  load_increments<CPAD>(p, ds, tstride, stage, traj0, ntraj);
   __syncthreads();
   const int tl = threadIdx.x / C, i = threadIdx.x - tl * C;
   if (tl < ntraj) {
@@ -148,7 +177,7 @@ __global__ void __launch_bounds__(512) signature3_kernel(SigArgs p) {
   float* stage = smem + (size_t)p.tpb * tstride;        // [tpb][siglen]
   const int64_t traj0 = (int64_t)blockIdx.x * p.tpb;
   const int ntraj = (int)min((int64_t)p.tpb, p.n - traj0);
-  load_increments<CPAD>(p, ds, tstride, traj0, ntraj);
+  load_increments<CPAD>(p, ds, tstride, stage, traj0, ntraj);
   __syncthreads();
 
   const int tl = threadIdx.x / CC;
@@ -235,7 +264,8 @@ extern "C" int bsig_signature_fwd(const float* states, const float* actions, flo
     const int64_t steps = len - 1;
     if (C <= 8) {
       int tpb = 256 / (int)C;
-      const int64_t per_traj = (steps * 8 + 8 + p.siglen) * 4;
+      // staging buffer doubles as the raw-rollout buffer of load_increments
+      const int64_t per_traj = (steps * 8 + 8 + std::max<int64_t>(p.siglen, len * (d + a))) * 4;
       tpb = (int)std::max<int64_t>(1, std::min<int64_t>(tpb, (100 * 1024) / per_traj));
       if (tpb > 1) tpb &= ~1;               // even -> CTA bases stay 16B aligned (siglen even)
       p.tpb = tpb;
@@ -256,7 +286,7 @@ extern "C" int bsig_signature_fwd(const float* states, const float* actions, flo
       const int cc = (int)(C * C);
       const int cpad = C <= 16 ? 16 : 24;
       int tpb = std::max(1, 256 / cc);
-      const int64_t per_traj = (steps * cpad + p.siglen) * 4;
+      const int64_t per_traj = (steps * cpad + std::max<int64_t>(p.siglen, len * (d + a))) * 4;
       tpb = (int)std::max<int64_t>(1, std::min<int64_t>(tpb, (100 * 1024) / per_traj));
       p.tpb = tpb;
       const int threads = (int)(ceil_div((int64_t)tpb * cc, 32) * 32);

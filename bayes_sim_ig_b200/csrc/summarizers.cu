@@ -80,7 +80,8 @@ __device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
 // wrap-extended copy, so the common case has no per-element branches.
 // Finiteness: inputs are checked while staging; with finite inputs a product
 // can only be non-finite by overflow, tracked with one max per element.
-__global__ void __launch_bounds__(256) crosscorr_kernel(CrossArgs p, FastDiv divF, FastDiv divQ) {
+__global__ void __launch_bounds__(256) crosscorr_kernel(CrossArgs p, FastDiv divF, FastDiv divQ,
+                                                        FastDiv divP, FastDiv divD, FastDiv divQx) {
   extern __shared__ float smem[];
   const int Qx = p.Qn + 3;                  // action features + 3 wrap-around copies
   float* sf = smem;                         // [G][Pn]
@@ -102,46 +103,69 @@ __global__ void __launch_bounds__(256) crosscorr_kernel(CrossArgs p, FastDiv div
   const int nrows = g_hi - g_lo + 1;
   bool bad = false;
 
-  for (int i = threadIdx.x; i < nrows * p.Pn; i += blockDim.x) {
-    const int g = g_lo + i / p.Pn, e = i % p.Pn;
-    const int t = e / Dm1, j = e - t * Dm1;
+  for (uint32_t i = threadIdx.x; i < (uint32_t)(nrows * p.Pn); i += blockDim.x) {
+    const uint32_t gl = fdiv(i, divP), e = i - gl * (uint32_t)p.Pn;
+    const uint32_t t = fdiv(e, divD), j = e - t * (uint32_t)Dm1;
+    const int g = g_lo + (int)gl;
     const float* s = p.states + (traj0 + g) * p.s_stride + t * p.D + j;
     const float lo = __ldg(s);
     const float v = p.use_diff ? (__ldg(s + 1) - lo) : lo;
     bad |= !finite_f(v);
     sf[g * p.Pn + e] = v;
   }
-  for (int i = threadIdx.x; i < nrows * Qx; i += blockDim.x) {
-    const int g = g_lo + i / Qx, e = i % Qx;
+  for (uint32_t i = threadIdx.x; i < (uint32_t)(nrows * Qx); i += blockDim.x) {
+    const uint32_t gl = fdiv(i, divQx), e = i - gl * (uint32_t)Qx;
+    const int g = g_lo + (int)gl;
     // actions of the first W steps are contiguous: [t*A + k]; entries >= Qn wrap
-    const float v = __ldg(p.actions + (traj0 + g) * p.a_stride + (e % p.Qn));
+    const float v = __ldg(p.actions + (traj0 + g) * p.a_stride + (e >= Qn ? e - Qn : e));
     bad |= !finite_f(v);
     af[g * Qx + e] = v;
   }
   __syncthreads();
 
-  // mean / unbiased std of sf for trajectories whose stat slots are in range:
-  // one warp per trajectory, float64 accumulation, two passes.
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-  for (int g = g_lo + warp; g <= g_hi; g += nwarp) {
-    const uint32_t slot = (uint32_t)g * F + PQ;
-    if (slot + 1 < c0 || slot >= c1) continue;
-    const float* v = sf + g * p.Pn;
-    double acc = 0.0;
-    for (int i = lane; i < p.Pn; i += 32) acc += (double)v[i];
-    acc = warp_sum(acc);
-    const double mean = acc / (double)p.Pn;
-    double sq = 0.0;
-    for (int i = lane; i < p.Pn; i += 32) {
-      const double dlt = (double)v[i] - mean;
-      sq += dlt * dlt;
-    }
-    sq = warp_sum(sq);
-    if (lane == 0) {
+  // mean / unbiased std of sf (float64, two passes) for the trajectories whose
+  // stat slots fall in this chunk: a thread per trajectory when the feature
+  // vector is short, a warp per trajectory when it is long.
+  if (p.Pn <= 64) {
+    for (int g = g_lo + threadIdx.x; g <= g_hi; g += blockDim.x) {
+      const uint32_t slot = (uint32_t)g * F + PQ;
+      if (slot + 1 < c0 || slot >= c1) continue;
+      const float* v = sf + g * p.Pn;
+      double acc = 0.0;
+      for (int i = 0; i < p.Pn; ++i) acc += (double)v[i];
+      const double mean = acc / (double)p.Pn;
+      double sq = 0.0;
+      for (int i = 0; i < p.Pn; ++i) {
+        const double dlt = (double)v[i] - mean;
+        sq += dlt * dlt;
+      }
       const float sd = p.Pn < 2 ? 0.f : (float)sqrt(sq / (double)(p.Pn - 1));
       st[g * 2 + 0] = (float)mean;
       st[g * 2 + 1] = sd;
       bad |= !finite_f(sd);
+    }
+  } else {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    for (int g = g_lo + warp; g <= g_hi; g += nwarp) {
+      const uint32_t slot = (uint32_t)g * F + PQ;
+      if (slot + 1 < c0 || slot >= c1) continue;
+      const float* v = sf + g * p.Pn;
+      double acc = 0.0;
+      for (int i = lane; i < p.Pn; i += 32) acc += (double)v[i];
+      acc = warp_sum(acc);
+      const double mean = acc / (double)p.Pn;
+      double sq = 0.0;
+      for (int i = lane; i < p.Pn; i += 32) {
+        const double dlt = (double)v[i] - mean;
+        sq += dlt * dlt;
+      }
+      sq = warp_sum(sq);
+      if (lane == 0) {
+        const float sd = p.Pn < 2 ? 0.f : (float)sqrt(sq / (double)(p.Pn - 1));
+        st[g * 2 + 0] = (float)mean;
+        st[g * 2 + 1] = sd;
+        bad |= !finite_f(sd);
+      }
     }
   }
   __syncthreads();
@@ -271,12 +295,20 @@ extern "C" int bsig_summary_crosscorr(const float* states, const float* actions,
   FastDiv divF, divQ;
   divF.d = (uint32_t)p.F;
   divF.m = ((1ull << 40) + (uint64_t)p.F - 1) / (uint64_t)p.F;
-  divQ.d = (uint32_t)p.Qn;
-  divQ.m = ((1ull << 40) + (uint64_t)p.Qn - 1) / (uint64_t)p.Qn;
+  auto mk = [](uint64_t d) {
+    FastDiv f;
+    f.d = (uint32_t)d;
+    f.m = ((1ull << 40) + d - 1) / d;
+    return f;
+  };
+  divQ = mk((uint64_t)p.Qn);
+  const FastDiv divP = mk((uint64_t)p.Pn), divD = mk((uint64_t)(p.D - 1)),
+                divQx = mk((uint64_t)(p.Qn + 3));
+  // staging indices stay below G*(Pn+Qn+3) <= 16K floats: far inside the FastDiv bound
   if (smem > 48 * 1024)
     BSIG_CUDA(cudaFuncSetAttribute(crosscorr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
-  crosscorr_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p, divF, divQ);
+  crosscorr_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p, divF, divQ, divP, divD, divQx);
   BSIG_LAUNCH_CHECK();
   return 0;
 }

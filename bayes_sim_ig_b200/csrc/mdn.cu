@@ -426,6 +426,20 @@ __global__ void __launch_bounds__(128) nll_kernel(NllArgs a) {
   }
 }
 
+// Sum one float per CTA over the cluster (call after cluster.sync()): the first
+// warp gathers the NC partials through DSMEM in parallel and adds them in a fixed
+// butterfly order, so every CTA obtains the bit-identical total.
+__device__ __forceinline__ float cluster_sum(cg::cluster_group& cluster, float* slot, int NC,
+                                             float* bcast) {
+  if (threadIdx.x < 32) {
+    float v = ((int)threadIdx.x < NC) ? *cluster.map_shared_rank(slot, threadIdx.x) : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) *bcast = v;
+  }
+  __syncthreads();
+  return *bcast;
+}
+
 // Small-batch form (B*GW <= 8*512 lanes, i.e. the reference's minibatch of 100
 // and its 200-row test split): exp-sum, NLL forward/backward, eps-term fix-up and
 // the loss in ONE launch.  The CTAs form a single thread-block cluster; the three
@@ -486,6 +500,125 @@ __global__ void __launch_bounds__(512) nll_cluster_kernel(NllArgs a) {
         if (b < B)
           a.d_zd[(int64_t)b * a.ldo_zd + col] += expf(__ldg(a.zd + (int64_t)b * a.ld_zd + col)) * c;
       }
+    }
+  }
+  cluster.sync();       // keep red[] alive until every CTA has read it
+}
+
+// Register-resident minibatch form (diagonal covariance, P <= PMAX, one sample
+// per lane group, B*GW <= 8*256): every input of a (sample, component) pair is
+// requested up front -- ONE round trip to L2 -- and stays in registers through
+// the forward, the backward and the eps-term fix-up; the two batch-wide sums
+// (exp-sum for eps, the eps gradient) are cluster all-reduces through DSMEM.
+template <int GW, int PMAX, bool BWD>
+__global__ void __launch_bounds__(256) nll_small_kernel(NllArgs a) {
+  __shared__ float scratch[33];
+  __shared__ float red[3], bc[3];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int tid = threadIdx.x;
+  const int NC = gridDim.x, rank = blockIdx.x;
+  constexpr int GPB = 256 / GW;
+  const int lane_g = tid & (GW - 1), gid = tid / GW;
+  const int B = a.B, P = a.P, K = a.K, PK = P * K;
+  const int b = rank * GPB + gid, k = lane_g;
+  const bool ok = (b < B) && (k < K);
+  const int64_t bb = ok ? b : 0;
+  const int kk = ok ? k : 0;
+
+  // ---- all loads
+  const int64_t yrow = (a.y_rows ? __ldg(a.y_rows + bb) : bb) * P;
+  float zpi = ok ? __ldg(a.z_pi + bb * a.ld_pi + kk) : -INFINITY;
+  float e[PMAX], zi[PMAX], nz[PMAX];
+#pragma unroll
+  for (int i = 0; i < PMAX; ++i) {
+    const int ii = i < P ? i : 0;
+    e[i] = __ldg(a.zd + bb * a.ld_zd + ii * K + kk);
+    zi[i] = __ldg(a.y + yrow + ii) - __ldg(a.mu + bb * a.ld_mu + ii * K + kk);
+    nz[i] = __ldg(a.noise + bb * (int64_t)PK + ii * K + kk);
+  }
+
+  // ---- eps = 1e-5 * mean(exp(z_d)) over the batch
+  float esum = 0.f;
+  bool bad = false;
+#pragma unroll
+  for (int i = 0; i < PMAX; ++i) {
+    e[i] = expf(e[i]);
+    if (ok && i < P) esum += e[i];
+  }
+  esum = block_sum(esum, scratch);
+  if (tid == 0) red[0] = esum;
+  cluster.sync();
+  const float etot = cluster_sum(cluster, &red[0], NC, &bc[0]);
+  const float eps = kEpsNoise * (etot / (float)((int64_t)B * PK));
+
+  // ---- mixture weights: softmax -> clamp -> renormalise
+  float mx = group_max<GW>(zpi);
+  float soft = (zpi == -INFINITY) ? 0.f : expf(zpi - mx);
+  const float sm = group_sum<GW>(soft);
+  soft = soft / sm;
+  float w = (k < K) ? fminf(fmaxf(soft, kMinWeight), 1.0f) : 0.f;
+  const float csum = group_sum<GW>(w);
+  w = w / csum;
+
+  // ---- log density of this component
+  float quad = 0.f, logdet = 0.f;
+#pragma unroll
+  for (int i = 0; i < PMAX; ++i) {
+    if (i < P) {
+      const float ldv = e[i] + nz[i] * eps;
+      bad |= ok && !(finite_f(ldv) && finite_f(zi[i]));
+      zi[i] = zi[i] / ldv;                 // z = (y - mu) / L_d
+      quad += zi[i] * zi[i];
+      logdet += logf(ldv);
+    }
+  }
+  const float gj = -0.5f * ((float)P * kLog2Pi + quad) - logdet;
+  bad |= ok && !(finite_f(gj) && finite_f(w));
+  const float wc = fminf(fmaxf(w, kMinWeight), 1.0f);
+  const float rk = ok ? fminf(fmaxf(gj, -kLLLimit), kLLLimit) + logf(wc) : -INFINITY;
+  mx = group_max<GW>(rk);
+  const float se = group_sum<GW>(rk == -INFINITY ? 0.f : expf(rk - mx));
+  const float lse = mx + logf(se);
+  float loss_acc = (b < B && lane_g == 0) ? -lse : 0.f;
+  if (bad) atomicOr(a.flag, 1);
+
+  float s_acc = 0.f;
+  if (BWD) {
+    const float coef = ok ? -expf(rk - lse) / (float)B : 0.f;
+    const bool in_w = (w >= kMinWeight) && (w <= 1.0f);
+    const float dw = (ok && in_w) ? coef / wc : 0.f;
+    const float t1 = group_sum<GW>(dw * w);
+    const float dc = (dw - t1) / csum;
+    const float dp = ((soft >= kMinWeight) && (soft <= 1.0f)) ? dc : 0.f;
+    const float t2 = group_sum<GW>(dp * soft);
+    if (ok) a.d_pi[bb * a.ldo_pi + k] = soft * (dp - t2);
+    const float cg = ((gj >= -kLLLimit) && (gj <= kLLLimit)) ? coef : 0.f;
+#pragma unroll
+    for (int i = 0; i < PMAX; ++i) {
+      if (i < P) {
+        const float ldv = e[i] + nz[i] * eps;
+        const float inv = 1.0f / ldv;
+        const float vi = zi[i] * inv;
+        const float dld = cg * (vi * zi[i] - inv);
+        if (ok) a.d_mu[bb * a.ldo_mu + i * K + k] = cg * vi;
+        s_acc += ok ? dld * nz[i] : 0.f;
+        zi[i] = dld;                       // keep d L_d for the final store
+      }
+    }
+  }
+  const float lsum = block_sum(loss_acc, scratch);
+  const float ssum = BWD ? block_sum(s_acc, scratch) : 0.f;
+  if (tid == 0) { red[1] = lsum; red[2] = ssum; }
+  cluster.sync();
+  const float ltot = cluster_sum(cluster, &red[1], NC, &bc[1]);
+  if (rank == 0 && tid == 0) a.loss[0] = ltot / (float)B;
+  if (BWD) {
+    const float S = cluster_sum(cluster, &red[2], NC, &bc[2]);
+    const float c = kEpsNoise * S / (float)((int64_t)B * PK);
+    if (ok) {
+#pragma unroll
+      for (int i = 0; i < PMAX; ++i)
+        if (i < P) a.d_zd[bb * a.ldo_zd + i * K + k] = e[i] * (zi[i] + c);
     }
   }
   cluster.sync();       // keep red[] alive until every CTA has read it
@@ -690,6 +823,46 @@ static int launch_nll_cluster_t(const NllArgs& a, int nc, int tpb, size_t smem, 
   return 0;
 }
 
+template <int GW, int PMAX, bool BWD>
+static int launch_nll_small_t(const NllArgs& a, int nc, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)nc);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)nc;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  BSIG_CUDA(cudaLaunchKernelEx(&cfg, nll_small_kernel<GW, PMAX, BWD>, a));
+  BSIG_LAUNCH_CHECK();
+  return 0;
+}
+
+// Register-resident minibatch form; -1 if not applicable.
+static int launch_nll_small(const NllArgs& a, bool bwd, cudaStream_t st) {
+  if (a.L > 0 || a.K > 32 || a.P > 40) return -1;
+  int gw = 1;
+  while (gw < a.K) gw <<= 1;
+  const int gpb = 256 / gw;
+  const int nc = (int)ceil_div(a.B, gpb);
+  if (nc > 8) return -1;
+#define BSIG_NS(GWV)                                                                  \
+  case GWV:                                                                           \
+    if (a.P <= 16) return bwd ? launch_nll_small_t<GWV, 16, true>(a, nc, st)          \
+                              : launch_nll_small_t<GWV, 16, false>(a, nc, st);        \
+    return bwd ? launch_nll_small_t<GWV, 40, true>(a, nc, st)                         \
+               : launch_nll_small_t<GWV, 40, false>(a, nc, st);
+  switch (gw) {
+    BSIG_NS(1) BSIG_NS(2) BSIG_NS(4) BSIG_NS(8) BSIG_NS(16) BSIG_NS(32)
+  }
+#undef BSIG_NS
+  return -1;
+}
+
 // Returns 0 if launched, -1 if the problem does not fit one cluster, >0 on error.
 static int launch_nll_cluster(const NllArgs& a, bool bwd, cudaStream_t st) {
   const int K = a.K;
@@ -844,7 +1017,9 @@ extern "C" int bsig_mdn_nll_fused(const float* z, const float* noise, const floa
     a.d_low = L ? dz + k + 2 * PK : nullptr; a.ldo_low = NH;
   }
   {
-    const int rc = launch_nll_cluster(a, bwd, st);   // one launch when the batch fits a cluster
+    int rc = launch_nll_small(a, bwd, st);           // register-resident minibatch form
+    if (rc >= 0) return rc;
+    rc = launch_nll_cluster(a, bwd, st);             // one launch when the batch fits a cluster
     if (rc >= 0) return rc;
   }
   if (launch_exp_sum(a.zd, NH, (int)b, (int)PK, (float*)ws, st, &a.nparts_e)) return 1;

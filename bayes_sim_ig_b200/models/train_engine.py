@@ -90,6 +90,13 @@ class TrainPlan(object):
                        for rows in (batch, rows_max) for n_out, k_in in shapes)
         self.ws_gemm = torch.empty(int(ws_bytes) + 256, dtype=torch.uint8, device=dev)
         self.ws_mdn = torch.zeros(lib.bsig_mdn_ws_bytes(rows_max), dtype=torch.uint8, device=dev)
+        # weight-gradient GEMMs run on a side stream, concurrently with the dgrad chain,
+        # when every GEMM of the step is a single-launch (workspace-free) kernel
+        def single_launch(m_, n_, k_):
+            return m_ * n_ <= 128 * 1024 and k_ <= 8192
+        self.fork_wgrad = all(single_launch(batch, n_out, k_in) and single_launch(batch, k_in, n_out)
+                              and single_launch(n_out, k_in, batch) for n_out, k_in in shapes)
+        self.side = torch.cuda.Stream(device=dev) if self.fork_wgrad else None
         self.loss_buf = torch.zeros(2 * n_log + 1, **f32)   # [train..., test..., scratch]
         self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
         self.graph = None
@@ -152,10 +159,22 @@ class TrainPlan(object):
                   self.y_train.data_ptr(), rows.data_ptr(), loss_ptr, self.dz.data_ptr(),
                   b, p, k, 1 if m.full_covariance else 0, self.ws_mdn.data_ptr(),
                   self.ws_mdn.numel(), self.flag.data_ptr(), st)
-        # heads: wgrad (+bias), then dgrad into the last hidden layer
-        _lib.call('bsig_linear_wgrad', self.dz.data_ptr(), hin.data_ptr(), hin_ld, hin_rows,
-                  head['dw'].data_ptr(), head['db'].data_ptr(), b, head['n'], head['k'], eng,
-                  wsp, wsn, st)
+        # backward: the dgrad chain stays on the main stream; each wgrad (+ fused bias
+        # gradient) is forked to the side stream as soon as its dY exists
+        main = torch.cuda.current_stream(self.dev)
+        side = self.side if self.fork_wgrad else None
+
+        def wgrad(dy, xin, xld, xrows, lay, n_out, k_in):
+            if side is not None:
+                side.wait_stream(main)
+                stream = side.cuda_stream
+            else:
+                stream = st
+            _lib.call('bsig_linear_wgrad', dy.data_ptr(), xin.data_ptr(), xld, xrows,
+                      lay['dw'].data_ptr(), lay['db'].data_ptr(), b, n_out, k_in, eng, wsp, wsn,
+                      stream)
+
+        wgrad(self.dz, hin, hin_ld, hin_rows, head, head['n'], head['k'])
         dcur = self.dz
         nxt = head
         for li in reversed(range(len(layers))):
@@ -170,10 +189,10 @@ class TrainPlan(object):
                 xin, xld, xrows = self.tr['feat'], self.feat_dim, None
             else:
                 xin, xld, xrows = self.x_train, self.in_dim, rows.data_ptr()
-            _lib.call('bsig_linear_wgrad', self.dh[li].data_ptr(), xin.data_ptr(), xld, xrows,
-                      lay['dw'].data_ptr(), lay['db'].data_ptr(), b, lay['n'], lay['k'], eng,
-                      wsp, wsn, st)
+            wgrad(self.dh[li], xin, xld, xrows, lay, lay['n'], lay['k'])
             dcur, nxt = self.dh[li], lay
+        if side is not None:
+            main.wait_stream(side)
         # data parallel: one NCCL sum of the flat gradient buffer, mean taken in Adam
         world = data_parallel.world_of(m)
         data_parallel.allreduce_gradients(m, self.grads)

@@ -1,0 +1,360 @@
+// tcgen05 tensor-core GEMM engine (BSIG_GEMM_TC_TF32 / BSIG_GEMM_TC_TF32X3) for
+// the dense contractions of the path: the RFF projection (models/rff.py:128-132)
+// and the MLP / head layers at large batch (models/mdnn.py:108-119).
+//
+//   C[M,N] = epi( A[M,K] * B[N,K]^T ),  A and B row-major with K contiguous
+//
+// Blackwell-native structure: TMA (cp.async.bulk.tensor, 128B swizzle) stages
+// 128x32 fp32 operand tiles in shared memory, ONE elected thread issues
+// tcgen05.mma.kind::tf32 (M=128, N=128, K=8) accumulating fp32 in tensor memory,
+// completion is tracked with mbarriers (tcgen05.commit), the epilogue warps read
+// the accumulator with tcgen05.ld and apply bias / tanh / scaled cos|sin.
+//
+// fp32 parity (TF32X3): the fp32 operands are split in shared memory into
+// hi = tf32(a) and lo = a - hi by the converter warps, and every K step issues
+// three MMAs (hi*hi + hi*lo + lo*hi): the dropped lo*lo term is 2^-22 relative,
+// so the result matches an fp32 FFMA GEMM to ~1e-6.  Plain TF32 issues one MMA.
+//
+// Requirements: K % 4 == 0 and 16-byte aligned operand rows (TMA global strides),
+// no row gather.  Other shapes use the SIMT engines.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace bsig {
+
+namespace tc {
+
+constexpr int BM = 128, BN = 128, BK = 32;       // BK fp32 = one 128-byte swizzle row
+constexpr int STAGES_X1 = 6, STAGES_X3 = 3;
+constexpr int TILE_BYTES = BM * BK * 4;           // 16 KB
+constexpr int NUM_THREADS = 192;                  // warp0 TMA, warp1 MMA, warps2-5 convert+epilogue
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c_inner, int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+// K-major, 128B-swizzled operand tile: 8-row groups are 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);           // start address
+  d |= (uint64_t)1 << 16;                           // leading byte offset (unused for SW128 K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset
+  d |= (uint64_t)1 << 46;                           // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+
+struct TcArgs {
+  float* C;
+  int64_t ldc;
+  const float* bias;
+  int M, N, K;
+  int epi;
+  float scale;
+};
+
+template <bool X3>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               TcArgs g) {
+  constexpr int STAGES = X3 ? STAGES_X3 : STAGES_X1;
+  constexpr int TILES_PER_STAGE = X3 ? 4 : 2;      // A, B (+ A_lo, B_lo)
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[STAGES], conv_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int num_kb = (g.K + BK - 1) / BK;
+
+  auto tile_a = [&](int s) { return smem + (size_t)s * TILES_PER_STAGE * TILE_BYTES; };
+  auto tile_b = [&](int s) { return tile_a(s) + TILE_BYTES; };
+  auto tile_alo = [&](int s) { return tile_a(s) + 2 * TILE_BYTES; };
+  auto tile_blo = [&](int s) { return tile_a(s) + 3 * TILE_BYTES; };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&conv_bar[s], 128);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    // 128 fp32 accumulator columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_slot)),
+                 "r"(128)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
+        mbar_expect_tx(&full_bar[s], 2 * TILE_BYTES);
+        tma_load_2d(tile_a(s), &map_a, &full_bar[s], kb * BK, m0);
+        tma_load_2d(tile_b(s), &map_b, &full_bar[s], kb * BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=tf32, K-major both, N=128, M=128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)(BM >> 4) << 24);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t parity = (kb / STAGES) & 1;
+        if (X3) mbar_wait(&conv_bar[s], parity);
+        else mbar_wait(&full_bar[s], parity);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_hi = smem_u32(tile_a(s)), b_hi = smem_u32(tile_b(s));
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {
+          const uint32_t off = k * 32;          // 8 tf32 = 32 bytes along the swizzled row
+          const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+          umma_tf32(tmem_base, umma_desc(a_hi + off), umma_desc(b_hi + off), idesc, acc);
+          if (X3) {
+            const uint32_t a_lo = smem_u32(tile_alo(s)), b_lo = smem_u32(tile_blo(s));
+            umma_tf32(tmem_base, umma_desc(a_hi + off), umma_desc(b_lo + off), idesc, 1u);
+            umma_tf32(tmem_base, umma_desc(a_lo + off), umma_desc(b_hi + off), idesc, 1u);
+          }
+        }
+        umma_commit(&empty_bar[s]);             // stage reusable once these MMAs retire
+      }
+      umma_commit(&tmem_full_bar);              // accumulator complete
+    }
+  } else {
+    // ------------------------------------------- converter (X3) + epilogue warps
+    const int t = threadIdx.x - 64;             // 0..127
+    if (X3) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        mbar_wait(&full_bar[s], (kb / STAGES) & 1);
+        float4* a = reinterpret_cast<float4*>(tile_a(s));
+        float4* b = reinterpret_cast<float4*>(tile_b(s));
+        float4* alo = reinterpret_cast<float4*>(tile_alo(s));
+        float4* blo = reinterpret_cast<float4*>(tile_blo(s));
+        auto split = [](float4* hi_p, float4* lo_p, int idx) {
+          const float4 v = hi_p[idx];
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+          h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+          h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+          h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+          l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+          hi_p[idx] = h;
+          lo_p[idx] = l;
+        };
+#pragma unroll
+        for (int q = 0; q < TILE_BYTES / 16 / 128; ++q) {   // 8 float4 per thread per tile
+          split(a, alo, t + 128 * q);
+          split(b, blo, t + 128 * q);
+        }
+        // make the generic-proxy writes visible to the tensor core (async proxy)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(&conv_bar[s]);
+      }
+    }
+    // epilogue: warp q = warp % 4 owns TMEM lanes [32q, 32q+32) = rows of the tile
+    mbar_wait(&tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < g.M;
+    float* crow = g.C + (int64_t)(row_ok ? row : 0) * g.ldc;
+    const bool vec_ok = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) &&
+                        (g.epi != EPI_SINCOS || (g.N & 3) == 0);
+#pragma unroll 1
+    for (int cb = 0; cb < BN / 32; ++cb) {
+      uint32_t r[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+            "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+            "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+            "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+            "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (!row_ok) continue;
+      const int jbase = n0 + cb * 32;
+      if (jbase >= g.N) continue;
+      float v[32], v2[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const int j = jbase + c;
+        float acc = __uint_as_float(r[c]);
+        v2[c] = 0.f;
+        if (g.epi == EPI_BIAS || g.epi == EPI_BIAS_TANH) acc += (j < g.N) ? __ldg(g.bias + j) : 0.f;
+        if (g.epi == EPI_BIAS_TANH) acc = tanhf(acc);
+        if (g.epi == EPI_SINCOS) {
+          float sn, cs;
+          sincosf(acc, &sn, &cs);
+          acc = g.scale * cs;
+          v2[c] = g.scale * sn;
+        }
+        v[c] = acc;
+      }
+      const int ncols = min(32, g.N - jbase);
+      if (vec_ok && ncols == 32) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 4)
+          *reinterpret_cast<float4*>(crow + jbase + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+        if (g.epi == EPI_SINCOS) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 4)
+            *reinterpret_cast<float4*>(crow + g.N + jbase + c) =
+                make_float4(v2[c], v2[c + 1], v2[c + 2], v2[c + 3]);
+        }
+      } else {
+        for (int c = 0; c < ncols; ++c) {
+          crow[jbase + c] = v[c];
+          if (g.epi == EPI_SINCOS) crow[g.N + jbase + c] = v2[c];
+        }
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128)
+                 : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// [rows, K] fp32 row-major, row stride ld floats; box = BK x 128 rows, 128B swizzle
+static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t K, int64_t ld) {
+  EncodeTiledFn fn = encode_fn();
+  BSIG_REQUIRE(fn != nullptr, "gemm_tc: cuTensorMapEncodeTiled is not available");
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  BSIG_REQUIRE(r == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+}  // namespace tc
+
+bool gemm_tc_applicable(const GemmArgs& g) {
+  const bool fwd_form = g.a_sr == 1 && g.b_sr == 1 && g.b_sj >= g.K && g.a_si >= g.K;
+  const bool aligned = (g.K % 4 == 0) && (g.a_si % 4 == 0) && (g.b_sj % 4 == 0) &&
+                       ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(g.B) & 15) == 0);
+  const bool epi_ok = g.epi == EPI_STORE || g.epi == EPI_BIAS || g.epi == EPI_BIAS_TANH ||
+                      g.epi == EPI_SINCOS;
+  return fwd_form && aligned && epi_ok && g.a_rows == nullptr && g.b_rows == nullptr &&
+         g.rowsum == nullptr && g.M >= 1 && g.N >= 1 && g.K >= 4;
+}
+
+int gemm_tc(const GemmArgs& g, bool x3, cudaStream_t st) {
+  using namespace tc;
+  CUtensorMap map_a, map_b;
+  if (make_map(&map_a, g.A, g.M, g.K, g.a_si)) return 1;
+  if (make_map(&map_b, g.B, g.N, g.K, g.b_sj)) return 1;
+  TcArgs a;
+  a.C = g.C; a.ldc = g.ldc; a.bias = g.bias; a.M = g.M; a.N = g.N; a.K = g.K; a.epi = g.epi;
+  a.scale = g.scale;
+  const dim3 grid((unsigned)ceil_div(g.M, BM), (unsigned)ceil_div(g.N, BN));
+  const size_t smem = (size_t)(x3 ? STAGES_X3 * 4 : STAGES_X1 * 2) * TILE_BYTES + 1024;
+  if (x3) {
+    BSIG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    gemm_tc_kernel<true><<<grid, NUM_THREADS, smem, st>>>(map_a, map_b, a);
+  } else {
+    BSIG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gemm_tc_kernel<false><<<grid, NUM_THREADS, smem, st>>>(map_a, map_b, a);
+  }
+  BSIG_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace bsig

@@ -6,7 +6,10 @@
 using namespace bsig;
 
 static int run_gemm(const GemmArgs& g, int engine, void* ws, int64_t ws_bytes, cudaStream_t st) {
-  (void)engine;  // BSIG_GEMM_TC_* engines are wired in gemm_tc.cu
+  // tensor-core engines take the GEMMs they can express (K-contiguous operands,
+  // 16-byte aligned rows, no gather); everything else runs on the SIMT engines
+  if ((engine == BSIG_GEMM_TC_TF32 || engine == BSIG_GEMM_TC_TF32X3) && gemm_tc_applicable(g))
+    return gemm_tc(g, engine == BSIG_GEMM_TC_TF32X3, st);
   if (gemm_small_applicable(g)) return gemm_small(g, st);
   return gemm_simt(g, ws, ws_bytes, st);
 }

@@ -27,9 +27,9 @@ namespace bsig {
 namespace tc {
 
 constexpr int BM = 128, BN = 128, BK = 32;       // BK fp32 = one 128-byte swizzle row
-constexpr int STAGES_X1 = 6, STAGES_X3 = 3;
+constexpr int STAGES_X1 = 3, STAGES_X3 = 3;       // X1: 97 KB -> two CTAs per SM overlap epilogue and mainloop
 constexpr int TILE_BYTES = BM * BK * 4;           // 16 KB
-constexpr int NUM_THREADS = 192;                  // warp0 TMA, warp1 MMA, warps2-5 convert+epilogue
+constexpr int NUM_THREADS = 320;                  // warp0 TMA, warp1 MMA, warps2-9 convert+epilogue
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -103,7 +103,7 @@ struct TcArgs {
 };
 
 template <bool X3>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS, X3 ? 1 : 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                TcArgs g) {
   constexpr int STAGES = X3 ? STAGES_X3 : STAGES_X1;
@@ -126,7 +126,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&conv_bar[s], 128);
+      mbar_init(&conv_bar[s], 256);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&tmem_full_bar, 1);
@@ -186,7 +186,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else {
     // ------------------------------------------- converter (X3) + epilogue warps
-    const int t = threadIdx.x - 64;             // 0..127
+    const int t = threadIdx.x - 64;             // 0..255
     if (X3) {
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES;
@@ -207,26 +207,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           lo_p[idx] = l;
         };
 #pragma unroll
-        for (int q = 0; q < TILE_BYTES / 16 / 128; ++q) {   // 8 float4 per thread per tile
-          split(a, alo, t + 128 * q);
-          split(b, blo, t + 128 * q);
+        for (int q = 0; q < TILE_BYTES / 16 / 256; ++q) {   // 4 float4 per thread per tile
+          split(a, alo, t + 256 * q);
+          split(b, blo, t + 256 * q);
         }
         // make the generic-proxy writes visible to the tensor core (async proxy)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(&conv_bar[s]);
       }
     }
-    // epilogue: warp q = warp % 4 owns TMEM lanes [32q, 32q+32) = rows of the tile
+    // epilogue: warp quadrant q = warp % 4 owns TMEM lanes [32q, 32q+32) = rows of
+    // the tile; the two warps of a quadrant take alternate 32-column blocks
     mbar_wait(&tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;           // 0 or 1
     const int row = m0 + q * 32 + lane;
     const bool row_ok = row < g.M;
     float* crow = g.C + (int64_t)(row_ok ? row : 0) * g.ldc;
     const bool vec_ok = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) &&
                         (g.epi != EPI_SINCOS || (g.N & 3) == 0);
 #pragma unroll 1
-    for (int cb = 0; cb < BN / 32; ++cb) {
+    for (int cb = half; cb < BN / 32; cb += 2) {
+      const int jbase = n0 + cb * 32;
+      if (jbase >= g.N) break;                  // warp-uniform
       uint32_t r[32];
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32);
       asm volatile(
@@ -241,39 +245,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       if (!row_ok) continue;
-      const int jbase = n0 + cb * 32;
-      if (jbase >= g.N) continue;
-      float v[32], v2[32];
+      const bool full_block = jbase + 32 <= g.N;
+      // four columns at a time, everything statically indexed (stays in registers)
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const int j = jbase + c;
-        float acc = __uint_as_float(r[c]);
-        v2[c] = 0.f;
-        if (g.epi == EPI_BIAS || g.epi == EPI_BIAS_TANH) acc += (j < g.N) ? __ldg(g.bias + j) : 0.f;
-        if (g.epi == EPI_BIAS_TANH) acc = tanhf(acc);
-        if (g.epi == EPI_SINCOS) {
-          float sn, cs;
-          sincosf(acc, &sn, &cs);
-          acc = g.scale * cs;
-          v2[c] = g.scale * sn;
+      for (int c = 0; c < 32; c += 4) {
+        float v[4], w2[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = min(jbase + c + u, g.N - 1);
+          float acc = __uint_as_float(r[c + u]);
+          w2[u] = 0.f;
+          if (g.epi == EPI_BIAS || g.epi == EPI_BIAS_TANH) acc += __ldg(g.bias + j);
+          if (g.epi == EPI_BIAS_TANH) acc = tanhf(acc);
+          if (g.epi == EPI_SINCOS) {
+            // two-term Cody-Waite reduction to [-pi, pi], then the SFU sin/cos
+            // (abs error ~5e-7 on features of magnitude `scale`)
+            const float kf = rintf(acc * 0.15915494309189535f);
+            float red = fmaf(-kf, 6.2831854820251465f, acc);
+            red = fmaf(-kf, -1.7484555e-7f, red);
+            acc = g.scale * __cosf(red);
+            w2[u] = g.scale * __sinf(red);
+          }
+          v[u] = acc;
         }
-        v[c] = acc;
-      }
-      const int ncols = min(32, g.N - jbase);
-      if (vec_ok && ncols == 32) {
+        if (vec_ok && (full_block || jbase + c + 4 <= g.N)) {
+          *reinterpret_cast<float4*>(crow + jbase + c) = make_float4(v[0], v[1], v[2], v[3]);
+          if (g.epi == EPI_SINCOS)
+            *reinterpret_cast<float4*>(crow + g.N + jbase + c) = make_float4(w2[0], w2[1], w2[2], w2[3]);
+        } else {
 #pragma unroll
-        for (int c = 0; c < 32; c += 4)
-          *reinterpret_cast<float4*>(crow + jbase + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-        if (g.epi == EPI_SINCOS) {
-#pragma unroll
-          for (int c = 0; c < 32; c += 4)
-            *reinterpret_cast<float4*>(crow + g.N + jbase + c) =
-                make_float4(v2[c], v2[c + 1], v2[c + 2], v2[c + 3]);
-        }
-      } else {
-        for (int c = 0; c < ncols; ++c) {
-          crow[jbase + c] = v[c];
-          if (g.epi == EPI_SINCOS) crow[g.N + jbase + c] = v2[c];
+          for (int u = 0; u < 4; ++u) {
+            if (jbase + c + u < g.N) {
+              crow[jbase + c + u] = v[u];
+              if (g.epi == EPI_SINCOS) crow[g.N + jbase + c + u] = w2[u];
+            }
+          }
         }
       }
     }

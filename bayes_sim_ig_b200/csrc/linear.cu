@@ -8,6 +8,9 @@ using namespace bsig;
 static int run_gemm(const GemmArgs& g, int engine, void* ws, int64_t ws_bytes, cudaStream_t st) {
   // tensor-core engines take the GEMMs they can express (K-contiguous operands,
   // 16-byte aligned rows, no gather); everything else runs on the SIMT engines
+  if (engine == BSIG_GEMM_AUTO)   // tensor cores once the problem is big enough to feed them
+    engine = ((int64_t)g.M * g.N * g.K >= (1ll << 26) && g.M >= 1024) ? BSIG_GEMM_TC_TF32X3
+                                                                       : BSIG_GEMM_SIMT;
   if ((engine == BSIG_GEMM_TC_TF32 || engine == BSIG_GEMM_TC_TF32X3) && gemm_tc_applicable(g))
     return gemm_tc(g, engine == BSIG_GEMM_TC_TF32X3, st);
   if (gemm_small_applicable(g)) return gemm_small(g, st);

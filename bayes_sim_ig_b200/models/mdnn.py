@@ -211,7 +211,7 @@ class MDNN(nn.Module):
         self.lr = lr
         self.device = device
         self.input_dim = input_dim
-        self.gemm_engine = 0     # BSIG_GEMM_* selector for the dense layers
+        self.gemm_engine = -1    # BSIG_GEMM_* selector for the dense layers (-1 = auto)
         # Modules are created on the host in the reference's order so that a
         # given torch seed yields the reference's initial weights.
         net = OrderedDict()

@@ -29,7 +29,7 @@ class RFF:
         self.a = 1.0
         self.device = device
         self.cos_only = bool(cos_only)
-        self.gemm_engine = 0            # BSIG_GEMM_* selector
+        self.gemm_engine = -1           # BSIG_GEMM_* selector (-1 = auto)
         dev = _lib.require_cuda(device)
         if isinstance(sigma, list):
             assert (len(sigma) == d)

@@ -281,6 +281,23 @@ def kernel_rooflines(dev, flush, peak_gbs, peak_src):
     # algorithmic: read z + noise + y, write dz  (3 launches: exp-sum, nll, eps fix-up)
     entry('mdn_nll_fused_fwd_bwd', 4 * b * (2 * nh + p * k + p), time_kernel(nll, flush),
           'B=%d P=13 K=10 diag, fwd+bwd (3 launches)' % b)
+    # RFF projection + sincos, Ant-shaped summary_start (configs[2]): N=65536, d=680 -> 200
+    del z, dz, noise, y
+    n3, d3, nf = 1 << 16, 680, 100
+    x3 = torch.randn(n3, d3, device=dev)
+    coeff = torch.randn(nf, d3, device=dev) / 4.0
+    feat = torch.empty(n3, 2 * nf, device=dev)
+    wsl = torch.empty(max(_lib.load().bsig_linear_ws_bytes(n3, nf, d3), 16), dtype=torch.uint8,
+                      device=dev)
+    for eng, tag in ((0, 'simt_fp32'), (1, 'tcgen05_tf32'), (2, 'tcgen05_tf32x3')):
+        def rff(eng=eng):
+            _lib.call('bsig_rff_features', x3.data_ptr(), d3, None, coeff.data_ptr(), feat.data_ptr(),
+                      n3, d3, nf, 0.1, eng, wsl.data_ptr(), wsl.numel(), st())
+        ms = time_kernel(rff, flush)
+        entry('rff_projection_ant_64k_' + tag, 4 * (n3 * (d3 + 2 * nf) + nf * d3), ms,
+              'N=65536 d=680 -> 200 features, engine %s' % tag)
+        out['rff_projection_ant_64k_' + tag]['tflops'] = round(2.0 * n3 * d3 * nf / (ms * 1e-3) / 1e12, 2)
+    del x3, feat
     # Adam over 13.5 M parameters (ShadowHand MDNN): 28 B/param
     cnt = 13540748
     pr, g, m, v = (torch.zeros(cnt, device=dev) for _ in range(4))

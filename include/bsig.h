@@ -37,6 +37,7 @@ extern "C" {
 /* GEMM engines: SIMT fp32 FFMA tiles, or tcgen05 tensor cores (tf32 operands,
  * fp32 accumulate in TMEM; TF32X3 = error-compensated 3-pass split that keeps
  * fp32-level accuracy). */
+#define BSIG_GEMM_AUTO (-1)   /* TC_TF32X3 for large K-contiguous problems, SIMT otherwise */
 #define BSIG_GEMM_SIMT 0
 #define BSIG_GEMM_TC_TF32 1
 #define BSIG_GEMM_TC_TF32X3 2

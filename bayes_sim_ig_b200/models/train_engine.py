@@ -193,9 +193,15 @@ class TrainPlan(object):
             dcur, nxt = self.dh[li], lay
         if side is not None:
             main.wait_stream(side)
-        # data parallel: one NCCL sum of the flat gradient buffer, mean taken in Adam
+
+    def _enqueue_update(self, step, st):
+        """Second half of a step: Adam (gradient mean over the replicas folded in) and,
+        on logging steps, the held-out loss."""
+        m = self.model
+        p, k = self.p, self.k
+        slot = self.logs.index(step) if step in self.logs else None
+        n_log = len(self.logs)
         world = data_parallel.world_of(m)
-        data_parallel.allreduce_gradients(m, self.grads)
         _lib.call('bsig_adam_step', m.flat_params.data_ptr(), self.grads.data_ptr(),
                   self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), m.flat_params.numel(),
                   step + 1, float(m.lr), 0.9, 0.999, 1e-8, 1.0 / world, st)
@@ -213,12 +219,37 @@ class TrainPlan(object):
         self.exp_avg_sq.zero_()
         for step in range(self.n_updates):
             self._enqueue_step(step, st)
+            self._enqueue_update(step, st)
 
     def capture(self):
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             self.enqueue_all()
         self.graph = graph
+
+    # ---- data parallel: two graphs per step with the NCCL all-reduce launched between
+    # them (collectives stay out of graph capture; 2 graph launches + 1 collective per
+    # step keep the host far ahead of the ~50 us the device needs)
+    def capture_dp(self):
+        self.dp_graphs = []
+        pool = None
+        for step in range(self.n_updates):
+            pair = []
+            for half in (self._enqueue_step, self._enqueue_update):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    half(step, _lib.stream_ptr(self.dev))
+                pool = g.pool()
+                pair.append(g)
+            self.dp_graphs.append(pair)
+
+    def replay_dp(self):
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        for fwd_bwd, update in self.dp_graphs:
+            fwd_bwd.replay()
+            data_parallel.allreduce_gradients(self.model, self.grads)
+            update.replay()
 
 
 def _stage_inputs(plan, model, x_data, y_data):
@@ -255,7 +286,8 @@ def run_training_captured(model, x_data, y_data, n_updates, batch_size, test_fra
     n_train = max(int(n_tot * (1.0 - test_frac)), 1)
     n_test = n_tot - n_train
     in_dim = x_data.shape[1]
-    key = (n_train, n_test, n_updates, batch_size, in_dim, bool(use_graph))
+    dp = data_parallel.world_of(model) > 1
+    key = (n_train, n_test, n_updates, batch_size, in_dim, bool(use_graph), dp)
     with torch.cuda.device(dev):
         plan = model._plans.get(key)
         if plan is None:
@@ -281,7 +313,14 @@ def run_training_captured(model, x_data, y_data, n_updates, batch_size, test_fra
         plan.flag.zero_()
         if n_test == 0:
             plan.loss_buf.fill_(float('nan'))
-        if use_graph:
+        if use_graph and dp:
+            if getattr(plan, 'dp_graphs', None) is None:
+                before = _lib.load().bsig_launch_count()
+                plan.capture_dp()
+                plan.launches_per_replay = _lib.load().bsig_launch_count() - before
+            plan.replay_dp()
+            _REPLAYED[0] += int(getattr(plan, 'launches_per_replay', 0))
+        elif use_graph:
             if plan.graph is None:
                 before = _lib.load().bsig_launch_count()
                 plan.capture()
@@ -289,7 +328,13 @@ def run_training_captured(model, x_data, y_data, n_updates, batch_size, test_fra
             plan.graph.replay()
             _REPLAYED[0] += int(getattr(plan, 'launches_per_replay', 0))
         else:
-            plan.enqueue_all()
+            plan.exp_avg.zero_()
+            plan.exp_avg_sq.zero_()
+            st = _lib.stream_ptr(dev)
+            for step in range(plan.n_updates):
+                plan._enqueue_step(step, st)
+                data_parallel.allreduce_gradients(model, plan.grads)
+                plan._enqueue_update(step, st)
         n_log = len(plan.logs)
         host = torch.cat([plan.loss_buf[:2 * n_log], plan.flag.float()]).cpu().numpy()
     assert (host[-1] == 0), 'non-finite value in MDNN training (forward / log-likelihood)'

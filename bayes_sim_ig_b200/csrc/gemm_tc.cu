@@ -27,7 +27,7 @@ namespace bsig {
 namespace tc {
 
 constexpr int BM = 128, BN = 128, BK = 32;       // BK fp32 = one 128-byte swizzle row
-constexpr int STAGES_X1 = 3, STAGES_X3 = 3;       // X1: 97 KB -> two CTAs per SM overlap epilogue and mainloop
+constexpr int STAGES_X1 = 6, STAGES_X3 = 3;       // 192 KB of operand stages per (persistent) CTA
 constexpr int TILE_BYTES = BM * BK * 4;           // 16 KB
 constexpr int NUM_THREADS = 320;                  // warp0 TMA, warp1 MMA, warps2-9 convert+epilogue
 
@@ -102,21 +102,30 @@ struct TcArgs {
   float scale;
 };
 
+// Persistent, warp-specialised kernel: one CTA per SM walks the output tiles.
+//   warp 0      TMA producer          (smem ring of STAGES stages)
+//   warp 1      MMA issuer            (two 128-column TMEM accumulators, ping-pong)
+//   warps 2-5   X3: hi/lo converters; X1: second epilogue group
+//   warps 6-9   epilogue              (tcgen05.ld -> bias/tanh/sincos -> global)
+// The epilogue of tile t overlaps the TMA + MMA mainloop of tile t+1.
 template <bool X3>
-__global__ void __launch_bounds__(NUM_THREADS, X3 ? 1 : 2)
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                TcArgs g) {
   constexpr int STAGES = X3 ? STAGES_X3 : STAGES_X1;
   constexpr int TILES_PER_STAGE = X3 ? 4 : 2;      // A, B (+ A_lo, B_lo)
+  constexpr int EPI_WARPS = X3 ? 4 : 8;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
-  __shared__ uint64_t full_bar[STAGES], conv_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
+  __shared__ uint64_t full_bar[STAGES], conv_bar[STAGES], empty_bar[STAGES];
+  __shared__ uint64_t tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int num_kb = (g.K + BK - 1) / BK;
+  const int n_tiles = (g.N + BN - 1) / BN;
+  const int num_tiles = ((g.M + BM - 1) / BM) * n_tiles;
 
   auto tile_a = [&](int s) { return smem + (size_t)s * TILES_PER_STAGE * TILE_BYTES; };
   auto tile_b = [&](int s) { return tile_a(s) + TILE_BYTES; };
@@ -126,17 +135,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&conv_bar[s], 256);
+      mbar_init(&conv_bar[s], 128);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&tmem_full_bar, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], EPI_WARPS * 32);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    // 128 fp32 accumulator columns
+    // two ping-pong accumulators of 128 fp32 columns
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(&tmem_base_slot)),
-                 "r"(128)
+                 "r"(256)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -148,12 +160,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
-        mbar_expect_tx(&full_bar[s], 2 * TILE_BYTES);
-        tma_load_2d(tile_a(s), &map_a, &full_bar[s], kb * BK, m0);
-        tma_load_2d(tile_b(s), &map_b, &full_bar[s], kb * BK, n0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+          mbar_expect_tx(&full_bar[s], 2 * TILE_BYTES);
+          tma_load_2d(tile_a(s), &map_a, &full_bar[s], kb * BK, m0);
+          tma_load_2d(tile_b(s), &map_b, &full_bar[s], kb * BK, n0);
+        }
       }
     }
   } else if (warp == 1) {
@@ -162,35 +178,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // instruction descriptor: D=f32, A=B=tf32, K-major both, N=128, M=128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
                              ((uint32_t)(BM >> 4) << 24);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t parity = (kb / STAGES) & 1;
-        if (X3) mbar_wait(&conv_bar[s], parity);
-        else mbar_wait(&full_bar[s], parity);
+      int it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+        const int buf = tcount & 1;
+        mbar_wait(&tmem_empty_bar[buf], ((tcount >> 1) & 1) ^ 1);   // epilogue drained it
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_hi = smem_u32(tile_a(s)), b_hi = smem_u32(tile_b(s));
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t parity = (it / STAGES) & 1;
+          if (X3) mbar_wait(&conv_bar[s], parity);
+          else mbar_wait(&full_bar[s], parity);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_hi = smem_u32(tile_a(s)), b_hi = smem_u32(tile_b(s));
 #pragma unroll
-        for (int k = 0; k < BK / 8; ++k) {
-          const uint32_t off = k * 32;          // 8 tf32 = 32 bytes along the swizzled row
-          const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-          umma_tf32(tmem_base, umma_desc(a_hi + off), umma_desc(b_hi + off), idesc, acc);
-          if (X3) {
-            const uint32_t a_lo = smem_u32(tile_alo(s)), b_lo = smem_u32(tile_blo(s));
-            umma_tf32(tmem_base, umma_desc(a_hi + off), umma_desc(b_lo + off), idesc, 1u);
-            umma_tf32(tmem_base, umma_desc(a_lo + off), umma_desc(b_hi + off), idesc, 1u);
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint32_t off = k * 32;        // 8 tf32 = 32 bytes along the swizzled row
+            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+            umma_tf32(d_tmem, umma_desc(a_hi + off), umma_desc(b_hi + off), idesc, acc);
+            if (X3) {
+              const uint32_t a_lo = smem_u32(tile_alo(s)), b_lo = smem_u32(tile_blo(s));
+              umma_tf32(d_tmem, umma_desc(a_hi + off), umma_desc(b_lo + off), idesc, 1u);
+              umma_tf32(d_tmem, umma_desc(a_lo + off), umma_desc(b_hi + off), idesc, 1u);
+            }
           }
+          umma_commit(&empty_bar[s]);           // stage reusable once these MMAs retire
         }
-        umma_commit(&empty_bar[s]);             // stage reusable once these MMAs retire
+        umma_commit(&tmem_full_bar[buf]);       // accumulator of this tile complete
       }
-      umma_commit(&tmem_full_bar);              // accumulator complete
     }
-  } else {
-    // ------------------------------------------- converter (X3) + epilogue warps
-    const int t = threadIdx.x - 64;             // 0..255
-    if (X3) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        mbar_wait(&full_bar[s], (kb / STAGES) & 1);
+  } else if (X3 && warp < 6) {
+    // ------------------------------------------------- hi/lo converters (X3 only)
+    const int t = threadIdx.x - 64;             // 0..127
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&full_bar[s], (it / STAGES) & 1);
         float4* a = reinterpret_cast<float4*>(tile_a(s));
         float4* b = reinterpret_cast<float4*>(tile_b(s));
         float4* alo = reinterpret_cast<float4*>(tile_alo(s));
@@ -207,88 +231,102 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           lo_p[idx] = l;
         };
 #pragma unroll
-        for (int q = 0; q < TILE_BYTES / 16 / 256; ++q) {   // 4 float4 per thread per tile
-          split(a, alo, t + 256 * q);
-          split(b, blo, t + 256 * q);
+        for (int q = 0; q < TILE_BYTES / 16 / 128; ++q) {   // 8 float4 per thread per tile
+          split(a, alo, t + 128 * q);
+          split(b, blo, t + 128 * q);
         }
         // make the generic-proxy writes visible to the tensor core (async proxy)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(&conv_bar[s]);
       }
     }
-    // epilogue: warp quadrant q = warp % 4 owns TMEM lanes [32q, 32q+32) = rows of
-    // the tile; the two warps of a quadrant take alternate 32-column blocks
-    mbar_wait(&tmem_full_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  } else {
+    // ---------------------------------------------------------------- epilogue
+    // warp quadrant q = warp % 4 owns TMEM lanes [32q, 32q+32) = rows of the tile;
+    // with two warps per quadrant (X1) they take alternate 32-column blocks
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;           // 0 or 1
-    const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < g.M;
-    float* crow = g.C + (int64_t)(row_ok ? row : 0) * g.ldc;
+    const int half = X3 ? 0 : ((warp - 2) >> 2);
+    constexpr int CB_STEP = X3 ? 1 : 2;
     const bool vec_ok = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) &&
                         (g.epi != EPI_SINCOS || (g.N & 3) == 0);
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+      const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+      const int buf = tcount & 1;
+      mbar_wait(&tmem_full_bar[buf], (tcount >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < g.M;
+      float* crow = g.C + (int64_t)(row_ok ? row : 0) * g.ldc;
 #pragma unroll 1
-    for (int cb = half; cb < BN / 32; cb += 2) {
-      const int jbase = n0 + cb * 32;
-      if (jbase >= g.N) break;                  // warp-uniform
-      uint32_t r[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32);
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-            "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
-            "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
-            "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
-            "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (!row_ok) continue;
-      const bool full_block = jbase + 32 <= g.N;
-      // four columns at a time, everything statically indexed (stays in registers)
+      for (int cb = half; cb < BN / 32; cb += CB_STEP) {
+        const int jbase = n0 + cb * 32;
+        if (jbase >= g.N) break;                // warp-uniform
+        uint32_t r[32];
+        const uint32_t taddr =
+            tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + cb * 32);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+              "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]),
+              "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+              "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+              "=r"(r[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (!row_ok) continue;
+        const bool full_block = jbase + 32 <= g.N;
+        // four columns at a time, everything statically indexed (stays in registers)
 #pragma unroll
-      for (int c = 0; c < 32; c += 4) {
-        float v[4], w2[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int j = min(jbase + c + u, g.N - 1);
-          float acc = __uint_as_float(r[c + u]);
-          w2[u] = 0.f;
-          if (g.epi == EPI_BIAS || g.epi == EPI_BIAS_TANH) acc += __ldg(g.bias + j);
-          if (g.epi == EPI_BIAS_TANH) acc = tanhf(acc);
-          if (g.epi == EPI_SINCOS) {
-            // two-term Cody-Waite reduction to [-pi, pi], then the SFU sin/cos
-            // (abs error ~5e-7 on features of magnitude `scale`)
-            const float kf = rintf(acc * 0.15915494309189535f);
-            float red = fmaf(-kf, 6.2831854820251465f, acc);
-            red = fmaf(-kf, -1.7484555e-7f, red);
-            acc = g.scale * __cosf(red);
-            w2[u] = g.scale * __sinf(red);
-          }
-          v[u] = acc;
-        }
-        if (vec_ok && (full_block || jbase + c + 4 <= g.N)) {
-          *reinterpret_cast<float4*>(crow + jbase + c) = make_float4(v[0], v[1], v[2], v[3]);
-          if (g.epi == EPI_SINCOS)
-            *reinterpret_cast<float4*>(crow + g.N + jbase + c) = make_float4(w2[0], w2[1], w2[2], w2[3]);
-        } else {
+        for (int c = 0; c < 32; c += 4) {
+          float v[4], w2[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            if (jbase + c + u < g.N) {
-              crow[jbase + c + u] = v[u];
-              if (g.epi == EPI_SINCOS) crow[g.N + jbase + c + u] = w2[u];
+            const int j = min(jbase + c + u, g.N - 1);
+            float acc = __uint_as_float(r[c + u]);
+            w2[u] = 0.f;
+            if (g.epi == EPI_BIAS || g.epi == EPI_BIAS_TANH) acc += __ldg(g.bias + j);
+            if (g.epi == EPI_BIAS_TANH) acc = tanhf(acc);
+            if (g.epi == EPI_SINCOS) {
+              // two-term Cody-Waite reduction to [-pi, pi], then the SFU sin/cos
+              // (abs error ~5e-7 on features of magnitude `scale`)
+              const float kf = rintf(acc * 0.15915494309189535f);
+              float red = fmaf(-kf, 6.2831854820251465f, acc);
+              red = fmaf(-kf, -1.7484555e-7f, red);
+              acc = g.scale * __cosf(red);
+              w2[u] = g.scale * __sinf(red);
+            }
+            v[u] = acc;
+          }
+          if (vec_ok && (full_block || jbase + c + 4 <= g.N)) {
+            *reinterpret_cast<float4*>(crow + jbase + c) = make_float4(v[0], v[1], v[2], v[3]);
+            if (g.epi == EPI_SINCOS)
+              *reinterpret_cast<float4*>(crow + g.N + jbase + c) =
+                  make_float4(w2[0], w2[1], w2[2], w2[3]);
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (jbase + c + u < g.N) {
+                crow[jbase + c + u] = v[u];
+                if (g.epi == EPI_SINCOS) crow[g.N + jbase + c + u] = w2[u];
+              }
             }
           }
         }
       }
+      // this warp has read everything it needs from the accumulator
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&tmem_empty_bar[buf]);
     }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256)
                  : "memory");
   }
 }
@@ -348,7 +386,8 @@ int gemm_tc(const GemmArgs& g, bool x3, cudaStream_t st) {
   TcArgs a;
   a.C = g.C; a.ldc = g.ldc; a.bias = g.bias; a.M = g.M; a.N = g.N; a.K = g.K; a.epi = g.epi;
   a.scale = g.scale;
-  const dim3 grid((unsigned)ceil_div(g.M, BM), (unsigned)ceil_div(g.N, BN));
+  const int64_t num_tiles = ceil_div(g.M, BM) * ceil_div(g.N, BN);
+  const dim3 grid((unsigned)std::min<int64_t>(num_tiles, sm_count()));
   const size_t smem = (size_t)(x3 ? STAGES_X3 * 4 : STAGES_X1 * 2) * TILE_BYTES + 1024;
   if (x3) {
     BSIG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,

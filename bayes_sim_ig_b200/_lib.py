@@ -27,6 +27,7 @@ SIGNATURES = {
     'bsig_summary_start': (_int, [_c_ptr, _c_ptr, _c_ptr] + [_i64] * 6 + [_c_ptr]),
     'bsig_summary_crosscorr': (_int, [_c_ptr, _c_ptr, _c_ptr] + [_i64] * 6 + [_int, _c_ptr, _c_ptr]),
     'bsig_signature_fwd': (_int, [_c_ptr, _c_ptr, _c_ptr] + [_i64] * 6 + [_int, _c_ptr]),
+    'bsig_signature_bwd': (_int, [_c_ptr] * 5 + [_i64] * 6 + [_int, _c_ptr]),
     'bsig_linear_ws_bytes': (_i64, [_i64] * 3),
     'bsig_linear_fwd': (_int, [_c_ptr, _i64, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _i64, _i64, _i64,
                                _int, _int, _c_ptr, _i64, _c_ptr]),

@@ -318,3 +318,230 @@ extern "C" int bsig_signature_fwd(const float* states, const float* actions, flo
   BSIG_LAUNCH_CHECK();
   return 0;
 }
+
+// ===================================================================== backward
+// Reverse sweep of the Chen recursion.  With S' = S (x) exp(d) and adjoints
+// (G1', G2', G3) of the levels after a step (G3 never changes), the adjoint of
+// the increment is
+//   dd[a] = G1'[a] + 1/2 sum_j G2'[a,j] d_j + 1/6 sum_jk G3[a,j,k] d_j d_k          (own row)
+//         + sum_i { G2'[i,a] (S1_i + d_i/2) + sum_j G3[i,j,a] (S2_ij + S1_i d_j/2 + d_i d_j/6)
+//                   + (S1_i/2 + d_i/6) sum_k G3[i,a,k] d_k }                        (all rows)
+// and the adjoints before the step are
+//   G2[i,j] = G2'[i,j] + sum_k G3[i,j,k] d_k,
+//   G1[i]   = G1'[i] + sum_j G2'[i,j] d_j + 1/2 sum_jk G3[i,j,k] d_j d_k.
+// S1 before a step is the prefix sum of increments; S2 before a step is recovered
+// by undoing the forward update (S2 -= (S1 + d/2) (x) d), so nothing is stored.
+// The path gradient is dx_{t+1} += dd_t, dx_t -= dd_t (time channel dropped).
+namespace bsig {
+
+struct SigBwdArgs {
+  const float* states;
+  const float* actions;
+  const float* grad;        // [n, siglen]
+  float* d_states;          // [n, L, D]
+  float* d_actions;         // [n, L, A]
+  int64_t n;
+  int64_t s_stride, a_stride;
+  int L, D, A, C;
+  int tpb;
+  int64_t siglen;
+};
+
+__device__ __forceinline__ void store_path_grad(const SigBwdArgs& p, int64_t traj, int t, int c,
+                                                float v) {
+  if (c == 0) return;                                   // time channel
+  if (c <= p.D) p.d_states[(traj * p.L + t) * p.D + (c - 1)] = v;
+  else p.d_actions[(traj * p.L + t) * p.A + (c - 1 - p.D)] = v;
+}
+
+// depth 3, C <= 8: thread i of a trajectory owns row i of every level.  The C
+// threads of a trajectory are consecutive lanes of one warp; the per-step sum
+// over rows goes through a warp-private shared-memory tile.
+template <int C>
+__global__ void __launch_bounds__(256) signature3_bwd_small_kernel(SigBwdArgs p) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int CPAD = 8;
+  constexpr int TPW = 32 / C;                 // trajectories per warp
+  const int steps = p.L - 1;
+  const int tstride = steps * CPAD + 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  float* ds = smem;                                        // [tpb][tstride]
+  float* xch = smem + (size_t)p.tpb * tstride;             // [nwarp][TPW][C][C] exchange tiles
+  float* raw = xch + (size_t)nwarp * TPW * C * C;          // raw rollouts (load_increments)
+  const int64_t traj0 = (int64_t)blockIdx.x * p.tpb;
+  const int ntraj = (int)min((int64_t)p.tpb, p.n - traj0);
+  SigArgs q;
+  q.states = p.states; q.actions = p.actions; q.out = nullptr; q.n = p.n;
+  q.s_stride = p.s_stride; q.a_stride = p.a_stride; q.L = p.L; q.D = p.D; q.A = p.A; q.C = p.C;
+  q.tpb = p.tpb; q.siglen = p.siglen;
+  load_increments<CPAD>(q, ds, tstride, raw, traj0, ntraj);
+  __syncthreads();
+
+  const int tw = lane / C, i = lane - tw * C;              // trajectory within the warp, row
+  const int tl = warp * TPW + tw;
+  const bool active = (tw < TPW) && (tl < ntraj);
+  const int tls = active ? tl : 0;
+  const float* d = ds + tls * tstride;
+  const int64_t traj = traj0 + tls;
+  const float* gr = p.grad + traj * p.siglen;
+  float* x = xch + ((size_t)warp * TPW + (tw < TPW ? tw : 0)) * C * C;
+
+  float g1 = active ? __ldg(gr + i) : 0.f;
+  float g2[C], g3[C][C], s2[C];
+  float s1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < C; ++j) {
+    g2[j] = active ? __ldg(gr + C + i * C + j) : 0.f;
+    s2[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < C; ++k) g3[j][k] = active ? __ldg(gr + C + C * C + (i * C + j) * C + k) : 0.f;
+  }
+  // forward pass for S2 (row i) and the total S1
+  for (int t = 0; t < steps; ++t) {
+    const float di = d[t * CPAD + i];
+    const float a2 = s1 + di * 0.5f;
+#pragma unroll
+    for (int j = 0; j < C; ++j) s2[j] = fmaf(a2, d[t * CPAD + j], s2[j]);
+    s1 += di;
+  }
+  float dd_next = 0.f;                                     // dd of step t+1 (for dx_{t+1})
+  for (int t = steps - 1; t >= 0; --t) {
+    const float4 lo = *reinterpret_cast<const float4*>(d + t * CPAD);
+    const float4 hi = *reinterpret_cast<const float4*>(d + t * CPAD + 4);
+    const float dv[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    const float di = d[t * CPAD + i];
+    s1 -= di;                                              // S1 before this step
+    const float a2 = s1 + di * 0.5f;
+    const float u = s1 * 0.5f + di * (1.0f / 6.0f);
+    float own = g1, g1_add = 0.f, bsum = 0.f;
+    float contrib[C];
+#pragma unroll
+    for (int a = 0; a < C; ++a) contrib[a] = g2[a] * a2;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      s2[j] = fmaf(-a2, dv[j], s2[j]);                     // undo the forward update
+      const float tij = s2[j] + (s1 * 0.5f + di * (1.0f / 6.0f)) * dv[j];
+      float aij = 0.f;
+#pragma unroll
+      for (int k = 0; k < C; ++k) {
+        aij = fmaf(g3[j][k], dv[k], aij);
+        contrib[k] = fmaf(g3[j][k], tij, contrib[k]);      // sum_j G3[i,j,a] T_ij  (a = k)
+      }
+      contrib[j] = fmaf(u, aij, contrib[j]);               // (S1_i/2 + d_i/6) A_ia  (a = j)
+      own = fmaf(0.5f * g2[j], dv[j], own);
+      g1_add = fmaf(g2[j], dv[j], g1_add);
+      bsum = fmaf(aij, dv[j], bsum);
+      g2[j] += aij;                                        // adjoint of S2 before the step
+    }
+    own = fmaf(bsum, 1.0f / 6.0f, own);
+    g1 += g1_add + 0.5f * bsum;
+    // dd[a] = own(a) + sum_i contrib_i[a]
+    __syncwarp();
+    if (tw < TPW) {
+#pragma unroll
+      for (int a = 0; a < C; ++a) x[i * C + a] = contrib[a];
+    }
+    __syncwarp();
+    float dd = own;
+#pragma unroll
+    for (int r = 0; r < C; ++r) dd += x[r * C + i];
+    if (active) store_path_grad(p, traj, t + 1, i, dd - dd_next);
+    dd_next = dd;
+  }
+  if (active) store_path_grad(p, traj, 0, i, -dd_next);
+}
+
+// depth 1 and 2, any C: one CTA per trajectory.  At depth 2 the level-2 adjoint is
+// constant (G2) and G1 before step t is G1 + G2 (x_{L-1} - x_{t+1}).
+__global__ void __launch_bounds__(256) signature12_bwd_kernel(SigBwdArgs p, int depth) {
+  extern __shared__ float smem[];
+  const int C = p.C, L = p.L;
+  float* x = smem;                              // [L][C]
+  float* g2 = smem + (size_t)L * C;             // [C][C] (depth 2)
+  const int64_t traj = blockIdx.x;
+  SigArgs q;
+  q.states = p.states; q.actions = p.actions; q.out = nullptr; q.n = p.n;
+  q.s_stride = p.s_stride; q.a_stride = p.a_stride; q.L = L; q.D = p.D; q.A = p.A; q.C = C;
+  q.tpb = 1; q.siglen = p.siglen;
+  load_paths(q, x, traj, 1);
+  const float* gr = p.grad + traj * p.siglen;
+  if (depth >= 2)
+    for (int e = threadIdx.x; e < C * C; e += blockDim.x) g2[e] = __ldg(gr + C + e);
+  __syncthreads();
+  for (int a = threadIdx.x; a < C; a += blockDim.x) {
+    const float g1 = __ldg(gr + a);
+    float dd_next = 0.f;
+    for (int t = L - 2; t >= 0; --t) {
+      float dd = g1;
+      if (depth >= 2) {
+        const float* x0 = x + t * C;
+        const float* x1 = x0 + C;
+        const float* xl = x + (L - 1) * C;
+        float acc = 0.f;
+        for (int j = 0; j < C; ++j) {
+          const float dj = x1[j] - x0[j];
+          // row a:  G2[a,j] ((x_last - x_{t+1})_j + d_j/2);  column a: G2[j,a] (S1_j + d_j/2)
+          acc = fmaf(g2[a * C + j], (xl[j] - x1[j]) + 0.5f * dj, acc);
+          acc = fmaf(g2[j * C + a], (x0[j] - x[j]) + 0.5f * dj, acc);
+        }
+        dd += acc;
+      }
+      store_path_grad(p, traj, t + 1, a, dd - dd_next);
+      dd_next = dd;
+    }
+    store_path_grad(p, traj, 0, a, -dd_next);
+  }
+}
+
+}  // namespace bsig
+
+extern "C" int bsig_signature_bwd(const float* states, const float* actions, const float* grad_out,
+                                  float* d_states, float* d_actions, int64_t n, int64_t len,
+                                  int64_t t_states, int64_t t_actions, int64_t d, int64_t a,
+                                  int depth, void* stream) {
+  BSIG_REQUIRE(n >= 0 && d >= 1 && a >= 0, "signature_bwd: bad sizes");
+  BSIG_REQUIRE(len >= 2 && t_states >= len && (a == 0 || t_actions >= len),
+               "signature_bwd: need >= 2 path points and len <= stored steps");
+  BSIG_REQUIRE(depth >= 1 && depth <= 3, "signature_bwd: depth must be 1, 2 or 3");
+  if (n == 0) return 0;
+  SigBwdArgs p;
+  p.states = states; p.actions = actions; p.grad = grad_out;
+  p.d_states = d_states; p.d_actions = d_actions; p.n = n;
+  p.s_stride = t_states * d; p.a_stride = t_actions * a;
+  p.L = (int)len; p.D = (int)d; p.A = (int)a; p.C = (int)(1 + d + a);
+  const int64_t C = p.C;
+  p.siglen = C + (depth >= 2 ? C * C : 0) + (depth >= 3 ? C * C * C : 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (depth == 3) {
+    BSIG_REQUIRE(C <= 8, "signature_bwd: depth-3 gradients are implemented for <= 8 channels "
+                         "(got %d)", (int)C);
+    const int tpw = 32 / (int)C, nwarp = 8;
+    p.tpb = tpw * nwarp;
+    const int64_t steps = len - 1;
+    const size_t smem = ((size_t)p.tpb * (steps * 8 + 8) + (size_t)nwarp * tpw * C * C +
+                         (size_t)p.tpb * len * (d + a)) * 4;
+    BSIG_REQUIRE(smem <= 200 * 1024, "signature_bwd: path too long for shared memory");
+    const unsigned grid = (unsigned)ceil_div(n, p.tpb);
+#define BSIG_SIGB(CV)                                                                        \
+  case CV:                                                                                   \
+    if (smem > 48 * 1024)                                                                    \
+      BSIG_CUDA(cudaFuncSetAttribute(signature3_bwd_small_kernel<CV>,                        \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    signature3_bwd_small_kernel<CV><<<grid, 256, smem, st>>>(p);                             \
+    break;
+    switch ((int)C) {
+      BSIG_SIGB(2) BSIG_SIGB(3) BSIG_SIGB(4) BSIG_SIGB(5) BSIG_SIGB(6) BSIG_SIGB(7) BSIG_SIGB(8)
+    }
+#undef BSIG_SIGB
+  } else {
+    p.tpb = 1;
+    const size_t smem = ((size_t)len * C + (depth >= 2 ? (size_t)C * C : 0)) * 4;
+    BSIG_REQUIRE(smem <= 200 * 1024, "signature_bwd: path too large for shared memory");
+    if (smem > 48 * 1024)
+      BSIG_CUDA(cudaFuncSetAttribute(signature12_bwd_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    signature12_bwd_kernel<<<(unsigned)n, 256, smem, st>>>(p, depth);
+  }
+  BSIG_LAUNCH_CHECK();
+  return 0;
+}

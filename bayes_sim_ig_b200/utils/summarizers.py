@@ -127,6 +127,52 @@ def signature_depth(ndim):
     return 1
 
 
+class _SignatureFn(torch.autograd.Function):
+    """Truncated signature of [t | states | actions] with our forward and backward
+    kernels (the reference's signatory.signature is differentiable too)."""
+
+    @staticmethod
+    def forward(ctx, states, actions, depth):
+        bsz, path_len, state_dim = states.shape
+        act_dim = actions.shape[2]
+        c = 1 + state_dim + act_dim
+        width = sum(c ** k for k in range(1, depth + 1))
+        out = torch.empty((bsz, width), dtype=torch.float32, device=states.device)
+        with torch.cuda.device(states.device):
+            _lib.call('bsig_signature_fwd', _lib.ptr(states), _lib.ptr(actions), _lib.ptr(out),
+                      bsz, path_len, states.shape[1], actions.shape[1], state_dim, act_dim, depth,
+                      _lib.stream_ptr(states.device))
+        ctx.save_for_backward(states, actions)
+        ctx.depth = depth
+        ctx.path_len = path_len
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        states, actions = ctx.saved_tensors
+        bsz, _, state_dim = states.shape
+        act_dim = actions.shape[2]
+        path_len = ctx.path_len
+        grad_out = grad_out.contiguous().float()
+        d_states = torch.zeros_like(states)
+        d_actions = torch.zeros_like(actions)
+        # kernels write dense [n, len, dim] gradients
+        ds = d_states if states.shape[1] == path_len else torch.zeros(
+            (bsz, path_len, state_dim), dtype=torch.float32, device=states.device)
+        da = d_actions if actions.shape[1] == path_len else torch.zeros(
+            (bsz, path_len, act_dim), dtype=torch.float32, device=states.device)
+        with torch.cuda.device(states.device):
+            _lib.call('bsig_signature_bwd', _lib.ptr(states), _lib.ptr(actions),
+                      _lib.ptr(grad_out), _lib.ptr(ds), _lib.ptr(da), bsz, path_len,
+                      states.shape[1], actions.shape[1], state_dim, act_dim, ctx.depth,
+                      _lib.stream_ptr(states.device))
+        if ds is not d_states:
+            d_states[:, :path_len] = ds
+        if da is not d_actions:
+            d_actions[:, :path_len] = da
+        return d_states, d_actions, None
+
+
 def summary_signatory(states, actions):
     """Reference summarizers.py:144-168: signature of the time-augmented path
     [t | s_t | a_t] truncated at signature_depth(1 + D + A)."""
@@ -139,13 +185,7 @@ def summary_signatory(states, actions):
     depth = signature_depth(c)
     if depth == 0:
         return torch.zeros((bsz, 0), dtype=torch.float32, device=states.device)
-    width = sum(c ** k for k in range(1, depth + 1))
-    out = torch.empty((bsz, width), dtype=torch.float32, device=states.device)
-    with torch.cuda.device(states.device):
-        _lib.call('bsig_signature_fwd', _lib.ptr(states), _lib.ptr(actions), _lib.ptr(out),
-                  bsz, path_len, states.shape[1], actions.shape[1], state_dim, act_dim, depth,
-                  _lib.stream_ptr(states.device))
-    return out
+    return _SignatureFn.apply(states, actions, depth)
 
 
 def summary_width(name, traj_len, obs_dim, act_dim):

@@ -79,6 +79,14 @@ int bsig_summary_crosscorr(const float* states, const float* actions, float* out
 int bsig_signature_fwd(const float* states, const float* actions, float* out,
                        int64_t n, int64_t len, int64_t t_states, int64_t t_actions,
                        int64_t d, int64_t a, int depth, void* stream);
+/* gradient of a scalar wrt the path given grad_out [n, siglen] (makes the summarizer
+ * differentiable, as signatory's is): d_states [n, len, d], d_actions [n, len, a]
+ * (the time channel has no gradient).  depth 3 is implemented for c <= 8 channels. */
+int bsig_signature_bwd(const float* states, const float* actions, const float* grad_out,
+                       float* d_states, float* d_actions,
+                       int64_t n, int64_t len, int64_t t_states, int64_t t_actions,
+                       int64_t d, int64_t a, int depth, void* stream);
+
 /* ---------------------------------------------------------------- dense layers
  * Replaces nn.Linear (+Tanh) at models/mdnn.py:68-87,108-119 and the RFF
  * projection at models/rff.py:128-132 (cuBLAS sgemm + pointwise in the

@@ -131,3 +131,52 @@ def test_signature_chen_identity_on_device():
     torch.testing.assert_close(s1, pathl - path0, rtol=1e-5, atol=1e-5)
     sym = s2 + s2.transpose(1, 2)
     torch.testing.assert_close(sym, s1[:, :, None] * s1[:, None, :], rtol=1e-4, atol=2e-4)
+
+
+def _torch_signature(path, depth):
+    """float64 torch restatement (Chen recursion) with autograd, the gradient oracle."""
+    n, length, c = path.shape
+    d = path[:, 1:] - path[:, :-1]
+    s1 = torch.zeros(n, c, dtype=path.dtype, device=path.device)
+    s2 = torch.zeros(n, c, c, dtype=path.dtype, device=path.device)
+    s3 = torch.zeros(n, c, c, c, dtype=path.dtype, device=path.device)
+    for t in range(length - 1):
+        dt = d[:, t]
+        if depth >= 3:
+            t2 = s2 + (s1 + dt / 3)[:, :, None] * dt[:, None, :] / 2
+            s3 = s3 + t2[:, :, :, None] * dt[:, None, None, :]
+        if depth >= 2:
+            s2 = s2 + (s1 + dt / 2)[:, :, None] * dt[:, None, :]
+        s1 = s1 + dt
+    parts = [s1, s2.reshape(n, -1), s3.reshape(n, -1)][:depth]
+    return torch.cat(parts, dim=1)
+
+
+@pytest.mark.parametrize('shape', [(7, 21, 3, 1), (40, 21, 4, 1), (33, 6, 5, 2), (3, 11, 15, 6),
+                                   (2, 11, 108, 21), (5, 2, 2, 1)])
+def test_signature_backward_vs_float64_autograd(shape):
+    """The differentiable summarizer: gradients of a random linear functional of the
+    signature wrt states/actions vs float64 autograd of the Chen recursion."""
+    from bayes_sim_ig.utils import summarizers as S
+    n, t1, d, a = shape
+    s, ac = synth_rollouts(21 + n, n, t1, d, a)
+    s = (s * 0.3).to(DEV).requires_grad_(True)
+    ac = ac.to(DEV).requires_grad_(True)
+    out = S.summary_signatory(s, ac)
+    w = torch.randn(out.shape, generator=torch.Generator('cpu').manual_seed(3)).to(DEV)
+    if osum.signature_depth(1 + d + a) == 3 and 1 + d + a > 8:
+        # documented limit: depth-3 gradients are implemented for <= 8 channels
+        from bayes_sim_ig_b200._lib import BsigError
+        with pytest.raises(BsigError):
+            (out * w).sum().backward()
+        return
+    (out * w).sum().backward()
+    s64 = s.detach().double().requires_grad_(True)
+    a64 = ac.detach().double().requires_grad_(True)
+    tcol = torch.arange(1, t1 + 1, device=DEV, dtype=torch.float64).view(1, -1, 1).repeat(n, 1, 1)
+    depth = osum.signature_depth(1 + d + a)
+    ref = _torch_signature(torch.cat([tcol, s64, a64], dim=-1), depth)
+    assert rel_err(out.detach().cpu(), ref.detach().cpu()) < 2e-5
+    (ref * w.double()).sum().backward()
+    assert rel_err(s.grad.cpu(), s64.grad.cpu()) < 5e-5
+    assert rel_err(ac.grad.cpu(), a64.grad.cpu()) < 5e-5

@@ -173,3 +173,46 @@ def test_nll_component_counts_vs_oracle(k):
     assert abs(loss.item() - ref_loss) <= 1e-5 * abs(ref_loss)
     for got, ref in zip(t, (d_w, d_mu, d_ld, d_low)):
         assert rel_err(got.grad.cpu(), ref) < GRAD_RTOL
+
+
+@pytest.mark.parametrize('cfg', [(3000, 13, 10, False), (700, 2, 4, False), (5000, 37, 10, False),
+                                 (3000, 4, 3, True), (300, 13, 10, False), (260, 5, 32, False)])
+def test_fused_head_nll_kernels_at_every_batch_regime(cfg):
+    """bsig_mdn_nll_fused picks a register-resident cluster kernel (minibatch), an
+    element-parallel kernel (large diagonal batches) or the group-per-sample kernel
+    (full covariance): all against the float64 oracle, loss and d loss / d z."""
+    from bayes_sim_ig_b200 import _lib
+    b, p, k, full = cfg
+    rs = np.random.RandomState(b + p)
+    lsz = p * (p - 1) // 2 if full else 0
+    nh = k * (1 + 2 * p + lsz)
+    z = (0.4 * rs.randn(b, nh)).astype(np.float32)
+    noise = rs.rand(b, p, k).astype(np.float32)
+    y = rs.rand(b + 10, p).astype(np.float32)
+    rows = rs.randint(0, b + 10, b).astype(np.int64)
+    zt, nt, yt, rt = (torch.from_numpy(v).to(DEV) for v in (z, noise, y, rows))
+    loss = torch.zeros(1, device=DEV)
+    dz = torch.empty_like(zt)
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    ws = torch.zeros(_lib.load().bsig_mdn_ws_bytes(b), dtype=torch.uint8, device=DEV)
+    for _ in range(2):      # twice: the workspace counters must self-reset
+        _lib.call('bsig_mdn_nll_fused', zt.data_ptr(), nt.data_ptr(), yt.data_ptr(), rt.data_ptr(),
+                  loss.data_ptr(), dz.data_ptr(), b, p, k, 1 if full else 0, ws.data_ptr(),
+                  ws.numel(), flag.data_ptr(), _lib.stream_ptr(DEV))
+    z64 = z.astype(np.float64)
+    pk = p * k
+    w, mu, ld, low, cache = mdn_np.head_epilogue(
+        z64[:, :k], z64[:, k:k + pk], z64[:, k + pk:k + 2 * pk],
+        z64[:, k + 2 * pk:] if full else None, noise, p, k)
+    ref_loss, d_w, d_mu, d_ld, d_low = mdn_np.mdn_loss_backward(w, mu, ld, low, y[rows].astype(np.float64))
+    d_zpi, d_zmu, d_zd, d_zl = mdn_np.head_epilogue_backward(cache, w, d_w, d_mu, d_ld, d_low)
+    ref_dz = np.concatenate([d_zpi, d_zmu, d_zd] + ([d_zl] if full else []), axis=1)
+    assert int(flag.item()) == 0
+    assert abs(loss.item() - ref_loss) <= 1e-5 * abs(ref_loss)
+    assert rel_err(dz.cpu(), ref_dz) < GRAD_RTOL
+    # forward-only form gives the same loss
+    loss2 = torch.zeros(1, device=DEV)
+    _lib.call('bsig_mdn_nll_fused', zt.data_ptr(), nt.data_ptr(), yt.data_ptr(), rt.data_ptr(),
+              loss2.data_ptr(), None, b, p, k, 1 if full else 0, ws.data_ptr(), ws.numel(),
+              flag.data_ptr(), _lib.stream_ptr(DEV))
+    assert abs(loss2.item() - ref_loss) <= 1e-5 * abs(ref_loss)

@@ -297,9 +297,10 @@ def run_training_captured(model, x_data, y_data, n_updates, batch_size, test_fra
         if injected is None:
             # same generator and call pattern as the reference: numpy's global RNG,
             # one randint(0, n_train, batch) per update (mdnn.py:221)
-            ids = np.stack([np.random.randint(0, n_train, batch_size)
-                            for _ in range(n_updates)]) if n_updates > 0 else \
-                np.zeros((0, batch_size), dtype=np.int64)
+            # (one vectorised call draws the identical stream and leaves the identical
+            # generator state as n_updates calls of size batch_size -- checked in
+            # tests/test_cabi_and_host.py)
+            ids = np.random.randint(0, n_train, (n_updates, batch_size))
             plan.idx.copy_(torch.from_numpy(ids.astype(np.int64)), non_blocking=False)
             plan.noise_train.uniform_(0.0, 1.0)
             plan.noise_test.uniform_(0.0, 1.0)

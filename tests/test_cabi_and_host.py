@@ -84,11 +84,17 @@ def test_log_steps_match_reference_rule():
 
 def test_minibatch_index_stream_matches_reference_pattern():
     # one randint(0, n, B) per update == the reference's generator (mdnn.py:221)
-    np.random.seed(3)
-    a = np.stack([np.random.randint(0, 800, 100) for _ in range(7)])
-    np.random.seed(3)
-    b = np.stack([np.random.randint(0, len(range(800)), 100) for _ in range(7)])
-    np.testing.assert_array_equal(a, b)
+    # the engine draws all updates with ONE call; the reference draws one call per
+    # update: same values, same generator state afterwards
+    for n in (800, 76, 5, 1):
+        np.random.seed(3)
+        a = np.stack([np.random.randint(0, n, 100) for _ in range(7)])
+        tail_a = np.random.rand(3)
+        np.random.seed(3)
+        b = np.random.randint(0, n, (7, 100))
+        tail_b = np.random.rand(3)
+        np.testing.assert_array_equal(a, b)
+        np.testing.assert_array_equal(tail_a, tail_b)
 
 
 PDF_CASES = ['f32', 'f64', 'p1', 'p13']

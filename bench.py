@@ -373,7 +373,11 @@ def dominant_kernel_roofline(dev, peak_gbs, peak_src):
     us_per_launch = e0.elapsed_time(e1) * 1e3 / (4 * 25 * 8)
     ach = (algo / 8) / (us_per_launch * 1e-6) / 1e9
     return {'kernel': 'gemm_small_kernel', 'bound': 'hbm', 'achieved': round(ach, 2),
-            'peak': peak_gbs, 'unit': 'GB/s', 'frac': round(ach / peak_gbs, 5), 'traffic': None,
+            'peak': peak_gbs, 'unit': 'GB/s', 'frac': round(ach / peak_gbs, 5),
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture
+            # profiles/r1_ncu_step_kernels.summary.txt (operands live in L2: ~0 B read, the
+            # rest is write-back)
+            'traffic': 15000,
             'us_per_launch': round(us_per_launch, 2), 'algorithmic_bytes': int(algo / 8),
             'peak_source': peak_src,
             'note': 'dominant kernel of the step (8 of 10 launches per Adam update); minibatch-100 '

@@ -505,22 +505,27 @@ __global__ void __launch_bounds__(512) nll_cluster_kernel(NllArgs a) {
   cluster.sync();       // keep red[] alive until every CTA has read it
 }
 
-// Register-resident minibatch form (diagonal covariance, P <= PMAX, one sample
-// per lane group, B*GW <= 8*256): every input of a (sample, component) pair is
-// requested up front -- ONE round trip to L2 -- and stays in registers through
-// the forward, the backward and the eps-term fix-up; the two batch-wide sums
+// Register-resident minibatch form (diagonal covariance, one sample per lane group,
+// whole batch in one cluster of <= 8 CTAs): every input of a (sample, component)
+// pair is requested up front -- ONE round trip to L2 -- and stays in registers
+// through the forward, the backward and the eps-term fix-up; the two batch-wide sums
 // (exp-sum for eps, the eps gradient) are cluster all-reduces through DSMEM.
-template <int GW, int PMAX, bool BWD>
-__global__ void __launch_bounds__(256) nll_small_kernel(NllArgs a) {
+// A sample is owned by PS*GW lanes: lane = (ph, k), k < GW components, and the P
+// output dimensions are dealt round-robin over the PS "p-halves" (p = ii*PS + ph),
+// which divides the per-lane transcendental work by PS; PL = ceil(P / PS) <= PLMAX.
+template <int GW, int PS, int PLMAX, bool BWD>
+__global__ void __launch_bounds__(512) nll_small_kernel(NllArgs a) {
   __shared__ float scratch[33];
   __shared__ float red[3], bc[3];
   cg::cluster_group cluster = cg::this_cluster();
+  constexpr int LPS = GW * PS;             // lanes per sample (<= 32)
   const int tid = threadIdx.x;
   const int NC = gridDim.x, rank = blockIdx.x;
-  constexpr int GPB = 256 / GW;
-  const int lane_g = tid & (GW - 1), gid = tid / GW;
+  const int SPB = blockDim.x / LPS;        // samples per CTA
+  const int lane_s = tid & (LPS - 1), gid = tid / LPS;
+  const int k = lane_s & (GW - 1), ph = lane_s / GW;
   const int B = a.B, P = a.P, K = a.K, PK = P * K;
-  const int b = rank * GPB + gid, k = lane_g;
+  const int b = rank * SPB + gid;
   const bool ok = (b < B) && (k < K);
   const int64_t bb = ok ? b : 0;
   const int kk = ok ? k : 0;
@@ -528,22 +533,23 @@ __global__ void __launch_bounds__(256) nll_small_kernel(NllArgs a) {
   // ---- all loads
   const int64_t yrow = (a.y_rows ? __ldg(a.y_rows + bb) : bb) * P;
   float zpi = ok ? __ldg(a.z_pi + bb * a.ld_pi + kk) : -INFINITY;
-  float e[PMAX], zi[PMAX], nz[PMAX];
+  float e[PLMAX], zi[PLMAX], nz[PLMAX];
 #pragma unroll
-  for (int i = 0; i < PMAX; ++i) {
-    const int ii = i < P ? i : 0;
-    e[i] = __ldg(a.zd + bb * a.ld_zd + ii * K + kk);
-    zi[i] = __ldg(a.y + yrow + ii) - __ldg(a.mu + bb * a.ld_mu + ii * K + kk);
-    nz[i] = __ldg(a.noise + bb * (int64_t)PK + ii * K + kk);
+  for (int ii = 0; ii < PLMAX; ++ii) {
+    const int i = ii * PS + ph;
+    const int ic = i < P ? i : 0;
+    e[ii] = __ldg(a.zd + bb * a.ld_zd + ic * K + kk);
+    zi[ii] = __ldg(a.y + yrow + ic) - __ldg(a.mu + bb * a.ld_mu + ic * K + kk);
+    nz[ii] = __ldg(a.noise + bb * (int64_t)PK + ic * K + kk);
   }
 
   // ---- eps = 1e-5 * mean(exp(z_d)) over the batch
   float esum = 0.f;
   bool bad = false;
 #pragma unroll
-  for (int i = 0; i < PMAX; ++i) {
-    e[i] = expf(e[i]);
-    if (ok && i < P) esum += e[i];
+  for (int ii = 0; ii < PLMAX; ++ii) {
+    e[ii] = expf(e[ii]);
+    if (ok && ii * PS + ph < P) esum += e[ii];
   }
   esum = block_sum(esum, scratch);
   if (tid == 0) red[0] = esum;
@@ -551,7 +557,8 @@ __global__ void __launch_bounds__(256) nll_small_kernel(NllArgs a) {
   const float etot = cluster_sum(cluster, &red[0], NC, &bc[0]);
   const float eps = kEpsNoise * (etot / (float)((int64_t)B * PK));
 
-  // ---- mixture weights: softmax -> clamp -> renormalise
+  // ---- mixture weights: softmax -> clamp -> renormalise (every p-half computes
+  // the same values; xor offsets < GW stay inside one p-half)
   float mx = group_max<GW>(zpi);
   float soft = (zpi == -INFINITY) ? 0.f : expf(zpi - mx);
   const float sm = group_sum<GW>(soft);
@@ -560,17 +567,23 @@ __global__ void __launch_bounds__(256) nll_small_kernel(NllArgs a) {
   const float csum = group_sum<GW>(w);
   w = w / csum;
 
-  // ---- log density of this component
+  // ---- log density of this component: partial sums over this lane's p, then
+  // across the PS p-halves
   float quad = 0.f, logdet = 0.f;
 #pragma unroll
-  for (int i = 0; i < PMAX; ++i) {
-    if (i < P) {
-      const float ldv = e[i] + nz[i] * eps;
-      bad |= ok && !(finite_f(ldv) && finite_f(zi[i]));
-      zi[i] = zi[i] / ldv;                 // z = (y - mu) / L_d
-      quad += zi[i] * zi[i];
+  for (int ii = 0; ii < PLMAX; ++ii) {
+    if (ii * PS + ph < P) {
+      const float ldv = e[ii] + nz[ii] * eps;
+      bad |= ok && !(finite_f(ldv) && finite_f(zi[ii]));
+      zi[ii] = zi[ii] / ldv;               // z = (y - mu) / L_d
+      quad += zi[ii] * zi[ii];
       logdet += logf(ldv);
     }
+  }
+#pragma unroll
+  for (int o = GW; o < LPS; o <<= 1) {
+    quad += __shfl_xor_sync(0xffffffffu, quad, o);
+    logdet += __shfl_xor_sync(0xffffffffu, logdet, o);
   }
   const float gj = -0.5f * ((float)P * kLog2Pi + quad) - logdet;
   bad |= ok && !(finite_f(gj) && finite_f(w));
@@ -579,7 +592,7 @@ __global__ void __launch_bounds__(256) nll_small_kernel(NllArgs a) {
   mx = group_max<GW>(rk);
   const float se = group_sum<GW>(rk == -INFINITY ? 0.f : expf(rk - mx));
   const float lse = mx + logf(se);
-  float loss_acc = (b < B && lane_g == 0) ? -lse : 0.f;
+  float loss_acc = (b < B && lane_s == 0) ? -lse : 0.f;
   if (bad) atomicOr(a.flag, 1);
 
   float s_acc = 0.f;
@@ -591,18 +604,19 @@ __global__ void __launch_bounds__(256) nll_small_kernel(NllArgs a) {
     const float dc = (dw - t1) / csum;
     const float dp = ((soft >= kMinWeight) && (soft <= 1.0f)) ? dc : 0.f;
     const float t2 = group_sum<GW>(dp * soft);
-    if (ok) a.d_pi[bb * a.ldo_pi + k] = soft * (dp - t2);
+    if (ok && ph == 0) a.d_pi[bb * a.ldo_pi + k] = soft * (dp - t2);
     const float cg = ((gj >= -kLLLimit) && (gj <= kLLLimit)) ? coef : 0.f;
 #pragma unroll
-    for (int i = 0; i < PMAX; ++i) {
+    for (int ii = 0; ii < PLMAX; ++ii) {
+      const int i = ii * PS + ph;
       if (i < P) {
-        const float ldv = e[i] + nz[i] * eps;
+        const float ldv = e[ii] + nz[ii] * eps;
         const float inv = 1.0f / ldv;
-        const float vi = zi[i] * inv;
-        const float dld = cg * (vi * zi[i] - inv);
+        const float vi = zi[ii] * inv;
+        const float dld = cg * (vi * zi[ii] - inv);
         if (ok) a.d_mu[bb * a.ldo_mu + i * K + k] = cg * vi;
-        s_acc += ok ? dld * nz[i] : 0.f;
-        zi[i] = dld;                       // keep d L_d for the final store
+        s_acc += ok ? dld * nz[ii] : 0.f;
+        zi[ii] = dld;                      // keep d L_d for the final store
       }
     }
   }
@@ -617,8 +631,10 @@ __global__ void __launch_bounds__(256) nll_small_kernel(NllArgs a) {
     const float c = kEpsNoise * S / (float)((int64_t)B * PK);
     if (ok) {
 #pragma unroll
-      for (int i = 0; i < PMAX; ++i)
-        if (i < P) a.d_zd[bb * a.ldo_zd + i * K + k] = e[i] * (zi[i] + c);
+      for (int ii = 0; ii < PLMAX; ++ii) {
+        const int i = ii * PS + ph;
+        if (i < P) a.d_zd[bb * a.ldo_zd + i * K + k] = e[ii] * (zi[ii] + c);
+      }
     }
   }
   cluster.sync();       // keep red[] alive until every CTA has read it
@@ -823,11 +839,11 @@ static int launch_nll_cluster_t(const NllArgs& a, int nc, int tpb, size_t smem, 
   return 0;
 }
 
-template <int GW, int PMAX, bool BWD>
-static int launch_nll_small_t(const NllArgs& a, int nc, cudaStream_t st) {
+template <int GW, int PS, int PLMAX, bool BWD>
+static int launch_nll_small_t(const NllArgs& a, int nc, int tpb, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)nc);
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3((unsigned)tpb);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -837,9 +853,21 @@ static int launch_nll_small_t(const NllArgs& a, int nc, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  BSIG_CUDA(cudaLaunchKernelEx(&cfg, nll_small_kernel<GW, PMAX, BWD>, a));
+  BSIG_CUDA(cudaLaunchKernelEx(&cfg, nll_small_kernel<GW, PS, PLMAX, BWD>, a));
   BSIG_LAUNCH_CHECK();
   return 0;
+}
+
+template <int GW, int PS>
+static int launch_nll_small_p(const NllArgs& a, bool bwd, int nc, int tpb, cudaStream_t st) {
+  const int pl = (a.P + PS - 1) / PS;
+#define BSIG_PL(PLV)                                                                    \
+  if (pl <= PLV)                                                                        \
+    return bwd ? launch_nll_small_t<GW, PS, PLV, true>(a, nc, tpb, st)                  \
+               : launch_nll_small_t<GW, PS, PLV, false>(a, nc, tpb, st);
+  BSIG_PL(4) BSIG_PL(8) BSIG_PL(16) BSIG_PL(40)
+#undef BSIG_PL
+  return -1;
 }
 
 // Register-resident minibatch form; -1 if not applicable.
@@ -847,18 +875,20 @@ static int launch_nll_small(const NllArgs& a, bool bwd, cudaStream_t st) {
   if (a.L > 0 || a.K > 32 || a.P > 40) return -1;
   int gw = 1;
   while (gw < a.K) gw <<= 1;
-  const int gpb = 256 / gw;
-  const int nc = (int)ceil_div(a.B, gpb);
+  // split the P dimension over up to 4 lanes per component while a sample still
+  // fits one warp and a lane keeps at least two output dimensions
+  int ps = 1;
+  while (ps < 4 && gw * ps * 2 <= 32 && a.P >= 4 * ps) ps <<= 1;
+  const int lps = gw * ps;
+  int tpb = 256;
+  if (ceil_div(a.B, tpb / lps) > 8) tpb = 512;
+  const int nc = (int)ceil_div(a.B, tpb / lps);
   if (nc > 8) return -1;
-#define BSIG_NS(GWV)                                                                  \
-  case GWV:                                                                           \
-    if (a.P <= 16) return bwd ? launch_nll_small_t<GWV, 16, true>(a, nc, st)          \
-                              : launch_nll_small_t<GWV, 16, false>(a, nc, st);        \
-    return bwd ? launch_nll_small_t<GWV, 40, true>(a, nc, st)                         \
-               : launch_nll_small_t<GWV, 40, false>(a, nc, st);
-  switch (gw) {
-    BSIG_NS(1) BSIG_NS(2) BSIG_NS(4) BSIG_NS(8) BSIG_NS(16) BSIG_NS(32)
-  }
+#define BSIG_NS(GWV, PSV) \
+  if (gw == GWV && ps == PSV) return launch_nll_small_p<GWV, PSV>(a, bwd, nc, tpb, st);
+  BSIG_NS(1, 1) BSIG_NS(1, 2) BSIG_NS(1, 4) BSIG_NS(2, 1) BSIG_NS(2, 2) BSIG_NS(2, 4)
+  BSIG_NS(4, 1) BSIG_NS(4, 2) BSIG_NS(4, 4) BSIG_NS(8, 1) BSIG_NS(8, 2) BSIG_NS(8, 4)
+  BSIG_NS(16, 1) BSIG_NS(16, 2) BSIG_NS(32, 1)
 #undef BSIG_NS
   return -1;
 }

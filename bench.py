@@ -385,6 +385,50 @@ def dominant_kernel_roofline(dev, peak_gbs, peak_src):
                     'see `rooflines` for the HBM-bound kernels at sizes that exceed L2'}
 
 
+def extra_configs(dev):
+    """Other BASELINE.json configurations, measured once each (not the headline):
+    configs[2] -- Ant-shaped 65 536 trajectories, summary_start (F=680) + MDRFF fit with the
+    reference's constants (66 run_training calls = 6 600 Adam updates; the RFF projection of
+    the whole-batch predict runs on the tcgen05 engine)."""
+    import contextlib
+    import io
+    from bayes_sim_ig.bayes_sim import BayesSim
+    task = dict(name='ant', D=60, A=8, T1=51, P=17, K=10)
+    n = 1 << 16
+    states, actions, params, lows, highs = synth(7, n, task)
+    states, actions, params = states.to(dev), actions.to(dev), params.to(dev)
+    cfg = {'modelClass': 'MDRFF', 'summarizerFxn': 'summary_start', 'trainTrajLen': 50,
+           'components': 10, 'hiddenLayers': [128, 128], 'lr': 1e-4}
+    out = {}
+    with contextlib.redirect_stdout(io.StringIO()):
+        bsim = BayesSim(cfg, task['D'], task['A'], task['P'], lows, highs, prior=None,
+                        proposal=None, device=str(dev))
+
+        def fit():
+            for lo in range(0, n, CHUNK):
+                logs = bsim.run_training(params[lo:lo + CHUNK], states[lo:lo + CHUNK],
+                                         actions[lo:lo + CHUNK])
+            return logs
+        fit()                                   # capture + warm up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        logs = fit()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        feats = bsim.summarizer_fxn(states, actions)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        mogs_in = bsim.model.rff.to_features(feats)      # 65536 x 680 -> 200 on tcgen05
+        torch.cuda.synchronize()
+        t_rff = time.perf_counter() - t1
+    out['mdrff_ant_64k'] = {
+        'config': 'configs[2]: Ant-shaped 65536 trajectories [T1=51,D=60,A=8,P=17], '
+                  'summary_start(F=680) + MDRFF(n_feat=200, sigma=4, RBF) fit, reference constants',
+        'fit_trajectories_per_s': n / dt, 'seconds': dt, 'final_test_loss': logs['test_loss'][-1],
+        'rff_features_whole_batch_ms': 1e3 * t_rff, 'features_shape': list(mogs_in.shape)}
+    return out
+
+
 def run_b200(args):
     import contextlib
     import io
@@ -482,6 +526,7 @@ def run_b200(args):
         roofs = kernel_rooflines(dev, flush, peak, src)
         line['roofline'] = dominant_kernel_roofline(dev, peak, src)
         line['rooflines'] = roofs
+        line['extra'] = extra_configs(dev)
         threads = os.cpu_count() or 1
         rate, dt = cpu_pipeline_rate(1000, threads)
         line['cpu_baseline'] = {

@@ -79,21 +79,15 @@ __device__ __forceinline__ void load_increments(const SigArgs& p, float* ds, int
   }
   __syncthreads();
   const int steps = p.L - 1;
-  const int per = steps * CPAD;
-  for (int e = threadIdx.x; e < ntraj * per; e += blockDim.x) {
-    const int tl = e / per, r = e - tl * per;
-    const int t = r / CPAD, c = r - t * CPAD;
-    float v = 0.f;
-    if (c == 0) {
-      v = 1.0f;                                         // time channel t+1 -> t+2
-    } else if (c <= p.D) {
-      const float* s = raw_s + tl * LD + t * p.D + (c - 1);
-      v = s[p.D] - s[0];
-    } else if (c < p.C) {
-      const float* a = raw_a + tl * LA + t * p.A + (c - 1 - p.D);
-      v = a[p.A] - a[0];
-    }
-    ds[tl * traj_stride + r] = v;
+  for (int e = threadIdx.x; e < ntraj * steps; e += blockDim.x) {
+    const int tl = e / steps, t = e - tl * steps;
+    float* drow = ds + tl * traj_stride + t * CPAD;
+    const float* s = raw_s + tl * LD + t * p.D;
+    const float* a = raw_a + tl * LA + t * p.A;
+    drow[0] = 1.0f;                                       // time channel t+1 -> t+2
+    for (int c = 0; c < p.D; ++c) drow[1 + c] = s[p.D + c] - s[c];
+    for (int c = 0; c < p.A; ++c) drow[1 + p.D + c] = a[p.A + c] - a[c];
+    for (int c = p.C; c < CPAD; ++c) drow[c] = 0.f;
   }
 }
 
@@ -115,27 +109,30 @@ __device__ __forceinline__ void store_staged(const SigArgs& p, const float* stag
 // of every level -- S1[i], S2[i,:], S3[i,:,:] (C*C registers) -- so a step is
 // C*C + 2C FFMAs against three shared-memory loads.
 template <int C>
-__global__ void __launch_bounds__(256) signature3_small_kernel(SigArgs p) {
+__global__ void __launch_bounds__(256, 4) signature3_small_kernel(SigArgs p) {
   extern __shared__ __align__(16) float smem[];
   constexpr int CPAD = 8;
   const int steps = p.L - 1;
   const int tstride = steps * CPAD + 8;                 // +8: spreads trajectories over banks
+  // shared memory: [ increments | raw rollouts ] during the recursion, then the same
+  // bytes are reused as the output staging buffer (halves the footprint -> more CTAs/SM)
   float* ds = smem;                                     // [tpb][tstride]
-  float* stage = smem + (size_t)p.tpb * tstride;        // [tpb][siglen]
+  float* raw = smem + (size_t)p.tpb * tstride;          // [tpb][L*(D+A)]
+  float* stage = smem;                                  // [tpb][siglen], after the recursion
   const int64_t traj0 = (int64_t)blockIdx.x * p.tpb;
   const int ntraj = (int)min((int64_t)p.tpb, p.n - traj0);
-  load_increments<CPAD>(p, ds, tstride, stage, traj0, ntraj);
+  load_increments<CPAD>(p, ds, tstride, raw, traj0, ntraj);
   __syncthreads();
   const int tl = threadIdx.x / C, i = threadIdx.x - tl * C;
+  float s1 = 0.f, s2[C], s3[C][C];
+#pragma unroll
+  for (int j = 0; j < C; ++j) {
+    s2[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < C; ++k) s3[j][k] = 0.f;
+  }
   if (tl < ntraj) {
     const float* d = ds + tl * tstride;
-    float s1 = 0.f, s2[C], s3[C][C];
-#pragma unroll
-    for (int j = 0; j < C; ++j) {
-      s2[j] = 0.f;
-#pragma unroll
-      for (int k = 0; k < C; ++k) s3[j][k] = 0.f;
-    }
     for (int t = 0; t < steps; ++t) {
       const float4 lo = *reinterpret_cast<const float4*>(d + t * CPAD);
       const float4 hi = *reinterpret_cast<const float4*>(d + t * CPAD + 4);
@@ -152,6 +149,9 @@ __global__ void __launch_bounds__(256) signature3_small_kernel(SigArgs p) {
       }
       s1 += di;
     }
+  }
+  __syncthreads();                                      // everyone is done reading ds
+  if (tl < ntraj) {
     float* o = stage + (size_t)tl * p.siglen;
     o[i] = s1;
 #pragma unroll
@@ -265,7 +265,7 @@ extern "C" int bsig_signature_fwd(const float* states, const float* actions, flo
     if (C <= 8) {
       int tpb = 256 / (int)C;
       // staging buffer doubles as the raw-rollout buffer of load_increments
-      const int64_t per_traj = (steps * 8 + 8 + std::max<int64_t>(p.siglen, len * (d + a))) * 4;
+      const int64_t per_traj = std::max<int64_t>(steps * 8 + 8 + len * (d + a), p.siglen) * 4;
       tpb = (int)std::max<int64_t>(1, std::min<int64_t>(tpb, (100 * 1024) / per_traj));
       if (tpb > 1) tpb &= ~1;               // even -> CTA bases stay 16B aligned (siglen even)
       p.tpb = tpb;

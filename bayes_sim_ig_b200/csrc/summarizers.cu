@@ -172,11 +172,13 @@ __global__ void __launch_bounds__(256) crosscorr_kernel(CrossArgs p, FastDiv div
 
   float* out = p.out + traj0 * p.F;
   float vmax = 0.f;
+  // ---- main loop: float4s that lie entirely inside one row's product block
+  // (the others are skipped here -- no divergent slow path -- and written below)
+  const bool fast_ok = Qn >= 4;
   for (uint32_t e0 = c0 + 4u * threadIdx.x; e0 < c1; e0 += 4u * 256u) {
     const uint32_t g = fdiv(e0, divF);
     const uint32_t r = e0 - g * F;
-    float4 v;
-    if (r + 3 < PQ && Qn >= 4) {
+    if (fast_ok && r + 3 < PQ) {
       const uint32_t pi = fdiv(r, divQ);
       const uint32_t qi = r - pi * Qn;
       const float* sfg = sf + g * p.Pn;
@@ -184,37 +186,53 @@ __global__ void __launch_bounds__(256) crosscorr_kernel(CrossArgs p, FastDiv div
       const float s0 = sfg[pi];
       const float s1 = sfg[min(pi + 1, (uint32_t)p.Pn - 1)];
       const uint32_t nfirst = Qn - qi;       // elements still in feature row pi
+      float4 v;
       v.x = s0 * afg[0];
       v.y = (nfirst > 1 ? s0 : s1) * afg[1];
       v.z = (nfirst > 2 ? s0 : s1) * afg[2];
       v.w = (nfirst > 3 ? s0 : s1) * afg[3];
       vmax = fmaxf(fmaxf(vmax, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
       st_stream_f4(out + e0, v);
+    }
+  }
+  // ---- boundary float4s: per row, the (at most three) aligned float4s that start in
+  // [row0 + PQ - 3, row0 + F): last products, the two statistics, head of the next row.
+  // When the product block cannot use the fast path at all (Qn < 4) every float4 of the
+  // chunk is handled here.
+  const uint32_t n_items = fast_ok ? (uint32_t)nrows * 3u : (c1 - c0 + 3u) / 4u;
+  for (uint32_t it = threadIdx.x; it < n_items; it += 256u) {
+    uint32_t e0;
+    if (fast_ok) {
+      const uint32_t g = (uint32_t)g_lo + it / 3u, m = it % 3u;
+      const uint32_t row0 = g * F;
+      const uint32_t first = (row0 + (PQ >= 3 ? PQ - 3 : 0) + 3u) & ~3u;   // first aligned e0 >= row0+PQ-3
+      e0 = first + 4u * m;
+      if (e0 < row0 || e0 >= row0 + F || e0 < c0 || e0 >= c1) continue;
+      if (e0 - row0 + 3 < PQ) continue;                                    // a fast float4
     } else {
-      // row boundary (last products, the two statistics, next row's head) or the
-      // ragged end of the chunk: element by element
-      float t[4];
+      e0 = c0 + 4u * it;
+    }
+    float t[4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint32_t e = e0 + c;
-        t[c] = 0.f;
-        if (e < c1) {
-          const uint32_t gg = fdiv(e, divF);
-          const uint32_t rr = e - gg * F;
-          if (rr < PQ) {
-            const uint32_t pp = fdiv(rr, divQ);
-            t[c] = sf[gg * p.Pn + pp] * af[gg * Qx + (rr - pp * Qn)];
-          } else {
-            t[c] = st[gg * 2 + (rr - PQ)];
-          }
-          vmax = fmaxf(vmax, fabsf(t[c]));
+    for (int c = 0; c < 4; ++c) {
+      const uint32_t e = e0 + c;
+      t[c] = 0.f;
+      if (e < c1) {
+        const uint32_t gg = fdiv(e, divF);
+        const uint32_t rr = e - gg * F;
+        if (rr < PQ) {
+          const uint32_t pp = fdiv(rr, divQ);
+          t[c] = sf[gg * p.Pn + pp] * af[gg * Qx + (rr - pp * Qn)];
+        } else {
+          t[c] = st[gg * 2 + (rr - PQ)];
         }
+        vmax = fmaxf(vmax, fabsf(t[c]));
       }
-      if (e0 + 3 < c1) {
-        st_stream_f4(out + e0, make_float4(t[0], t[1], t[2], t[3]));
-      } else {
-        for (int c = 0; c < 4 && e0 + c < c1; ++c) out[e0 + c] = t[c];
-      }
+    }
+    if (e0 + 3 < c1) {
+      st_stream_f4(out + e0, make_float4(t[0], t[1], t[2], t[3]));
+    } else {
+      for (int c = 0; c < 4 && e0 + c < c1; ++c) out[e0 + c] = t[c];
     }
   }
   if (bad || !(vmax <= 3.402823466e38f)) atomicOr(p.flag, 1);

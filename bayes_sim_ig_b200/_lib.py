@@ -48,6 +48,13 @@ SIGNATURES = {
                                 _c_ptr, _i64, _c_ptr]),
     'bsig_mdn_nll_fused': (_int, [_c_ptr] * 6 + [_i64] * 3 + [_int, _c_ptr, _i64, _c_ptr, _c_ptr]),
     'bsig_adam_step': (_int, [_c_ptr] * 4 + [_i64, _i64, _f32, _f32, _f32, _f32, _f32, _c_ptr]),
+    'bsig_p2p_alloc': (_int, [ctypes.POINTER(_c_ptr), _i64, ctypes.c_char_p]),
+    'bsig_p2p_open': (_int, [ctypes.c_char_p, ctypes.POINTER(_c_ptr)]),
+    'bsig_p2p_close': (_int, [_c_ptr]),
+    'bsig_p2p_free': (_int, [_c_ptr]),
+    'bsig_adam_allreduce_step': (_int, [_c_ptr, ctypes.POINTER(_c_ptr), ctypes.POINTER(_c_ptr),
+                                        _c_ptr, _int, _int, _c_ptr, _c_ptr, _i64, _i64,
+                                        _f32, _f32, _f32, _f32, _c_ptr]),
     'bsig_gather_rows': (_int, [_c_ptr, _i64, _c_ptr, _c_ptr, _i64, _i64, _c_ptr]),
     'bsig_finite_flag': (_int, [_c_ptr, _i64, _c_ptr, _c_ptr]),
     'bsig_normalize_rows': (_int, [_c_ptr] * 4 + [_i64, _i64, _c_ptr]),

@@ -1,0 +1,174 @@
+// Data-parallel exchange step fused with the optimiser: a one-shot all-reduce of the
+// flat gradient buffer over NVLink peer memory + Adam, in ONE kernel per update.
+//
+// The reference has no multi-GPU path; the exchange a data-parallel
+// MDNN / MDRFF needs is one sum of a 0.1-0.4 MB gradient vector per update -- pure
+// latency.  Instead of an NCCL launch between two graphs, every rank's Adam kernel
+//   1. publishes "my gradients of this update are complete" by storing the update's
+//      epoch into every peer's flag array (st.release.sys over NVLink),
+//   2. waits until all peers' epochs have arrived in its own flag array,
+//   3. reads the gradient of each element from all peers' buffers (peer loads over
+//      NVSwitch, summed in rank order => bit-identical on every rank) and applies Adam.
+// Gradient buffers are double-buffered by update parity, so a rank can start the next
+// backward pass while peers still read the previous buffer.  The epoch lives in device
+// memory and is advanced by the kernel itself, so the launch is CUDA-graph capturable
+// and replayable.  Buffers are cudaMalloc'ed here (IPC handles need whole allocations).
+#include "common.cuh"
+
+namespace bsig {
+
+constexpr int kMaxPeers = 8;
+
+struct P2PArgs {
+  const float* grads[kMaxPeers];     // gradient buffer of every rank (this update's parity)
+  unsigned int* flags[kMaxPeers];    // flag array of every rank: flags[r][q] = epoch published by q
+  unsigned int* ctrl;                // local: [0] epoch counter, [1] finished-block counter
+  int rank, world;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(256)
+adam_allreduce_kernel(P2PArgs a, float* __restrict__ p, float* __restrict__ m,
+                      float* __restrict__ v, int64_t count, float one_minus_b1, float b2,
+                      float one_minus_b2, float step_size, float inv_bc2_sqrt, float eps,
+                      float gscale) {
+  __shared__ unsigned int s_epoch;
+  if (threadIdx.x == 0) {
+    const unsigned int epoch = a.ctrl[0] + 1u;
+    s_epoch = epoch;
+    if (blockIdx.x == 0) {
+      // my backward kernels precede this kernel in stream order: their writes are
+      // complete; make them visible system-wide, then publish the epoch to every rank
+      __threadfence_system();
+      for (int q = 0; q < a.world; ++q) st_release_sys(a.flags[q] + a.rank, epoch);
+    }
+  }
+  __syncthreads();
+  const unsigned int epoch = s_epoch;
+  if (threadIdx.x < a.world) {
+    const unsigned int* mine = a.flags[a.rank] + threadIdx.x;
+    while ((int)(ld_acquire_sys(mine) - epoch) < 0) { /* spin: peers are at most one update behind */ }
+  }
+  __syncthreads();
+
+  const int64_t n4 = count / 4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  auto upd = [&](float& pp, float gg, float& mm, float& vv) {
+    gg *= gscale;
+    mm = mm + (gg - mm) * one_minus_b1;
+    vv = vv * b2 + one_minus_b2 * gg * gg;
+    const float denom = sqrtf(vv) * inv_bc2_sqrt + eps;
+    pp = pp - step_size * (mm / denom);
+  };
+  float4* p4 = reinterpret_cast<float4*>(p);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  for (int64_t i = t0; i < n4; i += stride) {
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < kMaxPeers; ++q) {
+      if (q < a.world) {
+        const float4 t = __ldcv(reinterpret_cast<const float4*>(a.grads[q]) + i);
+        g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+      }
+    }
+    float4 pp = p4[i], mm = m4[i], vv = v4[i];
+    upd(pp.x, g.x, mm.x, vv.x);
+    upd(pp.y, g.y, mm.y, vv.y);
+    upd(pp.z, g.z, mm.z, vv.z);
+    upd(pp.w, g.w, mm.w, vv.w);
+    p4[i] = pp; m4[i] = mm; v4[i] = vv;
+  }
+  for (int64_t i = n4 * 4 + t0; i < count; i += stride) {
+    float g = 0.f;
+    for (int q = 0; q < a.world; ++q) g += __ldcv(a.grads[q] + i);
+    upd(p[i], g, m[i], v[i]);
+  }
+
+  // the last block to finish advances the epoch for the next update
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int done = atomicAdd(a.ctrl + 1, 1u);
+    if (done == gridDim.x - 1) {
+      a.ctrl[1] = 0u;
+      __threadfence();
+      a.ctrl[0] = epoch;
+    }
+  }
+}
+
+}  // namespace bsig
+
+using namespace bsig;
+
+extern "C" int bsig_p2p_alloc(void** ptr, int64_t bytes, unsigned char* handle64) {
+  BSIG_REQUIRE(ptr != nullptr && handle64 != nullptr && bytes > 0, "p2p_alloc: bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* p = nullptr;
+  BSIG_CUDA(cudaMalloc(&p, (size_t)bytes));
+  BSIG_CUDA(cudaMemset(p, 0, (size_t)bytes));
+  BSIG_CUDA(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  BSIG_CUDA(cudaIpcGetMemHandle(&h, p));
+  memcpy(handle64, &h, 64);
+  *ptr = p;
+  return 0;
+}
+
+extern "C" int bsig_p2p_open(const unsigned char* handle64, void** ptr) {
+  BSIG_REQUIRE(ptr != nullptr && handle64 != nullptr, "p2p_open: bad arguments");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  BSIG_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+extern "C" int bsig_p2p_close(void* ptr) {
+  BSIG_CUDA(cudaIpcCloseMemHandle(ptr));
+  return 0;
+}
+
+extern "C" int bsig_p2p_free(void* ptr) {
+  BSIG_CUDA(cudaFree(ptr));
+  return 0;
+}
+
+extern "C" int bsig_adam_allreduce_step(float* param, const void* const* peer_grads,
+                                        void* const* peer_flags, void* ctrl, int rank, int world,
+                                        float* exp_avg, float* exp_avg_sq, int64_t count,
+                                        int64_t step, float lr, float beta1, float beta2, float eps,
+                                        void* stream) {
+  BSIG_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world,
+               "adam_allreduce: world must be 1..%d", kMaxPeers);
+  BSIG_REQUIRE(count >= 1 && step >= 1, "adam_allreduce: bad count/step");
+  P2PArgs a;
+  for (int q = 0; q < kMaxPeers; ++q) {
+    a.grads[q] = q < world ? (const float*)peer_grads[q] : nullptr;
+    a.flags[q] = q < world ? (unsigned int*)peer_flags[q] : nullptr;
+  }
+  a.ctrl = (unsigned int*)ctrl;
+  a.rank = rank;
+  a.world = world;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr / bc1);
+  const float inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+  // every block must be resident at once (blocks spin on the peers' flags)
+  const int blocks =
+      (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(count / 4 + 1, 256), sm_count()));
+  adam_allreduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      a, param, exp_avg, exp_avg_sq, count, 1.0f - beta1, beta2, 1.0f - beta2, step_size,
+      inv_bc2_sqrt, eps, 1.0f / (float)world);
+  BSIG_LAUNCH_CHECK();
+  return 0;
+}

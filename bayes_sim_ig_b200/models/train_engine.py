@@ -79,6 +79,9 @@ class TrainPlan(object):
         self.dz = torch.empty((batch, nh), **f32)
         self.dh = [torch.empty((batch, w), **f32) for w in widths]
         self.grads = torch.zeros_like(model.flat_params)
+        # data parallel on <= 8 GPUs with a small model: gradients live in peer-mapped
+        # buffers and the exchange is fused into the Adam kernel (csrc/p2p.cu)
+        self.p2p = data_parallel.p2p_comm_for(model)
         self.exp_avg = torch.zeros_like(model.flat_params)
         self.exp_avg_sq = torch.zeros_like(model.flat_params)
         lib = _lib.load()
@@ -102,21 +105,23 @@ class TrainPlan(object):
         self.graph = None
 
     # ------------------------------------------------------------- kernel sequence
-    def _views(self):
+    def _views(self, gbase=None):
+        """Per-layer weight / bias tensors and the DEVICE POINTERS of their gradients
+        inside the flat gradient buffer that starts at ``gbase``."""
         m = self.model
-        flat, g = m.flat_params, self.grads
+        flat = m.flat_params
+        gbase = self.grads.data_ptr() if gbase is None else gbase
         out, off = [], 0
         for lin in m._trunk_layers():
             nw, nb = lin.weight.numel(), lin.bias.numel()
             out.append(dict(w=flat[off:off + nw], b=flat[off + nw:off + nw + nb],
-                            dw=g[off:off + nw], db=g[off + nw:off + nw + nb],
+                            dw=gbase + 4 * off, db=gbase + 4 * (off + nw),
                             n=lin.weight.shape[0], k=lin.weight.shape[1]))
             off += nw + nb
         nhw = m.n_head * m.head_in
         head = dict(w=flat[m._head_w_off:m._head_w_off + nhw],
                     b=flat[m._head_b_off:m._head_b_off + m.n_head],
-                    dw=g[m._head_w_off:m._head_w_off + nhw],
-                    db=g[m._head_b_off:m._head_b_off + m.n_head],
+                    dw=gbase + 4 * m._head_w_off, db=gbase + 4 * m._head_b_off,
                     n=m.n_head, k=m.head_in)
         return out, head
 
@@ -150,7 +155,7 @@ class TrainPlan(object):
         wsp, wsn = self.ws_gemm.data_ptr(), self.ws_gemm.numel()
         b, p, k = self.batch, self.p, self.k
         rows = self.idx[step]
-        layers, head = self._views()
+        layers, head = self._views(self.p2p.local_grads(step) if self.p2p is not None else None)
         slot = self.logs.index(step) if step in self.logs else None
         n_log = len(self.logs)
         loss_ptr = self.loss_buf.data_ptr() + 4 * (slot if slot is not None else 2 * n_log)
@@ -171,7 +176,7 @@ class TrainPlan(object):
             else:
                 stream = st
             _lib.call('bsig_linear_wgrad', dy.data_ptr(), xin.data_ptr(), xld, xrows,
-                      lay['dw'].data_ptr(), lay['db'].data_ptr(), b, n_out, k_in, eng, wsp, wsn,
+                      lay['dw'], lay['db'], b, n_out, k_in, eng, wsp, wsn,
                       stream)
 
         wgrad(self.dz, hin, hin_ld, hin_rows, head, head['n'], head['k'])
@@ -202,9 +207,13 @@ class TrainPlan(object):
         slot = self.logs.index(step) if step in self.logs else None
         n_log = len(self.logs)
         world = data_parallel.world_of(m)
-        _lib.call('bsig_adam_step', m.flat_params.data_ptr(), self.grads.data_ptr(),
-                  self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), m.flat_params.numel(),
-                  step + 1, float(m.lr), 0.9, 0.999, 1e-8, 1.0 / world, st)
+        if self.p2p is not None:
+            # one kernel: all-reduce over NVLink peer memory (1/world folded in) + Adam
+            self.p2p.adam_allreduce(m, self.exp_avg, self.exp_avg_sq, step, step + 1, st)
+        else:
+            _lib.call('bsig_adam_step', m.flat_params.data_ptr(), self.grads.data_ptr(),
+                      self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), m.flat_params.numel(),
+                      step + 1, float(m.lr), 0.9, 0.999, 1e-8, 1.0 / world, st)
         if slot is not None and self.n_test > 0:
             self._forward(self.te, self.x_test, None, self.n_test, st)
             _lib.call('bsig_mdn_nll_fused', self.te['z'].data_ptr(),
@@ -314,7 +323,10 @@ def run_training_captured(model, x_data, y_data, n_updates, batch_size, test_fra
         plan.flag.zero_()
         if n_test == 0:
             plan.loss_buf.fill_(float('nan'))
-        if use_graph and dp:
+        if dp and plan.p2p is not None:
+            # all ranks must have retired the previous call before gradient buffer 0 is reused
+            torch.distributed.barrier(group=getattr(model, '_dp_group', None))
+        if use_graph and dp and plan.p2p is None:
             if getattr(plan, 'dp_graphs', None) is None:
                 before = _lib.load().bsig_launch_count()
                 plan.capture_dp()
@@ -334,7 +346,8 @@ def run_training_captured(model, x_data, y_data, n_updates, batch_size, test_fra
             st = _lib.stream_ptr(dev)
             for step in range(plan.n_updates):
                 plan._enqueue_step(step, st)
-                data_parallel.allreduce_gradients(model, plan.grads)
+                if plan.p2p is None:
+                    data_parallel.allreduce_gradients(model, plan.grads)
                 plan._enqueue_update(step, st)
         n_log = len(plan.logs)
         host = torch.cat([plan.loss_buf[:2 * n_log], plan.flag.float()]).cpu().numpy()

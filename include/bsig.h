@@ -173,6 +173,21 @@ int bsig_mdn_nll_fused(const float* z, const float* noise, const float* y,
 int bsig_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                    int64_t count, int64_t step, float lr, float beta1, float beta2,
                    float eps, float grad_scale, void* stream);
+/* Data-parallel exchange fused with the optimiser (no counterpart in the single-process
+ * reference; the exchange step of SURVEY 8.e): one-shot all-reduce of the flat gradient
+ * buffer over NVLink peer memory + Adam in ONE kernel.  peer_grads / peer_flags are HOST
+ * arrays of `world` device pointers (this rank's own buffers at index `rank`, the others
+ * opened from IPC handles); ctrl is this rank's 2-word control block.  All buffers come
+ * from bsig_p2p_alloc (zero-initialised).  Graph-capturable and replayable: the epoch
+ * that orders the ranks lives in device memory and is advanced by the kernel. */
+int bsig_p2p_alloc(void** ptr, int64_t bytes, unsigned char* handle64);   /* host call */
+int bsig_p2p_open(const unsigned char* handle64, void** ptr);             /* host call */
+int bsig_p2p_close(void* ptr);
+int bsig_p2p_free(void* ptr);
+int bsig_adam_allreduce_step(float* param, const void* const* peer_grads,
+                             void* const* peer_flags, void* ctrl, int rank, int world,
+                             float* exp_avg, float* exp_avg_sq, int64_t count, int64_t step,
+                             float lr, float beta1, float beta2, float eps, void* stream);
 /* out[i,:] = src[rows[i],:]  (x_train[ids], mdnn.py:222) */
 int bsig_gather_rows(const float* src, int64_t ld_src, const int64_t* rows, float* out,
                      int64_t n_rows, int64_t width, void* stream);

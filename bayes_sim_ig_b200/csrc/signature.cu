@@ -15,6 +15,7 @@
 // finished levels are staged in shared memory and leave with coalesced stores.
 // ~2C^3 flop per step against 4(L(D+A) + C + C^2 + C^3) bytes per trajectory:
 // HBM-bound for small C, FFMA-bound around C = 22.
+#include "async_copy.cuh"
 #include "common.cuh"
 
 namespace bsig {
@@ -28,6 +29,8 @@ struct SigArgs {
   int L, D, A, C;
   int tpb;          // trajectories per CTA
   int64_t siglen;
+  int bulk;         // small-C kernel: tiles may travel by cp.async.bulk
+  int raw_stride;   // small-C kernel: floats per raw-rollout buffer
 };
 
 __device__ __forceinline__ void load_paths(const SigArgs& p, float* xs, int64_t traj0, int ntraj) {
@@ -107,62 +110,171 @@ __device__ __forceinline__ void store_staged(const SigArgs& p, const float* stag
 
 // Small channel counts (C <= 8; Pendulum C=5, Cartpole C=6): one thread owns row i
 // of every level -- S1[i], S2[i,:], S3[i,:,:] (C*C registers) -- so a step is
-// C*C + 2C FFMAs against three shared-memory loads.
+// C*C + 2C FFMAs.  Persistent CTAs walk tiles of `tpb` trajectories:
+//   * the raw rollouts of a tile are contiguous in HBM ([tpb][L*D], [tpb][L*A]) and
+//     arrive by cp.async.bulk into a double buffer (tile it+2 is in flight while
+//     tile it is being computed) -- no load instructions, no exposed latency;
+//   * increments are formed on the fly from the raw rows (per-channel shared-memory
+//     cursors), so there is no separate differencing pass;
+//   * the finished levels are staged densely in shared memory and leave as ONE bulk
+//     store per tile, which overlaps the next tile's recursion.
+// Tiles that cannot use bulk copies (strided rollouts, misaligned pointers, a ragged
+// last tile) take plain cooperative loads / stores through the same buffers.
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
 template <int C>
-__global__ void __launch_bounds__(256, 4) signature3_small_kernel(SigArgs p) {
+__global__ void __launch_bounds__(256, (C >= 7 ? 2 : 3)) signature3_small_kernel(SigArgs p) {
   extern __shared__ __align__(16) float smem[];
-  constexpr int CPAD = 8;
-  const int steps = p.L - 1;
-  const int tstride = steps * CPAD + 8;                 // +8: spreads trajectories over banks
-  // shared memory: [ increments | raw rollouts ] during the recursion, then the same
-  // bytes are reused as the output staging buffer (halves the footprint -> more CTAs/SM)
-  float* ds = smem;                                     // [tpb][tstride]
-  float* raw = smem + (size_t)p.tpb * tstride;          // [tpb][L*(D+A)]
-  float* stage = smem;                                  // [tpb][siglen], after the recursion
-  const int64_t traj0 = (int64_t)blockIdx.x * p.tpb;
-  const int ntraj = (int)min((int64_t)p.tpb, p.n - traj0);
-  load_increments<CPAD>(p, ds, tstride, raw, traj0, ntraj);
+  __shared__ __align__(8) uint64_t full[2];
+  const int tid = threadIdx.x;
+  const int L = p.L, D = p.D, A = p.A, LD = L * D, LA = L * A;
+  const int steps = L - 1, tpb = p.tpb;
+  auto rawb = [&](int b) { return smem + (size_t)b * p.raw_stride; };   // each [tpb][L*D] | [tpb][L*A]
+  float* stage = smem + 2 * (size_t)p.raw_stride;        // [tpb][siglen]
+  const int64_t ntiles = (p.n + tpb - 1) / tpb;
+  const int tl = tid / C, i = tid - tl * C;
+
+  auto tile_rows = [&](int64_t tile) { return (int)min((int64_t)tpb, p.n - tile * tpb); };
+  auto tile_bulk = [&](int64_t tile) { return p.bulk && (tile_rows(tile) & 3) == 0; };
+  auto issue_load = [&](int64_t tile, int b) {            // one thread
+    const int64_t traj0 = tile * tpb;
+    const uint32_t bs = (uint32_t)tile_rows(tile) * LD * 4, ba = (uint32_t)tile_rows(tile) * LA * 4;
+    ac::mbar_expect_tx(&full[b], bs + ba);
+    ac::bulk_g2s(rawb(b), p.states + traj0 * LD, bs, &full[b]);
+    if (ba) ac::bulk_g2s(rawb(b) + (size_t)tpb * LD, p.actions + traj0 * LA, ba, &full[b]);
+  };
+
+  if (tid == 0) {
+    ac::mbar_init(&full[0], 1);
+    ac::mbar_init(&full[1], 1);
+    ac::fence_barrier_init();
+    int64_t t0 = blockIdx.x, t1 = (int64_t)blockIdx.x + gridDim.x;
+    if (t0 < ntiles && tile_bulk(t0)) issue_load(t0, 0);
+    if (t1 < ntiles && tile_bulk(t1)) issue_load(t1, 1);
+  }
   __syncthreads();
-  const int tl = threadIdx.x / C, i = threadIdx.x - tl * C;
-  float s1 = 0.f, s2[C], s3[C][C];
-#pragma unroll
-  for (int j = 0; j < C; ++j) {
-    s2[j] = 0.f;
-#pragma unroll
-    for (int k = 0; k < C; ++k) s3[j][k] = 0.f;
-  }
-  if (tl < ntraj) {
-    const float* d = ds + tl * tstride;
-    for (int t = 0; t < steps; ++t) {
-      const float4 lo = *reinterpret_cast<const float4*>(d + t * CPAD);
-      const float4 hi = *reinterpret_cast<const float4*>(d + t * CPAD + 4);
-      const float dv[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-      const float di = d[t * CPAD + i];
-      const float a3 = (s1 + di * (1.0f / 3.0f)) * 0.5f;
-      const float a2 = s1 + di * 0.5f;
-#pragma unroll
-      for (int j = 0; j < C; ++j) {
-        const float t2 = fmaf(a3, dv[j], s2[j]);
-#pragma unroll
-        for (int k = 0; k < C; ++k) s3[j][k] = fmaf(t2, dv[k], s3[j][k]);
-        s2[j] = fmaf(a2, dv[j], s2[j]);
+
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int b = it & 1;
+    const int64_t traj0 = tile * tpb;
+    const int ntraj = tile_rows(tile);
+    const bool bulk = tile_bulk(tile);
+    float* raw_s = rawb(b);
+    float* raw_a = rawb(b) + (size_t)tpb * LD;
+    if (bulk) {
+      ac::mbar_wait(&full[b], (uint32_t)(it >> 1) & 1u);
+    } else {
+      for (int e = tid; e < ntraj * LD; e += blockDim.x) {
+        const int r = e / LD, c = e - r * LD;
+        raw_s[e] = __ldg(p.states + (traj0 + r) * p.s_stride + c);
       }
-      s1 += di;
+      for (int e = tid; e < ntraj * LA; e += blockDim.x) {
+        const int r = e / LA, c = e - r * LA;
+        raw_a[e] = __ldg(p.actions + (traj0 + r) * p.a_stride + c);
+      }
+      __syncthreads();
     }
-  }
-  __syncthreads();                                      // everyone is done reading ds
-  if (tl < ntraj) {
-    float* o = stage + (size_t)tl * p.siglen;
-    o[i] = s1;
+
+    float s1 = 0.f, s2[C], s3[C][C];
 #pragma unroll
     for (int j = 0; j < C; ++j) {
-      o[C + i * C + j] = s2[j];
+      s2[j] = 0.f;
 #pragma unroll
-      for (int k = 0; k < C; ++k) o[C + C * C + (i * C + j) * C + k] = s3[j][k];
+      for (int k = 0; k < C; ++k) s3[j][k] = 0.f;
+    }
+    const bool active = tl < ntraj;
+    if (active) {
+      // shared-memory cursor (32-bit shared address) of every channel; channel 0 is
+      // the time channel, whose increment is exactly 1
+      const uint32_t base = ac::smem_u32(rawb(b));
+      const uint32_t s_off = base + 4u * (uint32_t)(tl * LD);
+      const uint32_t a_off = base + 4u * (uint32_t)(tpb * LD + tl * LA);
+      uint32_t cur[C], str[C];
+      float prev[C];
+#pragma unroll
+      for (int c = 1; c < C; ++c) {
+        const bool is_s = c <= D;
+        cur[c] = is_s ? s_off + 4u * (c - 1) : a_off + 4u * (c - 1 - D);
+        str[c] = 4u * (uint32_t)(is_s ? D : A);
+        prev[c] = lds_f32(cur[c]);
+      }
+      const bool own_s = i <= D;
+      uint32_t ocur = (i == 0) ? s_off : (own_s ? s_off + 4u * (i - 1) : a_off + 4u * (i - 1 - D));
+      const uint32_t ostr = (i == 0) ? 0u : 4u * (uint32_t)(own_s ? D : A);
+      float oprev = lds_f32(ocur);
+      for (int t = 0; t < steps; ++t) {
+        float dv[C];
+        dv[0] = 1.0f;
+#pragma unroll
+        for (int c = 1; c < C; ++c) {
+          cur[c] += str[c];
+          const float x = lds_f32(cur[c]);
+          dv[c] = x - prev[c];
+          prev[c] = x;
+        }
+        ocur += ostr;
+        const float ox = lds_f32(ocur);
+        const float di = (i == 0) ? 1.0f : ox - oprev;
+        oprev = ox;
+        const float a3 = (s1 + di * (1.0f / 3.0f)) * 0.5f;
+        const float a2 = s1 + di * 0.5f;
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+          const float t2 = fmaf(a3, dv[j], s2[j]);
+#pragma unroll
+          for (int k = 0; k < C; ++k) s3[j][k] = fmaf(t2, dv[k], s3[j][k]);
+          s2[j] = fmaf(a2, dv[j], s2[j]);
+        }
+        s1 += di;
+      }
+    }
+    // the previous tile's bulk store must have finished reading `stage`
+    if (tid == 0) ac::bulk_wait_read<0>();
+    __syncthreads();                       // + everyone is done reading rawb(b)
+    if (tid == 0) {
+      const int64_t nxt = tile + 2 * (int64_t)gridDim.x;
+      if (nxt < ntiles && tile_bulk(nxt)) issue_load(nxt, b);
+    }
+    if (active) {
+      float* o = stage + (size_t)tl * p.siglen;
+      o[i] = s1;
+      if ((C & 1) == 0) {                  // even C: every block below starts at an even offset
+        float2* o2 = reinterpret_cast<float2*>(o + C + i * C);
+#pragma unroll
+        for (int j = 0; j < C / 2; ++j) o2[j] = make_float2(s2[2 * j], s2[2 * j + 1]);
+        float2* o3 = reinterpret_cast<float2*>(o + C + C * C + i * C * C);
+#pragma unroll
+        for (int j = 0; j < C; ++j)
+#pragma unroll
+          for (int k = 0; k < C / 2; ++k) o3[j * (C / 2) + k] = make_float2(s3[j][2 * k], s3[j][2 * k + 1]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+          o[C + i * C + j] = s2[j];
+#pragma unroll
+          for (int k = 0; k < C; ++k) o[C + C * C + (i * C + j) * C + k] = s3[j][k];
+        }
+      }
+    }
+    if (bulk) {
+      ac::fence_proxy_async();
+      __syncthreads();
+      if (tid == 0) {
+        ac::bulk_s2g(p.out + traj0 * p.siglen, stage, (uint32_t)ntraj * (uint32_t)p.siglen * 4u);
+        ac::bulk_commit();
+      }
+    } else {
+      __syncthreads();
+      store_staged(p, stage, traj0, ntraj);
+      __syncthreads();
     }
   }
-  __syncthreads();
-  store_staged(p, stage, traj0, ntraj);
+  if (tid == 0) ac::bulk_wait_read<0>();   // shared memory stays valid until the last store has read it
 }
 
 // 9 <= C <= 22 (depth 3 stops at C = 22): one thread owns one (i,j) pair --
@@ -263,20 +375,30 @@ extern "C" int bsig_signature_fwd(const float* states, const float* actions, flo
     BSIG_REQUIRE(C <= 22, "signature: depth 3 supports at most 22 channels (got %d)", (int)C);
     const int64_t steps = len - 1;
     if (C <= 8) {
-      int tpb = 256 / (int)C;
-      // staging buffer doubles as the raw-rollout buffer of load_increments
-      const int64_t per_traj = std::max<int64_t>(steps * 8 + 8 + len * (d + a), p.siglen) * 4;
-      tpb = (int)std::max<int64_t>(1, std::min<int64_t>(tpb, (100 * 1024) / per_traj));
-      if (tpb > 1) tpb &= ~1;               // even -> CTA bases stay 16B aligned (siglen even)
+      // shared memory per trajectory: two raw-rollout buffers + the staged signature;
+      // ~73 KB per CTA keeps three persistent CTAs on an SM (two for C >= 7, whose
+      // C*C accumulators need more than 80 registers)
+      const int ctas_per_sm = C >= 7 ? 2 : 3;
+      const int64_t budget = (C >= 7 ? 110 : 73) * 1024;
+      const int64_t per_traj = (2 * len * (d + a) + p.siglen) * 4;
+      BSIG_REQUIRE(per_traj <= 200 * 1024, "signature: path too long for shared memory");
+      int tpb = (int)std::min<int64_t>(256 / C, std::max<int64_t>(budget / per_traj, 1));
+      if (tpb >= 4) tpb &= ~3;              // multiples of 4 keep every tile 16-byte aligned
       p.tpb = tpb;
-      const size_t smem = (size_t)tpb * per_traj;
-      const unsigned grid = (unsigned)ceil_div(n, tpb);
+      p.raw_stride = (int)((tpb * len * (d + a) + 3) & ~(int64_t)3);
+      auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+      p.bulk = (tpb % 4 == 0) && t_states == len && (a == 0 || t_actions == len) &&
+               al16(states) && (a == 0 || al16(actions)) && al16(out);
+      const size_t smem = (size_t)(2 * p.raw_stride + tpb * p.siglen) * 4;
+      const int threads = (int)(ceil_div((int64_t)tpb * C, 32) * 32);
+      const unsigned grid =
+          (unsigned)std::min<int64_t>(ceil_div(n, tpb), ctas_per_sm * (int64_t)sm_count());
 #define BSIG_SIGS(CV)                                                                        \
   case CV:                                                                                   \
     if (smem > 48 * 1024)                                                                    \
       BSIG_CUDA(cudaFuncSetAttribute(signature3_small_kernel<CV>,                            \
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    signature3_small_kernel<CV><<<grid, 256, smem, st>>>(p);                                 \
+    signature3_small_kernel<CV><<<grid, threads, smem, st>>>(p);                             \
     break;
       switch ((int)C) {
         BSIG_SIGS(2) BSIG_SIGS(3) BSIG_SIGS(4) BSIG_SIGS(5) BSIG_SIGS(6) BSIG_SIGS(7) BSIG_SIGS(8)

@@ -115,6 +115,39 @@ def test_signature_vs_float64_oracle(shape):
         off += w
 
 
+@pytest.mark.parametrize('shape', [(70001, 21, 4, 1), (50003, 21, 3, 1), (20000, 8, 5, 2),
+                                   (33333, 6, 1, 0)])
+def test_signature_persistent_bulk_tiles(shape):
+    """Many tiles per persistent CTA (cp.async.bulk double buffer, mbarrier phase
+    wrap-around, ragged last tile): same tolerance against the float64 oracle, and
+    rows must not depend on the tiling (bit-identical to small ragged launches)."""
+    from bayes_sim_ig.utils import summarizers as S
+    n, t1, d, a = shape
+    s, ac = synth_rollouts(11, n, t1, d, max(a, 1))
+    s = s * 0.3
+    if a == 0:
+        ac = ac[:, :, :0]
+    sd, ad = s.to(DEV), ac.to(DEV)
+    got_t = S.summary_signatory(sd, ad)
+    got = got_t.cpu().numpy()
+    ref = osum.summary_signatory(s.numpy(), ac.numpy()).astype(np.float64)
+    assert got.shape == ref.shape
+    c = 1 + d + a
+    off = 0
+    for lvl in range(1, osum.signature_depth(c) + 1):
+        w = c ** lvl
+        assert rel_err(got[:, off:off + w], ref[:, off:off + w]) < 2e-5, lvl
+        off += w
+    for lo, hi in ((0, 7), (n // 2 + 1, n // 2 + 4), (n - 5, n)):
+        part = S.summary_signatory(sd[lo:hi], ad[lo:hi])
+        assert torch.equal(part, got_t[lo:hi]), (lo, hi)
+    # actions stored with more steps than the path uses (strided rows -> plain loads)
+    if a > 0:
+        longer = torch.cat([ad, ad[:, :3]], 1)[:4099].contiguous()
+        part = S.summary_signatory(sd[:4099], longer)
+        assert torch.equal(part, got_t[:4099])
+
+
 def test_signature_chen_identity_on_device():
     """Concatenating two paths multiplies their signatures (level 2 check) --
     a property test that needs no oracle."""

@@ -18,6 +18,10 @@
 // loss, the eps-term gradient) is two-stage and fixed-order => deterministic.
 #include <cooperative_groups.h>
 
+#include <algorithm>
+#include <cstdlib>
+
+#include "async_copy.cuh"
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -118,7 +122,27 @@ __device__ __forceinline__ float group_max(float v) {
 // Per-sample work shared by the grid-wide and the single-cluster kernels.
 // Groups of GW lanes own samples base+gid for base = first, first+stride, ...
 // TS = threads per CTA (stride of the per-thread z/v vectors in shared memory).
-template <int GW, int KPL, bool FUSED, bool FULL, bool BWD>
+// Operand load of the per-sample routines: read-only global path, or a plain load when
+// the operands were staged in shared memory (nll_stream_kernel).
+template <bool SM>
+__device__ __forceinline__ float ldf(const float* p) {
+  if (SM) return *p;
+  return __ldg(p);
+}
+
+// Transcendentals / division of the per-sample routines.  The shared-memory staged
+// streaming kernel (SM) is instruction-issue bound, so it uses the SFU forms
+// (ex2.approx / lg2.approx / rcp.approx: <= 2 ulp, i.e. ~2e-7 relative, two orders below
+// the 1e-5 parity tolerance); the minibatch kernels keep the full-precision functions.
+// In the SM form the per-element finite checks are dropped: a non-finite mu / L_d entry
+// always reaches the component's log-density, which is checked.
+template <bool SM> __device__ __forceinline__ float xexp(float x) { return SM ? __expf(x) : expf(x); }
+template <bool SM> __device__ __forceinline__ float xlog(float x) { return SM ? __logf(x) : logf(x); }
+template <bool SM> __device__ __forceinline__ float xdiv(float a, float b) {
+  return SM ? __fdividef(a, b) : a / b;
+}
+
+template <int GW, int KPL, bool FUSED, bool FULL, bool BWD, bool SM = false>
 __device__ __forceinline__ void nll_samples(const NllArgs& a, const float eps,
                                             const float coef_scale, const int first,
                                             const int stride, const int TS, float* zs, float* vs,
@@ -145,14 +169,14 @@ __device__ __forceinline__ void nll_samples(const NllArgs& a, const float eps,
 #pragma unroll
       for (int j = 0; j < KPL; ++j) {
         const int k = lane_g + j * GW;
-        soft[j] = (row_ok && k < K) ? __ldg(a.z_pi + bb * a.ld_pi + k) : -INFINITY;
+        soft[j] = (row_ok && k < K) ? ldf<SM>(a.z_pi + bb * a.ld_pi + k) : -INFINITY;
         mx = fmaxf(mx, soft[j]);
       }
       mx = group_max<GW>(mx);
       float sm = 0.f;
 #pragma unroll
       for (int j = 0; j < KPL; ++j) {
-        soft[j] = (soft[j] == -INFINITY) ? 0.f : expf(soft[j] - mx);
+        soft[j] = (soft[j] == -INFINITY) ? 0.f : xexp<SM>(soft[j] - mx);
         sm += soft[j];
       }
       sm = group_sum<GW>(sm);
@@ -160,18 +184,18 @@ __device__ __forceinline__ void nll_samples(const NllArgs& a, const float eps,
 #pragma unroll
       for (int j = 0; j < KPL; ++j) {
         const int k = lane_g + j * GW;
-        soft[j] = soft[j] / sm;
+        soft[j] = xdiv<SM>(soft[j], sm);
         w[j] = (k < K) ? fminf(fmaxf(soft[j], kMinWeight), 1.0f) : 0.f;  // clamped
         cs += w[j];
       }
       csum = group_sum<GW>(cs);
 #pragma unroll
-      for (int j = 0; j < KPL; ++j) w[j] = w[j] / csum;
+      for (int j = 0; j < KPL; ++j) w[j] = xdiv<SM>(w[j], csum);
     } else {
 #pragma unroll
       for (int j = 0; j < KPL; ++j) {
         const int k = lane_g + j * GW;
-        w[j] = (row_ok && k < K) ? __ldg(a.z_pi + bb * a.ld_pi + k) : 0.f;
+        w[j] = (row_ok && k < K) ? ldf<SM>(a.z_pi + bb * a.ld_pi + k) : 0.f;
         soft[j] = 0.f;
       }
     }
@@ -194,35 +218,35 @@ __device__ __forceinline__ void nll_samples(const NllArgs& a, const float eps,
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const int i = min(i0 + u, P - 1);
-              zv[u] = __ldg(zd_r + i * K + k);
-              mv[u] = __ldg(mu_r + i * K + k);
-              nv[u] = FUSED ? __ldg(nz_r + i * K + k) : 0.f;
-              yv[u] = __ldg(yrow + i);
+              zv[u] = ldf<SM>(zd_r + i * K + k);
+              mv[u] = ldf<SM>(mu_r + i * K + k);
+              nv[u] = FUSED ? ldf<SM>(nz_r + i * K + k) : 0.f;
+              yv[u] = ldf<SM>(yrow + i);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               if (i0 + u < P) {
-                const float ldv = FUSED ? expf(zv[u]) + nv[u] * eps : zv[u];
-                const float zi = (yv[u] - mv[u]) / ldv;
+                const float ldv = FUSED ? xexp<SM>(zv[u]) + nv[u] * eps : zv[u];
+                const float zi = xdiv<SM>(yv[u] - mv[u], ldv);
                 quad += zi * zi;
-                logdet += logf(ldv);
-                bad |= !(finite_f(ldv) && finite_f(mv[u]));
+                logdet += xlog<SM>(ldv);
+                if (!SM) bad |= !(finite_f(ldv) && finite_f(mv[u]));
               }
             }
           }
         } else {
           for (int i = 0; i < P; ++i) {
-            float ldv = __ldg(zd_r + i * K + k);
-            if (FUSED) ldv = expf(ldv) + __ldg(nz_r + i * K + k) * eps;
-            const float m = __ldg(mu_r + i * K + k);
-            float acc = __ldg(yrow + i) - m;
+            float ldv = ldf<SM>(zd_r + i * K + k);
+            if (FUSED) ldv = xexp<SM>(ldv) + ldf<SM>(nz_r + i * K + k) * eps;
+            const float m = ldf<SM>(mu_r + i * K + k);
+            float acc = ldf<SM>(yrow + i) - m;
             const float* lrow = low_r + (int64_t)(i * (i - 1) / 2) * K + k;
-            for (int c = 0; c < i; ++c) acc -= __ldg(lrow + c * K) * zs[c * TS];
-            const float zi = acc / ldv;
+            for (int c = 0; c < i; ++c) acc -= ldf<SM>(lrow + c * K) * zs[c * TS];
+            const float zi = xdiv<SM>(acc, ldv);
             zs[i * TS] = zi;
             quad += zi * zi;
-            logdet += logf(ldv);
-            bad |= !(finite_f(ldv) && finite_f(m));
+            logdet += xlog<SM>(ldv);
+            if (!SM) bad |= !(finite_f(ldv) && finite_f(m));
           }
         }
         const float gj = -0.5f * ((float)P * kLog2Pi + quad) - logdet;
@@ -230,16 +254,16 @@ __device__ __forceinline__ void nll_samples(const NllArgs& a, const float eps,
         g[j] = gj;
         const float gc = fminf(fmaxf(gj, -kLLLimit), kLLLimit);
         const float wc = fminf(fmaxf(w[j], kMinWeight), 1.0f);
-        r[j] = gc + logf(wc);
+        r[j] = gc + xlog<SM>(wc);
         mx = fmaxf(mx, r[j]);
       }
     }
     mx = group_max<GW>(mx);
     float se = 0.f;
 #pragma unroll
-    for (int j = 0; j < KPL; ++j) se += (r[j] == -INFINITY) ? 0.f : expf(r[j] - mx);
+    for (int j = 0; j < KPL; ++j) se += (r[j] == -INFINITY) ? 0.f : xexp<SM>(r[j] - mx);
     se = group_sum<GW>(se);
-    const float lse = mx + logf(se);
+    const float lse = mx + xlog<SM>(se);
     if (row_ok && lane_g == 0) loss_acc -= lse;
 
     if (BWD) {
@@ -252,11 +276,11 @@ __device__ __forceinline__ void nll_samples(const NllArgs& a, const float eps,
         dw[j] = 0.f;
         coef[j] = 0.f;
         if (row_ok && k < K) {
-          const float rho = expf(r[j] - lse);
+          const float rho = xexp<SM>(r[j] - lse);
           coef[j] = -rho * coef_scale;                // d loss / d r_k
           const float wc = fminf(fmaxf(w[j], kMinWeight), 1.0f);
           const bool in_w = (w[j] >= kMinWeight) && (w[j] <= 1.0f);
-          dw[j] = in_w ? coef[j] / wc : 0.f;
+          dw[j] = in_w ? xdiv<SM>(coef[j], wc) : 0.f;
           t1 += dw[j] * w[j];
         }
       }
@@ -265,7 +289,7 @@ __device__ __forceinline__ void nll_samples(const NllArgs& a, const float eps,
         float dp[KPL], t2 = 0.f;
 #pragma unroll
         for (int j = 0; j < KPL; ++j) {
-          const float dc = (dw[j] - t1) / csum;
+          const float dc = xdiv<SM>(dw[j] - t1, csum);
           const bool in_c = (soft[j] >= kMinWeight) && (soft[j] <= 1.0f);
           dp[j] = in_c ? dc : 0.f;
           t2 += dp[j] * soft[j];
@@ -299,18 +323,18 @@ __device__ __forceinline__ void nll_samples(const NllArgs& a, const float eps,
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const int i = min(i0 + u, P - 1);
-              zv[u] = __ldg(zd_r + i * K + k);
-              mv[u] = __ldg(mu_r + i * K + k);
-              nv[u] = FUSED ? __ldg(nz_r + i * K + k) : 0.f;
-              yv[u] = __ldg(yrow + i);
+              zv[u] = ldf<SM>(zd_r + i * K + k);
+              mv[u] = ldf<SM>(mu_r + i * K + k);
+              nv[u] = FUSED ? ldf<SM>(nz_r + i * K + k) : 0.f;
+              yv[u] = ldf<SM>(yrow + i);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const int i = i0 + u;
               if (i < P) {
-                const float e = FUSED ? expf(zv[u]) : zv[u];
+                const float e = FUSED ? xexp<SM>(zv[u]) : zv[u];
                 const float ldv = FUSED ? e + nv[u] * eps : zv[u];
-                const float inv = 1.0f / ldv;
+                const float inv = xdiv<SM>(1.0f, ldv);
                 const float zi = (yv[u] - mv[u]) * inv;
                 const float vi = zi * inv;
                 const float dld = cg * (vi * zi - inv);
@@ -329,30 +353,30 @@ __device__ __forceinline__ void nll_samples(const NllArgs& a, const float eps,
           if (KPL > 1) {
             // zs holds the LAST component's solve: redo the forward substitution
             for (int i = 0; i < P; ++i) {
-              float ldv = __ldg(zd_r + i * K + k);
-              if (FUSED) ldv = expf(ldv) + __ldg(nz_r + i * K + k) * eps;
-              float acc = __ldg(yrow + i) - __ldg(mu_r + i * K + k);
+              float ldv = ldf<SM>(zd_r + i * K + k);
+              if (FUSED) ldv = xexp<SM>(ldv) + ldf<SM>(nz_r + i * K + k) * eps;
+              float acc = ldf<SM>(yrow + i) - ldf<SM>(mu_r + i * K + k);
               const float* lrow = low_r + (int64_t)(i * (i - 1) / 2) * K + k;
-              for (int c = 0; c < i; ++c) acc -= __ldg(lrow + c * K) * zs[c * TS];
-              zs[i * TS] = acc / ldv;
+              for (int c = 0; c < i; ++c) acc -= ldf<SM>(lrow + c * K) * zs[c * TS];
+              zs[i * TS] = xdiv<SM>(acc, ldv);
             }
           }
           // back substitution v = L^-T z, rows descending
           for (int i = P - 1; i >= 0; --i) {
-            const float raw = __ldg(zd_r + i * K + k);
+            const float raw = ldf<SM>(zd_r + i * K + k);
             float e = raw, ldv = raw, nz = 0.f;
             if (FUSED) {
-              e = expf(raw);
-              nz = __ldg(nz_r + i * K + k);
+              e = xexp<SM>(raw);
+              nz = ldf<SM>(nz_r + i * K + k);
               ldv = e + nz * eps;
             }
             float acc = zs[i * TS];
             for (int c = i + 1; c < P; ++c)
-              acc -= __ldg(low_r + (int64_t)(c * (c - 1) / 2 + i) * K + k) * vs[c * TS];
-            const float vi = acc / ldv;
+              acc -= ldf<SM>(low_r + (int64_t)(c * (c - 1) / 2 + i) * K + k) * vs[c * TS];
+            const float vi = xdiv<SM>(acc, ldv);
             vs[i * TS] = vi;
             const float zi = zs[i * TS];
-            const float dld = cg * (vi * zi - 1.0f / ldv);
+            const float dld = cg * (vi * zi - xdiv<SM>(1.0f, ldv));
             dmu_r[i * K + k] = cg * vi;
             if (FUSED) {
               s_acc += dld * nz;
@@ -422,6 +446,184 @@ __global__ void __launch_bounds__(128) nll_kernel(NllArgs a) {
     if (tid == 0) {
       a.loss[0] = acc / (float)B;
       *counter = 0u;   // ready for the next launch
+    }
+  }
+}
+
+// Large-batch streaming form of the fused head + NLL (forward, or forward + backward):
+// persistent CTAs walk tiles of R consecutive samples.  A tile of z ([R, NH]) and of the
+// eps-noise ([R, P*K]) is contiguous in HBM and arrives with cp.async.bulk into a double
+// buffer (tile it+2 in flight while tile it is computed); the per-sample routine runs
+// entirely out of shared memory (conflict-free: lane k of a sample reads column
+// i*K + k); dz is staged in shared memory and leaves as ONE bulk store per tile that
+// overlaps the next tile.  HBM sees only full-line bulk traffic, the SM's load/store
+// pipes only shared memory.  y rows (optionally gathered through y_rows) are fetched
+// with plain loads one tile ahead.  The ragged last tile (rows % 4 != 0) takes plain
+// cooperative loads / stores through the same buffers.
+struct NllStream {
+  const float* z;       // [B, NH]
+  float* dz;            // [B, NH] (BWD)
+  int NH, R;            // row width, rows per tile (multiple of 4)
+};
+
+template <int GW, int KPL, bool FULL, bool BWD>
+__global__ void __launch_bounds__(256) nll_stream_kernel(NllArgs a, NllStream q) {
+  extern __shared__ __align__(16) float dyn[];
+  __shared__ float scratch[33];
+  __shared__ __align__(8) uint64_t full[2];
+  __shared__ bool is_last;
+  const int tid = threadIdx.x, TS = blockDim.x;
+  const int B = a.B, P = a.P, K = a.K, PK = P * K, NH = q.NH, R = q.R;
+  constexpr int GPB = 256 / GW;
+  // shared memory: z[2][R*NH] | noise[2][R*PK] | y[2][R*P (padded to 4)] | dz[R*NH] | zs,vs
+  const int ypad = (R * P + 3) & ~3;
+  float* zb = dyn;
+  float* nb = zb + 2 * (size_t)R * NH;
+  float* yb = nb + 2 * (size_t)R * PK;
+  float* dzb = yb + 2 * (size_t)ypad;
+  float* fs = dzb + (BWD ? (size_t)R * NH : 0);
+  float* zs = fs + tid;
+  float* vs = fs + (size_t)P * TS + tid;
+
+  const float esum = sum_parts(a.ws, a.nparts_e, scratch);
+  const float eps = kEpsNoise * (esum / (float)((int64_t)B * PK));
+  const float coef_scale = 1.0f / (float)B;
+  const int64_t ntiles = ((int64_t)B + R - 1) / R;
+  auto tile_rows = [&](int64_t tile) { return (int)min((int64_t)R, (int64_t)B - tile * R); };
+  auto issue_load = [&](int64_t tile, int b) {            // one thread; rows % 4 == 0
+    const uint32_t rows = (uint32_t)tile_rows(tile);
+    ac::mbar_expect_tx(&full[b], rows * (uint32_t)(NH + PK) * 4u);
+    ac::bulk_g2s(zb + (size_t)b * R * NH, q.z + tile * R * (int64_t)NH, rows * NH * 4u, &full[b]);
+    ac::bulk_g2s(nb + (size_t)b * R * PK, a.noise + tile * R * (int64_t)PK, rows * PK * 4u,
+                 &full[b]);
+  };
+  auto load_y = [&](int64_t tile, int b) {                // all threads
+    const int rows = tile_rows(tile);
+    for (int e = tid; e < rows * P; e += TS) {
+      const int r = e / P, c = e - r * P;
+      const int64_t row = tile * R + r;
+      yb[(size_t)b * ypad + e] = __ldg(a.y + (a.y_rows ? __ldg(a.y_rows + row) : row) * P + c);
+    }
+  };
+
+  if (tid == 0) {
+    ac::mbar_init(&full[0], 1);
+    ac::mbar_init(&full[1], 1);
+    ac::fence_barrier_init();
+    const int64_t t0 = blockIdx.x, t1 = (int64_t)blockIdx.x + gridDim.x;
+    if (t0 < ntiles && (tile_rows(t0) & 3) == 0) issue_load(t0, 0);
+    if (t1 < ntiles && (tile_rows(t1) & 3) == 0) issue_load(t1, 1);
+  }
+  if ((int64_t)blockIdx.x < ntiles) load_y(blockIdx.x, 0);
+  __syncthreads();
+
+  float loss_acc = 0.f, s_acc = 0.f;
+  bool bad = false;
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int b = it & 1;
+    const int rows = tile_rows(tile);
+    const bool bulk = (rows & 3) == 0;
+    float* zt = zb + (size_t)b * R * NH;
+    float* nt = nb + (size_t)b * R * PK;
+    if (bulk) {
+      ac::mbar_wait(&full[b], (uint32_t)(it >> 1) & 1u);
+    } else {
+      const float* zg = q.z + tile * R * (int64_t)NH;
+      const float* ng = a.noise + tile * R * (int64_t)PK;
+      for (int e = tid; e < rows * NH; e += TS) zt[e] = __ldg(zg + e);
+      for (int e = tid; e < rows * PK; e += TS) nt[e] = __ldg(ng + e);
+      __syncthreads();
+    }
+    // y rows of the next tile: the loads stay in flight (in registers) during this
+    // tile's arithmetic and are parked in shared memory afterwards
+    const int64_t nxt1 = tile + gridDim.x;
+    const bool y_regs = R * P <= 2 * TS;
+    float yreg[2] = {0.f, 0.f};
+    if (nxt1 < ntiles && y_regs) {
+      const int rows_n = tile_rows(nxt1);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int e = tid + u * TS;
+        if (e < rows_n * P) {
+          const int r = e / P, c = e - r * P;
+          const int64_t row = nxt1 * R + r;
+          yreg[u] = __ldg(a.y + (a.y_rows ? __ldg(a.y_rows + row) : row) * P + c);
+        }
+      }
+    }
+
+    NllArgs t = a;
+    t.B = rows;
+    t.z_pi = zt; t.ld_pi = NH;
+    t.mu = zt + K; t.ld_mu = NH;
+    t.zd = zt + K + PK; t.ld_zd = NH;
+    t.low = FULL ? zt + K + 2 * PK : nullptr; t.ld_low = NH;
+    t.noise = nt;
+    t.y = yb + (size_t)b * ypad; t.y_rows = nullptr;
+    if (BWD) {
+      t.d_pi = dzb; t.ldo_pi = NH;
+      t.d_mu = dzb + K; t.ldo_mu = NH;
+      t.d_zd = dzb + K + PK; t.ldo_zd = NH;
+      t.d_low = FULL ? dzb + K + 2 * PK : nullptr; t.ldo_low = NH;
+      // the previous tile's bulk store must have finished reading the dz stage
+      if (tid == 0) ac::bulk_wait_read<0>();
+      __syncthreads();
+    }
+    nll_samples<GW, KPL, true, FULL, BWD, true>(t, eps, coef_scale, 0, GPB, TS, zs, vs, loss_acc,
+                                                s_acc, bad);
+    if (nxt1 < ntiles) {
+      if (y_regs) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          if (tid + u * TS < R * P) yb[(size_t)(b ^ 1) * ypad + tid + u * TS] = yreg[u];
+      } else {
+        load_y(nxt1, b ^ 1);
+      }
+    }
+    if (BWD && bulk) ac::fence_proxy_async();
+    __syncthreads();                       // dz stage complete; z/noise/y buffers b are free
+    if (BWD) {
+      float* dzg = q.dz + tile * R * (int64_t)NH;
+      if (bulk) {
+        if (tid == 0) {
+          ac::bulk_s2g(dzg, dzb, (uint32_t)rows * (uint32_t)NH * 4u);
+          ac::bulk_commit();
+        }
+      } else {
+        for (int e = tid; e < rows * NH; e += TS) dzg[e] = dzb[e];
+      }
+    }
+    if (tid == 0) {
+      const int64_t nxt2 = tile + 2 * (int64_t)gridDim.x;
+      if (nxt2 < ntiles && (tile_rows(nxt2) & 3) == 0) issue_load(nxt2, b);
+    }
+  }
+  if (tid == 0) ac::bulk_wait_read<0>();
+  if (bad) atomicOr(a.flag, 1);
+
+  // ---- deterministic cross-block reductions (same scheme as nll_kernel)
+  float* loss_parts = a.ws + kMaxParts;
+  float* s_parts = a.ws + 2 * kMaxParts;
+  unsigned int* counter = reinterpret_cast<unsigned int*>(a.ws + 3 * kMaxParts);
+  const float lsum = block_sum(loss_acc, scratch);
+  const float ssum = BWD ? block_sum(s_acc, scratch) : 0.f;
+  if (tid == 0) {
+    loss_parts[blockIdx.x] = lsum;
+    if (BWD) s_parts[blockIdx.x] = ssum;
+    __threadfence();
+    const unsigned int done = atomicAdd(counter, 1u);
+    is_last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    float acc = 0.f;
+    for (int i = tid; i < (int)gridDim.x; i += blockDim.x) acc += __ldcg(loss_parts + i);
+    acc = block_sum(acc, scratch);
+    if (tid == 0) {
+      a.loss[0] = acc / (float)B;
+      *counter = 0u;
     }
   }
 }
@@ -919,6 +1121,72 @@ static int launch_nll_cluster(const NllArgs& a, bool bwd, cudaStream_t st) {
   return -1;
 }
 
+template <int GW, int KPL, bool FULL, bool BWD>
+static int launch_nll_stream_t(const NllArgs& a, const NllStream& q, size_t smem, int* nparts,
+                               cudaStream_t st) {
+  auto kern = nll_stream_kernel<GW, KPL, FULL, BWD>;
+  if (smem > 48 * 1024)
+    BSIG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 1;
+  BSIG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
+  const int64_t ntiles = ceil_div(a.B, q.R);
+  const int grid = (int)std::min<int64_t>(
+      std::min<int64_t>(ntiles, (int64_t)std::max(occ, 1) * sm_count()), kMaxParts);
+  kern<<<grid, 256, smem, st>>>(a, q);
+  BSIG_LAUNCH_CHECK();
+  *nparts = grid;
+  return 0;
+}
+
+template <int GW, int KPL>
+static int launch_nll_stream_gw(const NllArgs& a, const NllStream& q, bool full, bool bwd,
+                                size_t smem, int* nparts, cudaStream_t st) {
+  if (full)
+    return bwd ? launch_nll_stream_t<GW, KPL, true, true>(a, q, smem, nparts, st)
+               : launch_nll_stream_t<GW, KPL, true, false>(a, q, smem, nparts, st);
+  return bwd ? launch_nll_stream_t<GW, KPL, false, true>(a, q, smem, nparts, st)
+             : launch_nll_stream_t<GW, KPL, false, false>(a, q, smem, nparts, st);
+}
+
+// Streaming (bulk-copy staged) form of the fused NLL for batches beyond one cluster.
+// Returns 0 if launched (*nparts = number of S partials), -1 if not applicable.
+static int launch_nll_stream(const NllArgs& a, const float* z, float* dz, int64_t NH, bool bwd,
+                             int* nparts, cudaStream_t st) {
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (!al16(z) || !al16(a.noise) || (bwd && !al16(dz))) return -1;
+  const int K = a.K, P = a.P;
+  if (K < 1 || K > 128 || P < 1 || P > 192) return -1;
+  const bool full = a.L > 0;
+  int gw = 1;
+  while (gw < K && gw < 32) gw <<= 1;
+  const int gpb = 256 / gw;
+  const int64_t PK = (int64_t)P * K;
+  const int64_t per_row = (2 * (NH + PK) + 2 * P + (bwd ? NH : 0)) * 4;
+  const int64_t fixed = (full ? 2 * (int64_t)P * 256 * 4 : 0) + 64;
+  int r = 0;
+  for (int64_t budget : {72 * 1024, 110 * 1024, 220 * 1024}) {
+    r = (int)std::min<int64_t>((budget - fixed) / per_row, 4 * gpb);
+    if (r >= gpb) r = (r / gpb) * gpb;
+    r &= ~3;
+    if (r >= std::min(gpb, 8)) break;
+  }
+  if (r < 4) return -1;
+  NllStream q;
+  q.z = z; q.dz = dz; q.NH = (int)NH; q.R = r;
+  const size_t smem = (size_t)r * per_row + (size_t)fixed;
+  switch (gw) {
+    case 1: return launch_nll_stream_gw<1, 1>(a, q, full, bwd, smem, nparts, st);
+    case 2: return launch_nll_stream_gw<2, 1>(a, q, full, bwd, smem, nparts, st);
+    case 4: return launch_nll_stream_gw<4, 1>(a, q, full, bwd, smem, nparts, st);
+    case 8: return launch_nll_stream_gw<8, 1>(a, q, full, bwd, smem, nparts, st);
+    case 16: return launch_nll_stream_gw<16, 1>(a, q, full, bwd, smem, nparts, st);
+    default:
+      if (K <= 32) return launch_nll_stream_gw<32, 1>(a, q, full, bwd, smem, nparts, st);
+      if (K <= 64) return launch_nll_stream_gw<32, 2>(a, q, full, bwd, smem, nparts, st);
+      return launch_nll_stream_gw<32, 4>(a, q, full, bwd, smem, nparts, st);
+  }
+}
+
 static int launch_exp_sum(const float* zd, int64_t ld_zd, int B, int PK, float* ws,
                           cudaStream_t st, int* nparts) {
   const int64_t total = (int64_t)B * PK;
@@ -1053,11 +1321,17 @@ extern "C" int bsig_mdn_nll_fused(const float* z, const float* noise, const floa
     if (rc >= 0) return rc;
   }
   if (launch_exp_sum(a.zd, NH, (int)b, (int)PK, (float*)ws, st, &a.nparts_e)) return 1;
-  if (launch_nll(a, true, bwd, st)) return 1;
-  if (bwd) {
+  int nparts = 0;
+  const bool no_stream = getenv("BSIG_NLL_NO_STREAM") != nullptr;     // A/B switch (profiling)
+  int rc = no_stream ? -1 : launch_nll_stream(a, z, dz, NH, bwd, &nparts, st);
+  if (rc > 0) return rc;
+  if (rc < 0) {
+    if (launch_nll(a, true, bwd, st)) return 1;
     int gw = 1;
     while (gw < k && gw < 32) gw <<= 1;
-    const int nparts = (int)std::min<int64_t>(ceil_div(b, 128 / gw), kMaxParts);
+    nparts = (int)std::min<int64_t>(ceil_div(b, 128 / gw), kMaxParts);
+  }
+  if (bwd) {
     const int grid = (int)std::min<int64_t>(ceil_div(b * PK, 256), (int64_t)sm_count() * 8);
     eps_fixup_kernel<<<grid, 256, 0, st>>>(a.zd, NH, a.d_zd, NH, (int)b, (int)PK,
                                            (float*)ws + 2 * kMaxParts, nparts);

@@ -15,6 +15,9 @@
 // finished levels are staged in shared memory and leave with coalesced stores.
 // ~2C^3 flop per step against 4(L(D+A) + C + C^2 + C^3) bytes per trajectory:
 // HBM-bound for small C, FFMA-bound around C = 22.
+#include <algorithm>
+#include <cstdlib>
+
 #include "async_copy.cuh"
 #include "common.cuh"
 
@@ -133,6 +136,7 @@ __global__ void __launch_bounds__(256, (C >= 7 ? 2 : 3)) signature3_small_kernel
   const int tid = threadIdx.x;
   const int L = p.L, D = p.D, A = p.A, LD = L * D, LA = L * A;
   const int steps = L - 1, tpb = p.tpb;
+  constexpr int CP = (C + 1) / 2;                          // packed pairs per level-3 row
   auto rawb = [&](int b) { return smem + (size_t)b * p.raw_stride; };   // each [tpb][L*D] | [tpb][L*A]
   float* stage = smem + 2 * (size_t)p.raw_stride;        // [tpb][siglen]
   const int64_t ntiles = (p.n + tpb - 1) / tpb;
@@ -180,12 +184,15 @@ __global__ void __launch_bounds__(256, (C >= 7 ? 2 : 3)) signature3_small_kernel
       __syncthreads();
     }
 
-    float s1 = 0.f, s2[C], s3[C][C];
+    // level-3 rows are kept as packed pairs (k, k+1) and updated with FFMA2 (two fp32
+    // FMAs per issued instruction, same rounding as fmaf); odd C pads each row by one
+    float s1 = 0.f, s2[C];
+    float2 s3[C][CP];
 #pragma unroll
     for (int j = 0; j < C; ++j) {
       s2[j] = 0.f;
 #pragma unroll
-      for (int k = 0; k < C; ++k) s3[j][k] = 0.f;
+      for (int k = 0; k < CP; ++k) s3[j][k] = make_float2(0.f, 0.f);
     }
     const bool active = tl < ntraj;
     if (active) {
@@ -194,26 +201,27 @@ __global__ void __launch_bounds__(256, (C >= 7 ? 2 : 3)) signature3_small_kernel
       const uint32_t base = ac::smem_u32(rawb(b));
       const uint32_t s_off = base + 4u * (uint32_t)(tl * LD);
       const uint32_t a_off = base + 4u * (uint32_t)(tpb * LD + tl * LA);
-      uint32_t cur[C], str[C];
+      // all state channels share one cursor, all action channels another (shifted by
+      // -4D so that channel c sits at offset 4(c-1) from either)
+      uint32_t s_cur = s_off, a_cur = a_off - 4u * (uint32_t)D;
+      const uint32_t s_str = 4u * (uint32_t)D, a_str = 4u * (uint32_t)A;
       float prev[C];
 #pragma unroll
-      for (int c = 1; c < C; ++c) {
-        const bool is_s = c <= D;
-        cur[c] = is_s ? s_off + 4u * (c - 1) : a_off + 4u * (c - 1 - D);
-        str[c] = 4u * (uint32_t)(is_s ? D : A);
-        prev[c] = lds_f32(cur[c]);
-      }
+      for (int c = 1; c < C; ++c) prev[c] = lds_f32((c <= D ? s_cur : a_cur) + 4u * (c - 1));
       const bool own_s = i <= D;
       uint32_t ocur = (i == 0) ? s_off : (own_s ? s_off + 4u * (i - 1) : a_off + 4u * (i - 1 - D));
-      const uint32_t ostr = (i == 0) ? 0u : 4u * (uint32_t)(own_s ? D : A);
+      const uint32_t ostr = (i == 0) ? 0u : (own_s ? s_str : a_str);
       float oprev = lds_f32(ocur);
+#pragma unroll 2
       for (int t = 0; t < steps; ++t) {
-        float dv[C];
+        float dv[2 * CP];
         dv[0] = 1.0f;
+        dv[2 * CP - 1] = 0.f;                 // pad lane of odd C
+        s_cur += s_str;
+        a_cur += a_str;
 #pragma unroll
         for (int c = 1; c < C; ++c) {
-          cur[c] += str[c];
-          const float x = lds_f32(cur[c]);
+          const float x = lds_f32((c <= D ? s_cur : a_cur) + 4u * (c - 1));
           dv[c] = x - prev[c];
           prev[c] = x;
         }
@@ -226,8 +234,10 @@ __global__ void __launch_bounds__(256, (C >= 7 ? 2 : 3)) signature3_small_kernel
 #pragma unroll
         for (int j = 0; j < C; ++j) {
           const float t2 = fmaf(a3, dv[j], s2[j]);
+          const float2 t22 = make_float2(t2, t2);
 #pragma unroll
-          for (int k = 0; k < C; ++k) s3[j][k] = fmaf(t2, dv[k], s3[j][k]);
+          for (int k = 0; k < CP; ++k)
+            s3[j][k] = __ffma2_rn(t22, make_float2(dv[2 * k], dv[2 * k + 1]), s3[j][k]);
           s2[j] = fmaf(a2, dv[j], s2[j]);
         }
         s1 += di;
@@ -251,13 +261,14 @@ __global__ void __launch_bounds__(256, (C >= 7 ? 2 : 3)) signature3_small_kernel
 #pragma unroll
         for (int j = 0; j < C; ++j)
 #pragma unroll
-          for (int k = 0; k < C / 2; ++k) o3[j * (C / 2) + k] = make_float2(s3[j][2 * k], s3[j][2 * k + 1]);
+          for (int k = 0; k < CP; ++k) o3[j * CP + k] = s3[j][k];
       } else {
 #pragma unroll
         for (int j = 0; j < C; ++j) {
           o[C + i * C + j] = s2[j];
 #pragma unroll
-          for (int k = 0; k < C; ++k) o[C + C * C + (i * C + j) * C + k] = s3[j][k];
+          for (int k = 0; k < C; ++k)
+            o[C + C * C + (i * C + j) * C + k] = (k & 1) ? s3[j][k / 2].y : s3[j][k / 2].x;
         }
       }
     }
@@ -377,12 +388,13 @@ extern "C" int bsig_signature_fwd(const float* states, const float* actions, flo
     if (C <= 8) {
       // shared memory per trajectory: two raw-rollout buffers + the staged signature;
       // ~73 KB per CTA keeps three persistent CTAs on an SM (two for C >= 7, whose
-      // C*C accumulators need more than 80 registers)
-      const int ctas_per_sm = C >= 7 ? 2 : 3;
+      // C*C accumulators need more than 80 registers); the grid is exactly the number
+      // of co-resident CTAs
       const int64_t budget = (C >= 7 ? 110 : 73) * 1024;
       const int64_t per_traj = (2 * len * (d + a) + p.siglen) * 4;
       BSIG_REQUIRE(per_traj <= 200 * 1024, "signature: path too long for shared memory");
       int tpb = (int)std::min<int64_t>(256 / C, std::max<int64_t>(budget / per_traj, 1));
+      if (const char* e = getenv("BSIG_SIG_TPB")) tpb = std::max(1, std::min(tpb, atoi(e)));
       if (tpb >= 4) tpb &= ~3;              // multiples of 4 keep every tile 16-byte aligned
       p.tpb = tpb;
       p.raw_stride = (int)((tpb * len * (d + a) + 3) & ~(int64_t)3);
@@ -391,15 +403,19 @@ extern "C" int bsig_signature_fwd(const float* states, const float* actions, flo
                al16(states) && (a == 0 || al16(actions)) && al16(out);
       const size_t smem = (size_t)(2 * p.raw_stride + tpb * p.siglen) * 4;
       const int threads = (int)(ceil_div((int64_t)tpb * C, 32) * 32);
-      const unsigned grid =
-          (unsigned)std::min<int64_t>(ceil_div(n, tpb), ctas_per_sm * (int64_t)sm_count());
+      const int64_t ntiles = ceil_div(n, tpb);
 #define BSIG_SIGS(CV)                                                                        \
-  case CV:                                                                                   \
+  case CV: {                                                                                 \
     if (smem > 48 * 1024)                                                                    \
       BSIG_CUDA(cudaFuncSetAttribute(signature3_small_kernel<CV>,                            \
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    int occ = 1;                                                                             \
+    BSIG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, signature3_small_kernel<CV>, \
+                                                            threads, smem));                 \
+    const unsigned grid =                                                                    \
+        (unsigned)std::min<int64_t>(ntiles, std::max(occ, 1) * (int64_t)sm_count());         \
     signature3_small_kernel<CV><<<grid, threads, smem, st>>>(p);                             \
-    break;
+  } break;
       switch ((int)C) {
         BSIG_SIGS(2) BSIG_SIGS(3) BSIG_SIGS(4) BSIG_SIGS(5) BSIG_SIGS(6) BSIG_SIGS(7) BSIG_SIGS(8)
       }

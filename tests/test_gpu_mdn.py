@@ -176,11 +176,14 @@ def test_nll_component_counts_vs_oracle(k):
 
 
 @pytest.mark.parametrize('cfg', [(3000, 13, 10, False), (700, 2, 4, False), (5000, 37, 10, False),
-                                 (3000, 4, 3, True), (300, 13, 10, False), (260, 5, 32, False)])
+                                 (3000, 4, 3, True), (300, 13, 10, False), (260, 5, 32, False),
+                                 (30001, 13, 10, False), (5003, 13, 10, True), (4000, 3, 40, False),
+                                 (9001, 2, 70, True), (2050, 37, 10, True)])
 def test_fused_head_nll_kernels_at_every_batch_regime(cfg):
-    """bsig_mdn_nll_fused picks a register-resident cluster kernel (minibatch), an
-    element-parallel kernel (large diagonal batches) or the group-per-sample kernel
-    (full covariance): all against the float64 oracle, loss and d loss / d z."""
+    """bsig_mdn_nll_fused picks a register-resident cluster kernel (minibatch), the
+    persistent bulk-copy staged streaming kernel (large batches; many tiles per CTA,
+    ragged last tile, K > 32) or the plain group-per-sample kernel (rows too wide
+    for shared memory): all against the float64 oracle, loss and d loss / d z."""
     from bayes_sim_ig_b200 import _lib
     b, p, k, full = cfg
     rs = np.random.RandomState(b + p)
@@ -216,3 +219,42 @@ def test_fused_head_nll_kernels_at_every_batch_regime(cfg):
               loss2.data_ptr(), None, b, p, k, 1 if full else 0, ws.data_ptr(), ws.numel(),
               flag.data_ptr(), _lib.stream_ptr(DEV))
     assert abs(loss2.item() - ref_loss) <= 1e-5 * abs(ref_loss)
+
+
+def test_streaming_nll_without_gather_and_with_misaligned_rows():
+    """y given in batch order (no row gather), and a z / dz pair that is only 4-byte
+    aligned (bulk copies impossible -> plain kernel): identical results."""
+    from bayes_sim_ig_b200 import _lib
+    b, p, k = 6000, 13, 10
+    rs = np.random.RandomState(3)
+    nh = k * (1 + 2 * p)
+    z = (0.4 * rs.randn(b, nh)).astype(np.float32)
+    noise = rs.rand(b, p, k).astype(np.float32)
+    y = rs.rand(b, p).astype(np.float32)
+    nt, yt = torch.from_numpy(noise).to(DEV), torch.from_numpy(y).to(DEV)
+    ws = torch.zeros(_lib.load().bsig_mdn_ws_bytes(b), dtype=torch.uint8, device=DEV)
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    outs = []
+    for shift in (0, 1):
+        zbuf = torch.zeros(b * nh + 4, device=DEV)
+        dzbuf = torch.zeros(b * nh + 4, device=DEV)
+        zt = zbuf[shift:shift + b * nh].view(b, nh)
+        zt.copy_(torch.from_numpy(z))
+        dz = dzbuf[shift:shift + b * nh].view(b, nh)
+        loss = torch.zeros(1, device=DEV)
+        _lib.call('bsig_mdn_nll_fused', zt.data_ptr(), nt.data_ptr(), yt.data_ptr(), None,
+                  loss.data_ptr(), dz.data_ptr(), b, p, k, 0, ws.data_ptr(), ws.numel(),
+                  flag.data_ptr(), _lib.stream_ptr(DEV))
+        outs.append((loss.item(), dz.clone()))
+    z64 = z.astype(np.float64)
+    pk = p * k
+    w, mu, ld, low, cache = mdn_np.head_epilogue(z64[:, :k], z64[:, k:k + pk], z64[:, k + pk:], None,
+                                                 noise, p, k)
+    ref_loss, d_w, d_mu, d_ld, d_low = mdn_np.mdn_loss_backward(w, mu, ld, low, y.astype(np.float64))
+    d_zpi, d_zmu, d_zd, _ = mdn_np.head_epilogue_backward(cache, w, d_w, d_mu, d_ld, d_low)
+    ref_dz = np.concatenate([d_zpi, d_zmu, d_zd], axis=1)
+    for loss, dz in outs:
+        assert abs(loss - ref_loss) <= 1e-5 * abs(ref_loss)
+        assert rel_err(dz.cpu(), ref_dz) < GRAD_RTOL
+    # same per-sample formulas in both kernels (SFU vs full-precision transcendentals)
+    assert rel_err(outs[0][1].cpu(), outs[1][1].cpu()) < 1e-5

@@ -142,19 +142,74 @@ template <bool SM> __device__ __forceinline__ float xdiv(float a, float b) {
   return SM ? __fdividef(a, b) : a / b;
 }
 
+// Lanes that own one sample.  GW > 0: aligned groups of GW (power of two) lanes, xor
+// butterflies.  GW == 0 (one component per lane, K <= 32): groups of exactly K lanes
+// packed floor(32 / K) to a warp -- no padding lanes for K = 10 -- reduced with cyclic
+// rotations: window sums of width 1, 2, 4, ... are combined along the binary digits of
+// K, then lane 0's total is broadcast so that every lane of the group holds the same bits.
+template <int GW>
+struct LaneGroup {
+  int lane_g, gid;
+  bool active;
+  __device__ __forceinline__ LaneGroup(int tid, int) : lane_g(tid & (GW - 1)), gid(tid / GW),
+                                                       active(true) {}
+  __device__ __forceinline__ float sum(float v) const { return group_sum<GW>(v); }
+  __device__ __forceinline__ float max(float v) const { return group_max<GW>(v); }
+  static __device__ __forceinline__ int per_cta(int threads, int) { return threads / GW; }
+};
+template <>
+struct LaneGroup<0> {
+  int lane_g, gid, K, base;
+  bool active;
+  __device__ __forceinline__ LaneGroup(int tid, int k) : K(k) {
+    const int lane = tid & 31, rpw = 32 / k, gi = lane / k;
+    lane_g = lane - gi * k;
+    active = gi < rpw;
+    gid = (tid >> 5) * rpw + gi;
+    base = lane - lane_g;
+  }
+  // lane holding element (lane_g + j) mod K of this group, 0 <= j < K; idle lanes: self
+  __device__ __forceinline__ int rot(int j) const {
+    int t = lane_g + j;
+    if (t >= K) t -= K;
+    return active ? base + t : base + lane_g;
+  }
+  __device__ __forceinline__ float sum(float v) const {
+    float w = v, tot = 0.f;
+    int off = 0;
+    for (int width = 1; width <= K; width <<= 1) {
+      if (K & width) {
+        tot = off ? tot + __shfl_sync(0xffffffffu, w, rot(off)) : w;
+        off += width;
+      }
+      if (2 * width <= K) w += __shfl_sync(0xffffffffu, w, rot(width));
+    }
+    return __shfl_sync(0xffffffffu, tot, base);
+  }
+  __device__ __forceinline__ float max(float v) const {
+    for (int width = 1; width < K; width <<= 1)
+      v = fmaxf(v, __shfl_sync(0xffffffffu, v, rot(width)));
+    return v;
+  }
+  static __device__ __forceinline__ int per_cta(int threads, int k) {
+    return (threads >> 5) * (32 / k);
+  }
+};
+
 template <int GW, int KPL, bool FUSED, bool FULL, bool BWD, bool SM = false>
 __device__ __forceinline__ void nll_samples(const NllArgs& a, const float eps,
                                             const float coef_scale, const int first,
                                             const int stride, const int TS, float* zs, float* vs,
                                             float& loss_acc, float& s_acc, bool& bad) {
   const int tid = threadIdx.x;
-  const int lane_g = tid & (GW - 1);
-  const int gid = tid / GW;
+  const LaneGroup<GW> grp(tid, a.K);
+  const int lane_g = grp.lane_g;
+  const int gid = grp.gid;
   const int B = a.B, P = a.P, K = a.K;
 
   for (int base = first; base < B; base += stride) {
     const int b = base + gid;
-    const bool row_ok = b < B;
+    const bool row_ok = (b < B) && grp.active;
     const int64_t bb = row_ok ? b : 0;
     const float* yrow = a.y + (a.y_rows ? __ldg(a.y_rows + bb) : bb) * P;
     const float* mu_r = a.mu + bb * a.ld_mu;
@@ -172,14 +227,14 @@ __device__ __forceinline__ void nll_samples(const NllArgs& a, const float eps,
         soft[j] = (row_ok && k < K) ? ldf<SM>(a.z_pi + bb * a.ld_pi + k) : -INFINITY;
         mx = fmaxf(mx, soft[j]);
       }
-      mx = group_max<GW>(mx);
+      mx = grp.max(mx);
       float sm = 0.f;
 #pragma unroll
       for (int j = 0; j < KPL; ++j) {
         soft[j] = (soft[j] == -INFINITY) ? 0.f : xexp<SM>(soft[j] - mx);
         sm += soft[j];
       }
-      sm = group_sum<GW>(sm);
+      sm = grp.sum(sm);
       float cs = 0.f;
 #pragma unroll
       for (int j = 0; j < KPL; ++j) {
@@ -188,7 +243,7 @@ __device__ __forceinline__ void nll_samples(const NllArgs& a, const float eps,
         w[j] = (k < K) ? fminf(fmaxf(soft[j], kMinWeight), 1.0f) : 0.f;  // clamped
         cs += w[j];
       }
-      csum = group_sum<GW>(cs);
+      csum = grp.sum(cs);
 #pragma unroll
       for (int j = 0; j < KPL; ++j) w[j] = xdiv<SM>(w[j], csum);
     } else {
@@ -210,7 +265,20 @@ __device__ __forceinline__ void nll_samples(const NllArgs& a, const float eps,
       g[j] = 0.f;
       if (row_ok && k < K) {
         float quad = 0.f, logdet = 0.f;
-        if (!FULL) {
+        if (!FULL && SM) {
+          // staged operands: plain strided walk (column k, stride K) -- the compiler
+          // strength-reduces the addresses to one add per operand and element
+          const float* pz = zd_r + k;
+          const float* pm = mu_r + k;
+          const float* pn = nz_r + k;
+#pragma unroll 4
+          for (int i = 0; i < P; ++i) {
+            const float ldv = xexp<SM>(pz[i * K]) + pn[i * K] * eps;
+            const float zi = xdiv<SM>(yrow[i] - pm[i * K], ldv);
+            quad = fmaf(zi, zi, quad);
+            logdet += xlog<SM>(ldv);
+          }
+        } else if (!FULL) {
           // diagonal covariance: no dependence between rows -> issue the loads of
           // four rows together (memory-level parallelism; the batch is latency-bound)
           for (int i0 = 0; i0 < P; i0 += 4) {
@@ -258,11 +326,11 @@ __device__ __forceinline__ void nll_samples(const NllArgs& a, const float eps,
         mx = fmaxf(mx, r[j]);
       }
     }
-    mx = group_max<GW>(mx);
+    mx = grp.max(mx);
     float se = 0.f;
 #pragma unroll
     for (int j = 0; j < KPL; ++j) se += (r[j] == -INFINITY) ? 0.f : xexp<SM>(r[j] - mx);
-    se = group_sum<GW>(se);
+    se = grp.sum(se);
     const float lse = mx + xlog<SM>(se);
     if (row_ok && lane_g == 0) loss_acc -= lse;
 
@@ -285,7 +353,7 @@ __device__ __forceinline__ void nll_samples(const NllArgs& a, const float eps,
         }
       }
       if (FUSED) {
-        t1 = group_sum<GW>(t1);
+        t1 = grp.sum(t1);
         float dp[KPL], t2 = 0.f;
 #pragma unroll
         for (int j = 0; j < KPL; ++j) {
@@ -294,7 +362,7 @@ __device__ __forceinline__ void nll_samples(const NllArgs& a, const float eps,
           dp[j] = in_c ? dc : 0.f;
           t2 += dp[j] * soft[j];
         }
-        t2 = group_sum<GW>(t2);
+        t2 = grp.sum(t2);
 #pragma unroll
         for (int j = 0; j < KPL; ++j) {
           const int k = lane_g + j * GW;
@@ -317,7 +385,25 @@ __device__ __forceinline__ void nll_samples(const NllArgs& a, const float eps,
         const float cg = in_g ? coef[j] : 0.f;
         float* dmu_r = a.d_mu + bb * a.ldo_mu;
         float* dzd_r = a.d_zd + bb * a.ldo_zd;
-        if (!FULL) {
+        if (!FULL && SM) {
+          const float* pz = zd_r + k;
+          const float* pm = mu_r + k;
+          const float* pn = nz_r + k;
+          float* qm = dmu_r + k;
+          float* qz = dzd_r + k;
+#pragma unroll 4
+          for (int i = 0; i < P; ++i) {
+            const float nv = pn[i * K];
+            const float e = xexp<SM>(pz[i * K]);
+            const float inv = xdiv<SM>(1.0f, fmaf(nv, eps, e));
+            const float zi = (yrow[i] - pm[i * K]) * inv;
+            const float vi = zi * inv;
+            const float dld = cg * fmaf(vi, zi, -inv);
+            qm[i * K] = cg * vi;
+            s_acc = fmaf(dld, nv, s_acc);
+            qz[i * K] = e * dld;
+          }
+        } else if (!FULL) {
           for (int i0 = 0; i0 < P; i0 += 4) {
             float zv[4], mv[4], nv[4], yv[4];
 #pragma unroll
@@ -451,15 +537,20 @@ __global__ void __launch_bounds__(128) nll_kernel(NllArgs a) {
 }
 
 // Large-batch streaming form of the fused head + NLL (forward, or forward + backward):
-// persistent CTAs walk tiles of R consecutive samples.  A tile of z ([R, NH]) and of the
-// eps-noise ([R, P*K]) is contiguous in HBM and arrives with cp.async.bulk into a double
-// buffer (tile it+2 in flight while tile it is computed); the per-sample routine runs
-// entirely out of shared memory (conflict-free: lane k of a sample reads column
-// i*K + k); dz is staged in shared memory and leaves as ONE bulk store per tile that
-// overlaps the next tile.  HBM sees only full-line bulk traffic, the SM's load/store
-// pipes only shared memory.  y rows (optionally gathered through y_rows) are fetched
-// with plain loads one tile ahead.  The ragged last tile (rows % 4 != 0) takes plain
-// cooperative loads / stores through the same buffers.
+// persistent, warp-specialised CTAs walk tiles of R consecutive samples.
+//   producer warp : per tile, one cp.async.bulk of the z tile ([R, NH], contiguous in
+//                   HBM) and one of the eps-noise tile ([R, P*K]) into a double buffer
+//                   (completion on an mbarrier), the (optionally gathered) y rows with
+//                   plain loads, and -- once the consumers have finished a tile -- ONE
+//                   bulk store of its dz back to HBM;
+//   consumer warps: the per-sample routine, entirely out of shared memory (lane k of a
+//                   sample reads column i*K + k: conflict-free), synchronised with the
+//                   producer through mbarriers only (no CTA-wide barrier in the loop).
+// With diagonal covariance dz is formed in place (a lane overwrites exactly the entries
+// of z it has read); the full-covariance back substitution re-reads strict-lower entries
+// of finished rows, so dz gets its own stage there.  HBM sees only full-line bulk
+// traffic.  A ragged last tile (rows % 4 != 0: bulk copies need 16-byte multiples) is
+// moved with plain loads / stores by the producer warp.
 struct NllStream {
   const float* z;       // [B, NH]
   float* dz;            // [B, NH] (BWD)
@@ -467,139 +558,153 @@ struct NllStream {
 };
 
 template <int GW, int KPL, bool FULL, bool BWD>
-__global__ void __launch_bounds__(256) nll_stream_kernel(NllArgs a, NllStream q) {
+__global__ void __launch_bounds__(288) nll_stream_kernel(NllArgs a, NllStream q) {
   extern __shared__ __align__(16) float dyn[];
   __shared__ float scratch[33];
-  __shared__ __align__(8) uint64_t full[2];
+  __shared__ __align__(8) uint64_t full[2], done[2];
   __shared__ bool is_last;
-  const int tid = threadIdx.x, TS = blockDim.x;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int TC = blockDim.x - 32;                 // consumer threads (warps 0 .. n-1)
+  const bool producer = tid >= TC;
   const int B = a.B, P = a.P, K = a.K, PK = P * K, NH = q.NH, R = q.R;
-  constexpr int GPB = 256 / GW;
-  // shared memory: z[2][R*NH] | noise[2][R*PK] | y[2][R*P (padded to 4)] | dz[R*NH] | zs,vs
+  const int GPB = LaneGroup<GW>::per_cta(TC, K);
+  constexpr bool STAGE = BWD && FULL;             // separate dz stage
+  // per buffer: z[R*NH] | noise[R*PK] | y[R*P padded to 4] | (dz[R*NH]);  then zs, vs
   const int ypad = (R * P + 3) & ~3;
-  float* zb = dyn;
-  float* nb = zb + 2 * (size_t)R * NH;
-  float* yb = nb + 2 * (size_t)R * PK;
-  float* dzb = yb + 2 * (size_t)ypad;
-  float* fs = dzb + (BWD ? (size_t)R * NH : 0);
+  const size_t bufsz = (size_t)R * NH + (size_t)R * PK + ypad + (STAGE ? (size_t)R * NH : 0);
+  auto zbuf = [&](int b) { return dyn + b * bufsz; };
+  auto nbuf = [&](int b) { return dyn + b * bufsz + (size_t)R * NH; };
+  auto ybuf = [&](int b) { return dyn + b * bufsz + (size_t)R * NH + (size_t)R * PK; };
+  auto dbuf = [&](int b) { return STAGE ? ybuf(b) + ypad : zbuf(b); };
+  float* fs = dyn + 2 * bufsz;
   float* zs = fs + tid;
-  float* vs = fs + (size_t)P * TS + tid;
+  float* vs = fs + (size_t)P * TC + tid;
 
   const float esum = sum_parts(a.ws, a.nparts_e, scratch);
   const float eps = kEpsNoise * (esum / (float)((int64_t)B * PK));
   const float coef_scale = 1.0f / (float)B;
   const int64_t ntiles = ((int64_t)B + R - 1) / R;
+  // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+  const int my_tiles = (int64_t)blockIdx.x < ntiles
+                           ? (int)((ntiles - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
+  auto tile_of = [&](int it) { return (int64_t)blockIdx.x + (int64_t)it * gridDim.x; };
   auto tile_rows = [&](int64_t tile) { return (int)min((int64_t)R, (int64_t)B - tile * R); };
-  auto issue_load = [&](int64_t tile, int b) {            // one thread; rows % 4 == 0
-    const uint32_t rows = (uint32_t)tile_rows(tile);
-    ac::mbar_expect_tx(&full[b], rows * (uint32_t)(NH + PK) * 4u);
-    ac::bulk_g2s(zb + (size_t)b * R * NH, q.z + tile * R * (int64_t)NH, rows * NH * 4u, &full[b]);
-    ac::bulk_g2s(nb + (size_t)b * R * PK, a.noise + tile * R * (int64_t)PK, rows * PK * 4u,
-                 &full[b]);
-  };
-  auto load_y = [&](int64_t tile, int b) {                // all threads
-    const int rows = tile_rows(tile);
-    for (int e = tid; e < rows * P; e += TS) {
-      const int r = e / P, c = e - r * P;
-      const int64_t row = tile * R + r;
-      yb[(size_t)b * ypad + e] = __ldg(a.y + (a.y_rows ? __ldg(a.y_rows + row) : row) * P + c);
-    }
-  };
 
   if (tid == 0) {
-    ac::mbar_init(&full[0], 1);
-    ac::mbar_init(&full[1], 1);
+    ac::mbar_init(&full[0], 2);                  // bulk copies (expect_tx) + y rows
+    ac::mbar_init(&full[1], 2);
+    ac::mbar_init(&done[0], TC >> 5);
+    ac::mbar_init(&done[1], TC >> 5);
     ac::fence_barrier_init();
-    const int64_t t0 = blockIdx.x, t1 = (int64_t)blockIdx.x + gridDim.x;
-    if (t0 < ntiles && (tile_rows(t0) & 3) == 0) issue_load(t0, 0);
-    if (t1 < ntiles && (tile_rows(t1) & 3) == 0) issue_load(t1, 1);
   }
-  if ((int64_t)blockIdx.x < ntiles) load_y(blockIdx.x, 0);
   __syncthreads();
 
   float loss_acc = 0.f, s_acc = 0.f;
   bool bad = false;
-  int it = 0;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-    const int b = it & 1;
-    const int rows = tile_rows(tile);
-    const bool bulk = (rows & 3) == 0;
-    float* zt = zb + (size_t)b * R * NH;
-    float* nt = nb + (size_t)b * R * PK;
-    if (bulk) {
+  if (producer) {
+    constexpr int YR = 8;                          // y values a lane keeps in flight
+    for (int it = 0; it < my_tiles + 2; ++it) {
+      const int b = it & 1;
+      // y rows of tile `it`: request them now, park them in shared memory further down
+      // (their latency hides behind the wait for the consumers)
+      float yreg[YR];
+      const bool load_tile = it < my_tiles;
+      const int64_t ltile = load_tile ? tile_of(it) : 0;
+      const int lrows = load_tile ? tile_rows(ltile) : 0;
+      const bool y_regs = R * P <= YR * 32;
+      if (load_tile && y_regs) {
+#pragma unroll
+        for (int u = 0; u < YR; ++u) {
+          const int e = lane + u * 32;
+          yreg[u] = 0.f;
+          if (e < lrows * P) {
+            const int r = e / P, c = e - r * P;
+            const int64_t row = ltile * R + r;
+            yreg[u] = __ldg(a.y + (a.y_rows ? __ldg(a.y_rows + row) : row) * P + c);
+          }
+        }
+      }
+      if (it >= 2) {
+        // retire tile it-2: consumers are done with buffer b -> write its dz back
+        const int64_t tile = tile_of(it - 2);
+        const int rows = tile_rows(tile);
+        ac::mbar_wait(&done[b], (uint32_t)((it - 2) >> 1) & 1u);
+        if (BWD) {
+          float* dzg = q.dz + tile * R * (int64_t)NH;
+          if ((rows & 3) == 0) {
+            if (lane == 0) {
+              ac::bulk_s2g(dzg, dbuf(b), (uint32_t)rows * (uint32_t)NH * 4u);
+              ac::bulk_commit();
+              ac::bulk_wait_read<0>();           // buffer b is refilled below
+            }
+          } else {
+            const float* src = dbuf(b);
+            for (int e = lane; e < rows * NH; e += 32) dzg[e] = src[e];
+          }
+          __syncwarp();
+        }
+      }
+      if (load_tile) {
+        const float* zg = q.z + ltile * R * (int64_t)NH;
+        const float* ng = a.noise + ltile * R * (int64_t)PK;
+        if ((lrows & 3) == 0) {
+          if (lane == 0) {
+            ac::mbar_expect_tx(&full[b], (uint32_t)lrows * (uint32_t)(NH + PK) * 4u);
+            ac::bulk_g2s(zbuf(b), zg, (uint32_t)lrows * NH * 4u, &full[b]);
+            ac::bulk_g2s(nbuf(b), ng, (uint32_t)lrows * PK * 4u, &full[b]);
+          }
+        } else {
+          float* zt = zbuf(b);
+          float* nt = nbuf(b);
+          for (int e = lane; e < lrows * NH; e += 32) zt[e] = __ldg(zg + e);
+          for (int e = lane; e < lrows * PK; e += 32) nt[e] = __ldg(ng + e);
+          __syncwarp();
+          if (lane == 0) ac::mbar_arrive(&full[b]);
+        }
+        float* yt = ybuf(b);
+        if (y_regs) {
+#pragma unroll
+          for (int u = 0; u < YR; ++u)
+            if (lane + u * 32 < lrows * P) yt[lane + u * 32] = yreg[u];
+        } else {
+          for (int e = lane; e < lrows * P; e += 32) {
+            const int r = e / P, c = e - r * P;
+            const int64_t row = ltile * R + r;
+            yt[e] = __ldg(a.y + (a.y_rows ? __ldg(a.y_rows + row) : row) * P + c);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) ac::mbar_arrive(&full[b]);   // second arrival: y is in place
+      }
+    }
+  } else {
+    for (int it = 0; it < my_tiles; ++it) {
+      const int b = it & 1;
+      const int rows = tile_rows(tile_of(it));
       ac::mbar_wait(&full[b], (uint32_t)(it >> 1) & 1u);
-    } else {
-      const float* zg = q.z + tile * R * (int64_t)NH;
-      const float* ng = a.noise + tile * R * (int64_t)PK;
-      for (int e = tid; e < rows * NH; e += TS) zt[e] = __ldg(zg + e);
-      for (int e = tid; e < rows * PK; e += TS) nt[e] = __ldg(ng + e);
-      __syncthreads();
-    }
-    // y rows of the next tile: the loads stay in flight (in registers) during this
-    // tile's arithmetic and are parked in shared memory afterwards
-    const int64_t nxt1 = tile + gridDim.x;
-    const bool y_regs = R * P <= 2 * TS;
-    float yreg[2] = {0.f, 0.f};
-    if (nxt1 < ntiles && y_regs) {
-      const int rows_n = tile_rows(nxt1);
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int e = tid + u * TS;
-        if (e < rows_n * P) {
-          const int r = e / P, c = e - r * P;
-          const int64_t row = nxt1 * R + r;
-          yreg[u] = __ldg(a.y + (a.y_rows ? __ldg(a.y_rows + row) : row) * P + c);
-        }
+      float* zt = zbuf(b);
+      float* dzt = dbuf(b);
+      NllArgs t = a;
+      t.B = rows;
+      t.z_pi = zt; t.ld_pi = NH;
+      t.mu = zt + K; t.ld_mu = NH;
+      t.zd = zt + K + PK; t.ld_zd = NH;
+      t.low = FULL ? zt + K + 2 * PK : nullptr; t.ld_low = NH;
+      t.noise = nbuf(b);
+      t.y = ybuf(b); t.y_rows = nullptr;
+      if (BWD) {
+        t.d_pi = dzt; t.ldo_pi = NH;
+        t.d_mu = dzt + K; t.ldo_mu = NH;
+        t.d_zd = dzt + K + PK; t.ldo_zd = NH;
+        t.d_low = FULL ? dzt + K + 2 * PK : nullptr; t.ldo_low = NH;
       }
-    }
-
-    NllArgs t = a;
-    t.B = rows;
-    t.z_pi = zt; t.ld_pi = NH;
-    t.mu = zt + K; t.ld_mu = NH;
-    t.zd = zt + K + PK; t.ld_zd = NH;
-    t.low = FULL ? zt + K + 2 * PK : nullptr; t.ld_low = NH;
-    t.noise = nt;
-    t.y = yb + (size_t)b * ypad; t.y_rows = nullptr;
-    if (BWD) {
-      t.d_pi = dzb; t.ldo_pi = NH;
-      t.d_mu = dzb + K; t.ldo_mu = NH;
-      t.d_zd = dzb + K + PK; t.ldo_zd = NH;
-      t.d_low = FULL ? dzb + K + 2 * PK : nullptr; t.ldo_low = NH;
-      // the previous tile's bulk store must have finished reading the dz stage
-      if (tid == 0) ac::bulk_wait_read<0>();
-      __syncthreads();
-    }
-    nll_samples<GW, KPL, true, FULL, BWD, true>(t, eps, coef_scale, 0, GPB, TS, zs, vs, loss_acc,
-                                                s_acc, bad);
-    if (nxt1 < ntiles) {
-      if (y_regs) {
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-          if (tid + u * TS < R * P) yb[(size_t)(b ^ 1) * ypad + tid + u * TS] = yreg[u];
-      } else {
-        load_y(nxt1, b ^ 1);
-      }
-    }
-    if (BWD && bulk) ac::fence_proxy_async();
-    __syncthreads();                       // dz stage complete; z/noise/y buffers b are free
-    if (BWD) {
-      float* dzg = q.dz + tile * R * (int64_t)NH;
-      if (bulk) {
-        if (tid == 0) {
-          ac::bulk_s2g(dzg, dzb, (uint32_t)rows * (uint32_t)NH * 4u);
-          ac::bulk_commit();
-        }
-      } else {
-        for (int e = tid; e < rows * NH; e += TS) dzg[e] = dzb[e];
-      }
-    }
-    if (tid == 0) {
-      const int64_t nxt2 = tile + 2 * (int64_t)gridDim.x;
-      if (nxt2 < ntiles && (tile_rows(nxt2) & 3) == 0) issue_load(nxt2, b);
+      nll_samples<GW, KPL, true, FULL, BWD, true>(t, eps, coef_scale, 0, GPB, TC, zs, vs,
+                                                  loss_acc, s_acc, bad);
+      if (BWD) ac::fence_proxy_async();    // dz (generic writes) -> visible to the bulk store
+      __syncwarp();
+      if (lane == 0) ac::mbar_arrive(&done[b]);
     }
   }
-  if (tid == 0) ac::bulk_wait_read<0>();
   if (bad) atomicOr(a.flag, 1);
 
   // ---- deterministic cross-block reductions (same scheme as nll_kernel)
@@ -612,8 +717,8 @@ __global__ void __launch_bounds__(256) nll_stream_kernel(NllArgs a, NllStream q)
     loss_parts[blockIdx.x] = lsum;
     if (BWD) s_parts[blockIdx.x] = ssum;
     __threadfence();
-    const unsigned int done = atomicAdd(counter, 1u);
-    is_last = (done == gridDim.x - 1);
+    const unsigned int done_ctas = atomicAdd(counter, 1u);
+    is_last = (done_ctas == gridDim.x - 1);
   }
   __syncthreads();
   if (is_last) {
@@ -1122,17 +1227,17 @@ static int launch_nll_cluster(const NllArgs& a, bool bwd, cudaStream_t st) {
 }
 
 template <int GW, int KPL, bool FULL, bool BWD>
-static int launch_nll_stream_t(const NllArgs& a, const NllStream& q, size_t smem, int* nparts,
-                               cudaStream_t st) {
+static int launch_nll_stream_t(const NllArgs& a, const NllStream& q, int threads, size_t smem,
+                               int* nparts, cudaStream_t st) {
   auto kern = nll_stream_kernel<GW, KPL, FULL, BWD>;
   if (smem > 48 * 1024)
     BSIG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 1;
-  BSIG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
+  BSIG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
   const int64_t ntiles = ceil_div(a.B, q.R);
   const int grid = (int)std::min<int64_t>(
       std::min<int64_t>(ntiles, (int64_t)std::max(occ, 1) * sm_count()), kMaxParts);
-  kern<<<grid, 256, smem, st>>>(a, q);
+  kern<<<grid, threads, smem, st>>>(a, q);
   BSIG_LAUNCH_CHECK();
   *nparts = grid;
   return 0;
@@ -1140,12 +1245,12 @@ static int launch_nll_stream_t(const NllArgs& a, const NllStream& q, size_t smem
 
 template <int GW, int KPL>
 static int launch_nll_stream_gw(const NllArgs& a, const NllStream& q, bool full, bool bwd,
-                                size_t smem, int* nparts, cudaStream_t st) {
+                                int threads, size_t smem, int* nparts, cudaStream_t st) {
   if (full)
-    return bwd ? launch_nll_stream_t<GW, KPL, true, true>(a, q, smem, nparts, st)
-               : launch_nll_stream_t<GW, KPL, true, false>(a, q, smem, nparts, st);
-  return bwd ? launch_nll_stream_t<GW, KPL, false, true>(a, q, smem, nparts, st)
-             : launch_nll_stream_t<GW, KPL, false, false>(a, q, smem, nparts, st);
+    return bwd ? launch_nll_stream_t<GW, KPL, true, true>(a, q, threads, smem, nparts, st)
+               : launch_nll_stream_t<GW, KPL, true, false>(a, q, threads, smem, nparts, st);
+  return bwd ? launch_nll_stream_t<GW, KPL, false, true>(a, q, threads, smem, nparts, st)
+             : launch_nll_stream_t<GW, KPL, false, false>(a, q, threads, smem, nparts, st);
 }
 
 // Streaming (bulk-copy staged) form of the fused NLL for batches beyond one cluster.
@@ -1157,34 +1262,32 @@ static int launch_nll_stream(const NllArgs& a, const float* z, float* dz, int64_
   const int K = a.K, P = a.P;
   if (K < 1 || K > 128 || P < 1 || P > 192) return -1;
   const bool full = a.L > 0;
-  int gw = 1;
-  while (gw < K && gw < 32) gw <<= 1;
-  const int gpb = 256 / gw;
+  // K <= 32: one component per lane, groups of exactly K lanes packed into the warps
+  const int rpw = K <= 32 ? 32 / K : 1;                     // samples per warp and pass
   const int64_t PK = (int64_t)P * K;
-  const int64_t per_row = (2 * (NH + PK) + 2 * P + (bwd ? NH : 0)) * 4;
-  const int64_t fixed = (full ? 2 * (int64_t)P * 256 * 4 : 0) + 64;
-  int r = 0;
-  for (int64_t budget : {72 * 1024, 110 * 1024, 220 * 1024}) {
-    r = (int)std::min<int64_t>((budget - fixed) / per_row, 4 * gpb);
-    if (r >= gpb) r = (r / gpb) * gpb;
-    r &= ~3;
-    if (r >= std::min(gpb, 8)) break;
+  const int64_t per_row = 2 * (NH + PK + P + ((bwd && full) ? NH : 0)) * 4;
+  // tile height R (multiple of 4) and CTA width (consumer warps + the producer warp):
+  // maximise (samples resident on an SM) x (fraction of lane groups that own a sample)
+  int best_r = 0, best_threads = 0;
+  double best_score = 0.0;
+  for (int r = 4; r <= 8 * rpw && r <= 64; r += 4) {
+    const int warps = (int)ceil_div(r, rpw);
+    if (warps > 8) break;
+    const int64_t smem = r * per_row + (full ? 2 * (int64_t)P * warps * 32 * 4 : 0) + 64;
+    if (smem > 220 * 1024) break;
+    const int ctas = (int)std::min<int64_t>(
+        std::min<int64_t>((226 * 1024) / (smem + 1024), 64 / (warps + 1)), 32);
+    const double score = (double)ctas * r * ((double)r / (warps * rpw));
+    if (score >= best_score) { best_score = score; best_r = r; best_threads = (warps + 1) * 32; }
   }
-  if (r < 4) return -1;
+  if (best_r < 4) return -1;
   NllStream q;
-  q.z = z; q.dz = dz; q.NH = (int)NH; q.R = r;
-  const size_t smem = (size_t)r * per_row + (size_t)fixed;
-  switch (gw) {
-    case 1: return launch_nll_stream_gw<1, 1>(a, q, full, bwd, smem, nparts, st);
-    case 2: return launch_nll_stream_gw<2, 1>(a, q, full, bwd, smem, nparts, st);
-    case 4: return launch_nll_stream_gw<4, 1>(a, q, full, bwd, smem, nparts, st);
-    case 8: return launch_nll_stream_gw<8, 1>(a, q, full, bwd, smem, nparts, st);
-    case 16: return launch_nll_stream_gw<16, 1>(a, q, full, bwd, smem, nparts, st);
-    default:
-      if (K <= 32) return launch_nll_stream_gw<32, 1>(a, q, full, bwd, smem, nparts, st);
-      if (K <= 64) return launch_nll_stream_gw<32, 2>(a, q, full, bwd, smem, nparts, st);
-      return launch_nll_stream_gw<32, 4>(a, q, full, bwd, smem, nparts, st);
-  }
+  q.z = z; q.dz = dz; q.NH = (int)NH; q.R = best_r;
+  const size_t smem =
+      (size_t)best_r * per_row + (full ? (size_t)2 * P * (best_threads - 32) * 4 : 0) + 64;
+  if (K <= 32) return launch_nll_stream_gw<0, 1>(a, q, full, bwd, best_threads, smem, nparts, st);
+  if (K <= 64) return launch_nll_stream_gw<32, 2>(a, q, full, bwd, best_threads, smem, nparts, st);
+  return launch_nll_stream_gw<32, 4>(a, q, full, bwd, best_threads, smem, nparts, st);
 }
 
 static int launch_exp_sum(const float* zd, int64_t ld_zd, int B, int PK, float* ws,

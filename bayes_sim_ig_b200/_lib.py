@@ -23,6 +23,7 @@ SIGNATURES = {
     'bsig_last_error': (ctypes.c_char_p, []),
     'bsig_version': (_int, []),
     'bsig_launch_count': (_i64, []),
+    'bsig_set_pdl': (_int, [_int]),
     'bsig_device_info': (_int, [ctypes.POINTER(_int)] * 3),
     'bsig_summary_start': (_int, [_c_ptr, _c_ptr, _c_ptr] + [_i64] * 6 + [_c_ptr]),
     'bsig_summary_crosscorr': (_int, [_c_ptr, _c_ptr, _c_ptr] + [_i64] * 6 + [_int, _c_ptr, _c_ptr]),

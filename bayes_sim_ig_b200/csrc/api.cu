@@ -1,5 +1,6 @@
 // Error reporting and device queries of the C ABI.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -11,6 +12,17 @@ static thread_local char g_err[1024] = "";
 static std::atomic<long long> g_launches{0};
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static std::atomic<int> g_pdl{-1};
+bool pdl_enabled() {
+  int v = g_pdl.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("BSIG_PDL");
+    v = (e != nullptr && atoi(e) == 0) ? 0 : 1;
+    g_pdl.store(v, std::memory_order_relaxed);
+  }
+  return v != 0;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -37,6 +49,10 @@ int sm_count() {
 extern "C" const char* bsig_last_error(void) { return bsig::g_err; }
 extern "C" int bsig_version(void) { return BSIG_VERSION; }
 extern "C" int64_t bsig_launch_count(void) { return (int64_t)bsig::g_launches.load(); }
+extern "C" int bsig_set_pdl(int enabled) {
+  bsig::g_pdl.store(enabled ? 1 : 0);
+  return 0;
+}
 
 extern "C" int bsig_device_info(int* sm, int* cc_major, int* cc_minor) {
   int dev = 0;

@@ -16,6 +16,29 @@ namespace bsig {
 void set_error(const char* fmt, ...);
 int sm_count();
 void count_launch();
+bool pdl_enabled();
+
+// Programmatic dependent launch (PDL): the step kernels of a training call form a
+// chain of short, dependent launches.  Each of them (1) does its operand-independent
+// set-up, (2) waits for the previous kernel in the stream to complete and flush
+// (griddepcontrol.wait), (3) immediately allows the NEXT kernel to be scheduled
+// (griddepcontrol.launch_dependents).  Because (3) comes after (2), kernel N+1 can only
+// become resident once kernel N-1 has finished, so N+1's set-up overlaps N's execution
+// and nothing N-1 or earlier wrote is read early.  Both instructions are no-ops when the
+// launch did not carry the programmatic-serialization attribute.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait_then_release() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+#endif
+// Appends the PDL launch attribute (if enabled) to attrs[n]; returns the new count.
+static inline int add_pdl_attr(cudaLaunchAttribute* attrs, int n) {
+  if (!pdl_enabled()) return n;
+  attrs[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[n].val.programmaticStreamSerializationAllowed = 1;
+  return n + 1;
+}
 
 #define BSIG_REQUIRE(cond, ...)            \
   do {                                     \

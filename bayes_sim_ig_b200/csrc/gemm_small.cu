@@ -45,17 +45,6 @@ __global__ void __launch_bounds__(256) gemm_small_kernel(GemmArgs g) {
   const int gi_out = i0 + ty, gj_out = j0 + tx * 4;
   const int gi_c = min(gi_out, g.M - 1);
 
-  // epilogue operands: requested now, consumed after the reduction
-  float ep4[4] = {0.f, 0.f, 0.f, 0.f};
-  if (EPI == EPI_BIAS || EPI == EPI_BIAS_TANH) {
-#pragma unroll
-    for (int v = 0; v < 4; ++v) ep4[v] = __ldg(g.bias + min(gj_out + v, g.N - 1));
-  } else if (EPI == EPI_MUL_DTANH) {
-#pragma unroll
-    for (int v = 0; v < 4; ++v)
-      ep4[v] = __ldg(g.aux + (int64_t)gi_c * g.ld_aux + min(gj_out + v, g.N - 1));
-  }
-
   // loader mappings: consecutive threads walk the contiguous dimension
   const bool a_r_contig = (g.a_sr == 1);
   const bool b_r_contig = (g.b_sr == 1) && (g.b_sj != 1);
@@ -76,11 +65,25 @@ __global__ void __launch_bounds__(256) gemm_small_kernel(GemmArgs g) {
     const int gi = i0 + a_i[q];
     a_ok[q] = gi < g.M;
   }
+  // minibatch row indices are written once per training call, before the graph
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const int gi = min(i0 + a_i[q], g.M - 1);
     const int64_t row = (GATHER == 1) ? __ldg(g.a_rows + gi) : (int64_t)gi;
     a_ptr[q] = g.A + row * g.a_si;
+  }
+  // everything above is operand-independent set-up: it overlaps the previous kernel
+  pdl_wait_then_release();
+
+  // epilogue operands: requested now, consumed after the reduction
+  float ep4[4] = {0.f, 0.f, 0.f, 0.f};
+  if (EPI == EPI_BIAS || EPI == EPI_BIAS_TANH) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v) ep4[v] = __ldg(g.bias + min(gj_out + v, g.N - 1));
+  } else if (EPI == EPI_MUL_DTANH) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+      ep4[v] = __ldg(g.aux + (int64_t)gi_c * g.ld_aux + min(gj_out + v, g.N - 1));
   }
 
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -169,23 +172,23 @@ __global__ void __launch_bounds__(256) gemm_small_kernel(GemmArgs g) {
 
 template <int EPI, int GATHER>
 static int launch_small(const GemmArgs& g, dim3 grid, int S, cudaStream_t st) {
-  if (S == 1) {     // no cluster needed: plain launch
-    gemm_small_kernel<EPI, GATHER><<<grid, 256, 0, st>>>(g);
-    BSIG_LAUNCH_CHECK();
-    return 0;
-  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(256);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = (unsigned)S;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (S > 1) {      // reduction split over a thread-block cluster
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = (unsigned)S;
+    ++na;
+  }
+  na = add_pdl_attr(attr, na);
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = na;
   BSIG_CUDA(cudaLaunchKernelEx(&cfg, gemm_small_kernel<EPI, GATHER>, g));
   BSIG_LAUNCH_CHECK();
   return 0;

@@ -84,13 +84,24 @@ struct RowCol {
 __global__ void __launch_bounds__(256)
 exp_sum_kernel(const float* __restrict__ zd, int64_t ld_zd, int B, int PK, float* ws) {
   __shared__ float scratch[33];
-  const int64_t total = (int64_t)B * PK;
   float acc = 0.f;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t start = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  RowCol rc(start, stride, PK);
-  for (int64_t i = start; i < total; i += stride, rc.next())
-    acc += expf(__ldg(zd + rc.row * ld_zd + rc.col));
+  if (((PK | ld_zd) & 1) == 0 && (reinterpret_cast<uintptr_t>(zd) & 7) == 0) {
+    // even widths: 64-bit loads (rows of the fused head output are only 8-byte aligned)
+    const int W = PK >> 1;
+    const int64_t total = (int64_t)B * W;
+    RowCol rc(start, stride, W);
+    for (int64_t i = start; i < total; i += stride, rc.next()) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(zd + rc.row * ld_zd) + rc.col);
+      acc += expf(v.x) + expf(v.y);
+    }
+  } else {
+    const int64_t total = (int64_t)B * PK;
+    RowCol rc(start, stride, PK);
+    for (int64_t i = start; i < total; i += stride, rc.next())
+      acc += expf(__ldg(zd + rc.row * ld_zd + rc.col));
+  }
   acc = block_sum(acc, scratch);
   if (threadIdx.x == 0) ws[blockIdx.x] = acc;
 }
@@ -763,6 +774,7 @@ __global__ void __launch_bounds__(512) nll_cluster_kernel(NllArgs a) {
   const int B = a.B, P = a.P, K = a.K, PK = P * K;
   float* zs = dyn + tid;
   float* vs = dyn + (size_t)P * TS + tid;
+  pdl_wait_then_release();
 
   // phase 0: sum of exp(z_d) over the whole batch
   {
@@ -837,8 +849,9 @@ __global__ void __launch_bounds__(512) nll_small_kernel(NllArgs a) {
   const int64_t bb = ok ? b : 0;
   const int kk = ok ? k : 0;
 
-  // ---- all loads
+  // ---- all loads (the minibatch row index is constant during a training call)
   const int64_t yrow = (a.y_rows ? __ldg(a.y_rows + bb) : bb) * P;
+  pdl_wait_then_release();
   float zpi = ok ? __ldg(a.z_pi + bb * a.ld_pi + kk) : -INFINITY;
   float e[PLMAX], zi[PLMAX], nz[PLMAX];
 #pragma unroll
@@ -953,13 +966,28 @@ eps_fixup_kernel(const float* __restrict__ zd, int64_t ld_zd, float* dzd, int64_
                  int B, int PK, const float* s_parts, int nparts) {
   __shared__ float scratch[33];
   const float S = sum_parts(s_parts, nparts, scratch);
-  const int64_t total = (int64_t)B * PK;
-  const float c = kEpsNoise * S / (float)total;
+  const float c = kEpsNoise * S / (float)((int64_t)B * PK);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t start = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  RowCol rc(start, stride, PK);
-  for (int64_t i = start; i < total; i += stride, rc.next())
-    dzd[rc.row * ldo_zd + rc.col] += expf(__ldg(zd + rc.row * ld_zd + rc.col)) * c;
+  if (((PK | ld_zd | ldo_zd) & 1) == 0 &&
+      ((reinterpret_cast<uintptr_t>(zd) | reinterpret_cast<uintptr_t>(dzd)) & 7) == 0) {
+    const int W = PK >> 1;
+    const int64_t total = (int64_t)B * W;
+    RowCol rc(start, stride, W);
+    for (int64_t i = start; i < total; i += stride, rc.next()) {
+      const float2 z2 = __ldg(reinterpret_cast<const float2*>(zd + rc.row * ld_zd) + rc.col);
+      float2* dp = reinterpret_cast<float2*>(dzd + rc.row * ldo_zd) + rc.col;
+      float2 d2 = *dp;
+      d2.x += expf(z2.x) * c;
+      d2.y += expf(z2.y) * c;
+      *dp = d2;
+    }
+  } else {
+    const int64_t total = (int64_t)B * PK;
+    RowCol rc(start, stride, PK);
+    for (int64_t i = start; i < total; i += stride, rc.next())
+      dzd[rc.row * ldo_zd + rc.col] += expf(__ldg(zd + rc.row * ld_zd + rc.col)) * c;
+  }
 }
 
 // --------------------------------------------------------- head epilogue (API path)
@@ -1134,13 +1162,13 @@ static int launch_nll_cluster_t(const NllArgs& a, int nc, int tpb, size_t smem, 
   cfg.blockDim = dim3((unsigned)tpb);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)nc;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = add_pdl_attr(attr, 1);
   BSIG_CUDA(cudaLaunchKernelEx(&cfg, nll_cluster_kernel<GW, KPL, FULL, BWD>, a));
   BSIG_LAUNCH_CHECK();
   return 0;
@@ -1153,13 +1181,13 @@ static int launch_nll_small_t(const NllArgs& a, int nc, int tpb, cudaStream_t st
   cfg.blockDim = dim3((unsigned)tpb);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)nc;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = add_pdl_attr(attr, 1);
   BSIG_CUDA(cudaLaunchKernelEx(&cfg, nll_small_kernel<GW, PS, PLMAX, BWD>, a));
   BSIG_LAUNCH_CHECK();
   return 0;

@@ -27,6 +27,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     const float denom = sqrtf(vv) * inv_bc2_sqrt + eps;
     pp = pp - step_size * (mm / denom);
   };
+  pdl_wait_then_release();
   for (int64_t i = t0; i < n4; i += stride) {
     float4 pp = p4[i], mm = m4[i], vv = v4[i];
     const float4 gg = g4[i];
@@ -92,9 +93,16 @@ extern "C" int bsig_adam_step(float* param, const float* grad, float* exp_avg, f
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   const float step_size = (float)((double)lr / bc1);
   const float inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
-  adam_kernel<<<grid_for(count / 4 + 1), 256, 0, (cudaStream_t)stream>>>(
-      param, grad, exp_avg, exp_avg_sq, count, 1.0f - beta1, beta2, 1.0f - beta2, step_size,
-      inv_bc2_sqrt, eps, grad_scale);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid_for(count / 4 + 1));
+  cfg.blockDim = dim3(256);
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.numAttrs = add_pdl_attr(attr, 0);
+  BSIG_CUDA(cudaLaunchKernelEx(&cfg, adam_kernel, param, grad, exp_avg, exp_avg_sq, count,
+                               1.0f - beta1, beta2, 1.0f - beta2, step_size, inv_bc2_sqrt, eps,
+                               grad_scale));
   BSIG_LAUNCH_CHECK();
   return 0;
 }

@@ -41,6 +41,7 @@ adam_allreduce_kernel(P2PArgs a, float* __restrict__ p, float* __restrict__ m,
                       float one_minus_b2, float step_size, float inv_bc2_sqrt, float eps,
                       float gscale) {
   __shared__ unsigned int s_epoch;
+  pdl_wait_then_release();       // the backward kernels of this update are complete
   if (threadIdx.x == 0) {
     const unsigned int epoch = a.ctrl[0] + 1u;
     s_epoch = epoch;
@@ -166,9 +167,16 @@ extern "C" int bsig_adam_allreduce_step(float* param, const void* const* peer_gr
   // every block must be resident at once (blocks spin on the peers' flags)
   const int blocks =
       (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(count / 4 + 1, 256), sm_count()));
-  adam_allreduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
-      a, param, exp_avg, exp_avg_sq, count, 1.0f - beta1, beta2, 1.0f - beta2, step_size,
-      inv_bc2_sqrt, eps, 1.0f / (float)world);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)blocks);
+  cfg.blockDim = dim3(256);
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.numAttrs = add_pdl_attr(attr, 0);
+  BSIG_CUDA(cudaLaunchKernelEx(&cfg, adam_allreduce_kernel, a, param, exp_avg, exp_avg_sq, count,
+                               1.0f - beta1, beta2, 1.0f - beta2, step_size, inv_bc2_sqrt, eps,
+                               1.0f / (float)world));
   BSIG_LAUNCH_CHECK();
   return 0;
 }

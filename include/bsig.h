@@ -47,6 +47,9 @@ int bsig_version(void);
 /* number of kernel launches this library has enqueued in this process (host counter;
  * launches recorded into a CUDA graph are counted once, at capture time) */
 int64_t bsig_launch_count(void);
+/* Programmatic dependent launch of the training-step kernels (default on; env BSIG_PDL=0
+ * or bsig_set_pdl(0) turns it off).  No reference counterpart (launch plumbing). */
+int bsig_set_pdl(int enabled);
 /* host query: SM count and compute capability of the current device */
 int bsig_device_info(int* sm_count, int* cc_major, int* cc_minor);
 

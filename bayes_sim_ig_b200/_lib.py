@@ -52,6 +52,7 @@ SIGNATURES = {
     'bsig_p2p_alloc': (_int, [ctypes.POINTER(_c_ptr), _i64, ctypes.c_char_p]),
     'bsig_p2p_open': (_int, [ctypes.c_char_p, ctypes.POINTER(_c_ptr)]),
     'bsig_p2p_close': (_int, [_c_ptr]),
+    'bsig_p2p_read': (_int, [_c_ptr, _c_ptr, _i64]),
     'bsig_p2p_free': (_int, [_c_ptr]),
     'bsig_adam_allreduce_step': (_int, [_c_ptr, ctypes.POINTER(_c_ptr), ctypes.POINTER(_c_ptr),
                                         _c_ptr, _int, _int, _c_ptr, _c_ptr, _i64, _i64,

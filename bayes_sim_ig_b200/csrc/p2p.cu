@@ -26,8 +26,16 @@ struct P2PArgs {
   int rank, world;
 };
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
   unsigned int v;
@@ -42,23 +50,29 @@ adam_allreduce_kernel(P2PArgs a, float* __restrict__ p, float* __restrict__ m,
                       float gscale) {
   __shared__ unsigned int s_epoch;
   pdl_wait_then_release();       // the backward kernels of this update are complete
-  if (threadIdx.x == 0) {
-    const unsigned int epoch = a.ctrl[0] + 1u;
-    s_epoch = epoch;
-    if (blockIdx.x == 0) {
-      // my backward kernels precede this kernel in stream order: their writes are
-      // complete; make them visible system-wide, then publish the epoch to every rank
-      __threadfence_system();
-      for (int q = 0; q < a.world; ++q) st_release_sys(a.flags[q] + a.rank, epoch);
-    }
-  }
+  // ctrl[8..15]: nanosecond stamps of block 0 (start, flags published, peers arrived,
+  // reduction + Adam done) of the most recent launch -- read by profiles/dp_smoke.py
+  unsigned long long* stamps = reinterpret_cast<unsigned long long*>(a.ctrl + 8);
+  const bool tracer = blockIdx.x == 0 && threadIdx.x == 0;
+  if (tracer) stamps[0] = globaltimer_ns();
+  if (threadIdx.x == 0) s_epoch = a.ctrl[0] + 1u;
   __syncthreads();
   const unsigned int epoch = s_epoch;
+  if (blockIdx.x == 0 && threadIdx.x < a.world) {
+    // my backward kernels precede this kernel in stream order, so their writes are
+    // complete; one system-scope fence per publishing thread (fence + relaxed store = a
+    // release), and the `world` flag stores travel over NVLink in parallel instead of
+    // waiting for each other's acknowledgement
+    __threadfence_system();
+    st_relaxed_sys(a.flags[threadIdx.x] + a.rank, epoch);
+  }
+  if (tracer) stamps[1] = globaltimer_ns();
   if (threadIdx.x < a.world) {
     const unsigned int* mine = a.flags[a.rank] + threadIdx.x;
     while ((int)(ld_acquire_sys(mine) - epoch) < 0) { /* spin: peers are at most one update behind */ }
   }
   __syncthreads();
+  if (tracer) stamps[2] = globaltimer_ns();
 
   const int64_t n4 = count / 4;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -97,6 +111,7 @@ adam_allreduce_kernel(P2PArgs a, float* __restrict__ p, float* __restrict__ m,
 
   // the last block to finish advances the epoch for the next update
   __syncthreads();
+  if (tracer) stamps[3] = globaltimer_ns();
   if (threadIdx.x == 0) {
     __threadfence();
     const unsigned int done = atomicAdd(a.ctrl + 1, 1u);
@@ -131,6 +146,11 @@ extern "C" int bsig_p2p_open(const unsigned char* handle64, void** ptr) {
   cudaIpcMemHandle_t h;
   memcpy(&h, handle64, 64);
   BSIG_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+extern "C" int bsig_p2p_read(const void* dev_ptr, void* host_ptr, int64_t bytes) {
+  BSIG_CUDA(cudaMemcpy(host_ptr, dev_ptr, (size_t)bytes, cudaMemcpyDeviceToHost));
   return 0;
 }
 

@@ -112,6 +112,14 @@ class P2PComm(object):
         self.ctrl = self.local[3]
         dist.barrier(group=group)
 
+    def last_launch_stamps(self):
+        """Nanosecond timestamps of block 0 in the most recent exchange kernel:
+        (start, flags published, all peers arrived, reduction + Adam done)."""
+        import ctypes
+        buf = (ctypes.c_uint64 * 4)()
+        self._lib.call('bsig_p2p_read', self.ctrl + 32, ctypes.addressof(buf), 32)
+        return [int(v) for v in buf]
+
     def local_grads(self, parity):
         return self.local[parity & 1]
 

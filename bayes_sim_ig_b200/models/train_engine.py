@@ -323,8 +323,10 @@ def run_training_captured(model, x_data, y_data, n_updates, batch_size, test_fra
         plan.flag.zero_()
         if n_test == 0:
             plan.loss_buf.fill_(float('nan'))
-        if dp and plan.p2p is not None:
-            # all ranks must have retired the previous call before gradient buffer 0 is reused
+        if dp and plan.p2p is not None and plan.n_updates % 2 == 1:
+            # gradient buffers alternate with the update parity; after an odd number of
+            # updates the next call starts on the buffer the last exchange is still
+            # reading on slower ranks: all ranks must have retired the previous call
             torch.distributed.barrier(group=getattr(model, '_dp_group', None))
         if use_graph and dp and plan.p2p is None:
             if getattr(plan, 'dp_graphs', None) is None:

@@ -186,6 +186,7 @@ int bsig_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
 int bsig_p2p_alloc(void** ptr, int64_t bytes, unsigned char* handle64);   /* host call */
 int bsig_p2p_open(const unsigned char* handle64, void** ptr);             /* host call */
 int bsig_p2p_close(void* ptr);
+int bsig_p2p_read(const void* dev_ptr, void* host_ptr, int64_t bytes);   /* blocking D2H copy */
 int bsig_p2p_free(void* ptr);
 int bsig_adam_allreduce_step(float* param, const void* const* peer_grads,
                              void* const* peer_flags, void* ctrl, int rank, int world,

@@ -45,6 +45,11 @@ with contextlib.redirect_stdout(io.StringIO()):
         torch.cuda.synchronize()
         sys.stderr.write('[rank %d] run_training %d: %.1f ms, last losses %s\n'
                          % (rank, i, 1e3 * (time.time() - t1), logs['train_loss'][-1]))
+plan = list(bsim.model._plans.values())[0]
+if plan.p2p is not None:
+    st = plan.p2p.last_launch_stamps()
+    say('exchange kernel (last launch): publish %.2f us, wait peers %.2f us, reduce+adam %.2f us'
+        % ((st[1] - st[0]) / 1e3, (st[2] - st[1]) / 1e3, (st[3] - st[2]) / 1e3))
 say('param checksum after', float(bsim.model.flat_params.double().sum()))
 dist.barrier()
 say('done')

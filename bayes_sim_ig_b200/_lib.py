@@ -26,7 +26,9 @@ SIGNATURES = {
     'bsig_set_pdl': (_int, [_int]),
     'bsig_device_info': (_int, [ctypes.POINTER(_int)] * 3),
     'bsig_summary_start': (_int, [_c_ptr, _c_ptr, _c_ptr] + [_i64] * 6 + [_c_ptr]),
+    'bsig_summary_start_tm': (_int, [_c_ptr, _c_ptr, _c_ptr] + [_i64] * 6 + [_c_ptr]),
     'bsig_summary_crosscorr': (_int, [_c_ptr, _c_ptr, _c_ptr] + [_i64] * 6 + [_int, _c_ptr, _c_ptr]),
+    'bsig_summary_crosscorr_tm': (_int, [_c_ptr, _c_ptr, _c_ptr] + [_i64] * 6 + [_int, _c_ptr, _c_ptr]),
     'bsig_signature_fwd': (_int, [_c_ptr, _c_ptr, _c_ptr] + [_i64] * 6 + [_int, _c_ptr]),
     'bsig_signature_bwd': (_int, [_c_ptr] * 5 + [_i64] * 6 + [_int, _c_ptr]),
     'bsig_linear_ws_bytes': (_i64, [_i64] * 3),
@@ -64,6 +66,8 @@ SIGNATURES = {
                                _c_ptr, _c_ptr, _c_ptr, _i64, _i64, _i64, _c_ptr]),
     'bsig_mog_sample': (_int, [_c_ptr, _int] + [_c_ptr] * 7 + [_i64] * 3 + [_c_ptr]),
     'bsig_mog_sample_philox': (_int, [_c_ptr] * 5 + [_u64, _i64, _i64, _i64, _c_ptr]),
+    'bsig_mog_sample_envs': (_int, [_c_ptr, _int] + [_c_ptr] * 8 + [_i64] * 3 + [_c_ptr]),
+    'bsig_mog_sample_envs_philox': (_int, [_c_ptr] * 7 + [_u64, _i64, _i64, _i64, _c_ptr]),
     'bsig_mog_logpdf': (_int, [_c_ptr, _int] + [_c_ptr] * 6 + [_i64] * 3 + [_int, _c_ptr]),
 }
 

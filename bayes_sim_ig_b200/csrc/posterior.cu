@@ -102,6 +102,39 @@ mog_affine_kernel(const double* __restrict__ z, const double* __restrict__ means
   }
 }
 
+// One clipped draw per environment, in draw order (the batched form of
+// sim/params_generator.py:115-118: distr.gen(n_samples=1)[0] then np.clip): environment e
+// uses its own uniform u[e] and normals z[e,:]; nothing is grouped by component.
+template <typename A_T>
+__global__ void __launch_bounds__(256)
+mog_sample_envs_kernel(const A_T* __restrict__ a, const double* __restrict__ u,
+                       const double* __restrict__ z, const double* __restrict__ means,
+                       const double* __restrict__ cmats, const double* __restrict__ lows,
+                       const double* __restrict__ highs, double* __restrict__ samples,
+                       int32_t* __restrict__ comp_idx, int64_t n, int P, int K) {
+  const int64_t total = n * P;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = e / P;
+    const int c = (int)(e - row * P);
+    const double ui = u[row];
+    A_T cs = A_T(0);
+    int k = 0;
+    for (int j = 0; j + 1 < K; ++j) {
+      cs = cs + a[j];                        // running sum in a's own dtype (pdf.py:70-73)
+      k += (ui > (double)cs) ? 1 : 0;
+    }
+    if (c == 0 && comp_idx != nullptr) comp_idx[row] = k;
+    const double* C = cmats + (int64_t)k * P * P;
+    const double* zr = z + row * P;
+    double acc = 0.0;
+    for (int r = 0; r < P; ++r) acc += zr[r] * __ldg(C + r * P + c);
+    acc += __ldg(means + k * P + c);
+    if (lows != nullptr) acc = fmin(fmax(acc, __ldg(lows + c)), __ldg(highs + c));
+    samples[e] = acc;
+  }
+}
+
 // Philox4x32-10
 __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
@@ -120,7 +153,8 @@ __device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5
 __global__ void __launch_bounds__(256)
 mog_sample_philox_kernel(const float* __restrict__ a, const float* __restrict__ means,
                          const float* __restrict__ cmats, int32_t* comp_idx,
-                         float* __restrict__ samples, uint64_t seed, int64_t n, int P, int K) {
+                         float* __restrict__ samples, uint64_t seed, int64_t n, int P, int K,
+                         const float* __restrict__ lows, const float* __restrict__ highs) {
   const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -149,6 +183,9 @@ mog_sample_philox_kernel(const float* __restrict__ a, const float* __restrict__ 
         out[cidx] = acc;
       }
     }
+    if (lows != nullptr)
+      for (int cidx = 0; cidx < P; ++cidx)
+        out[cidx] = fminf(fmaxf(out[cidx], __ldg(lows + cidx)), __ldg(highs + cidx));
   }
 }
 
@@ -241,7 +278,7 @@ extern "C" int bsig_mog_sample_philox(const float* a, const float* means, const 
   BSIG_REQUIRE(n >= 0 && p >= 1 && k >= 1, "mog_sample_philox: bad sizes");
   if (n == 0) return 0;
   mog_sample_philox_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
-      a, means, cmats, comp_idx, samples, seed, n, (int)p, (int)k);
+      a, means, cmats, comp_idx, samples, seed, n, (int)p, (int)k, nullptr, nullptr);
   BSIG_LAUNCH_CHECK();
   return 0;
 }
@@ -259,6 +296,39 @@ extern "C" int bsig_mog_logpdf(const void* x, int x_is_f32, const double* a, con
   else
     mog_logpdf_kernel<double><<<grid, 128, 0, st>>>((const double*)x, a, log_a, means, precs, logdet_p,
                                                     out, m, (int)p, (int)k, log_space);
+  BSIG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int bsig_mog_sample_envs(const void* a, int a_is_f32, const double* u, const double* z,
+                                    const double* means, const double* cmats, const double* lows,
+                                    const double* highs, double* samples, int32_t* comp_idx,
+                                    int64_t n, int64_t p, int64_t k, void* stream) {
+  BSIG_REQUIRE(n >= 0 && p >= 1 && k >= 1, "mog_sample_envs: bad sizes");
+  BSIG_REQUIRE((lows == nullptr) == (highs == nullptr), "mog_sample_envs: lows/highs must both be set");
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = grid_for(n * p, 256);
+  if (a_is_f32)
+    mog_sample_envs_kernel<float><<<grid, 256, 0, st>>>((const float*)a, u, z, means, cmats, lows,
+                                                        highs, samples, comp_idx, n, (int)p, (int)k);
+  else
+    mog_sample_envs_kernel<double><<<grid, 256, 0, st>>>((const double*)a, u, z, means, cmats, lows,
+                                                         highs, samples, comp_idx, n, (int)p, (int)k);
+  BSIG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int bsig_mog_sample_envs_philox(const float* a, const float* means, const float* cmats,
+                                           const float* lows, const float* highs, int32_t* comp_idx,
+                                           float* samples, uint64_t seed, int64_t n, int64_t p,
+                                           int64_t k, void* stream) {
+  BSIG_REQUIRE(n >= 0 && p >= 1 && k >= 1, "mog_sample_envs_philox: bad sizes");
+  BSIG_REQUIRE((lows == nullptr) == (highs == nullptr),
+               "mog_sample_envs_philox: lows/highs must both be set");
+  if (n == 0) return 0;
+  mog_sample_philox_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      a, means, cmats, comp_idx, samples, seed, n, (int)p, (int)k, lows, highs);
   BSIG_LAUNCH_CHECK();
   return 0;
 }

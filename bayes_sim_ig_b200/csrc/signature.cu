@@ -113,7 +113,8 @@ __device__ __forceinline__ void store_staged(const SigArgs& p, const float* stag
 
 // Small channel counts (C <= 8; Pendulum C=5, Cartpole C=6): one thread owns row i
 // of every level -- S1[i], S2[i,:], S3[i,:,:] (C*C registers) -- so a step is
-// C*C + 2C FFMAs.  Persistent CTAs walk tiles of `tpb` trajectories:
+// C*C + 2C FFMAs.  Persistent, warp-specialised CTAs walk tiles of `tpb` trajectories
+// (one producer warp, the others consumers, synchronised through mbarriers only):
 //   * the raw rollouts of a tile are contiguous in HBM ([tpb][L*D], [tpb][L*A]) and
 //     arrive by cp.async.bulk into a double buffer (tile it+2 is in flight while
 //     tile it is being computed) -- no load instructions, no exposed latency;
@@ -132,57 +133,92 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
 template <int C>
 __global__ void __launch_bounds__(256, (C >= 7 ? 2 : 3)) signature3_small_kernel(SigArgs p) {
   extern __shared__ __align__(16) float smem[];
-  __shared__ __align__(8) uint64_t full[2];
-  const int tid = threadIdx.x;
+  // full[b]: raw buffer b holds a tile;  done: the consumers have finished a tile (raw
+  // buffer free, stage written);  stage_free: the previous tile's bulk store has read
+  // the stage
+  __shared__ __align__(8) uint64_t full[2], done, stage_free;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int TC = blockDim.x - 32;                        // consumer threads; last warp = producer
+  const bool producer = tid >= TC;
   const int L = p.L, D = p.D, A = p.A, LD = L * D, LA = L * A;
   const int steps = L - 1, tpb = p.tpb;
   constexpr int CP = (C + 1) / 2;                          // packed pairs per level-3 row
   auto rawb = [&](int b) { return smem + (size_t)b * p.raw_stride; };   // each [tpb][L*D] | [tpb][L*A]
   float* stage = smem + 2 * (size_t)p.raw_stride;        // [tpb][siglen]
   const int64_t ntiles = (p.n + tpb - 1) / tpb;
-  const int tl = tid / C, i = tid - tl * C;
-
+  const int my_tiles = (int64_t)blockIdx.x < ntiles
+                           ? (int)((ntiles - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
+  auto tile_of = [&](int it) { return (int64_t)blockIdx.x + (int64_t)it * gridDim.x; };
   auto tile_rows = [&](int64_t tile) { return (int)min((int64_t)tpb, p.n - tile * tpb); };
   auto tile_bulk = [&](int64_t tile) { return p.bulk && (tile_rows(tile) & 3) == 0; };
-  auto issue_load = [&](int64_t tile, int b) {            // one thread
-    const int64_t traj0 = tile * tpb;
-    const uint32_t bs = (uint32_t)tile_rows(tile) * LD * 4, ba = (uint32_t)tile_rows(tile) * LA * 4;
-    ac::mbar_expect_tx(&full[b], bs + ba);
-    ac::bulk_g2s(rawb(b), p.states + traj0 * LD, bs, &full[b]);
-    if (ba) ac::bulk_g2s(rawb(b) + (size_t)tpb * LD, p.actions + traj0 * LA, ba, &full[b]);
-  };
 
   if (tid == 0) {
     ac::mbar_init(&full[0], 1);
     ac::mbar_init(&full[1], 1);
+    ac::mbar_init(&done, TC >> 5);
+    ac::mbar_init(&stage_free, 1);
     ac::fence_barrier_init();
-    int64_t t0 = blockIdx.x, t1 = (int64_t)blockIdx.x + gridDim.x;
-    if (t0 < ntiles && tile_bulk(t0)) issue_load(t0, 0);
-    if (t1 < ntiles && tile_bulk(t1)) issue_load(t1, 1);
   }
   __syncthreads();
 
-  int it = 0;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-    const int b = it & 1;
-    const int64_t traj0 = tile * tpb;
-    const int ntraj = tile_rows(tile);
-    const bool bulk = tile_bulk(tile);
-    float* raw_s = rawb(b);
-    float* raw_a = rawb(b) + (size_t)tpb * LD;
-    if (bulk) {
-      ac::mbar_wait(&full[b], (uint32_t)(it >> 1) & 1u);
-    } else {
-      for (int e = tid; e < ntraj * LD; e += blockDim.x) {
-        const int r = e / LD, c = e - r * LD;
-        raw_s[e] = __ldg(p.states + (traj0 + r) * p.s_stride + c);
+  if (producer) {
+    // ---- producer warp: loads run two tiles ahead, stores trail the consumers
+    auto load_tile = [&](int it) {
+      const int b = it & 1;
+      const int64_t tile = tile_of(it), traj0 = tile * tpb;
+      const int ntraj = tile_rows(tile);
+      float* raw_s = rawb(b);
+      float* raw_a = rawb(b) + (size_t)tpb * LD;
+      if (tile_bulk(tile)) {
+        if (lane == 0) {
+          const uint32_t bs = (uint32_t)ntraj * LD * 4, ba = (uint32_t)ntraj * LA * 4;
+          ac::mbar_expect_tx(&full[b], bs + ba);
+          ac::bulk_g2s(raw_s, p.states + traj0 * LD, bs, &full[b]);
+          if (ba) ac::bulk_g2s(raw_a, p.actions + traj0 * LA, ba, &full[b]);
+        }
+      } else {
+        for (int e = lane; e < ntraj * LD; e += 32) {
+          const int r = e / LD, c = e - r * LD;
+          raw_s[e] = __ldg(p.states + (traj0 + r) * p.s_stride + c);
+        }
+        for (int e = lane; e < ntraj * LA; e += 32) {
+          const int r = e / LA, c = e - r * LA;
+          raw_a[e] = __ldg(p.actions + (traj0 + r) * p.a_stride + c);
+        }
+        __syncwarp();
+        if (lane == 0) ac::mbar_arrive(&full[b]);
       }
-      for (int e = tid; e < ntraj * LA; e += blockDim.x) {
-        const int r = e / LA, c = e - r * LA;
-        raw_a[e] = __ldg(p.actions + (traj0 + r) * p.a_stride + c);
+    };
+    if (my_tiles > 0) load_tile(0);
+    if (my_tiles > 1) load_tile(1);
+    for (int it = 0; it < my_tiles; ++it) {
+      const int64_t tile = tile_of(it), traj0 = tile * tpb;
+      const int ntraj = tile_rows(tile);
+      ac::mbar_wait(&done, (uint32_t)it & 1u);           // tile computed and staged
+      if (tile_bulk(tile)) {
+        if (lane == 0) {
+          ac::bulk_s2g(p.out + traj0 * p.siglen, stage, (uint32_t)ntraj * (uint32_t)p.siglen * 4u);
+          ac::bulk_commit();
+        }
+      } else {
+        float* out = p.out + traj0 * p.siglen;
+        const int64_t total = (int64_t)ntraj * p.siglen;
+        for (int64_t e = lane; e < total; e += 32) out[e] = stage[e];
       }
-      __syncthreads();
+      if (it + 2 < my_tiles) load_tile(it + 2);          // raw buffer it & 1 is free again
+      if (lane == 0) ac::bulk_wait_read<0>();
+      __syncwarp();
+      if (lane == 0) ac::mbar_arrive(&stage_free);
     }
+    return;
+  }
+
+  // ---- consumer warps
+  const int tl = tid / C, i = tid - tl * C;
+  for (int it = 0; it < my_tiles; ++it) {
+    const int b = it & 1;
+    const int ntraj = tile_rows(tile_of(it));
+    ac::mbar_wait(&full[b], (uint32_t)(it >> 1) & 1u);
 
     // level-3 rows are kept as packed pairs (k, k+1) and updated with FFMA2 (two fp32
     // FMAs per issued instruction, same rounding as fmaf); odd C pads each row by one
@@ -244,12 +280,7 @@ __global__ void __launch_bounds__(256, (C >= 7 ? 2 : 3)) signature3_small_kernel
       }
     }
     // the previous tile's bulk store must have finished reading `stage`
-    if (tid == 0) ac::bulk_wait_read<0>();
-    __syncthreads();                       // + everyone is done reading rawb(b)
-    if (tid == 0) {
-      const int64_t nxt = tile + 2 * (int64_t)gridDim.x;
-      if (nxt < ntiles && tile_bulk(nxt)) issue_load(nxt, b);
-    }
+    if (it > 0) ac::mbar_wait(&stage_free, (uint32_t)(it - 1) & 1u);
     if (active) {
       float* o = stage + (size_t)tl * p.siglen;
       o[i] = s1;
@@ -272,20 +303,10 @@ __global__ void __launch_bounds__(256, (C >= 7 ? 2 : 3)) signature3_small_kernel
         }
       }
     }
-    if (bulk) {
-      ac::fence_proxy_async();
-      __syncthreads();
-      if (tid == 0) {
-        ac::bulk_s2g(p.out + traj0 * p.siglen, stage, (uint32_t)ntraj * (uint32_t)p.siglen * 4u);
-        ac::bulk_commit();
-      }
-    } else {
-      __syncthreads();
-      store_staged(p, stage, traj0, ntraj);
-      __syncthreads();
-    }
+    ac::fence_proxy_async();               // staged signature -> visible to the bulk store
+    __syncwarp();
+    if (lane == 0) ac::mbar_arrive(&done);
   }
-  if (tid == 0) ac::bulk_wait_read<0>();   // shared memory stays valid until the last store has read it
 }
 
 // 9 <= C <= 22 (depth 3 stops at C = 22): one thread owns one (i,j) pair --
@@ -393,7 +414,8 @@ extern "C" int bsig_signature_fwd(const float* states, const float* actions, flo
       const int64_t budget = (C >= 7 ? 110 : 73) * 1024;
       const int64_t per_traj = (2 * len * (d + a) + p.siglen) * 4;
       BSIG_REQUIRE(per_traj <= 200 * 1024, "signature: path too long for shared memory");
-      int tpb = (int)std::min<int64_t>(256 / C, std::max<int64_t>(budget / per_traj, 1));
+      // seven consumer warps + the producer warp = 256 threads
+      int tpb = (int)std::min<int64_t>(224 / C, std::max<int64_t>(budget / per_traj, 1));
       if (const char* e = getenv("BSIG_SIG_TPB")) tpb = std::max(1, std::min(tpb, atoi(e)));
       if (tpb >= 4) tpb &= ~3;              // multiples of 4 keep every tile 16-byte aligned
       p.tpb = tpb;
@@ -402,7 +424,7 @@ extern "C" int bsig_signature_fwd(const float* states, const float* actions, flo
       p.bulk = (tpb % 4 == 0) && t_states == len && (a == 0 || t_actions == len) &&
                al16(states) && (a == 0 || al16(actions)) && al16(out);
       const size_t smem = (size_t)(2 * p.raw_stride + tpb * p.siglen) * 4;
-      const int threads = (int)(ceil_div((int64_t)tpb * C, 32) * 32);
+      const int threads = (int)(ceil_div((int64_t)tpb * C, 32) * 32) + 32;   // + producer warp
       const int64_t ntiles = ceil_div(n, tpb);
 #define BSIG_SIGS(CV)                                                                        \
   case CV: {                                                                                 \

@@ -17,7 +17,8 @@ template <typename idx_t>
 __global__ void __launch_bounds__(256)
 summary_start_kernel(const float* __restrict__ states, const float* __restrict__ actions,
                      float* __restrict__ out, idx_t total, uint32_t F, uint32_t DA,
-                     uint32_t D, uint32_t A, idx_t s_stride, idx_t a_stride) {
+                     uint32_t D, uint32_t A, idx_t s_stride, idx_t a_stride, idx_t s_tstride,
+                     idx_t a_tstride) {
   const idx_t n4 = (total + 3) / 4;
   for (idx_t i = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (idx_t)gridDim.x * blockDim.x) {
@@ -30,8 +31,8 @@ summary_start_kernel(const float* __restrict__ states, const float* __restrict__
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       if (e0 + c < total) {
-        v[c] = (j < D) ? __ldg(states + traj * s_stride + (idx_t)t * D + j)
-                       : __ldg(actions + traj * a_stride + (idx_t)t * A + (j - D));
+        v[c] = (j < D) ? __ldg(states + traj * s_stride + (idx_t)t * s_tstride + j)
+                       : __ldg(actions + traj * a_stride + (idx_t)t * a_tstride + (j - D));
       } else {
         v[c] = 0.f;
       }
@@ -57,7 +58,9 @@ struct CrossArgs {
   float* out;
   int* flag;
   int64_t n;
-  int64_t s_stride, a_stride;  // floats per trajectory in the inputs
+  int64_t s_stride, a_stride;  // floats between consecutive trajectories in the inputs
+  int64_t s_tstride, a_tstride;  // floats between consecutive time steps (D, A when
+                                 // trajectory-major; N*D, N*A for time-major buffers)
   int D, A, W, Pn, Qn;         // Pn = W*(D-1), Qn = W*A
   int64_t F;                   // Pn*Qn + 2
   int G;                       // trajectories per group
@@ -81,7 +84,8 @@ __device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
 // Finiteness: inputs are checked while staging; with finite inputs a product
 // can only be non-finite by overflow, tracked with one max per element.
 __global__ void __launch_bounds__(256) crosscorr_kernel(CrossArgs p, FastDiv divF, FastDiv divQ,
-                                                        FastDiv divP, FastDiv divD, FastDiv divQx) {
+                                                        FastDiv divP, FastDiv divD, FastDiv divQx,
+                                                        FastDiv divA) {
   extern __shared__ float smem[];
   const int Qx = p.Qn + 3;                  // action features + 3 wrap-around copies
   float* sf = smem;                         // [G][Pn]
@@ -107,7 +111,7 @@ __global__ void __launch_bounds__(256) crosscorr_kernel(CrossArgs p, FastDiv div
     const uint32_t gl = fdiv(i, divP), e = i - gl * (uint32_t)p.Pn;
     const uint32_t t = fdiv(e, divD), j = e - t * (uint32_t)Dm1;
     const int g = g_lo + (int)gl;
-    const float* s = p.states + (traj0 + g) * p.s_stride + t * p.D + j;
+    const float* s = p.states + (traj0 + g) * p.s_stride + t * p.s_tstride + j;
     const float lo = __ldg(s);
     const float v = p.use_diff ? (__ldg(s + 1) - lo) : lo;
     bad |= !finite_f(v);
@@ -116,8 +120,11 @@ __global__ void __launch_bounds__(256) crosscorr_kernel(CrossArgs p, FastDiv div
   for (uint32_t i = threadIdx.x; i < (uint32_t)(nrows * Qx); i += blockDim.x) {
     const uint32_t gl = fdiv(i, divQx), e = i - gl * (uint32_t)Qx;
     const int g = g_lo + (int)gl;
-    // actions of the first W steps are contiguous: [t*A + k]; entries >= Qn wrap
-    const float v = __ldg(p.actions + (traj0 + g) * p.a_stride + (e >= Qn ? e - Qn : e));
+    // action feature q = t*A + k; entries >= Qn wrap around
+    const uint32_t q = e >= Qn ? e - Qn : e;
+    const uint32_t tq = fdiv(q, divA);
+    const float v = __ldg(p.actions + (traj0 + g) * p.a_stride + tq * p.a_tstride +
+                          (q - tq * (uint32_t)p.A));
     bad |= !finite_f(v);
     af[g * Qx + e] = v;
   }
@@ -244,6 +251,31 @@ static int gcd_i(int a, int b) { return b == 0 ? a : gcd_i(b, a % b); }
 
 using namespace bsig;
 
+static int summary_start_impl(const float* states, const float* actions, float* out, int64_t n,
+                              int64_t d, int64_t a, int64_t max_t, int64_t s_stride,
+                              int64_t s_tstride, int64_t a_stride, int64_t a_tstride,
+                              int64_t s_extent, int64_t a_extent, cudaStream_t st) {
+  if (n == 0) return 0;
+  const int64_t DA = d + a, F = max_t * DA, total = n * F;
+  BSIG_REQUIRE(F < (1ll << 31), "summary_start: row too wide");
+  const int64_t n4 = (total + 3) / 4;
+  const int threads = 256;
+  const int64_t blocks = std::min<int64_t>(ceil_div(n4, threads), (int64_t)sm_count() * 16);
+  if (total < (1ll << 31) && s_extent < (1ll << 31) && a_extent < (1ll << 31)) {
+    summary_start_kernel<uint32_t><<<(unsigned)blocks, threads, 0, st>>>(
+        states, actions, out, (uint32_t)total, (uint32_t)F, (uint32_t)DA, (uint32_t)d,
+        (uint32_t)a, (uint32_t)s_stride, (uint32_t)a_stride, (uint32_t)s_tstride,
+        (uint32_t)a_tstride);
+  } else {
+    summary_start_kernel<uint64_t><<<(unsigned)blocks, threads, 0, st>>>(
+        states, actions, out, (uint64_t)total, (uint32_t)F, (uint32_t)DA, (uint32_t)d,
+        (uint32_t)a, (uint64_t)s_stride, (uint64_t)a_stride, (uint64_t)s_tstride,
+        (uint64_t)a_tstride);
+  }
+  BSIG_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int bsig_summary_start(const float* states, const float* actions, float* out,
                                   int64_t n, int64_t t_states, int64_t t_actions,
                                   int64_t d, int64_t a, int64_t max_t, void* stream) {
@@ -251,37 +283,36 @@ extern "C" int bsig_summary_start(const float* states, const float* actions, flo
   BSIG_REQUIRE(t_states >= max_t && t_actions >= max_t,
                "summary_start: need at least max_t=%lld steps (got %lld states, %lld actions)",
                (long long)max_t, (long long)t_states, (long long)t_actions);
-  if (n == 0) return 0;
-  const int64_t DA = d + a, F = max_t * DA, total = n * F;
-  BSIG_REQUIRE(F < (1ll << 31), "summary_start: row too wide");
-  const int64_t n4 = (total + 3) / 4;
-  const int threads = 256;
-  const int64_t blocks = std::min<int64_t>(ceil_div(n4, threads), (int64_t)sm_count() * 16);
-  cudaStream_t st = (cudaStream_t)stream;
-  if (total < (1ll << 31) && n * t_states * d < (1ll << 31) && n * t_actions * a < (1ll << 31)) {
-    summary_start_kernel<uint32_t><<<(unsigned)blocks, threads, 0, st>>>(
-        states, actions, out, (uint32_t)total, (uint32_t)F, (uint32_t)DA, (uint32_t)d,
-        (uint32_t)a, (uint32_t)(t_states * d), (uint32_t)(t_actions * a));
-  } else {
-    summary_start_kernel<uint64_t><<<(unsigned)blocks, threads, 0, st>>>(
-        states, actions, out, (uint64_t)total, (uint32_t)F, (uint32_t)DA, (uint32_t)d,
-        (uint32_t)a, (uint64_t)(t_states * d), (uint64_t)(t_actions * a));
-  }
-  BSIG_LAUNCH_CHECK();
-  return 0;
+  return summary_start_impl(states, actions, out, n, d, a, max_t, t_states * d, d, t_actions * a,
+                            a, n * t_states * d, n * t_actions * a, (cudaStream_t)stream);
 }
 
-extern "C" int bsig_summary_crosscorr(const float* states, const float* actions, float* out,
-                                      int64_t n, int64_t t_states, int64_t t_actions,
-                                      int64_t d, int64_t a, int64_t w, int use_state_diff,
-                                      int* nonfinite_flag, void* stream) {
+extern "C" int bsig_summary_start_tm(const float* states, const float* actions, float* out,
+                                     int64_t n, int64_t t_states, int64_t t_actions,
+                                     int64_t d, int64_t a, int64_t max_t, void* stream) {
+  BSIG_REQUIRE(n >= 0 && d >= 1 && a >= 0 && max_t >= 1, "summary_start_tm: bad sizes");
+  BSIG_REQUIRE(t_states >= max_t && t_actions >= max_t,
+               "summary_start_tm: need at least max_t=%lld steps (got %lld states, %lld actions)",
+               (long long)max_t, (long long)t_states, (long long)t_actions);
+  return summary_start_impl(states, actions, out, n, d, a, max_t, d, n * d, a, n * a,
+                            n * t_states * d, n * t_actions * a, (cudaStream_t)stream);
+}
+
+static int crosscorr_impl(const float* states, const float* actions, float* out, int64_t n,
+                          int64_t t_states, int64_t t_actions, int64_t d, int64_t a, int64_t w,
+                          int use_state_diff, int* nonfinite_flag, bool time_major, void* stream) {
   BSIG_REQUIRE(n >= 0 && d >= 2 && a >= 1 && w >= 1, "crosscorr: need d>=2, a>=1, w>=1");
   BSIG_REQUIRE(t_states >= w && t_actions >= w, "crosscorr: trajectories shorter than w");
   BSIG_REQUIRE(nonfinite_flag != nullptr, "crosscorr: flag pointer required");
   if (n == 0) return 0;
   CrossArgs p;
   p.states = states; p.actions = actions; p.out = out; p.flag = nonfinite_flag;
-  p.n = n; p.s_stride = t_states * d; p.a_stride = t_actions * a;
+  p.n = n;
+  if (time_major) {
+    p.s_stride = d; p.a_stride = a; p.s_tstride = n * d; p.a_tstride = n * a;
+  } else {
+    p.s_stride = t_states * d; p.a_stride = t_actions * a; p.s_tstride = d; p.a_tstride = a;
+  }
   p.D = (int)d; p.A = (int)a; p.W = (int)w;
   p.Pn = (int)(w * (d - 1)); p.Qn = (int)(w * a);
   const int64_t PQ = (int64_t)p.Pn * p.Qn;
@@ -321,12 +352,29 @@ extern "C" int bsig_summary_crosscorr(const float* states, const float* actions,
   };
   divQ = mk((uint64_t)p.Qn);
   const FastDiv divP = mk((uint64_t)p.Pn), divD = mk((uint64_t)(p.D - 1)),
-                divQx = mk((uint64_t)(p.Qn + 3));
+                divQx = mk((uint64_t)(p.Qn + 3)), divA = mk((uint64_t)p.A);
   // staging indices stay below G*(Pn+Qn+3) <= 16K floats: far inside the FastDiv bound
   if (smem > 48 * 1024)
     BSIG_CUDA(cudaFuncSetAttribute(crosscorr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
-  crosscorr_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p, divF, divQ, divP, divD, divQx);
+  crosscorr_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p, divF, divQ, divP, divD, divQx,
+                                                              divA);
   BSIG_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int bsig_summary_crosscorr(const float* states, const float* actions, float* out,
+                                      int64_t n, int64_t t_states, int64_t t_actions,
+                                      int64_t d, int64_t a, int64_t w, int use_state_diff,
+                                      int* nonfinite_flag, void* stream) {
+  return crosscorr_impl(states, actions, out, n, t_states, t_actions, d, a, w, use_state_diff,
+                        nonfinite_flag, false, stream);
+}
+
+extern "C" int bsig_summary_crosscorr_tm(const float* states, const float* actions, float* out,
+                                         int64_t n, int64_t t_states, int64_t t_actions,
+                                         int64_t d, int64_t a, int64_t w, int use_state_diff,
+                                         int* nonfinite_flag, void* stream) {
+  return crosscorr_impl(states, actions, out, n, t_states, t_actions, d, a, w, use_state_diff,
+                        nonfinite_flag, true, stream);
 }

@@ -335,6 +335,60 @@ class MoG:
         samples, _ = _mixture_sample_device(self.a, means, cmats, u, z)
         return samples
 
+    def gen_per_env(self, n_envs, lows=None, highs=None, method='random', u=None, z=None,
+                    return_components=False):
+        """One (optionally clipped) draw per environment in a single device call: the
+        batched form of ``ParamsGenerator.sample`` (reference sim/params_generator.py:
+        115-118 -- ``distr.gen(n_samples=1)[0]`` then ``np.clip``), which the reference
+        runs once per environment reset.  Row e equals what ``gen(n_samples=1)[0]`` returns
+        for the uniform ``u[e]`` and the normals ``z[e]`` (draw order, not grouped by
+        component).  ``method='random'`` draws u = rand(n,1) then z = randn(n,P) from the
+        module RNG (or takes them as arguments); ``'philox'`` uses the device RNG (fp32)."""
+        n_envs = int(n_envs)
+        means = np.stack([g.m for g in self.xs])
+        cmats = np.stack([g.C for g in self.xs])
+        k, p = means.shape
+        assert (lows is None) == (highs is None)
+        dev = _device()
+        comp = torch.empty(max(n_envs, 1), dtype=torch.int32, device=dev)
+        if method == 'philox':
+            f32 = lambda arr: torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32)).to(dev)
+            a_d, m_d, c_d = f32(self.a), f32(means), f32(cmats)
+            lo_d = f32(lows) if lows is not None else None
+            hi_d = f32(highs) if highs is not None else None
+            out = torch.empty((n_envs, p), dtype=torch.float32, device=dev)
+            seed = int(rng.randint(0, 2**31 - 1))
+            _lib.call('bsig_mog_sample_envs_philox', a_d.data_ptr(), m_d.data_ptr(), c_d.data_ptr(),
+                      None if lo_d is None else lo_d.data_ptr(),
+                      None if hi_d is None else hi_d.data_ptr(), comp.data_ptr(), out.data_ptr(),
+                      seed, n_envs, p, k, _lib.stream_ptr(dev))
+        elif method == 'random':
+            if u is None:
+                u = rng.rand(n_envs, 1)
+            if z is None:
+                z = rng.randn(n_envs, self.ndim)
+            a = np.ascontiguousarray(self.a)
+            a_is_f32 = a.dtype == np.float32
+            if not a_is_f32:
+                a = a.astype(np.float64)
+            a_d = torch.from_numpy(a).to(dev)
+            u_d, z_d = _dev64(np.asarray(u).reshape(-1), dev), _dev64(z, dev)
+            m_d, c_d = _dev64(means, dev), _dev64(cmats, dev)
+            lo_d = _dev64(lows, dev) if lows is not None else None
+            hi_d = _dev64(highs, dev) if highs is not None else None
+            out = torch.empty((n_envs, p), dtype=torch.float64, device=dev)
+            _lib.call('bsig_mog_sample_envs', a_d.data_ptr(), 1 if a_is_f32 else 0, u_d.data_ptr(),
+                      z_d.data_ptr(), m_d.data_ptr(), c_d.data_ptr(),
+                      None if lo_d is None else lo_d.data_ptr(),
+                      None if hi_d is None else hi_d.data_ptr(), out.data_ptr(), comp.data_ptr(),
+                      n_envs, p, k, _lib.stream_ptr(dev))
+        else:
+            raise ValueError('Unknown gen method ' + method)
+        res = out.cpu().numpy()
+        if return_components:
+            return res, comp[:n_envs].cpu().numpy()
+        return res
+
     def _gen_philox(self, n_samples, means, cmats):
         dev = _device()
         k, p = means.shape

@@ -63,35 +63,56 @@ def _leading_steps(states, actions, n_steps):
     return states, actions
 
 
-def summary_start(states, actions, max_t=10):
-    """Reference summarizers.py:65-70: first max_t steps, [s_t | a_t] per step."""
+def summary_start(states, actions, max_t=10, time_major=False):
+    """Reference summarizers.py:65-70: first max_t steps, [s_t | a_t] per step.
+    ``time_major=True`` (not in the reference signature): the inputs
+    are [n_steps, ntraj, dim] buffers as a vectorised simulator fills them step by step
+    (what collect_trajectories.py:55-69 re-assembles per episode); same output."""
     assert (len(states.shape) == 3), 'Need states: ntraj x n_steps x state_dim'
     assert (len(actions.shape) == 3), 'Need actions: ntraj x n_steps x state_dim'
-    assert states.shape[0] == actions.shape[0]
-    states, actions = _leading_steps(states, actions, max_t)
-    n, ts, d = states.shape
-    ta, a = actions.shape[1], actions.shape[2]
+    if time_major:
+        assert states.shape[1] == actions.shape[1]
+        assert states.shape[0] >= max_t and actions.shape[0] >= max_t, \
+            'time-major rollouts must hold at least max_t steps'
+        states, actions = _as_kernel_input(states), _as_kernel_input(actions)
+        ts, n, d = states.shape
+        ta, a = actions.shape[0], actions.shape[2]
+        entry = 'bsig_summary_start_tm'
+    else:
+        assert states.shape[0] == actions.shape[0]
+        states, actions = _leading_steps(states, actions, max_t)
+        n, ts, d = states.shape
+        ta, a = actions.shape[1], actions.shape[2]
+        entry = 'bsig_summary_start'
     out = torch.empty((n, max_t * (d + a)), dtype=torch.float32, device=states.device)
     with torch.cuda.device(states.device):
-        _lib.call('bsig_summary_start', _lib.ptr(states), _lib.ptr(actions), _lib.ptr(out),
+        _lib.call(entry, _lib.ptr(states), _lib.ptr(actions), _lib.ptr(out),
                   n, ts, ta, d, a, max_t, _lib.stream_ptr(states.device))
     return out
 
 
-def summary_waypts(states, actions, n_waypts=10):
+def summary_waypts(states, actions, n_waypts=10, time_major=False):
     """Reference summarizers.py:73-87.  The reference chops to n_waypts steps
     before computing its stride, so the stride is always 1 and the result is
     summary_start(max_t=n_waypts)."""
-    return summary_start(states, actions, max_t=n_waypts)
+    return summary_start(states, actions, max_t=n_waypts, time_major=time_major)
 
 
-def cross_correlation(states, actions, use_state_diff=False):
-    """Reference summarizers.py:90-122."""
+def cross_correlation(states, actions, use_state_diff=False, time_major=False):
+    """Reference summarizers.py:90-122 (``time_major``: see summary_start)."""
     assert (len(states.shape) == 3), 'Need states: ntraj x n_steps x state_dim'
     assert (len(actions.shape) == 3), 'Need actions: ntraj x n_steps x state_dim'
-    ntraj, traj_len, state_dim = states.shape
-    if actions.shape[1] < traj_len:      # reference pads actions up to the states' length
-        states, actions = pad_states_actions(states, actions)
+    if time_major:
+        traj_len, ntraj, state_dim = states.shape
+        assert actions.shape[0] >= min(traj_len, 10) and actions.shape[1] == ntraj
+        t_states, t_actions = states.shape[0], actions.shape[0]
+        entry = 'bsig_summary_crosscorr_tm'
+    else:
+        ntraj, traj_len, state_dim = states.shape
+        if actions.shape[1] < traj_len:      # reference pads actions up to the states' length
+            states, actions = pad_states_actions(states, actions)
+        t_states, t_actions = states.shape[1], actions.shape[1]
+        entry = 'bsig_summary_crosscorr'
     assert (traj_len > 1)  # empty episodes are problematic
     max_traj_len = 5 if state_dim > 50 else 10
     w = min(traj_len, max_traj_len)
@@ -101,8 +122,8 @@ def cross_correlation(states, actions, use_state_diff=False):
     feats = torch.empty((ntraj, width), dtype=torch.float32, device=states.device)
     flag = torch.zeros(1, dtype=torch.int32, device=states.device)
     with torch.cuda.device(states.device):
-        _lib.call('bsig_summary_crosscorr', _lib.ptr(states), _lib.ptr(actions), _lib.ptr(feats),
-                  ntraj, states.shape[1], actions.shape[1], state_dim, act_dim, w,
+        _lib.call(entry, _lib.ptr(states), _lib.ptr(actions), _lib.ptr(feats),
+                  ntraj, t_states, t_actions, state_dim, act_dim, w,
                   1 if use_state_diff else 0, _lib.ptr(flag, torch.int32),
                   _lib.stream_ptr(states.device))
     assert (int(flag.item()) == 0)       # torch.isfinite(feats).all() in the reference
@@ -110,12 +131,12 @@ def cross_correlation(states, actions, use_state_diff=False):
     return feats
 
 
-def summary_corrdiff(states, actions):
-    return cross_correlation(states, actions, use_state_diff=True)
+def summary_corrdiff(states, actions, time_major=False):
+    return cross_correlation(states, actions, use_state_diff=True, time_major=time_major)
 
 
-def summary_corr(states, actions):
-    return cross_correlation(states, actions, use_state_diff=False)
+def summary_corr(states, actions, time_major=False):
+    return cross_correlation(states, actions, use_state_diff=False, time_major=time_major)
 
 
 def signature_depth(ndim):

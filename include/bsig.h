@@ -75,6 +75,19 @@ int bsig_summary_crosscorr(const float* states, const float* actions, float* out
                            int64_t d, int64_t a, int64_t w, int use_state_diff,
                            int* nonfinite_flag, void* stream);
 
+/* Time-major rollout ingestion: the same two summarizers reading
+ * states [t_states, n, d] / actions [t_actions, n, a] exactly as a vectorised simulator
+ * writes them step by step -- no per-episode stack / cat assembly
+ * (utils/collect_trajectories.py:55-69,86-89) and no transpose.  Outputs are identical to
+ * the trajectory-major entry points on the transposed buffers. */
+int bsig_summary_start_tm(const float* states, const float* actions, float* out,
+                          int64_t n, int64_t t_states, int64_t t_actions,
+                          int64_t d, int64_t a, int64_t max_t, void* stream);
+int bsig_summary_crosscorr_tm(const float* states, const float* actions, float* out,
+                              int64_t n, int64_t t_states, int64_t t_actions,
+                              int64_t d, int64_t a, int64_t w, int use_state_diff,
+                              int* nonfinite_flag, void* stream);
+
 /* summary_signatory (summarizers.py:144-168; arithmetic = signatory.signature):
  * path_t = [t+1 | states[i,t,:] | actions[i,t,:]], t < len; depth in {1,2,3};
  * out [n, sum_{k<=depth} c^k], c = 1+d+a, levels concatenated, each C-order.
@@ -227,6 +240,21 @@ int bsig_mog_sample(const void* a, int a_is_f32, const double* u, const double* 
 int bsig_mog_sample_philox(const float* a, const float* means, const float* cmats,
                            int32_t* comp_idx, float* samples, uint64_t seed,
                            int64_t n, int64_t p, int64_t k, void* stream);
+/* One clipped posterior draw per environment in ONE launch -- the batched form of
+ * ParamsGenerator.sample (sim/params_generator.py:115-118: distr.gen(n_samples=1)[0] then
+ * np.clip(.., lows, highs)), which the reference calls once per environment reset
+ * (sim/apply_randomizations.py:154-158).  Environment e uses uniform u[e] and normals
+ * z[e,:]; samples [n,P] float64 in DRAW order, component choice bit-exact for identical
+ * uniforms; lows/highs [P] nullable (no clip); comp_idx [n] nullable. */
+int bsig_mog_sample_envs(const void* a, int a_is_f32, const double* u, const double* z,
+                         const double* means, const double* cmats, const double* lows,
+                         const double* highs, double* samples, int32_t* comp_idx,
+                         int64_t n, int64_t p, int64_t k, void* stream);
+/* Same with the device RNG of bsig_mog_sample_philox (fp32). */
+int bsig_mog_sample_envs_philox(const float* a, const float* means, const float* cmats,
+                                const float* lows, const float* highs, int32_t* comp_idx,
+                                float* samples, uint64_t seed, int64_t n, int64_t p,
+                                int64_t k, void* stream);
 
 /* MoG.eval, joint density (utils/pdf.py:474-491, 328-332):
  * x [m,P] (float32 if x_is_f32 else float64); a [K], log_a [K] (np.log(a) taken in

@@ -48,6 +48,21 @@ def mog_gen_from_draws(a, means, cmats, u, z):
     return np.concatenate(out, axis=0), idx, counts
 
 
+def params_samples_per_env(a, means, cmats, u, z, lows=None, highs=None):
+    """sim/params_generator.py:115-118 applied once per environment:
+    ``np.clip(distr.gen(n_samples=1)[0], lows, highs)`` with environment e consuming
+    the uniform u[e] and the normals z[e] (pdf.py:465-472, 296-300 with n_samples=1)."""
+    idx = discrete_sample_from_u(a, u)
+    z = np.asarray(z)
+    out = []
+    for e, k in enumerate(idx):
+        x = (np.dot(z[e:e + 1], cmats[k]) + means[k])[0]
+        if lows is not None:
+            x = np.clip(x, lows, highs)
+        out.append(x)
+    return np.stack(out), idx
+
+
 def gaussian_logpdf(x, m, prec, logdet_p):
     """pdf.py:328-332 (joint)."""
     xm = x - m

@@ -230,6 +230,21 @@ def golden_pdf():
         out[name + '.eval.log32'] = mog.eval(xq.astype(np.float32), log=True)
         one = mog.gen(n_samples=1)
         assert one.shape == (1, p)
+        # the posterior consumer: ParamsGenerator.sample (sim/params_generator.py:115-118),
+        # once per environment; its draws are replayed to record (u, z) per environment
+        n_env = 41
+        lows, highs = np.full(p, -0.8), np.full(p, 0.9)
+        np.random.seed(33)
+        envs = np.stack([np.clip(mog.gen(n_samples=1)[0], lows, highs) for _ in range(n_env)])
+        np.random.seed(33)
+        eu, ez = [], []
+        for _ in range(n_env):
+            eu.append(np.random.rand(1, 1))
+            ez.append(np.random.randn(1, p))
+        out[name + '.envs.lows'], out[name + '.envs.highs'] = lows, highs
+        out[name + '.envs.u'] = np.concatenate(eu)
+        out[name + '.envs.z'] = np.concatenate(ez)
+        out[name + '.envs.samples'] = envs
     # pruning (pdf.py:562-570)
     a = np.array([0.001, 0.5, 0.002, 0.497])
     mog = ref_pdf.MoG(a=a, ms=[np.zeros(2)] * 4, Ls=[np.ones(2)] * 4)

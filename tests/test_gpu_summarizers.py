@@ -213,3 +213,20 @@ def test_signature_backward_vs_float64_autograd(shape):
     (ref * w.double()).sum().backward()
     assert rel_err(s.grad.cpu(), s64.grad.cpu()) < 5e-5
     assert rel_err(ac.grad.cpu(), a64.grad.cpu()) < 5e-5
+
+
+@pytest.mark.parametrize('shape', [(37, 21, 4, 1), (5, 11, 108, 21), (1000, 51, 60, 8), (3, 7, 3, 2)])
+def test_time_major_ingestion_is_bit_identical(shape, capsys):
+    """[T, N, dim] buffers (a vectorised simulator's layout) give
+    exactly the summaries of the transposed [N, T, dim] rollouts."""
+    from bayes_sim_ig.utils import summarizers as S
+    n, t1, d, a = shape
+    s, ac = synth_rollouts(3, n, t1, d, a, DEV)
+    s_tm, a_tm = s.transpose(0, 1).contiguous(), ac.transpose(0, 1).contiguous()
+    for fxn in (S.summary_start, S.summary_waypts, S.summary_corr, S.summary_corrdiff):
+        if fxn in (S.summary_start, S.summary_waypts) and t1 < 10:
+            continue
+        assert torch.equal(fxn(s_tm, a_tm, time_major=True), fxn(s, ac)), fxn.__name__
+    # actions stored with extra steps
+    longer = torch.cat([a_tm, a_tm[:2]], 0).contiguous()
+    assert torch.equal(S.summary_corrdiff(s_tm, longer, time_major=True), S.summary_corrdiff(s, ac))

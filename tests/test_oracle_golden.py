@@ -155,6 +155,11 @@ def test_pdf_ctor_gen_eval(golden, case):
         a, ms, [x['C'] for x in gs], g[case + '.gen.u'], g[case + '.gen.z'])
     assert sum(counts) == smp.shape[0]
     np.testing.assert_array_equal(smp, g[case + '.gen.samples'])
+    # posterior consumer (ParamsGenerator.sample per environment): bit exact
+    env, _ = pdf_np.params_samples_per_env(a, ms, [x['C'] for x in gs], g[case + '.envs.u'],
+                                           g[case + '.envs.z'], g[case + '.envs.lows'],
+                                           g[case + '.envs.highs'])
+    np.testing.assert_array_equal(env, g[case + '.envs.samples'])
     x64 = g[case + '.eval.x64']
     precs = [x['P'] for x in gs]
     lds = [x['logdetP'] for x in gs]

@@ -17,6 +17,9 @@ Random inputs (minibatch rows, eps-noise uniforms) are generated up front for
 the whole call; the 2 x n_log losses and the finiteness flag are read back with
 one device->host copy when the graph has finished.
 """
+import contextlib
+import gc
+
 import numpy as np
 import torch
 
@@ -37,6 +40,21 @@ def replayed_launches():
 def log_steps(n_updates):
     every = max(n_updates // 5, 1)
     return [e for e in range(n_updates) if e % every == 0 or e + 1 == n_updates]
+
+
+@contextlib.contextmanager
+def _quiet_gc():
+    """No cyclic garbage collection while a stream is capturing: a collected TrainPlan of
+    a discarded model would destroy its CUDA graph in the middle of the capture, which
+    invalidates it (seen when several models are fitted one after the other)."""
+    gc.collect()
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        yield
+    finally:
+        if was_enabled:
+            gc.enable()
 
 
 class TrainPlan(object):
@@ -230,9 +248,35 @@ class TrainPlan(object):
             self._enqueue_step(step, st)
             self._enqueue_update(step, st)
 
+    def warm_up(self):
+        """Run update 0 once OUTSIDE graph capture, then undo its effects.  The first
+        launch of a kernel loads its code lazily and may grow the context's local-memory
+        pool -- neither is allowed while a stream is capturing (a first call that went
+        straight into capture failed for the ShadowHand-sized layers, whose engine had
+        never been launched before).  Step 0 is a logging step, so the held-out
+        evaluation kernels are covered too."""
+        m = self.model
+        saved = m.flat_params.detach().clone()
+        saved_loss, saved_flag = self.loss_buf.clone(), self.flag.clone()
+        st = _lib.stream_ptr(self.dev)
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        self._enqueue_step(0, st)
+        if self.p2p is None:
+            data_parallel.allreduce_gradients(m, self.grads)
+        self._enqueue_update(0, st)
+        torch.cuda.synchronize(self.dev)
+        m.flat_params.copy_(saved)
+        self.loss_buf.copy_(saved_loss)
+        self.flag.copy_(saved_flag)
+        if self.p2p is not None:
+            # the exchange used gradient buffer 0, which update 0 of the graph writes again:
+            # every rank must have finished reading it
+            torch.distributed.barrier(group=getattr(m, '_dp_group', None))
+
     def capture(self):
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        with _quiet_gc(), torch.cuda.graph(graph, capture_error_mode='relaxed'):
             self.enqueue_all()
         self.graph = graph
 
@@ -246,7 +290,7 @@ class TrainPlan(object):
             pair = []
             for half in (self._enqueue_step, self._enqueue_update):
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=pool):
+                with _quiet_gc(), torch.cuda.graph(g, pool=pool, capture_error_mode='relaxed'):
                     half(step, _lib.stream_ptr(self.dev))
                 pool = g.pool()
                 pair.append(g)
@@ -330,6 +374,7 @@ def run_training_captured(model, x_data, y_data, n_updates, batch_size, test_fra
             torch.distributed.barrier(group=getattr(model, '_dp_group', None))
         if use_graph and dp and plan.p2p is None:
             if getattr(plan, 'dp_graphs', None) is None:
+                plan.warm_up()
                 before = _lib.load().bsig_launch_count()
                 plan.capture_dp()
                 plan.launches_per_replay = _lib.load().bsig_launch_count() - before
@@ -337,6 +382,7 @@ def run_training_captured(model, x_data, y_data, n_updates, batch_size, test_fra
             _REPLAYED[0] += int(getattr(plan, 'launches_per_replay', 0))
         elif use_graph:
             if plan.graph is None:
+                plan.warm_up()
                 before = _lib.load().bsig_launch_count()
                 plan.capture()
                 plan.launches_per_replay = _lib.load().bsig_launch_count() - before

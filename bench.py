@@ -59,6 +59,11 @@ def workload_config(n_gpus):
             'trajectories_per_gpu': N_TRAJ, 'chunk': CHUNK, 'n_updates_per_chunk': 100,
             'minibatch': 100, 'posterior_samples': N_POSTERIOR_SAMPLES,
             'parallelism': 'dp%d' % n_gpus,
+            'gradient_exchange': ('none' if n_gpus == 1 else
+                                  os.environ.get('BSIG_DP_EXCHANGE', 'p2p') +
+                                  (' (one-shot all-reduce over NVLink peer memory fused into the '
+                                   'Adam kernel)' if os.environ.get('BSIG_DP_EXCHANGE', 'p2p') == 'p2p'
+                                   else ' (NCCL all-reduce between two CUDA graphs per update)')),
             'l2_policy': 'L2 flushed (256 MiB write) between timed steps'}
 
 
@@ -278,9 +283,12 @@ def kernel_rooflines(dev, flush, peak_gbs, peak_src):
         _lib.call('bsig_mdn_nll_fused', z.data_ptr(), noise.data_ptr(), y.data_ptr(), None,
                   loss.data_ptr(), dz.data_ptr(), b, p, k, 0, ws.data_ptr(), ws.numel(),
                   flag.data_ptr(), st())
-    # algorithmic: read z + noise + y, write dz  (3 launches: exp-sum, nll, eps fix-up)
+    # algorithmic: read z + noise + y, write dz.  3 launches (exp-sum for the batch-global
+    # eps, the streaming NLL kernel, the batch-global eps-gradient fix-up) whose exact
+    # semantics need 1.78x the algorithmic bytes: z_d read three times, dz_d written twice
     entry('mdn_nll_fused_fwd_bwd', 4 * b * (2 * nh + p * k + p), time_kernel(nll, flush),
-          'B=%d P=13 K=10 diag, fwd+bwd (3 launches)' % b)
+          'B=%d P=13 K=10 diag, fwd+bwd (3 launches; minimum traffic of the exact '
+          'batch-global eps semantics = 1.78x algorithmic)' % b)
     # RFF projection + sincos, Ant-shaped summary_start (configs[2]): N=65536, d=680 -> 200
     del z, dz, noise, y
     n3, d3, nf = 1 << 16, 680, 100
@@ -426,7 +434,101 @@ def extra_configs(dev):
                   'summary_start(F=680) + MDRFF(n_feat=200, sigma=4, RBF) fit, reference constants',
         'fit_trajectories_per_s': n / dt, 'seconds': dt, 'final_test_loss': logs['test_loss'][-1],
         'rff_features_whole_batch_ms': 1e3 * t_rff, 'features_shape': list(mogs_in.shape)}
+    del bsim, states, actions, params, feats, mogs_in
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    for fn in (extra_shadowhand, extra_signature_mdrff):
+        try:
+            out.update(fn(dev))
+        except Exception as exc:          # an extra must never take the headline line down
+            out[fn.__name__] = {'error': repr(exc)[:300]}
+            torch.cuda.empty_cache()
     return out
+
+
+def extra_shadowhand(dev):
+    """configs[3], single-GPU slice: ShadowHand-shaped rollouts [T1=51, D=211, A=20, P=32],
+    summary_corrdiff (F = 105 002, 420 KB per trajectory) + MDNN[128,128] K=10 diag
+    (13.5 M parameters), one reference-sized call: 1000 trajectories, 100 Adam updates of
+    minibatch 100.  At this shape an update is HBM-bound: 28 B/param of Adam traffic plus
+    the 54 MB first-layer weight read (forward) and gradient write."""
+    import contextlib
+    import io
+    from bayes_sim_ig.bayes_sim import BayesSim
+    task = dict(name='shadowhand', D=211, A=20, T1=51, P=32, K=10)
+    n = 1000
+    states, actions, params, lows, highs = synth(11, n, task)
+    states, actions, params = states.to(dev), actions.to(dev), params.to(dev)
+    cfg = {'modelClass': 'MDNN', 'summarizerFxn': 'summary_corrdiff', 'trainTrajLen': 50,
+           'components': 10, 'hiddenLayers': [128, 128], 'lr': 1e-4}
+    with contextlib.redirect_stdout(io.StringIO()):
+        bsim = BayesSim(cfg, task['D'], task['A'], task['P'], lows, highs, prior=None,
+                        proposal=None, device=str(dev))
+        bsim.run_training(params, states, actions)          # capture + warm up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        logs = bsim.run_training(params, states, actions)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    n_par = int(bsim.model.flat_params.numel())
+    res = {'shadowhand_corrdiff_mdnn_1k': {
+        'config': 'configs[3] (one GPU, one reference-sized call): ShadowHand-shaped 1000 '
+                  'trajectories, summary_corrdiff(F=105002) + MDNN[128,128] K=10, 100 Adam updates x '
+                  'minibatch 100 + 6 test evals',
+        'fit_trajectories_per_s': n / dt, 'seconds': dt, 'parameters': n_par,
+        'ms_per_update': 1e3 * dt / 100, 'final_test_loss': logs['test_loss'][-1]}}
+    del bsim, states, actions, params
+    torch.cuda.empty_cache()
+    return res
+
+
+def extra_signature_mdrff(dev):
+    """configs[4], single-GPU slice: depth-3 path-signature summarizer on Cartpole-shaped
+    rollouts (C = 6 -> 258 features) + MDRFF fit (reference constants, chunks of 1000) and a
+    posterior-sampling sweep with the device RNG."""
+    import contextlib
+    import io
+    from bayes_sim_ig.bayes_sim import BayesSim
+    res = {}
+    for n in (4096, 65536):
+        states, actions, params, lows, highs = synth(13, n, TASK)
+        states, actions, params = (states * 0.3).to(dev), actions.to(dev), params.to(dev)
+        cfg = {'modelClass': 'MDRFF', 'summarizerFxn': 'summary_signatory', 'trainTrajLen': 20,
+               'components': 10, 'hiddenLayers': [128, 128], 'lr': 1e-4}
+        with contextlib.redirect_stdout(io.StringIO()):
+            bsim = BayesSim(cfg, TASK['D'], TASK['A'], TASK['P'], lows, highs, prior=None,
+                            proposal=None, device=str(dev))
+
+            def fit():
+                for lo in range(0, n, CHUNK):
+                    logs = bsim.run_training(params[lo:lo + CHUNK], states[lo:lo + CHUNK],
+                                             actions[lo:lo + CHUNK])
+                return logs
+            fit()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            logs = fit()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            post = bsim.predict(states[:1], actions[:1])
+            sweep = {}
+            for ns in (10000, 1000000):
+                post.gen(ns, method='philox')
+                torch.cuda.synchronize()
+                t1 = time.perf_counter()
+                smp = post.gen(ns, method='philox')
+                sweep[str(ns)] = ns / (time.perf_counter() - t1)
+        res['signature_mdrff_%d' % n] = {
+            'config': 'configs[4] (one GPU): Cartpole-shaped %d trajectories, summary_signatory '
+                      '(depth 3, 258 features) + MDRFF fit, reference constants; posterior sampling '
+                      'with the device RNG (samples/s incl. D2H copy)' % n,
+            'fit_trajectories_per_s': n / dt, 'seconds': dt,
+            'final_test_loss': logs['test_loss'][-1], 'posterior_samples_per_s': sweep,
+            'sample_shape': list(smp.shape)}
+        del bsim, states, actions, params
+        torch.cuda.empty_cache()
+    return res
 
 
 def run_b200(args):
@@ -528,6 +630,7 @@ def run_b200(args):
         line['rooflines'] = roofs
         line['extra'] = extra_configs(dev)
         threads = os.cpu_count() or 1
+        cpu_pipeline_rate(200, threads)         # warm up the CPU thread pool / allocator
         rate, dt = cpu_pipeline_rate(1000, threads)
         line['cpu_baseline'] = {
             'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',

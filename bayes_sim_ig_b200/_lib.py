@@ -24,6 +24,7 @@ SIGNATURES = {
     'bsig_version': (_int, []),
     'bsig_launch_count': (_i64, []),
     'bsig_set_pdl': (_int, [_int]),
+    'bsig_bulk_copy_probe': (_int, [_c_ptr, _c_ptr, _i64, _i64, _int, _int, _c_ptr]),
     'bsig_device_info': (_int, [ctypes.POINTER(_int)] * 3),
     'bsig_summary_start': (_int, [_c_ptr, _c_ptr, _c_ptr] + [_i64] * 6 + [_c_ptr]),
     'bsig_summary_start_tm': (_int, [_c_ptr, _c_ptr, _c_ptr] + [_i64] * 6 + [_c_ptr]),

@@ -130,7 +130,7 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
   return v;
 }
 
-template <int C>
+template <int C, int JP>      // JP: level-3 rows updated with packed FFMA2 (the rest: FFMA)
 __global__ void __launch_bounds__(256, (C >= 7 ? 2 : 3)) signature3_small_kernel(SigArgs p) {
   extern __shared__ __align__(16) float smem[];
   // full[b]: raw buffer b holds a tile;  done: the consumers have finished a tile (raw
@@ -270,10 +270,18 @@ __global__ void __launch_bounds__(256, (C >= 7 ? 2 : 3)) signature3_small_kernel
 #pragma unroll
         for (int j = 0; j < C; ++j) {
           const float t2 = fmaf(a3, dv[j], s2[j]);
-          const float2 t22 = make_float2(t2, t2);
+          if (j < JP) {                      // packed rows: FFMA2 (fma-heavy pipe only)
+            const float2 t22 = make_float2(t2, t2);
 #pragma unroll
-          for (int k = 0; k < CP; ++k)
-            s3[j][k] = __ffma2_rn(t22, make_float2(dv[2 * k], dv[2 * k + 1]), s3[j][k]);
+            for (int k = 0; k < CP; ++k)
+              s3[j][k] = __ffma2_rn(t22, make_float2(dv[2 * k], dv[2 * k + 1]), s3[j][k]);
+          } else {                           // scalar rows: FFMA (either fma pipe)
+#pragma unroll
+            for (int k = 0; k < CP; ++k) {
+              s3[j][k].x = fmaf(t2, dv[2 * k], s3[j][k].x);
+              s3[j][k].y = fmaf(t2, dv[2 * k + 1], s3[j][k].y);
+            }
+          }
           s2[j] = fmaf(a2, dv[j], s2[j]);
         }
         s1 += di;
@@ -426,21 +434,36 @@ extern "C" int bsig_signature_fwd(const float* states, const float* actions, flo
       const size_t smem = (size_t)(2 * p.raw_stride + tpb * p.siglen) * 4;
       const int threads = (int)(ceil_div((int64_t)tpb * C, 32) * 32) + 32;   // + producer warp
       const int64_t ntiles = ceil_div(n, tpb);
-#define BSIG_SIGS(CV)                                                                        \
-  case CV: {                                                                                 \
+      // packed-FFMA2 rows: FFMA2 issues on the fma-heavy pipe only, FFMA on either, so
+      // the split is a throughput knob (measured)
+      static const int jp_env = [] {
+        const char* e = getenv("BSIG_SIG_JP");
+        return e ? atoi(e) : -1;
+      }();
+#define BSIG_SIG_LAUNCH(CV, JPV)                                                             \
+  {                                                                                          \
+    auto kern = signature3_small_kernel<CV, JPV>;                                            \
     if (smem > 48 * 1024)                                                                    \
-      BSIG_CUDA(cudaFuncSetAttribute(signature3_small_kernel<CV>,                            \
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      BSIG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                     (int)smem));                                            \
     int occ = 1;                                                                             \
-    BSIG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, signature3_small_kernel<CV>, \
-                                                            threads, smem));                 \
+    BSIG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));     \
     const unsigned grid =                                                                    \
         (unsigned)std::min<int64_t>(ntiles, std::max(occ, 1) * (int64_t)sm_count());         \
-    signature3_small_kernel<CV><<<grid, threads, smem, st>>>(p);                             \
+    kern<<<grid, threads, smem, st>>>(p);                                                    \
+  }
+#define BSIG_SIGS(CV)                                                                        \
+  case CV: {                                                                                 \
+    const int jp = jp_env < 0 ? CV / 2 : jp_env;                                             \
+    if (jp <= 0) BSIG_SIG_LAUNCH(CV, 0)                                                      \
+    else if (jp == 1) BSIG_SIG_LAUNCH(CV, 1)                                                 \
+    else if (jp < CV) BSIG_SIG_LAUNCH(CV, CV / 2)                                            \
+    else BSIG_SIG_LAUNCH(CV, CV)                                                             \
   } break;
       switch ((int)C) {
         BSIG_SIGS(2) BSIG_SIGS(3) BSIG_SIGS(4) BSIG_SIGS(5) BSIG_SIGS(6) BSIG_SIGS(7) BSIG_SIGS(8)
       }
+#undef BSIG_SIG_LAUNCH
 #undef BSIG_SIGS
     } else {
       const int cc = (int)(C * C);

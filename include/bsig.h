@@ -50,6 +50,10 @@ int64_t bsig_launch_count(void);
 /* Programmatic dependent launch of the training-step kernels (default on; env BSIG_PDL=0
  * or bsig_set_pdl(0) turns it off).  No reference counterpart (launch plumbing). */
 int bsig_set_pdl(int enabled);
+/* Profiling aid (no reference counterpart): persistent copy through the same cp.async.bulk
+ * double-buffer pipeline the streaming kernels use; measures what the 1-D bulk path sustains. */
+int bsig_bulk_copy_probe(const void* src, void* dst, int64_t bytes, int64_t tile_bytes,
+                         int stages, int ctas_per_sm, void* stream);
 /* host query: SM count and compute capability of the current device */
 int bsig_device_info(int* sm_count, int* cc_major, int* cc_minor);
 

@@ -143,3 +143,61 @@ def test_halton_points_in_open_unit_cube():
     pts = halton_points(100, 50)
     assert pts.shape == (100, 50) and (pts > 0).all() and (pts < 1).all()
     assert abs(pts.mean() - 0.5) < 0.05
+
+
+def test_next_row_entry_points_have_no_cpu_fallback_either(golden):
+    """Time-major ingestion and the batched per-environment sampler are
+    device paths like everything else: CPU tensors / a machine without CUDA raise."""
+    import torch
+    from bayes_sim_ig_b200 import _lib
+    from bayes_sim_ig.sim.params_generator import ParamsSampler
+    from bayes_sim_ig.utils import pdf, summarizers
+    with pytest.raises(_lib.BsigError):
+        summarizers.summary_start(torch.zeros(12, 2, 3), torch.zeros(12, 2, 1), time_major=True)
+    with pytest.raises(_lib.BsigError):
+        summarizers.summary_corrdiff(torch.zeros(12, 2, 3), torch.zeros(12, 2, 1), time_major=True)
+    if not torch.cuda.is_available():
+        g = golden('pdf')
+        mog = pdf.MoG(a=g['f32.a'], ms=list(g['f32.ms']), Ls=list(g['f32.Ls']))
+        sampler = ParamsSampler(g['f32.envs.lows'], g['f32.envs.highs'], mog)
+        with pytest.raises(_lib.BsigError):
+            sampler.sample_batch(4)
+
+
+def test_params_sampler_host_semantics():
+    """ParamsSampler.sample is the reference's three lines (params_generator.py:113-117);
+    sample_batch falls back to the distribution's own gen when it has no device sampler."""
+    from bayes_sim_ig.sim.params_generator import ParamsSampler
+
+    class Stub(object):
+        def __init__(self):
+            self.calls = []
+
+        def gen(self, n_samples=1):
+            self.calls.append(n_samples)
+            return np.tile(np.array([[-3.0, 0.25, 7.0]]), (n_samples, 1))
+
+    stub = Stub()
+    sampler = ParamsSampler([-1.0, 0.0, 0.0], [1.0, 1.0, 2.0])
+    sampler.set_distr(stub)
+    np.testing.assert_array_equal(sampler.sample(), [-1.0, 0.25, 2.0])
+    out = sampler.sample_batch(5)
+    assert out.shape == (5, 3) and stub.calls == [1, 5]
+    np.testing.assert_array_equal(out[3], [-1.0, 0.25, 2.0])
+    np.testing.assert_array_equal(sampler.lows, [-1.0, 0.0, 0.0])
+
+
+def test_capture_guard_restores_gc_state():
+    import gc
+    from bayes_sim_ig_b200.models.train_engine import _quiet_gc
+    assert gc.isenabled()
+    with _quiet_gc():
+        assert not gc.isenabled()
+    assert gc.isenabled()
+    gc.disable()
+    try:
+        with _quiet_gc():
+            assert not gc.isenabled()
+        assert not gc.isenabled()
+    finally:
+        gc.enable()

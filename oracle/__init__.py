@@ -19,6 +19,10 @@ Parity pinning
   imported live from ``/root/reference`` by ``tests/golden/make_golden.py``;
   the resulting vectors are committed under ``tests/golden/*.npz`` and
   ``tests/test_oracle_golden.py`` checks the oracle against them.
+* ``ParamsGenerator.sample`` per environment (the posterior consumer,
+  sim/params_generator.py:115-118): **pinned**, ``pdf_np.params_samples_per_env`` is
+  bit-exact against 41 sequential calls of the live reference (``*.envs.*`` in
+  ``tests/golden/pdf.npz``).
 * path signature (``summary_signatory``): **parity unpinned**.  The arithmetic
   lives in the third-party ``signatory`` package (patrick-kidger/signatory,
   un-pinned by the reference: README.md:345-350 installs master), which is

@@ -57,3 +57,29 @@ def test_two_rank_gradient_average_equals_full_batch(tmp_path):
         err = float(torch.load(os.path.join(str(tmp_path), 'err%d.pt' % r)))
         # the only difference is the local-vs-global eps mean: O(1e-5) relative
         assert err < 5e-5, err
+
+
+def test_fused_exchange_is_only_chosen_for_small_models_on_one_node(monkeypatch):
+    """Gating of the peer-memory exchange (no GPU needed: the communicator itself is
+    never built here): single rank, more than 8 ranks, models above P2P_MAX_PARAMS and
+    BSIG_DP_EXCHANGE=nccl all go through NCCL."""
+    from bayes_sim_ig_b200 import data_parallel
+
+    class FakeModel(object):
+        def __init__(self, world, n_params):
+            self._dp_world = world
+            self.flat_params = torch.zeros(n_params)
+
+    built = []
+    monkeypatch.setattr(data_parallel, 'P2PComm',
+                        lambda n, group=None: built.append(n) or type('C', (), {'n_floats': n})())
+    monkeypatch.delenv('BSIG_DP_EXCHANGE', raising=False)
+    assert data_parallel.p2p_comm_for(FakeModel(1, 1000)) is None
+    assert data_parallel.p2p_comm_for(FakeModel(16, 1000)) is None
+    assert data_parallel.p2p_comm_for(FakeModel(8, data_parallel.P2P_MAX_PARAMS + 1)) is None
+    m = FakeModel(8, 90126)
+    comm = data_parallel.p2p_comm_for(m)
+    assert comm is not None and built == [90126]
+    assert data_parallel.p2p_comm_for(m) is comm and built == [90126]      # cached per model
+    monkeypatch.setenv('BSIG_DP_EXCHANGE', 'nccl')
+    assert data_parallel.p2p_comm_for(FakeModel(8, 90126)) is None

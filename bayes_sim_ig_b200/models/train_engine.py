@@ -19,6 +19,7 @@ one device->host copy when the graph has finished.
 """
 import contextlib
 import gc
+import os
 
 import numpy as np
 import torch
@@ -121,6 +122,14 @@ class TrainPlan(object):
         self.loss_buf = torch.zeros(2 * n_log + 1, **f32)   # [train..., test..., scratch]
         self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
         self.graph = None
+        # EXPERIMENTAL, opt-in: forward + NLL + dgrad of an update as ONE cluster kernel
+        # (csrc/mdn.cu: mlp_chain_kernel; not yet validated on hardware, default off)
+        self.chain = False
+        if os.environ.get('BSIG_CHAIN') == '1' and self.rff is None and len(trunk) == 2:
+            layers, head = self._views()
+            self.chain = bool(lib.bsig_mlp_chain_supported(
+                layers[0]['w'].data_ptr(), layers[1]['w'].data_ptr(), head['w'].data_ptr(),
+                batch, in_dim, widths[0], widths[1], p, k, 1 if model.full_covariance else 0))
 
     # ------------------------------------------------------------- kernel sequence
     def _views(self, gbase=None):
@@ -167,7 +176,44 @@ class TrainPlan(object):
                   ACT_NONE, eng, wsp, wsn, st)
         return cur, ld, rows_p
 
+    def _enqueue_step_chain(self, step, st):
+        """Opt-in form of _enqueue_step: one cluster kernel for gather + forward + NLL +
+        dgrad, then the three weight-gradient GEMMs."""
+        m = self.model
+        eng = int(m.gemm_engine)
+        wsp, wsn = self.ws_gemm.data_ptr(), self.ws_gemm.numel()
+        b, p, k = self.batch, self.p, self.k
+        rows = self.idx[step]
+        layers, head = self._views(self.p2p.local_grads(step) if self.p2p is not None else None)
+        slot = self.logs.index(step) if step in self.logs else None
+        n_log = len(self.logs)
+        loss_ptr = self.loss_buf.data_ptr() + 4 * (slot if slot is not None else 2 * n_log)
+        h1, h2 = self.tr['h']
+        _lib.call('bsig_mlp_chain_step', self.x_train.data_ptr(), self.in_dim, rows.data_ptr(),
+                  self.y_train.data_ptr(), self.noise_train[step].data_ptr(),
+                  layers[0]['w'].data_ptr(), layers[0]['b'].data_ptr(),
+                  layers[1]['w'].data_ptr(), layers[1]['b'].data_ptr(),
+                  head['w'].data_ptr(), head['b'].data_ptr(), h1.data_ptr(), h2.data_ptr(),
+                  self.dz.data_ptr(), self.dh[1].data_ptr(), self.dh[0].data_ptr(), loss_ptr,
+                  self.flag.data_ptr(), b, self.in_dim, layers[0]['n'], layers[1]['n'], p, k,
+                  1 if m.full_covariance else 0, st)
+        main = torch.cuda.current_stream(self.dev)
+        side = self.side if self.fork_wgrad else None
+        if side is not None:
+            side.wait_stream(main)
+        wst = side.cuda_stream if side is not None else st
+        for dy, xin, xld, xrows, lay in (
+                (self.dz, h2, layers[1]['n'], None, head),
+                (self.dh[1], h1, layers[0]['n'], None, layers[1]),
+                (self.dh[0], self.x_train, self.in_dim, rows.data_ptr(), layers[0])):
+            _lib.call('bsig_linear_wgrad', dy.data_ptr(), xin.data_ptr(), xld, xrows, lay['dw'],
+                      lay['db'], b, lay['n'], lay['k'], eng, wsp, wsn, wst)
+        if side is not None:
+            main.wait_stream(side)
+
     def _enqueue_step(self, step, st):
+        if self.chain:
+            return self._enqueue_step_chain(step, st)
         m = self.model
         eng = int(m.gemm_engine)
         wsp, wsn = self.ws_gemm.data_ptr(), self.ws_gemm.numel()

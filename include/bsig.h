@@ -209,6 +209,25 @@ int bsig_adam_allreduce_step(float* param, const void* const* peer_grads,
                              void* const* peer_flags, void* ctrl, int rank, int world,
                              float* exp_avg, float* exp_avg_sq, int64_t count, int64_t step,
                              float lr, float beta1, float beta2, float eps, void* stream);
+/* EXPERIMENTAL, opt-in (BSIG_CHAIN=1 in the Python engine): the dependent chain of one
+ * minibatch update of a two-hidden-layer tanh MDNN -- gather, three forward layers
+ * (mdnn.py:108-119), fused head epilogue + mixture NLL forward/backward (mdnn.py:109-178),
+ * dgrad through the heads and the second hidden layer -- in ONE thread-block-cluster launch
+ * (rows are independent through the MLP; only the NLL's three batch-wide sums cross CTAs).
+ * Written and compiled in round 1, not yet validated on hardware; nothing calls it unless
+ * BSIG_CHAIN=1.  x [*, f] (ld ldx) and y [*, p] are gathered with rows [b]; noise [b,p,k];
+ * w0 [h1,f], w1 [h2,h1], wh [n_head,h2] 16-byte aligned; outputs h1_out [b,h1], h2_out [b,h2],
+ * dz [b,n_head], dh2 [b,h2], dh1 [b,h1] (pre-activation gradients), loss [1].
+ * bsig_mlp_chain_supported returns 1 if the shape is inside the kernel's envelope. */
+int bsig_mlp_chain_supported(const float* w0, const float* w1, const float* wh, int64_t b,
+                             int64_t f, int64_t h1, int64_t h2, int64_t p, int64_t k,
+                             int full_cov);
+int bsig_mlp_chain_step(const float* x, int64_t ldx, const int64_t* rows, const float* y,
+                        const float* noise, const float* w0, const float* b0, const float* w1,
+                        const float* b1, const float* wh, const float* bh, float* h1_out,
+                        float* h2_out, float* dz, float* dh2, float* dh1, float* loss, int* flag,
+                        int64_t b, int64_t f, int64_t h1, int64_t h2, int64_t p, int64_t k,
+                        int full_cov, void* stream);
 /* out[i,:] = src[rows[i],:]  (x_train[ids], mdnn.py:222) */
 int bsig_gather_rows(const float* src, int64_t ld_src, const int64_t* rows, float* out,
                      int64_t n_rows, int64_t width, void* stream);

@@ -62,6 +62,11 @@ SIGNATURES = {
                                         _f32, _f32, _f32, _f32, _c_ptr]),
     'bsig_mlp_chain_supported': (_int, [_c_ptr] * 3 + [_i64] * 6 + [_int]),
     'bsig_mlp_chain_step': (_int, [_c_ptr, _i64] + [_c_ptr] * 16 + [_i64] * 6 + [_int, _c_ptr]),
+    'bsig_wgrad3_adam_step': (_int, [_c_ptr, _c_ptr, _i64, _c_ptr, _i64, _i64, _i64, _i64,
+                                     _c_ptr, _c_ptr, _i64, _i64, _i64, _i64,
+                                     _c_ptr, _c_ptr, _i64, _i64, _i64, _i64,
+                                     _c_ptr, _c_ptr, _c_ptr, _i64, _i64, _f32, _f32, _f32, _f32,
+                                     _c_ptr]),
     'bsig_gather_rows': (_int, [_c_ptr, _i64, _c_ptr, _c_ptr, _i64, _i64, _c_ptr]),
     'bsig_finite_flag': (_int, [_c_ptr, _i64, _c_ptr, _c_ptr]),
     'bsig_normalize_rows': (_int, [_c_ptr] * 4 + [_i64, _i64, _c_ptr]),

@@ -40,6 +40,78 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   for (int64_t i = n4 * 4 + t0; i < count; i += stride) upd(p[i], g[i], m[i], v[i]);
 }
 
+// EXPERIMENTAL (opt-in with BSIG_CHAIN=1, single GPU; written and compiled in round 1, NOT yet
+// validated on hardware): the weight-gradient GEMMs of ALL layers of an update and Adam in one
+// launch.  After the chain kernel (mdn.cu) has produced dz / dh2 / dh1, the three
+// dW_l = dY_l^T X_l are independent reductions over the minibatch (B <= 128: one pass, no
+// split), nothing reads the old weights any more, so each CTA forms one 32x32 tile of one
+// dW_l (and, in the first column tile, the bias gradient = column sums of dY_l) and applies
+// Adam to exactly those parameters in its epilogue.
+struct Wgrad3Layer {
+  const float* dy; int ld_dy;          // [B, n]
+  const float* x; int ld_x;            // [*, k]
+  const int64_t* x_rows;               // nullable gather of the rows of x
+  int n, k;                            // weight [n, k], bias [n]
+  int64_t w_off, b_off;                // offsets of weight / bias in the flat parameter buffer
+  int tiles_k, tile0;                  // column tiles of this layer, first linear tile id
+};
+struct Wgrad3Args {
+  Wgrad3Layer layer[3];
+  float* p; float* m; float* v;        // flat parameters and Adam moments
+  int B;
+  float one_minus_b1, b2, one_minus_b2, step_size, inv_bc2_sqrt, eps;
+};
+
+__global__ void __launch_bounds__(256) wgrad3_adam_kernel(Wgrad3Args a) {
+  __shared__ float As[128][33];                      // dY tile  [batch row][output i]
+  __shared__ __align__(16) float Bs[128][36];        // X tile   [batch row][input j]
+  const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
+  int l = 0;
+  if ((int)blockIdx.x >= a.layer[1].tile0) l = 1;
+  if ((int)blockIdx.x >= a.layer[2].tile0) l = 2;
+  const Wgrad3Layer& L = a.layer[l];
+  const int tile = (int)blockIdx.x - L.tile0;
+  const int ti = tile / L.tiles_k, tj = tile - ti * L.tiles_k;
+  const int i0 = ti * 32, j0 = tj * 32;
+  pdl_wait_then_release();
+  for (int e = tid; e < a.B * 32; e += 256) {
+    const int r = e >> 5, c = e & 31;
+    As[r][c] = (i0 + c < L.n) ? __ldg(L.dy + (int64_t)r * L.ld_dy + i0 + c) : 0.f;
+    const int64_t xr = L.x_rows ? __ldg(L.x_rows + r) : (int64_t)r;
+    Bs[r][c] = (j0 + c < L.k) ? __ldg(L.x + xr * L.ld_x + j0 + c) : 0.f;
+  }
+  __syncthreads();
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float rs = 0.f;
+  for (int kk = 0; kk < a.B; ++kk) {
+    const float av = As[kk][ty];
+    const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+    acc[0] = fmaf(av, bv.x, acc[0]);
+    acc[1] = fmaf(av, bv.y, acc[1]);
+    acc[2] = fmaf(av, bv.z, acc[2]);
+    acc[3] = fmaf(av, bv.w, acc[3]);
+    rs += av;
+  }
+  auto adam = [&](int64_t idx, float g) {
+    float mm = a.m[idx], vv = a.v[idx];
+    mm = mm + (g - mm) * a.one_minus_b1;
+    vv = vv * a.b2 + a.one_minus_b2 * g * g;
+    const float denom = sqrtf(vv) * a.inv_bc2_sqrt + a.eps;
+    a.p[idx] = a.p[idx] - a.step_size * (mm / denom);
+    a.m[idx] = mm;
+    a.v[idx] = vv;
+  };
+  const int i = i0 + ty;
+  if (i < L.n) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = j0 + tx * 4 + q;
+      if (j < L.k) adam(L.w_off + (int64_t)i * L.k + j, acc[q]);
+    }
+    if (tj == 0 && tx == 0) adam(L.b_off + i, rs);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 gather_rows_kernel(const float* __restrict__ src, int64_t ld, const int64_t* __restrict__ rows,
                    float* __restrict__ out, int64_t n_rows, int64_t width) {
@@ -128,6 +200,55 @@ extern "C" int bsig_normalize_rows(const float* x, const float* lows, const floa
   if (n_rows * width <= 0) return 0;
   normalize_rows_kernel<<<grid_for(n_rows * width), 256, 0, (cudaStream_t)stream>>>(
       x, lows, highs, y, n_rows, width);
+  BSIG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int bsig_wgrad3_adam_step(const float* dy0, const float* x0, int64_t ld_x0,
+                                     const int64_t* x0_rows, int64_t n0, int64_t k0,
+                                     int64_t w_off0, int64_t b_off0,
+                                     const float* dy1, const float* x1, int64_t n1, int64_t k1,
+                                     int64_t w_off1, int64_t b_off1,
+                                     const float* dy2, const float* x2, int64_t n2, int64_t k2,
+                                     int64_t w_off2, int64_t b_off2,
+                                     float* param, float* exp_avg, float* exp_avg_sq, int64_t b,
+                                     int64_t step, float lr, float beta1, float beta2, float eps,
+                                     void* stream) {
+  BSIG_REQUIRE(b >= 1 && b <= 128 && step >= 1, "wgrad3_adam_step: minibatch must be 1..128 rows");
+  Wgrad3Args a;
+  const float* dys[3] = {dy0, dy1, dy2};
+  const float* xs[3] = {x0, x1, x2};
+  const int64_t ns[3] = {n0, n1, n2}, ks[3] = {k0, k1, k2};
+  const int64_t lds[3] = {ld_x0, k1, k2};
+  const int64_t wo[3] = {w_off0, w_off1, w_off2}, bo[3] = {b_off0, b_off1, b_off2};
+  int tiles = 0;
+  for (int l = 0; l < 3; ++l) {
+    BSIG_REQUIRE(ns[l] >= 1 && ks[l] >= 1, "wgrad3_adam_step: empty layer");
+    Wgrad3Layer& L = a.layer[l];
+    L.dy = dys[l]; L.ld_dy = (int)ns[l];
+    L.x = xs[l]; L.ld_x = (int)lds[l];
+    L.x_rows = l == 0 ? x0_rows : nullptr;
+    L.n = (int)ns[l]; L.k = (int)ks[l];
+    L.w_off = wo[l]; L.b_off = bo[l];
+    L.tiles_k = (int)ceil_div(ks[l], 32);
+    L.tile0 = tiles;
+    tiles += (int)ceil_div(ns[l], 32) * L.tiles_k;
+  }
+  a.p = param; a.m = exp_avg; a.v = exp_avg_sq; a.B = (int)b;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  a.one_minus_b1 = 1.0f - beta1; a.b2 = beta2; a.one_minus_b2 = 1.0f - beta2;
+  a.step_size = (float)((double)lr / bc1);
+  a.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+  a.eps = eps;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)tiles);
+  cfg.blockDim = dim3(256);
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.numAttrs = add_pdl_attr(attr, 0);
+  BSIG_CUDA(cudaLaunchKernelEx(&cfg, wgrad3_adam_kernel, a));
   BSIG_LAUNCH_CHECK();
   return 0;
 }

@@ -130,6 +130,9 @@ class TrainPlan(object):
             self.chain = bool(lib.bsig_mlp_chain_supported(
                 layers[0]['w'].data_ptr(), layers[1]['w'].data_ptr(), head['w'].data_ptr(),
                 batch, in_dim, widths[0], widths[1], p, k, 1 if model.full_covariance else 0))
+        # ... and, on a single GPU, the weight gradients + Adam as one more launch
+        self.chain_fused_adam = (self.chain and self.p2p is None and batch <= 128 and
+                                 data_parallel.world_of(model) == 1)
 
     # ------------------------------------------------------------- kernel sequence
     def _views(self, gbase=None):
@@ -197,6 +200,20 @@ class TrainPlan(object):
                   self.dz.data_ptr(), self.dh[1].data_ptr(), self.dh[0].data_ptr(), loss_ptr,
                   self.flag.data_ptr(), b, self.in_dim, layers[0]['n'], layers[1]['n'], p, k,
                   1 if m.full_covariance else 0, st)
+        if self.chain_fused_adam:
+            # single GPU: the three weight-gradient GEMMs and Adam in one more launch
+            nw0, nw1 = layers[0]['n'] * layers[0]['k'], layers[1]['n'] * layers[1]['k']
+            off1 = nw0 + layers[0]['n']
+            _lib.call('bsig_wgrad3_adam_step',
+                      self.dh[0].data_ptr(), self.x_train.data_ptr(), self.in_dim, rows.data_ptr(),
+                      layers[0]['n'], layers[0]['k'], 0, nw0,
+                      self.dh[1].data_ptr(), h1.data_ptr(), layers[1]['n'], layers[1]['k'],
+                      off1, off1 + nw1,
+                      self.dz.data_ptr(), h2.data_ptr(), head['n'], head['k'],
+                      m._head_w_off, m._head_b_off,
+                      m.flat_params.data_ptr(), self.exp_avg.data_ptr(),
+                      self.exp_avg_sq.data_ptr(), b, step + 1, float(m.lr), 0.9, 0.999, 1e-8, st)
+            return
         main = torch.cuda.current_stream(self.dev)
         side = self.side if self.fork_wgrad else None
         if side is not None:
@@ -271,7 +288,9 @@ class TrainPlan(object):
         slot = self.logs.index(step) if step in self.logs else None
         n_log = len(self.logs)
         world = data_parallel.world_of(m)
-        if self.p2p is not None:
+        if self.chain_fused_adam:
+            pass                                  # Adam ran in the epilogue of bsig_wgrad3_adam_step
+        elif self.p2p is not None:
             # one kernel: all-reduce over NVLink peer memory (1/world folded in) + Adam
             self.p2p.adam_allreduce(m, self.exp_avg, self.exp_avg_sq, step, step + 1, st)
         else:

@@ -228,6 +228,20 @@ int bsig_mlp_chain_step(const float* x, int64_t ldx, const int64_t* rows, const 
                         float* h2_out, float* dz, float* dh2, float* dh1, float* loss, int* flag,
                         int64_t b, int64_t f, int64_t h1, int64_t h2, int64_t p, int64_t k,
                         int full_cov, void* stream);
+/* EXPERIMENTAL, opt-in companion of bsig_mlp_chain_step (single GPU; not yet validated on
+ * hardware): the weight-gradient GEMMs of the three layers of an update (dW_l = dY_l^T X_l,
+ * db_l = column sums of dY_l; mdnn.py:233) and torch.optim.Adam (mdnn.py:234) in one launch.
+ * Layer l: dy_l [b, n_l], x_l [*, k_l] (layer 0 gathered with x0_rows, ld ld_x0), weight at
+ * param + w_off_l ([n_l, k_l]) and bias at param + b_off_l inside the flat buffers. */
+int bsig_wgrad3_adam_step(const float* dy0, const float* x0, int64_t ld_x0, const int64_t* x0_rows,
+                          int64_t n0, int64_t k0, int64_t w_off0, int64_t b_off0,
+                          const float* dy1, const float* x1, int64_t n1, int64_t k1,
+                          int64_t w_off1, int64_t b_off1,
+                          const float* dy2, const float* x2, int64_t n2, int64_t k2,
+                          int64_t w_off2, int64_t b_off2,
+                          float* param, float* exp_avg, float* exp_avg_sq, int64_t b,
+                          int64_t step, float lr, float beta1, float beta2, float eps,
+                          void* stream);
 /* out[i,:] = src[rows[i],:]  (x_train[ids], mdnn.py:222) */
 int bsig_gather_rows(const float* src, int64_t ld_src, const int64_t* rows, float* out,
                      int64_t n_rows, int64_t width, void* stream);

@@ -201,3 +201,25 @@ def test_capture_guard_restores_gc_state():
         assert not gc.isenabled()
     finally:
         gc.enable()
+
+
+def test_chain_kernel_envelope_is_a_pure_host_decision():
+    """bsig_mlp_chain_supported (experimental path, off by default) only inspects shapes and
+    pointer alignment: it can be exercised without a GPU."""
+    from bayes_sim_ig_b200 import _lib
+    lib = _lib.load()
+    ok = lambda w0, w1, wh, b, f, h1, h2, p, k, full: lib.bsig_mlp_chain_supported(
+        w0, w1, wh, b, f, h1, h2, p, k, full)
+    base = 1 << 20                                            # any 16-byte aligned address
+    # the bench shape (Cartpole corrdiff, 128/128, P=13, K=10, minibatch 100) and its test split
+    assert ok(base, base + 16, base + 32, 100, 302, 128, 128, 13, 10, 0) == 1
+    assert ok(base, base + 16, base + 32, 128, 302, 128, 128, 4, 10, 1) == 1
+    # full covariance at P = 13: z and dz rows (1050 wide) no longer fit next to the tile ring
+    assert ok(base, base + 16, base + 32, 100, 302, 128, 128, 13, 10, 1) == 0
+    assert ok(base, base + 16, base + 32, 200, 302, 128, 128, 13, 10, 0) == 0   # > 16 x 8 rows
+    assert ok(base, base + 16, base + 32, 100, 301, 128, 128, 13, 10, 0) == 0   # odd width
+    assert ok(base, base + 16, base + 32, 100, 302, 256, 128, 13, 10, 0) == 0   # hidden > 128
+    assert ok(base + 4, base + 16, base + 32, 100, 302, 128, 128, 13, 10, 0) == 0   # misaligned
+    assert ok(base, base + 16, base + 32, 100, 302, 128, 128, 13, 40, 0) == 0   # K > 32
+    # ShadowHand-sized first layer does not fit the tile ring
+    assert ok(base, base + 16, base + 32, 100, 105002, 128, 128, 32, 10, 0) == 0

@@ -31,10 +31,9 @@ def test_chain_kernel_matches_reference_training(golden, case, monkeypatch):
         logs = run_training_captured(model, x, y_raw, 3, b, test_frac=0.0, use_graph=use_graph,
                                      injected=inj)
         plan = list(model._plans.values())[0]
-        if len(model._trunk_layers()) != 2:
-            assert not plan.chain
-            continue
-        assert plan.chain, 'shape should be inside the chain kernel envelope'
+        # 'full' has one hidden layer and 'p1' an odd input width: outside the envelope,
+        # they must silently stay on the default path (and still match the reference)
+        assert plan.chain == (case in ('diag', 'full_big')), case
         ref_losses = [float(g['%s.step%d.loss' % (case, s)]) for s in range(3)]
         np.testing.assert_allclose(logs['train_loss'], ref_losses, rtol=2e-5, atol=1e-6)
         for name, ref in g.sub(case + '.step2.after.').items():

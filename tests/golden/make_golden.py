@@ -255,6 +255,79 @@ def golden_pdf():
     print('pdf.npz', len(out), 'arrays')
 
 
+def golden_pdf_host():
+    """Host-side pdf surface that is not on the device path (SURVEY 8.b list): Uniform,
+    Gaussian algebra / KL, MoG moments / projection / sampled KL, fit_mog.  Every value
+    comes from the live reference (py2-named operators are called explicitly)."""
+    out = {}
+    rs = np.random.RandomState(11)
+    # ---- Uniform (pdf.py:79-192)
+    lb, ub = np.array([0.0, 1.0, -2.0]), np.array([1.0, 3.0, 0.5])
+    uni = ref_pdf.Uniform(lb, ub)
+    np.random.seed(41)
+    out['uni.lb'], out['uni.ub'] = lb, ub
+    out['uni.gen'] = uni.gen(n_samples=7)                      # Q8: scrambled dimensions
+    xq = np.stack([rs.uniform(-0.5, 1.5, 9), rs.uniform(0.5, 3.5, 9), rs.uniform(-2.5, 1.0, 9)], 1)
+    xq[0] = [0.5, 2.0, -1.0]                                     # at least one point inside
+    out['uni.x'] = xq
+    out['uni.eval_lin'] = uni.eval(xq, log=False)
+    out['uni.eval_log'] = uni.eval(xq, log=True)
+    out['uni.eval_marg'] = uni.eval(xq[:, [0, 2]], ii=[0, 2], log=False)
+    # ---- Gaussian algebra (pdf.py:344-411)
+    def rand_gauss(p):
+        a = rs.randn(p, p)
+        return rs.randn(p), np.dot(a, a.T) + p * np.eye(p)
+    m1, s1 = rand_gauss(3)
+    m2, _ = rand_gauss(3)
+    s2 = 3.0 * s1 + np.eye(3)                                    # broader: g1 / g2 stays proper
+    g1, g2 = ref_pdf.Gaussian(m=m1, S=s1), ref_pdf.Gaussian(m=m2, S=s2)
+    out['g.m1'], out['g.S1'], out['g.m2'], out['g.S2'] = m1, s1, m2, s2
+    for name, g in (('mul', g1 * g2), ('div', g1.__div__(g2)), ('pow', g1 ** 2.5)):
+        out['g.%s.m' % name], out['g.%s.S' % name] = g.m, g.S
+        out['g.%s.logdetP' % name] = np.array(g.logdetP)
+    out['g.kl'] = np.array(g1.kl(g2))
+    xg = rs.randn(6, 3)
+    out['g.x'] = xg
+    out['g.eval'] = g1.eval(xg)
+    # ---- MoG moments / projection / sampled KL / algebra with a Gaussian (pdf.py:501-582)
+    a = np.array([0.2, 0.5, 0.3])
+    ms = [rs.randn(3) for _ in range(3)]
+    ss = [s1 * (0.5 + 0.3 * i) for i in range(3)]                # all narrower than g2
+    mog = ref_pdf.MoG(a=a, ms=ms, Ss=ss)
+    out['mog.a'], out['mog.ms'], out['mog.Ss'] = a, np.stack(ms), np.stack(ss)
+    # (MoG.calc_mean_and_cov / project_to_gaussian raise AttributeError in the reference --
+    #  pdf.py:553 reads a non-existent attribute `sigma` -- so they cannot be recorded)
+    try:
+        mog.calc_mean_and_cov()
+        raise SystemExit('reference calc_mean_and_cov unexpectedly works: record it')
+    except AttributeError:
+        pass
+    prod = mog * g2
+    out['mog.mul.a'] = prod.a
+    out['mog.mul.ms'] = np.stack([x.m for x in prod.xs])
+    out['mog.mul.Ss'] = np.stack([x.S for x in prod.xs])
+    # MoG.__div__ divides its components with `/`, which Python 3 does not map to the
+    # py2-named Gaussian.__div__ (SURVEY Q7): alias it on the live class for this call only
+    ref_pdf.Gaussian.__truediv__ = ref_pdf.Gaussian.__div__
+    try:
+        quot = mog.__div__(g2)
+    finally:
+        del ref_pdf.Gaussian.__truediv__
+    out['mog.div.a'] = quot.a
+    out['mog.div.ms'] = np.stack([x.m for x in quot.xs])
+    out['mog.div.Ss'] = np.stack([x.S for x in quot.xs])
+    # ---- fit_mog (pdf.py:584-642): EM from a seeded start on seeded data
+    data = np.concatenate([rs.randn(150, 2) * 0.4 + [2.0, 0.0], rs.randn(100, 2) * 0.7 + [-1.5, 1.0]])
+    out['fit.x'] = data
+    np.random.seed(43)
+    fit = ref_pdf.fit_mog(data, n_components=2, tol=1e-7, maxiter=200)
+    out['fit.a'] = fit.a
+    out['fit.ms'] = np.stack([x.m for x in fit.xs])
+    out['fit.Ss'] = np.stack([x.S for x in fit.xs])
+    np.savez_compressed(os.path.join(HERE, 'pdf_host.npz'), **out)
+    print('pdf_host.npz', len(out), 'arrays')
+
+
 def load_pendulum(fnm, limit=None):
     loaded = np.load(fnm)
     params = loaded['params']
@@ -333,4 +406,5 @@ if __name__ == '__main__':
     golden_summarizers()
     golden_mdn()
     golden_pdf()
+    golden_pdf_host()
     golden_bayessim()

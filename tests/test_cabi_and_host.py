@@ -223,3 +223,54 @@ def test_chain_kernel_envelope_is_a_pure_host_decision():
     assert ok(base, base + 16, base + 32, 100, 302, 128, 128, 13, 40, 0) == 0   # K > 32
     # ShadowHand-sized first layer does not fit the tile ring
     assert ok(base, base + 16, base + 32, 100, 105002, 128, 128, 32, 10, 0) == 0
+
+
+def test_host_pdf_surface_matches_live_reference(golden):
+    """Uniform, Gaussian algebra / KL, MoG x Gaussian product and quotient, fit_mog: host
+    (numpy) code of the drop-in surface against vectors recorded from the live
+    reference (tests/golden/pdf_host.npz)."""
+    import warnings
+    from bayes_sim_ig.utils import pdf
+    g = golden('pdf_host')
+    tol = dict(rtol=1e-10, atol=1e-12)
+    # ---- Uniform: same numpy stream, same (scrambled, Q8) layout, same densities
+    uni = pdf.Uniform(g['uni.lb'], g['uni.ub'])
+    np.random.seed(41)
+    np.testing.assert_array_equal(uni.gen(n_samples=7), g['uni.gen'])
+    np.testing.assert_allclose(uni.eval(g['uni.x'], log=False), g['uni.eval_lin'], **tol)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        np.testing.assert_allclose(uni.eval(g['uni.x'], log=True), g['uni.eval_log'], **tol)
+    np.testing.assert_allclose(uni.eval(g['uni.x'][:, [0, 2]], ii=[0, 2], log=False),
+                               g['uni.eval_marg'], **tol)
+    # ---- Gaussian algebra
+    g1 = pdf.Gaussian(m=g['g.m1'], S=g['g.S1'])
+    g2 = pdf.Gaussian(m=g['g.m2'], S=g['g.S2'])
+    for name, res in (('mul', g1 * g2), ('div', g1 / g2), ('pow', g1 ** 2.5)):
+        np.testing.assert_allclose(res.m, g['g.%s.m' % name], rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(res.S, g['g.%s.S' % name], rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(res.logdetP, g['g.%s.logdetP' % name], rtol=1e-10)
+    np.testing.assert_allclose(g1.kl(g2), g['g.kl'], rtol=1e-10)
+    # ---- MoG x Gaussian, MoG / Gaussian (the reference's py2 __div__, SURVEY Q7)
+    mog = pdf.MoG(a=g['mog.a'], ms=list(g['mog.ms']), Ss=list(g['mog.Ss']))
+    for name, res in (('mul', mog * g2), ('div', mog / g2)):
+        np.testing.assert_allclose(res.a, g['mog.%s.a' % name], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(np.stack([x.m for x in res.xs]), g['mog.%s.ms' % name],
+                                   rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(np.stack([x.S for x in res.xs]), g['mog.%s.Ss' % name],
+                                   rtol=1e-8, atol=1e-10)
+    # calc_mean_and_cov / project_to_gaussian raise in the reference (pdf.py:553 reads a
+    # non-existent attribute); here they work: check the moment identities instead
+    mean, cov = mog.calc_mean_and_cov()
+    np.testing.assert_allclose(mean, np.dot(g['mog.a'], g['mog.ms']), **tol)
+    second = sum(a * (s + np.outer(m, m)) for a, m, s in zip(g['mog.a'], g['mog.ms'], g['mog.Ss']))
+    np.testing.assert_allclose(cov, second - np.outer(mean, mean), rtol=1e-9, atol=1e-11)
+    pg = mog.project_to_gaussian()
+    np.testing.assert_allclose(pg.m, mean, **tol)
+    np.testing.assert_allclose(pg.S, cov, rtol=1e-9, atol=1e-11)
+    # ---- fit_mog: EM from the same seeded start on the same data
+    np.random.seed(43)
+    fit = pdf.fit_mog(g['fit.x'], n_components=2, tol=1e-7, maxiter=200)
+    np.testing.assert_allclose(fit.a, g['fit.a'], rtol=1e-7)
+    np.testing.assert_allclose(np.stack([x.m for x in fit.xs]), g['fit.ms'], rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(np.stack([x.S for x in fit.xs]), g['fit.Ss'], rtol=1e-6, atol=1e-8)

@@ -328,6 +328,25 @@ def golden_pdf_host():
     print('pdf_host.npz', len(out), 'arrays')
 
 
+def golden_rff_host():
+    """Row a7 (host construction of the RFF frequencies, rff.py:53-120,135-184): every
+    kernel class's sample_freqs (numpy stream) and inv_cdf, and draw_freqs without the
+    (absent, un-pinnable) ghalton sequence."""
+    ref_rff = load_reference.load('models.rff')
+    out = {}
+    u = np.linspace(0.03, 0.97, 21).reshape(7, 3)
+    out['u'] = u
+    for name in ('RFFKernelRBF', 'RFFKernelMatern12', 'RFFKernelMatern32', 'RFFKernelMatern52'):
+        kern = getattr(ref_rff, name)()
+        np.random.seed(51)
+        out[name + '.sample'] = kern.sample_freqs((5, 4))
+        out[name + '.inv_cdf'] = kern.inv_cdf(u)
+        np.random.seed(52)
+        out[name + '.draw'] = ref_rff.RFF.draw_freqs(kern, 6, 3, False)
+    np.savez_compressed(os.path.join(HERE, 'rff_host.npz'), **out)
+    print('rff_host.npz', len(out), 'arrays')
+
+
 def load_pendulum(fnm, limit=None):
     loaded = np.load(fnm)
     params = loaded['params']
@@ -407,4 +426,5 @@ if __name__ == '__main__':
     golden_mdn()
     golden_pdf()
     golden_pdf_host()
+    golden_rff_host()
     golden_bayessim()

@@ -274,3 +274,21 @@ def test_host_pdf_surface_matches_live_reference(golden):
     np.testing.assert_allclose(fit.a, g['fit.a'], rtol=1e-7)
     np.testing.assert_allclose(np.stack([x.m for x in fit.xs]), g['fit.ms'], rtol=1e-6, atol=1e-8)
     np.testing.assert_allclose(np.stack([x.S for x in fit.xs]), g['fit.Ss'], rtol=1e-6, atol=1e-8)
+
+
+def test_rff_kernel_classes_match_live_reference(golden):
+    """Row a7: RFFKernel*.sample_freqs consume numpy's global stream exactly like the
+    reference, inv_cdf agrees, and RFF.draw_freqs(quasi_random=False) is the same draw."""
+    from bayes_sim_ig.models import rff
+    g = golden('rff_host')
+    for name in ('RFFKernelRBF', 'RFFKernelMatern12', 'RFFKernelMatern32', 'RFFKernelMatern52'):
+        kern = getattr(rff, name)()
+        np.random.seed(51)
+        np.testing.assert_array_equal(kern.sample_freqs((5, 4)), g[name + '.sample'])
+        np.testing.assert_allclose(kern.inv_cdf(g['u']), g[name + '.inv_cdf'], rtol=1e-12, atol=1e-14)
+        np.random.seed(52)
+        np.testing.assert_array_equal(rff.RFF.draw_freqs(kern, 6, 3, False), g[name + '.draw'])
+    import torch
+    if torch.cuda.is_available():          # the constructor rejects non-CUDA devices first
+        with pytest.raises(ValueError):    # reference rff.py:96
+            rff.RFF(8, 3, 1.0, kernel='nope', device='cuda')

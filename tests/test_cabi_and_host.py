@@ -292,3 +292,84 @@ def test_rff_kernel_classes_match_live_reference(golden):
     if torch.cuda.is_available():          # the constructor rejects non-CUDA devices first
         with pytest.raises(ValueError):    # reference rff.py:96
             rff.RFF(8, 3, 1.0, kernel='nope', device='cuda')
+
+
+def test_packed_lane_group_reduction_scheme_for_every_width():
+    """csrc/mdn.cu LaneGroup<0>: groups of exactly K lanes packed floor(32/K) to a warp are
+    all-reduced with cyclic rotations -- window sums of width 1, 2, 4, ... combined along the
+    binary digits of K, then lane 0's total broadcast.  The GPU tests exercise K = 3, 4, 10,
+    32; this replays the same index arithmetic for every K in 1..32 on the host."""
+    rs = np.random.RandomState(0)
+    for k in range(1, 33):
+        rpw = 32 // k
+        vals = rs.randn(32)
+        lane = np.arange(32)
+        gi = lane // k
+        lane_g = lane - gi * k
+        active = gi < rpw
+        base = lane - lane_g
+
+        def rot(j):
+            t = lane_g + j
+            t = np.where(t >= k, t - k, t)
+            return np.where(active, base + t, base + lane_g)
+
+        def shfl(x, src):
+            return x[src]
+
+        w, tot, off = vals.copy(), np.zeros(32), 0
+        width = 1
+        while width <= k:
+            if k & width:
+                tot = tot + shfl(w, rot(off)) if off else w.copy()
+                off += width
+            if 2 * width <= k:
+                w = w + shfl(w, rot(width))
+            width <<= 1
+        tot = shfl(tot, base)
+        mx = vals.copy()
+        width = 1
+        while width < k:
+            mx = np.maximum(mx, shfl(mx, rot(width)))
+            width <<= 1
+        for g in range(rpw):
+            grp = vals[g * k:(g + 1) * k]
+            np.testing.assert_allclose(tot[g * k:(g + 1) * k], grp.sum(), rtol=1e-12, atol=1e-12)
+            assert len(set(tot[g * k:(g + 1) * k].tolist())) == 1      # identical bits per group
+            np.testing.assert_array_equal(mx[g * k:(g + 1) * k], grp.max())
+
+
+def test_chain_kernel_schedule_arithmetic_replayed_on_the_host():
+    """Index arithmetic of the experimental mlp_chain_kernel (csrc/mdn.cu), replayed: the flat
+    weight-tile schedule visits every 32-row tile of W0, W1, Wh (forward) and Wh, W1 (dgrad)
+    exactly once and in order, the 8 K-slices of a forward tile partition the reduction, and
+    the row split covers the minibatch."""
+    for (b, f, h1, h2, nh) in ((100, 302, 128, 128, 270), (9, 12, 16, 16, 28), (128, 10, 32, 32, 1050)):
+        n0, n1, n2 = (h1 + 31) // 32, (h2 + 31) // 32, (nh + 31) // 32
+        seg_end = [n0, n0 + n1, n0 + n1 + n2, n0 + n1 + 2 * n2, n0 + 2 * n1 + 2 * n2]
+        seen = []
+        for t_flat in range(seg_end[4]):
+            seg = 0
+            while t_flat >= seg_end[seg]:
+                seg += 1
+            seen.append((seg, t_flat - (seg_end[seg - 1] if seg else 0)))
+        expect = [(0, t) for t in range(n0)] + [(1, t) for t in range(n1)] + \
+                 [(2, t) for t in range(n2)] + [(3, t) for t in range(n2)] + [(4, t) for t in range(n1)]
+        assert seen == expect
+        for kd in (f, h1, h2):
+            v = 4 if kd % 4 == 0 else 2
+            units = kd // v
+            upw = (units + 7) // 8
+            covered = []
+            for warp in range(8):
+                covered += list(range(warp * upw, min(units, (warp + 1) * upw)))
+            assert covered == list(range(units)) and units * v == kd
+            pitch = kd if v == 2 else (kd if (kd // 4) % 2 else kd + 4)
+            if v == 4:
+                assert pitch % 4 == 0 and (pitch // 4) % 2 == 1     # conflict-free LDS.128
+            else:
+                assert (kd // 2) % 2 == 1                           # conflict-free LDS.64
+        nc = max((b + 7) // 8, min(16, b))
+        rpc = (b + nc - 1) // nc
+        nc = (b + rpc - 1) // rpc
+        assert rpc <= 8 and nc <= 16 and nc * rpc >= b and (nc - 1) * rpc < b

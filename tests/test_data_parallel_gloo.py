@@ -83,3 +83,65 @@ def test_fused_exchange_is_only_chosen_for_small_models_on_one_node(monkeypatch)
     assert data_parallel.p2p_comm_for(m) is comm and built == [90126]      # cached per model
     monkeypatch.setenv('BSIG_DP_EXCHANGE', 'nccl')
     assert data_parallel.p2p_comm_for(FakeModel(8, 90126)) is None
+
+
+def _simulate_exchange(world, calls, n_updates, seed):
+    """Discrete-event model of csrc/p2p.cu + train_engine: per update a rank (1) writes its
+    gradient buffer [update parity], (2) publishes its epoch to every peer, (3) waits until
+    all peers' epochs have arrived, (4) reads every rank's buffer [parity].  Ranks advance in
+    random order.  Returns the number of protocol violations: a buffer written while a peer
+    still has to read its previous content, or read with the wrong content."""
+    import random
+    rnd = random.Random(seed)
+    epoch = [0] * world                                   # per-rank device epoch counter
+    flags = [[0] * world for _ in range(world)]           # flags[r][q]: epoch published by q at r
+    content = [[None, None] for _ in range(world)]        # content[r][parity] = (call, update)
+    pending_reads = [[set(), set()] for _ in range(world)]  # readers that still need content
+    state = [dict(call=0, upd=0, phase=0) for _ in range(world)]
+    violations = 0
+    while any(s['call'] < calls for s in state):
+        r = rnd.choice([q for q in range(world) if state[q]['call'] < calls])
+        s = state[r]
+        par = s['upd'] & 1
+        if s['phase'] == 0:                               # backward: write own buffer
+            if pending_reads[r][par]:
+                violations += 1                           # a peer has not read the old data yet
+            content[r][par] = (s['call'], s['upd'])
+            pending_reads[r][par] = set(range(world))
+            s['phase'] = 1
+        elif s['phase'] == 1:                             # publish
+            epoch[r] += 1
+            for q in range(world):
+                flags[q][r] = epoch[r]
+            s['phase'] = 2
+        elif s['phase'] == 2:                             # wait for the peers, then read
+            if all(flags[r][q] >= epoch[r] for q in range(world)):
+                for q in range(world):
+                    if content[q][par] != (s['call'], s['upd']):
+                        violations += 1                   # read a buffer of another update
+                    pending_reads[q][par].discard(r)
+                s['phase'] = 3
+        else:                                             # next update / next call
+            s['upd'] += 1
+            s['phase'] = 0
+            if s['upd'] == n_updates:                     # next call starts at update 0 again
+                s['upd'] = 0
+                s['call'] += 1
+    return violations
+
+
+def test_double_buffered_exchange_protocol_has_no_hazard_for_even_update_counts():
+    """The fused exchange needs no host barrier between calls when n_updates is even (the
+    reference's 100 and 500): exhaustive-ish random interleavings of the protocol model."""
+    for world in (2, 4, 8):
+        for seed in range(25):
+            assert _simulate_exchange(world, calls=3, n_updates=4, seed=seed) == 0
+
+
+def test_exchange_protocol_model_detects_the_odd_count_hazard():
+    """With an odd number of updates the next call starts on the buffer the last exchange may
+    still be reading: the model finds violations without the barrier (which is why
+    train_engine inserts one in that case)."""
+    bad = sum(_simulate_exchange(4, calls=3, n_updates=3, seed=s)
+              for s in range(40))
+    assert bad > 0

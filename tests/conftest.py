@@ -16,6 +16,18 @@ def pytest_configure(config):
     config.addinivalue_line('markers', 'reference: needs /root/reference (build container only)')
 
 
+def pytest_sessionstart(session):
+    """Build libbsig_b200.so when the tree has none yet (a fresh checkout: built artefacts
+    are git-ignored); nvcc cross-compiles without a GPU.  An existing library is left alone
+    (bayes_sim_ig_b200.build only recompiles stale objects)."""
+    try:
+        from bayes_sim_ig_b200 import build as _build
+        if not os.path.exists(_build.LIB_PATH):
+            _build.build()
+    except Exception as exc:          # tests that need the library report the real problem
+        sys.stderr.write('could not build libbsig_b200.so: %r\n' % (exc,))
+
+
 def pytest_collection_modifyitems(config, items):
     try:
         import torch

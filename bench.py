@@ -135,15 +135,60 @@ def measured_peaks():
 
 
 # --------------------------------------------------------------------------- reference arm
+def reference_kind():
+    """'reference' when the UNMODIFIED reference modules can be imported (from
+    /root/reference in the build container, else from the verbatim staged copy under
+    oracle/_ref that travels to the GPU box), 'port' (oracle/torch_port.py) otherwise."""
+    try:
+        from oracle import load_reference
+        return 'reference' if load_reference.reference_available() else 'port'
+    except Exception:
+        return 'port'
+
+
+_REF_BSIM = {}
+
+
+def _reference_bsim(lows, highs):
+    """The reference's own BayesSim on the CPU (bayes_sim.py:27-82), built once."""
+    from oracle import load_reference
+    key = 'cpu'
+    if key not in _REF_BSIM:
+        ref_bs = load_reference.load('bayes_sim')
+        cfg = {'modelClass': 'MDNN', 'summarizerFxn': SUMMARIZER, 'trainTrajLen': TASK['T1'] - 1,
+               'components': TASK['K'], 'hiddenLayers': list(HIDDEN), 'lr': LR}
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):     # the width probe prints
+            _REF_BSIM[key] = ref_bs.BayesSim(cfg, TASK['D'], TASK['A'], TASK['P'], lows, highs,
+                                             prior=None, proposal=None, device='cpu')
+    return _REF_BSIM[key]
+
+
 def cpu_pipeline_rate(n_traj, threads, seed=0):
-    """Time the torch-CPU port of the reference pipeline on n_traj trajectories."""
+    """Time the reference CPU path on n_traj trajectories of the workload: per chunk of
+    <= 1000 trajectories BayesSim.run_training (summary_corrdiff + 100 Adam updates + 6
+    test evals, bayes_sim.py:91-114), then BayesSim.predict for one trajectory and
+    MoG.gen(10000).  Runs the unmodified reference when it is importable (kind
+    'reference'), the torch port otherwise (kind 'port')."""
     import contextlib
     import io
-    from oracle import torch_port
     torch.set_num_threads(threads)
     states, actions, params, lows, highs = synth(seed, n_traj, TASK)
     torch.manual_seed(seed)
     np.random.seed(seed)
+    if reference_kind() == 'reference':
+        bsim = _reference_bsim(lows, highs)
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            for lo in range(0, n_traj, CHUNK):
+                bsim.run_training(params[lo:lo + CHUNK], states[lo:lo + CHUNK],
+                                  actions[lo:lo + CHUNK])
+            post = bsim.predict(states[:1], actions[:1])
+            post.gen(N_POSTERIOR_SAMPLES)
+        dt = time.perf_counter() - t0
+        return n_traj / dt, dt
+    from oracle import torch_port
     width = 10 * (TASK['D'] - 1) * 10 * TASK['A'] + 2
     model = torch_port.PortModel(width, TASK['P'], lows, highs, TASK['K'], False, HIDDEN, LR)
     t0 = time.perf_counter()
@@ -154,11 +199,21 @@ def cpu_pipeline_rate(n_traj, threads, seed=0):
     return n_traj / dt, dt
 
 
+def cpu_sample_note(kind, sample):
+    src = ('the UNMODIFIED reference modules (bayes_sim.py, models/mdnn.py, utils/summarizers.py, '
+           'utils/pdf.py; verbatim copy staged by oracle/stage_reference.py) with device="cpu"'
+           if kind == 'reference' else
+           'oracle/torch_port.py (same torch ops as the reference CPU path)')
+    return ('%s; %d Cartpole trajectories per step = 1 chunk of the workload: corrdiff + 100 Adam '
+            'updates + 6 test evals + predict + 10000 samples' % (src, sample))
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
+    kind = reference_kind()
     # bounded sample: one 1000-trajectory chunk per step (about 1.5-6 s of CPU work)
     sample = 1000
     for _ in range(args.warmup):
@@ -174,11 +229,8 @@ def run_reference(args):
             'ms_per_step': 1e3 * float(np.mean(times)), 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': workload_config(args.gpus),
-            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-                             'sample': 'oracle/torch_port.py (same torch ops as the reference CPU '
-                                       'path); %d Cartpole trajectories per step = 1 chunk of the '
-                                       'workload: corrdiff + 100 Adam updates + predict + 10000 '
-                                       'samples' % sample},
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': kind,
+                             'sample': cpu_sample_note(kind, sample)},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0,
                     'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
@@ -632,11 +684,10 @@ def run_b200(args):
         threads = os.cpu_count() or 1
         cpu_pipeline_rate(200, threads)         # warm up the CPU thread pool / allocator
         rate, dt = cpu_pipeline_rate(1000, threads)
+        kind = reference_kind()
         line['cpu_baseline'] = {
-            'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-            'sample': 'oracle/torch_port.py (same torch ops as the reference CPU path) on 1000 of '
-                      'the 4096 trajectories: corrdiff + 100 Adam updates + 6 test evals + predict '
-                      '+ 10000 samples; %.2f s' % dt}
+            'value': rate, 'unit': UNIT, 'cores': threads, 'kind': kind,
+            'sample': cpu_sample_note(kind, 1000) + '; %.2f s' % dt}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -1,8 +1,11 @@
-"""Import the UNMODIFIED reference from /root/reference.  TEST INFRASTRUCTURE.
+"""Import the UNMODIFIED reference.  TEST INFRASTRUCTURE.
 
-Works only inside the build container (the GPU box has no /root/reference);
-used by tests/golden/make_golden.py to produce the committed golden vectors and
-by the optional live-reference tests (skipped when the directory is absent).
+Source of the modules, first that exists: $BSIG_REFERENCE_ROOT, /root/reference (build
+container only), oracle/_ref (the verbatim staged copy made by oracle/stage_reference.py,
+git-ignored, shipped to the GPU box with the snapshot).  Used by
+tests/golden/make_golden.py to produce the committed golden vectors, by the optional
+live-reference tests (skipped when no source is present) and by bench.py's CPU legs
+(``--impl reference`` / ``cpu_baseline``, kind "reference").
 
 The reference package is called ``bayes_sim_ig`` -- the same name as this
 repository's drop-in alias package -- so it is loaded under the private name
@@ -16,12 +19,21 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get('BSIG_REFERENCE_ROOT', '/root/reference')
+def _pick_root():
+    here = os.path.dirname(os.path.abspath(__file__))
+    for cand in (os.environ.get('BSIG_REFERENCE_ROOT'), '/root/reference',
+                 os.path.join(here, '_ref')):
+        if cand and os.path.isfile(os.path.join(cand, 'bayes_sim_ig', 'bayes_sim.py')):
+            return cand
+    return os.environ.get('BSIG_REFERENCE_ROOT', '/root/reference')
+
+
+REFERENCE_ROOT = _pick_root()
 _ALIAS = '_bsig_reference'
 
 
 def reference_available():
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, 'bayes_sim_ig'))
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, 'bayes_sim_ig', 'bayes_sim.py'))
 
 
 def _ensure_alias():

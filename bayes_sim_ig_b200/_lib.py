@@ -18,8 +18,26 @@ _int = ctypes.c_int
 _f32 = ctypes.c_float
 _u64 = ctypes.c_uint64
 
+
+
+class TpDesc(ctypes.Structure):
+    """bsig_tp_desc of include/bsig.h (persistent training kernel)."""
+    _fields_ = [('n_layers', ctypes.c_int32), ('in_dim', ctypes.c_int32 * 3),
+                ('out_dim', ctypes.c_int32 * 3), ('batch', ctypes.c_int32),
+                ('p', ctypes.c_int32), ('k', ctypes.c_int32), ('full_cov', ctypes.c_int32),
+                ('w_off', ctypes.c_int64 * 3), ('b_off', ctypes.c_int64 * 3),
+                ('x', _c_ptr), ('ldx', _i64), ('y', _c_ptr), ('idx', _c_ptr), ('noise', _c_ptr),
+                ('params', _c_ptr), ('exp_avg', _c_ptr), ('exp_avg_sq', _c_ptr),
+                ('scratch', _c_ptr), ('scratch_floats', _i64), ('loss_buf', _c_ptr),
+                ('loss_slot', _c_ptr), ('adam_coef', _c_ptr), ('flag', _c_ptr),
+                ('beta1', _f32), ('beta2', _f32), ('eps', _f32), ('prof', _c_ptr)]
+
+
 # name -> (restype, argtypes); must list every symbol of include/bsig.h
 SIGNATURES = {
+    'bsig_train_persistent_query': (_int, [ctypes.POINTER(TpDesc), ctypes.POINTER(_i64),
+                                           ctypes.POINTER(_i64)]),
+    'bsig_train_persistent': (_int, [ctypes.POINTER(TpDesc), _i64, _i64, _c_ptr]),
     'bsig_last_error': (ctypes.c_char_p, []),
     'bsig_version': (_int, []),
     'bsig_launch_count': (_i64, []),

@@ -72,7 +72,11 @@ class TrainPlan(object):
         f32 = dict(dtype=torch.float32, device=dev)
         self.logs = log_steps(n_updates)
         n_log = len(self.logs)
-        self.x_train = torch.empty((n_train, in_dim), **f32)
+        # training rows live in a zero-padded buffer whose pitch is a multiple of 4 floats, so
+        # that the persistent kernel can fetch a minibatch row with one 16-byte aligned bulk copy
+        self.x_ld = (in_dim + 3) // 4 * 4
+        self.x_train_buf = torch.zeros((n_train, self.x_ld), **f32)
+        self.x_train = self.x_train_buf[:, :in_dim]
         self.y_train = torch.empty((n_train, p), **f32)
         self.x_test = torch.empty((max(n_test, 1), in_dim), **f32)
         self.y_test = torch.empty((max(n_test, 1), p), **f32)
@@ -133,6 +137,97 @@ class TrainPlan(object):
         # ... and, on a single GPU, the weight gradients + Adam as one more launch
         self.chain_fused_adam = (self.chain and self.p2p is None and batch <= 128 and
                                  data_parallel.world_of(model) == 1)
+        # single GPU, two hidden layers: the three weight-gradient GEMMs and Adam are ONE
+        # launch (csrc/optim.cu: wgrad3_adam_kernel) on the critical path instead of three
+        # side-stream launches + the Adam launch.  Opt-in (BSIG_FUSED_WGRAD=1): measured equal to the default
+        # (4.80 vs 4.75 ms per 100 updates, profiles/r2/), it only lowers the launch count
+        self.fused_wgrad_adam = (not self.chain and self.rff is None and len(trunk) == 2 and
+                                 self.p2p is None and batch <= 128 and
+                                 data_parallel.world_of(model) == 1 and
+                                 os.environ.get('BSIG_FUSED_WGRAD', '0') == '1')
+        self._setup_persistent()
+
+    # ------------------------------------------------- persistent cluster kernel (default)
+    def _setup_persistent(self):
+        """Opt-in (BSIG_PERSISTENT=1): all updates between two logging steps as ONE launch of
+        csrc/train_persistent.cu (model resident in the shared memory of a 16-CTA cluster),
+        for shapes inside the kernel's envelope (bsig_train_persistent_query) on a single GPU.
+        Parity-green on hardware (tests/test_gpu_persistent.py) but NOT the default: measured
+        at 65-78 us per update against 47 us for the launch-per-GEMM path -- sixteen SMs of
+        fp32 FFMA are instruction-issue bound at this problem size (profiles/r2/)."""
+        import ctypes
+        self.persistent = False
+        m = self.model
+        if os.environ.get('BSIG_PERSISTENT', '0') != '1':
+            return
+        if data_parallel.world_of(m) > 1:
+            return
+        layers, head = self._views()
+        dense = layers + [head]
+        if len(dense) > 3:
+            return
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        d = _lib.TpDesc()
+        d.n_layers = len(dense)
+        flat0 = m.flat_params.data_ptr()
+        for i, lay in enumerate(dense):
+            d.in_dim[i], d.out_dim[i] = int(lay['k']), int(lay['n'])
+            d.w_off[i] = (lay['w'].data_ptr() - flat0) // 4
+            d.b_off[i] = (lay['b'].data_ptr() - flat0) // 4
+        d.batch, d.p, d.k = self.batch, self.p, self.k
+        d.full_cov = 1 if m.full_covariance else 0
+        if self.rff is not None:
+            # random Fourier features are not trained: computed once per call for the whole
+            # training split (instead of once per minibatch) and handed to the kernel as x
+            self.feat_train = torch.zeros((self.n_train, self.feat_dim), **f32)
+            d.x, d.ldx = self.feat_train.data_ptr(), self.feat_dim
+        else:
+            d.x, d.ldx = self.x_train_buf.data_ptr(), self.x_ld
+        need, smem = ctypes.c_int64(0), ctypes.c_int64(0)
+        lib = _lib.load()
+        if lib.bsig_train_persistent_query(ctypes.byref(d), ctypes.byref(need),
+                                           ctypes.byref(smem)) != 0:
+            self.persistent_reason = _lib.last_error()
+            return
+        self.tp_scratch = torch.zeros(int(need.value) + 64, **f32)
+        slots = np.full(self.n_updates, -1, dtype=np.int32)
+        for slot, step in enumerate(self.logs):
+            slots[step] = slot
+        self.tp_slots = torch.from_numpy(slots).to(self.dev)
+        t = np.arange(1, self.n_updates + 1, dtype=np.float64)
+        b1, b2 = 0.9, 0.999
+        coef = np.stack([float(m.lr) / (1.0 - b1 ** t), 1.0 / np.sqrt(1.0 - b2 ** t)], axis=1)
+        self.tp_coef = torch.from_numpy(coef.astype(np.float32)).to(self.dev)
+        d.y = self.y_train.data_ptr()
+        d.idx = self.idx.data_ptr()
+        d.noise = self.noise_train.data_ptr()
+        d.params = flat0
+        d.exp_avg, d.exp_avg_sq = self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr()
+        d.scratch, d.scratch_floats = self.tp_scratch.data_ptr(), self.tp_scratch.numel()
+        d.loss_buf = self.loss_buf.data_ptr()
+        d.loss_slot = self.tp_slots.data_ptr()
+        d.adam_coef = self.tp_coef.data_ptr()
+        d.flag = self.flag.data_ptr()
+        d.beta1, d.beta2, d.eps = b1, b2, 1e-8
+        self.tp_prof = None
+        if os.environ.get('BSIG_TP_PROF') == '1':       # per-phase cycle counters (profiles/)
+            self.tp_prof = torch.zeros(32, dtype=torch.int64, device=self.dev)
+            d.prof = self.tp_prof.data_ptr()
+        self.tp_desc = d
+        self.tp_smem = int(smem.value)
+        self.tp_lr = float(m.lr)
+        self.persistent = True
+
+    def _enqueue_segment(self, step0, step1, st):
+        import ctypes
+        _lib.call('bsig_train_persistent', ctypes.byref(self.tp_desc), step0, step1, st)
+
+    def _enqueue_rff_train_features(self, st):
+        coeff = self.rff.coeff()
+        _lib.call('bsig_rff_features', self.x_train_buf.data_ptr(), self.x_ld, None,
+                  coeff.data_ptr(), self.feat_train.data_ptr(), self.n_train, self.rff.d,
+                  coeff.shape[0], float(self.rff.a), int(self.rff.gemm_engine),
+                  self.ws_gemm.data_ptr(), self.ws_gemm.numel(), st)
 
     # ------------------------------------------------------------- kernel sequence
     def _views(self, gbase=None):
@@ -155,14 +250,14 @@ class TrainPlan(object):
                     n=m.n_head, k=m.head_in)
         return out, head
 
-    def _forward(self, acts, x, rows, n_rows, st):
-        """x (optionally row-gathered) -> acts['z']; returns the head input."""
+    def _forward(self, acts, x, rows, n_rows, st, ld=None):
+        """x (optionally row-gathered, row pitch ld) -> acts['z']; returns the head input."""
         m = self.model
         eng = int(m.gemm_engine)
         wsp, wsn = self.ws_gemm.data_ptr(), self.ws_gemm.numel()
         rows_p = None if rows is None else rows.data_ptr()
         layers, head = self._views()
-        cur, ld = x, x.shape[1]
+        cur, ld = x, (x.shape[1] if ld is None else ld)
         if self.rff is not None:
             coeff = self.rff.coeff()
             _lib.call('bsig_rff_features', cur.data_ptr(), ld, rows_p, coeff.data_ptr(),
@@ -192,7 +287,7 @@ class TrainPlan(object):
         n_log = len(self.logs)
         loss_ptr = self.loss_buf.data_ptr() + 4 * (slot if slot is not None else 2 * n_log)
         h1, h2 = self.tr['h']
-        _lib.call('bsig_mlp_chain_step', self.x_train.data_ptr(), self.in_dim, rows.data_ptr(),
+        _lib.call('bsig_mlp_chain_step', self.x_train_buf.data_ptr(), self.x_ld, rows.data_ptr(),
                   self.y_train.data_ptr(), self.noise_train[step].data_ptr(),
                   layers[0]['w'].data_ptr(), layers[0]['b'].data_ptr(),
                   layers[1]['w'].data_ptr(), layers[1]['b'].data_ptr(),
@@ -205,7 +300,7 @@ class TrainPlan(object):
             nw0, nw1 = layers[0]['n'] * layers[0]['k'], layers[1]['n'] * layers[1]['k']
             off1 = nw0 + layers[0]['n']
             _lib.call('bsig_wgrad3_adam_step',
-                      self.dh[0].data_ptr(), self.x_train.data_ptr(), self.in_dim, rows.data_ptr(),
+                      self.dh[0].data_ptr(), self.x_train_buf.data_ptr(), self.x_ld, rows.data_ptr(),
                       layers[0]['n'], layers[0]['k'], 0, nw0,
                       self.dh[1].data_ptr(), h1.data_ptr(), layers[1]['n'], layers[1]['k'],
                       off1, off1 + nw1,
@@ -222,7 +317,7 @@ class TrainPlan(object):
         for dy, xin, xld, xrows, lay in (
                 (self.dz, h2, layers[1]['n'], None, head),
                 (self.dh[1], h1, layers[0]['n'], None, layers[1]),
-                (self.dh[0], self.x_train, self.in_dim, rows.data_ptr(), layers[0])):
+                (self.dh[0], self.x_train_buf, self.x_ld, rows.data_ptr(), layers[0])):
             _lib.call('bsig_linear_wgrad', dy.data_ptr(), xin.data_ptr(), xld, xrows, lay['dw'],
                       lay['db'], b, lay['n'], lay['k'], eng, wsp, wsn, wst)
         if side is not None:
@@ -240,7 +335,7 @@ class TrainPlan(object):
         slot = self.logs.index(step) if step in self.logs else None
         n_log = len(self.logs)
         loss_ptr = self.loss_buf.data_ptr() + 4 * (slot if slot is not None else 2 * n_log)
-        hin, hin_ld, hin_rows = self._forward(self.tr, self.x_train, rows, b, st)
+        hin, hin_ld, hin_rows = self._forward(self.tr, self.x_train_buf, rows, b, st, ld=self.x_ld)
         _lib.call('bsig_mdn_nll_fused', self.tr['z'].data_ptr(), self.noise_train[step].data_ptr(),
                   self.y_train.data_ptr(), rows.data_ptr(), loss_ptr, self.dz.data_ptr(),
                   b, p, k, 1 if m.full_covariance else 0, self.ws_mdn.data_ptr(),
@@ -251,6 +346,8 @@ class TrainPlan(object):
         side = self.side if self.fork_wgrad else None
 
         def wgrad(dy, xin, xld, xrows, lay, n_out, k_in):
+            if self.fused_wgrad_adam:
+                return                          # formed by bsig_wgrad3_adam_step in _enqueue_update
             if side is not None:
                 side.wait_stream(main)
                 stream = side.cuda_stream
@@ -274,10 +371,10 @@ class TrainPlan(object):
             elif self.rff is not None:
                 xin, xld, xrows = self.tr['feat'], self.feat_dim, None
             else:
-                xin, xld, xrows = self.x_train, self.in_dim, rows.data_ptr()
+                xin, xld, xrows = self.x_train_buf, self.x_ld, rows.data_ptr()
             wgrad(self.dh[li], xin, xld, xrows, lay, lay['n'], lay['k'])
             dcur, nxt = self.dh[li], lay
-        if side is not None:
+        if side is not None and not self.fused_wgrad_adam:
             main.wait_stream(side)
 
     def _enqueue_update(self, step, st):
@@ -290,6 +387,21 @@ class TrainPlan(object):
         world = data_parallel.world_of(m)
         if self.chain_fused_adam:
             pass                                  # Adam ran in the epilogue of bsig_wgrad3_adam_step
+        elif self.fused_wgrad_adam:
+            layers, head = self._views()
+            h1, h2 = self.tr['h']
+            nw0, nw1 = layers[0]['n'] * layers[0]['k'], layers[1]['n'] * layers[1]['k']
+            off1 = nw0 + layers[0]['n']
+            _lib.call('bsig_wgrad3_adam_step',
+                      self.dh[0].data_ptr(), self.x_train_buf.data_ptr(), self.x_ld,
+                      self.idx[step].data_ptr(), layers[0]['n'], layers[0]['k'], 0, nw0,
+                      self.dh[1].data_ptr(), h1.data_ptr(), layers[1]['n'], layers[1]['k'],
+                      off1, off1 + nw1,
+                      self.dz.data_ptr(), h2.data_ptr(), head['n'], head['k'],
+                      m._head_w_off, m._head_b_off,
+                      m.flat_params.data_ptr(), self.exp_avg.data_ptr(),
+                      self.exp_avg_sq.data_ptr(), self.batch, step + 1, float(m.lr), 0.9, 0.999,
+                      1e-8, st)
         elif self.p2p is not None:
             # one kernel: all-reduce over NVLink peer memory (1/world folded in) + Adam
             self.p2p.adam_allreduce(m, self.exp_avg, self.exp_avg_sq, step, step + 1, st)
@@ -297,6 +409,14 @@ class TrainPlan(object):
             _lib.call('bsig_adam_step', m.flat_params.data_ptr(), self.grads.data_ptr(),
                       self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), m.flat_params.numel(),
                       step + 1, float(m.lr), 0.9, 0.999, 1e-8, 1.0 / world, st)
+        self._enqueue_eval(step, st)
+
+    def _enqueue_eval(self, step, st):
+        """Held-out loss after update `step` (logging steps only; mdnn.py:236-241)."""
+        m = self.model
+        p, k = self.p, self.k
+        slot = self.logs.index(step) if step in self.logs else None
+        n_log = len(self.logs)
         if slot is not None and self.n_test > 0:
             self._forward(self.te, self.x_test, None, self.n_test, st)
             _lib.call('bsig_mdn_nll_fused', self.te['z'].data_ptr(),
@@ -309,6 +429,18 @@ class TrainPlan(object):
         st = _lib.stream_ptr(self.dev)
         self.exp_avg.zero_()
         self.exp_avg_sq.zero_()
+        if self.persistent:
+            self.tp_scratch.zero_()           # Adam moments of the persistent kernel (Q9)
+            if self.rff is not None:
+                self._enqueue_rff_train_features(st)
+            prev = 0
+            for step in self.logs:            # one launch per stretch between two logging steps
+                self._enqueue_segment(prev, step + 1, st)
+                self._enqueue_eval(step, st)
+                prev = step + 1
+            if prev < self.n_updates:
+                self._enqueue_segment(prev, self.n_updates, st)
+            return
         for step in range(self.n_updates):
             self._enqueue_step(step, st)
             self._enqueue_update(step, st)
@@ -326,10 +458,17 @@ class TrainPlan(object):
         st = _lib.stream_ptr(self.dev)
         self.exp_avg.zero_()
         self.exp_avg_sq.zero_()
-        self._enqueue_step(0, st)
-        if self.p2p is None:
-            data_parallel.allreduce_gradients(m, self.grads)
-        self._enqueue_update(0, st)
+        if self.persistent:
+            self.tp_scratch.zero_()
+            if self.rff is not None:
+                self._enqueue_rff_train_features(st)
+            self._enqueue_segment(0, 1, st)
+            self._enqueue_eval(0, st)
+        else:
+            self._enqueue_step(0, st)
+            if self.p2p is None:
+                data_parallel.allreduce_gradients(m, self.grads)
+            self._enqueue_update(0, st)
         torch.cuda.synchronize(self.dev)
         m.flat_params.copy_(saved)
         self.loss_buf.copy_(saved_loss)
@@ -405,7 +544,8 @@ def run_training_captured(model, x_data, y_data, n_updates, batch_size, test_fra
     n_test = n_tot - n_train
     in_dim = x_data.shape[1]
     dp = data_parallel.world_of(model) > 1
-    key = (n_train, n_test, n_updates, batch_size, in_dim, bool(use_graph), dp)
+    key = (n_train, n_test, n_updates, batch_size, in_dim, bool(use_graph), dp,
+           float(model.lr), int(model.gemm_engine))
     with torch.cuda.device(dev):
         plan = model._plans.get(key)
         if plan is None:
@@ -454,10 +594,13 @@ def run_training_captured(model, x_data, y_data, n_updates, batch_size, test_fra
             plan.graph.replay()
             _REPLAYED[0] += int(getattr(plan, 'launches_per_replay', 0))
         else:
-            plan.exp_avg.zero_()
-            plan.exp_avg_sq.zero_()
+            if plan.persistent:
+                plan.enqueue_all()
+            else:
+                plan.exp_avg.zero_()
+                plan.exp_avg_sq.zero_()
             st = _lib.stream_ptr(dev)
-            for step in range(plan.n_updates):
+            for step in range(plan.n_updates if not plan.persistent else 0):
                 plan._enqueue_step(step, st)
                 if plan.p2p is None:
                     data_parallel.allreduce_gradients(model, plan.grads)

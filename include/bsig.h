@@ -228,6 +228,52 @@ int bsig_mlp_chain_step(const float* x, int64_t ldx, const int64_t* rows, const 
                         float* h2_out, float* dz, float* dh2, float* dh1, float* loss, int* flag,
                         int64_t b, int64_t f, int64_t h1, int64_t h2, int64_t p, int64_t k,
                         int full_cov, void* stream);
+/* ---------------------------------------------------------------- persistent training
+ * ALL Adam updates [step0, step1) of MDNN.run_training's loop (models/mdnn.py:217-234:
+ * np.random.randint rows -> gather -> forward (mdnn.py:89-125) -> mdn_loss_fn (mdnn.py:127-178)
+ * -> backward -> torch.optim.Adam.step) in ONE launch of one 16-CTA thread-block cluster that
+ * keeps the model resident in shared memory, partitioned by output column (csrc/
+ * train_persistent.cu).  Dense layers = hidden tanh layers followed by the concatenated heads
+ * [pi | mu | Diag | Lower] (1..3 layers; MDRFF passes its precomputed random Fourier features
+ * as x and n_layers = 1).  All pointers are device pointers.
+ *   x [n_train][ldx] (ldx % 4 == 0, pad columns zero, 16-byte aligned), y [n_train][p]
+ *   normalised targets, idx [n_updates][batch] minibatch rows (mdnn.py:221), noise
+ *   [n_updates][batch][p][k] eps-noise uniforms (mdnn.py:115-116), params / exp_avg /
+ *   exp_avg_sq flat fp32 buffers (w_off / b_off: float offsets of each layer's weight
+ *   [out,in] and bias), scratch >= the size reported by the query, loss_buf + loss_slot
+ *   [n_updates] (slot of update u's minibatch loss, -1 = not logged), adam_coef
+ *   [n_updates][2] = {lr / (1 - beta1^t), 1 / sqrt(1 - beta2^t)} for t = u + 1 (torch's host
+ *   doubles, rounded to fp32), flag: |= 1 on a non-finite value (mdnn.py:120-124,172-174).
+ * bsig_train_persistent_query returns 0 and the scratch / shared-memory needs if the shape is
+ * inside the kernel's envelope, non-zero (reason in bsig_last_error) otherwise. */
+typedef struct bsig_tp_desc {
+  int32_t n_layers;
+  int32_t in_dim[3];
+  int32_t out_dim[3];
+  int32_t batch, p, k, full_cov;
+  int64_t w_off[3];
+  int64_t b_off[3];
+  const float* x;
+  int64_t ldx;
+  const float* y;
+  const int64_t* idx;
+  const float* noise;
+  float* params;
+  float* exp_avg;
+  float* exp_avg_sq;
+  float* scratch;
+  int64_t scratch_floats;
+  float* loss_buf;
+  const int32_t* loss_slot;
+  const float* adam_coef;
+  int32_t* flag;
+  float beta1, beta2, eps;
+  int64_t* prof;   /* nullable profiling aid: 32 per-phase cycle counters of CTA 0, accumulated */
+} bsig_tp_desc;
+int bsig_train_persistent_query(const bsig_tp_desc* desc, int64_t* scratch_floats,
+                                int64_t* smem_bytes);
+int bsig_train_persistent(const bsig_tp_desc* desc, int64_t step0, int64_t step1, void* stream);
+
 /* EXPERIMENTAL, opt-in companion of bsig_mlp_chain_step (single GPU; not yet validated on
  * hardware): the weight-gradient GEMMs of the three layers of an update (dW_l = dY_l^T X_l,
  * db_l = column sums of dY_l; mdnn.py:233) and torch.optim.Adam (mdnn.py:234) in one launch.

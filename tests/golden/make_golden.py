@@ -192,6 +192,55 @@ def golden_mdn():
     print('mdn.npz', len(out), 'arrays')
 
 
+def golden_mdn_bench():
+    """A full training update at BASELINE configs[1]'s dimensions (minibatch 100, corrdiff
+    width 302, hidden 128 x 128, P = 13, K = 10; diagonal and full covariance): the reference's
+    own loop body (mdnn.py:221-234: randint rows -> forward -> loss -> backward -> Adam) for
+    four updates, with the minibatch rows and the eps-noise recorded.  Written to its own file
+    (mdn_bench.npz) because the parameter vectors are large."""
+    out = {}
+    for name, full, n_steps in (('bench_diag', False, 4), ('bench_full', True, 3)):
+        din, p, k, hidden, b, n_rows = 302, 13, 10, (128, 128), 100, 128
+        torch.manual_seed(7 + int(full))
+        np.random.seed(17 + int(full))
+        lows = np.full(p, 0.1)
+        highs = np.full(p, 2.0)
+        with quiet():
+            model = ref_mdnn.MDNN(input_dim=din, output_dim=p, output_lows=lows,
+                                  output_highs=highs, n_gaussians=k, full_covariance=full,
+                                  hidden_layers=hidden, activation=torch.nn.Tanh, lr=1e-3,
+                                  device='cpu')
+        x = torch.randn(n_rows, din)
+        y_raw = torch.from_numpy(lows + (highs - lows) * np.random.rand(n_rows, p)).float()
+        y = model.normalize_samples(y_raw)
+        out[name + '.meta'] = np.array([din, p, k, int(full), b] + list(hidden))
+        out[name + '.lows'], out[name + '.highs'] = lows, highs
+        out[name + '.x'], out[name + '.y_raw'] = x.numpy(), y_raw.numpy()
+        for key, val in state_to_np(model).items():
+            out[name + '.init.' + key] = val
+        opt = torch.optim.Adam(model.parameters(), lr=model.lr)
+        idx_all, noise_all, losses = [], [], []
+        for step in range(n_steps):
+            with RecordRandLike() as rec, RecordRandint() as ri:
+                ids = np.random.randint(0, n_rows, b)
+                opt.zero_grad()
+                w, mu, ld, low = model(x[ids])
+                loss = model.mdn_loss_fn(w, mu, ld, low, y[ids])
+                loss.backward()
+                opt.step()
+            assert len(rec.draws) == 1 and len(ri.draws) == 1
+            idx_all.append(ri.draws[0])
+            noise_all.append(rec.draws[0])
+            losses.append(loss.item())
+        out[name + '.idx'] = np.stack(idx_all).astype(np.int64)
+        out[name + '.noise'] = np.stack(noise_all)
+        out[name + '.loss'] = np.array(losses)
+        for key, val in state_to_np(model).items():
+            out[name + '.after.' + key] = val
+    np.savez_compressed(os.path.join(HERE, 'mdn_bench.npz'), **out)
+    print('mdn_bench.npz', len(out), 'arrays')
+
+
 def golden_pdf():
     out = {}
     rs = np.random.RandomState(7)
@@ -424,6 +473,8 @@ if __name__ == '__main__':
     torch.set_num_threads(1)   # reproducible reduction order
     golden_summarizers()
     golden_mdn()
+    if 'bench' in sys.argv[1:] or len(sys.argv) == 1:
+        golden_mdn_bench()
     golden_pdf()
     golden_pdf_host()
     golden_rff_host()

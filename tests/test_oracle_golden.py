@@ -209,3 +209,28 @@ def test_torch_port_summarizers_match_reference(golden):
         assert np.array_equal(torch_port.summary_start(s, a).numpy(), g[case + '.summary_start'])
         assert np.array_equal(torch_port.summary_corrdiff(s, a).numpy(), g[case + '.summary_corrdiff'])
         assert np.array_equal(torch_port.summary_corr(s, a).numpy(), g[case + '.summary_corr'])
+
+
+@pytest.mark.parametrize('case', ['bench_diag', 'bench_full'])
+def test_oracle_full_update_at_bench_shape(golden, case):
+    """The float64 oracle replays the reference's recorded updates at BASELINE configs[1]'s
+    dimensions (minibatch 100, F = 302, 128 x 128, P = 13, K = 10; tests/golden/mdn_bench.npz,
+    reference loop body mdnn.py:221-234): per-update losses and the final parameters."""
+    from oracle import mdn_np
+    g = golden('mdn_bench')
+    meta = g[case + '.meta']
+    p, k = int(meta[1]), int(meta[2])
+    idx, noise = g[case + '.idx'], g[case + '.noise']
+    prm = {key: val.astype(np.float64) for key, val in g.sub(case + '.init.').items()}
+    m = {key: np.zeros_like(val) for key, val in prm.items()}
+    v = {key: np.zeros_like(val) for key, val in prm.items()}
+    x = g[case + '.x'].astype(np.float64)
+    y = mdn_np.normalize_samples(g[case + '.y_raw'].astype(np.float64), g[case + '.lows'],
+                                 g[case + '.highs'])
+    for step in range(idx.shape[0]):
+        rows = idx[step]
+        loss, grads = mdn_np.mdnn_loss_and_grads(prm, x[rows], y[rows], noise[step], p, k)
+        assert abs(loss - float(g[case + '.loss'][step])) <= 1e-5 * abs(loss)
+        prm, m, v = mdn_np.adam_step(prm, grads, m, v, step + 1, 1e-3)
+    for key, ref in g.sub(case + '.after.').items():
+        assert np.abs(prm[key] - ref).max() <= 2e-5, key

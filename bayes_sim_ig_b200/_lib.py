@@ -75,6 +75,7 @@ SIGNATURES = {
     'bsig_p2p_close': (_int, [_c_ptr]),
     'bsig_p2p_read': (_int, [_c_ptr, _c_ptr, _i64]),
     'bsig_p2p_free': (_int, [_c_ptr]),
+    'bsig_p2p_set_timeout_ms': (_int, [_i64]),
     'bsig_adam_allreduce_step': (_int, [_c_ptr, ctypes.POINTER(_c_ptr), ctypes.POINTER(_c_ptr),
                                         _c_ptr, _int, _int, _c_ptr, _c_ptr, _i64, _i64,
                                         _f32, _f32, _f32, _f32, _c_ptr]),
@@ -131,6 +132,20 @@ def call(name, *args):
     rc = getattr(load(), name)(*args)
     if rc != 0:
         raise BsigError('%s failed (%d): %s' % (name, rc, last_error()))
+
+
+import contextlib
+
+
+@contextlib.contextmanager
+def nvtx_range(name):
+    """NVTX range around a stage of the path (summarize / train / predict / sample): shows up
+    in nsys / ncu --nvtx timelines; a no-op cost of two driver calls otherwise."""
+    torch.cuda.nvtx.range_push(name)
+    try:
+        yield
+    finally:
+        torch.cuda.nvtx.range_pop()
 
 
 def stream_ptr(device=None):

@@ -75,19 +75,23 @@ class BayesSim(object):
         """Reference bayes_sim.py:91-114: summarize, then NUM_GRAD_UPDATES Adam
         steps of MINIBATCH_SIZE on the summaries."""
         dev = self.model.flat_params.device
-        traj_summaries = self.summarizer_fxn(traj_states.to(dev), traj_actions.to(dev))
-        log_dict = self.model.run_training(
-            x_data=traj_summaries, y_data=params,
-            n_updates=BayesSim.NUM_GRAD_UPDATES,
-            batch_size=BayesSim.MINIBATCH_SIZE,
-            test_frac=BayesSim.TEST_FRACTION)
+        with _lib.nvtx_range('bsig.summarize'):
+            traj_summaries = self.summarizer_fxn(traj_states.to(dev), traj_actions.to(dev))
+        with _lib.nvtx_range('bsig.run_training'):
+            log_dict = self.model.run_training(
+                x_data=traj_summaries, y_data=params,
+                n_updates=BayesSim.NUM_GRAD_UPDATES,
+                batch_size=BayesSim.MINIBATCH_SIZE,
+                test_frac=BayesSim.TEST_FRACTION)
         return log_dict
 
     def predict(self, states, actions, threshold=0.005):
         """Reference bayes_sim.py:116-179 -> host ``pdf.MoG`` posterior."""
         dev = self.model.flat_params.device
-        xs = self.summarizer_fxn(states.to(dev), actions.to(dev))
-        mogs = self.model.predict_MoGs(xs)
+        with _lib.nvtx_range('bsig.summarize'):
+            xs = self.summarizer_fxn(states.to(dev), actions.to(dev))
+        with _lib.nvtx_range('bsig.predict_MoGs'):
+            mogs = self.model.predict_MoGs(xs)
         if self.proposal is not None:
             for tmp_i, mog in enumerate(mogs):
                 mog.prune_negligible_components(threshold=threshold)
@@ -100,29 +104,40 @@ class BayesSim(object):
                 mogs[tmp_i] = post
         if len(mogs) == 1:
             return mogs[0]
-        # Several real trajectories: resample the per-trajectory mixtures and fit
-        # one unconditional mixture to the pooled samples (bayes_sim.py:148-179).
-        kwargs = {'input_dim': 1,
-                  'output_dim': self.model.output_dim,
-                  'output_lows': self.model.output_lows.detach().cpu().numpy(),
-                  'output_highs': self.model.output_highs.detach().cpu().numpy(),
-                  'n_gaussians': self.model.n_gaussians,
-                  'hidden_layers': (128, 128),
-                  'lr': self.model.lr,
-                  'activation': self.model.activation,
-                  'full_covariance': self.model.L_size > 0,
-                  'device': self.model.device}
-        mog_model = MDNN(**kwargs)
-        tot_smpls = int(1e4)
-        n_smpls_per_mog = int(tot_smpls/xs.shape[0])
-        mog_smpls = np.concatenate(
-            [mogs[tmp_i].gen(n_samples=n_smpls_per_mog) for tmp_i in range(xs.shape[0])], axis=0)
-        mog_smpls = torch.from_numpy(mog_smpls).float().to(dev)
-        print(f'Fitting posterior from {len(mogs):d} mogs')
-        batch_size = 100
-        n_updates = 5*tot_smpls//batch_size
-        input = torch.zeros(mog_smpls.shape[0], 1).to(dev)
-        mog_model.run_training(input, mog_smpls, n_updates, batch_size)
-        fitted_mogs = mog_model.predict_MoGs(input[0:1, :])
-        assert (len(fitted_mogs) == 1)
-        return fitted_mogs[0]
+        with _lib.nvtx_range('bsig.refit_pooled_mixture'):
+            return self._refit_pooled_mixture(mogs)
+
+    # Constants of the multi-trajectory branch (reference bayes_sim.py:150-176, where they
+    # are literals): pool size, refit minibatch, passes over the pool, refit network.
+    POOL_SAMPLES = int(1e4)
+    REFIT_MINIBATCH = 100
+    REFIT_PASSES = 5
+    REFIT_HIDDEN = (128, 128)
+
+    def _refit_pooled_mixture(self, mogs):
+        """Several real trajectories -> one posterior (reference bayes_sim.py:148-179): draw
+        POOL_SAMPLES // R samples from each per-trajectory mixture, fit an UNCONDITIONAL
+        mixture-density net (constant input) to the pool and return its mixture.
+        The pool never leaves the GPU: every mixture samples into a device tensor
+        (MoG.gen(device_out=True): numpy draws the uniforms / normals exactly as the
+        reference does, the component choice and the affine map run on the device) and the
+        refit trains on it in place -- the reference moves the pool host -> device here."""
+        model = self.model
+        dev = model.flat_params.device
+        n_traj = len(mogs)
+        per_mog = int(self.POOL_SAMPLES / n_traj)
+        refit = MDNN(input_dim=1, output_dim=model.output_dim,
+                     output_lows=model.output_lows.detach().cpu().numpy(),
+                     output_highs=model.output_highs.detach().cpu().numpy(),
+                     n_gaussians=model.n_gaussians, full_covariance=model.L_size > 0,
+                     hidden_layers=self.REFIT_HIDDEN, activation=model.activation,
+                     lr=model.lr, device=model.device)
+        pool = torch.cat([mog.gen(n_samples=per_mog, device_out=True) for mog in mogs], dim=0)
+        pool = pool.to(dtype=torch.float32)
+        print(f'Fitting posterior from {n_traj:d} mogs')
+        n_updates = self.REFIT_PASSES * self.POOL_SAMPLES // self.REFIT_MINIBATCH
+        const_in = torch.zeros((pool.shape[0], 1), dtype=torch.float32, device=dev)
+        refit.run_training(const_in, pool, n_updates, self.REFIT_MINIBATCH)
+        fitted = refit.predict_MoGs(const_in[0:1, :])
+        assert (len(fitted) == 1)
+        return fitted[0]

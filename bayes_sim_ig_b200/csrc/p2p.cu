@@ -13,6 +13,9 @@
 // backward pass while peers still read the previous buffer.  The epoch lives in device
 // memory and is advanced by the kernel itself, so the launch is CUDA-graph capturable
 // and replayable.  Buffers are cudaMalloc'ed here (IPC handles need whole allocations).
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace bsig {
@@ -43,11 +46,16 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
   return v;
 }
 
+// Watchdog: a rank that died (exception, OOM) between two updates never publishes its epoch.
+// The wait is therefore bounded by %globaltimer; on expiry the waiting thread records
+// 1 + (index of the missing peer) in the STICKY error word ctrl[2], every later launch skips
+// its wait (fast fail instead of one time-out per update) and the host turns the flag into an
+// exception after the call (train_engine.py).  Results of a timed-out call are discarded.
 __global__ void __launch_bounds__(256)
 adam_allreduce_kernel(P2PArgs a, float* __restrict__ p, float* __restrict__ m,
                       float* __restrict__ v, int64_t count, float one_minus_b1, float b2,
                       float one_minus_b2, float step_size, float inv_bc2_sqrt, float eps,
-                      float gscale) {
+                      float gscale, unsigned long long timeout_ns) {
   __shared__ unsigned int s_epoch;
   pdl_wait_then_release();       // the backward kernels of this update are complete
   // ctrl[8..15]: nanosecond stamps of block 0 (start, flags published, peers arrived,
@@ -69,7 +77,17 @@ adam_allreduce_kernel(P2PArgs a, float* __restrict__ p, float* __restrict__ m,
   if (tracer) stamps[1] = globaltimer_ns();
   if (threadIdx.x < a.world) {
     const unsigned int* mine = a.flags[a.rank] + threadIdx.x;
-    while ((int)(ld_acquire_sys(mine) - epoch) < 0) { /* spin: peers are at most one update behind */ }
+    volatile unsigned int* err = a.ctrl + 2;
+    if (*err == 0u) {
+      const unsigned long long t_begin = globaltimer_ns();
+      unsigned int spins = 0;
+      while ((int)(ld_acquire_sys(mine) - epoch) < 0) {   // peers are at most one update behind
+        if ((++spins & 255u) == 0u && globaltimer_ns() - t_begin > timeout_ns) {
+          atomicCAS(a.ctrl + 2, 0u, 1u + threadIdx.x);
+          break;
+        }
+      }
+    }
   }
   __syncthreads();
   if (tracer) stamps[2] = globaltimer_ns();
@@ -126,6 +144,18 @@ adam_allreduce_kernel(P2PArgs a, float* __restrict__ p, float* __restrict__ m,
 }  // namespace bsig
 
 using namespace bsig;
+
+static unsigned long long g_p2p_timeout_ns = [] {
+  const char* e = getenv("BSIG_P2P_TIMEOUT_MS");
+  const long long ms = e ? atoll(e) : 20000;
+  return (unsigned long long)(ms < 1 ? 1 : ms) * 1000000ull;
+}();
+
+extern "C" int bsig_p2p_set_timeout_ms(int64_t ms) {
+  BSIG_REQUIRE(ms >= 1, "p2p_set_timeout_ms: time-out must be positive");
+  g_p2p_timeout_ns = (unsigned long long)ms * 1000000ull;
+  return 0;
+}
 
 extern "C" int bsig_p2p_alloc(void** ptr, int64_t bytes, unsigned char* handle64) {
   BSIG_REQUIRE(ptr != nullptr && handle64 != nullptr && bytes > 0, "p2p_alloc: bad arguments");
@@ -196,7 +226,7 @@ extern "C" int bsig_adam_allreduce_step(float* param, const void* const* peer_gr
   cfg.numAttrs = add_pdl_attr(attr, 0);
   BSIG_CUDA(cudaLaunchKernelEx(&cfg, adam_allreduce_kernel, a, param, exp_avg, exp_avg_sq, count,
                                1.0f - beta1, beta2, 1.0f - beta2, step_size, inv_bc2_sqrt, eps,
-                               1.0f / (float)world));
+                               1.0f / (float)world, g_p2p_timeout_ns));
   BSIG_LAUNCH_CHECK();
   return 0;
 }

@@ -213,6 +213,10 @@ mog_logpdf_kernel(const X_T* __restrict__ x, const double* __restrict__ a,
       const double lp = 0.5 * (-q + __ldg(logdet + k) - (double)P * log2pi);
       if (log_space) {
         const double t = lp + __ldg(log_a + k);
+        // a zero-weight component has log_a = -inf: it contributes nothing (scipy's
+        // logsumexp, pdf.py:489); without the guard exp(-inf - (-inf)) = NaN would
+        // poison the running sum when such a component comes first
+        if (t == -INFINITY) continue;
         if (t > run_max) {
           run_sum = run_sum * exp(run_max - t) + 1.0;
           run_max = t;

@@ -40,11 +40,12 @@ def enable(model, group=None):
         model._dp_world = 1
         return model
     model._ensure_flat()
-    dist.broadcast(model.flat_params, src=dist.get_global_rank(group, 0) if group else 0,
-                   group=group)
+    src = dist.get_global_rank(group, 0) if group else 0
+    dist.broadcast(model.flat_params, src=src, group=group)
     rff = getattr(model, 'rff', None)
     if rff is not None:
-        dist.broadcast(rff.freqs, src=0, group=group)
+        dist.broadcast(rff.freqs, src=src, group=group)
+        rff._coeff_key = None       # in-place collectives may not bump the tensor version
     model._dp_group = group
     model._dp_world = dist.get_world_size(group)
     model._plans = {}
@@ -119,6 +120,14 @@ class P2PComm(object):
         buf = (ctypes.c_uint64 * 4)()
         self._lib.call('bsig_p2p_read', self.ctrl + 32, ctypes.addressof(buf), 32)
         return [int(v) for v in buf]
+
+    def peer_timeout(self):
+        """0 if every peer arrived in time, else 1 + index of the first peer the exchange
+        kernel gave up waiting for (sticky; see the watchdog in csrc/p2p.cu)."""
+        import ctypes
+        word = ctypes.c_uint32(0)
+        self._lib.call('bsig_p2p_read', self.ctrl + 8, ctypes.addressof(word), 4)
+        return int(word.value)
 
     def local_grads(self, parity):
         return self.local[parity & 1]

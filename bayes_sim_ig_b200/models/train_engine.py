@@ -32,6 +32,11 @@ ACT_NONE, ACT_TANH = 0, 1
 
 _REPLAYED = [0]
 
+# Tests only: callable(plan) -> (noise_train [n_updates,B,P,K], noise_test [n_log,n_test,P,K])
+# that replaces the device RNG of a public run_training call, so that a whole
+# BayesSim.predict refit can be replayed against the reference draw for draw.
+NOISE_HOOK = None
+
 
 def replayed_launches():
     """Kernel launches executed through graph replays so far (bench accounting)."""
@@ -560,8 +565,14 @@ def run_training_captured(model, x_data, y_data, n_updates, batch_size, test_fra
             # tests/test_cabi_and_host.py)
             ids = np.random.randint(0, n_train, (n_updates, batch_size))
             plan.idx.copy_(torch.from_numpy(ids.astype(np.int64)), non_blocking=False)
-            plan.noise_train.uniform_(0.0, 1.0)
-            plan.noise_test.uniform_(0.0, 1.0)
+            if NOISE_HOOK is None:
+                plan.noise_train.uniform_(0.0, 1.0)
+                plan.noise_test.uniform_(0.0, 1.0)
+            else:
+                tr, te = NOISE_HOOK(plan)
+                plan.noise_train.copy_(torch.as_tensor(tr).reshape(plan.noise_train.shape))
+                if n_test > 0:
+                    plan.noise_test.copy_(torch.as_tensor(te).reshape(plan.noise_test.shape))
         else:
             plan.idx.copy_(torch.as_tensor(injected['idx'], dtype=torch.int64))
             plan.noise_train.copy_(torch.as_tensor(injected['noise_train']).reshape(
@@ -591,7 +602,8 @@ def run_training_captured(model, x_data, y_data, n_updates, batch_size, test_fra
                 before = _lib.load().bsig_launch_count()
                 plan.capture()
                 plan.launches_per_replay = _lib.load().bsig_launch_count() - before
-            plan.graph.replay()
+            with _lib.nvtx_range('bsig.train_graph'):
+                plan.graph.replay()
             _REPLAYED[0] += int(getattr(plan, 'launches_per_replay', 0))
         else:
             if plan.persistent:
@@ -607,6 +619,12 @@ def run_training_captured(model, x_data, y_data, n_updates, batch_size, test_fra
                 plan._enqueue_update(step, st)
         n_log = len(plan.logs)
         host = torch.cat([plan.loss_buf[:2 * n_log], plan.flag.float()]).cpu().numpy()
+    if plan.p2p is not None:
+        missing = plan.p2p.peer_timeout()
+        if missing:
+            raise _lib.BsigError('data-parallel exchange timed out waiting for rank %d: a peer '
+                                 'process died or stalled; the results of this call are invalid'
+                                 % (missing - 1))
     assert (host[-1] == 0), 'non-finite value in MDNN training (forward / log-likelihood)'
     train_loss = [float(v) for v in host[:n_log]]
     test_loss = [float(v) for v in host[n_log:2 * n_log]]

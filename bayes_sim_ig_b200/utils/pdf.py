@@ -40,26 +40,35 @@ def _dev64(arr, dev):
     return torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64)).to(dev)
 
 
-def _mixture_sample_device(a, means, cmats, u, z):
-    """a [K] (f32 or f64), means [K,P], cmats [K,P,P], u [n], z [n,P] (f64 draws)
-    -> (samples [n,P] f64 grouped by component, comp_idx [n] int32)."""
-    dev = _device()
+def _stage_mixture(a, means, cmats, dev):
+    """Mixture parameters as device tensors (a in its own dtype: the component choice
+    compares float64 uniforms with a float32 cumsum when a is float32)."""
     a = np.ascontiguousarray(a)
     a_is_f32 = a.dtype == np.float32
     if not a_is_f32:
         a = a.astype(np.float64)
+    return (torch.from_numpy(a).to(dev), a_is_f32, _dev64(means, dev), _dev64(cmats, dev))
+
+
+def _mixture_sample_device(a, means, cmats, u, z, want_comp=True, staged=None, device_out=False):
+    """a [K] (f32 or f64), means [K,P], cmats [K,P,P], u [n], z [n,P] (f64 draws)
+    -> (samples [n,P] f64 grouped by component, comp_idx [n] int32 or None).
+    ``staged``: parameters already on the device (_stage_mixture; MoG caches them across
+    calls); ``device_out``: leave the samples on the device (torch float64 tensor)."""
+    dev = _device()
     n, p = z.shape
-    k = a.shape[0]
-    a_d = torch.from_numpy(a).to(dev)
+    if staged is None:
+        staged = _stage_mixture(a, means, cmats, dev)
+    a_d, a_is_f32, m_d, c_d = staged
+    k = a_d.shape[0]
     u_d, z_d = _dev64(u.reshape(-1), dev), _dev64(z, dev)
-    m_d, c_d = _dev64(means, dev), _dev64(cmats, dev)
     comp = torch.empty(n, dtype=torch.int32, device=dev)
     counts = torch.zeros(k, dtype=torch.int32, device=dev)
     out = torch.empty((n, p), dtype=torch.float64, device=dev)
     _lib.call('bsig_mog_sample', a_d.data_ptr(), 1 if a_is_f32 else 0, u_d.data_ptr(),
               z_d.data_ptr(), m_d.data_ptr(), c_d.data_ptr(), comp.data_ptr(),
               counts.data_ptr(), out.data_ptr(), n, p, k, _lib.stream_ptr(dev))
-    return out.cpu().numpy(), comp.cpu().numpy()
+    return (out if device_out else out.cpu().numpy()), (comp.cpu().numpy() if want_comp else None)
 
 
 def _mixture_logpdf_device(x, a, means, precs, logdets, log):
@@ -311,9 +320,11 @@ class MoG:
     def components(self):
         return self.xs
 
-    def gen(self, n_samples=1, method='random'):
+    def gen(self, n_samples=1, method='random', device_out=False):
         """Reference pdf.py:465-472: pick components with discrete_sample, then
-        draw each component's block; the result is grouped by component."""
+        draw each component's block; the result is grouped by component.
+        ``device_out=True`` (not in the reference) returns the float64 samples as a CUDA
+        tensor instead of copying them to the host (BayesSim.predict's resample + refit)."""
         n_samples = int(n_samples)
         means = np.stack([g.m for g in self.xs])
         cmats = np.stack([g.C for g in self.xs])
@@ -332,8 +343,22 @@ class MoG:
             raise ValueError('Unknown gen method ' + method)
         if n_samples == 0:
             return np.zeros((0, self.ndim))
-        samples, _ = _mixture_sample_device(self.a, means, cmats, u, z)
+        with _lib.nvtx_range('bsig.MoG.gen'):
+            samples, _ = _mixture_sample_device(self.a, means, cmats, u, z, want_comp=False,
+                                                staged=self._staged(means, cmats),
+                                                device_out=device_out)
         return samples
+
+    def _staged(self, means, cmats):
+        """Device copies of (a, means, cmats), kept across gen calls while the mixture is
+        unchanged (the reference's consumers call gen once per environment reset)."""
+        dev = _device()
+        key = (dev, self.a.dtype.str, self.a.tobytes(), means.tobytes(), cmats.tobytes())
+        cache = getattr(self, '_stage_cache', None)
+        if cache is None or cache[0] != key:
+            cache = (key, _stage_mixture(self.a, means, cmats, dev))
+            self._stage_cache = cache
+        return cache[1]
 
     def gen_per_env(self, n_envs, lows=None, highs=None, method='random', u=None, z=None,
                     return_components=False):

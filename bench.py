@@ -58,6 +58,7 @@ def workload_config(n_gpus):
                         % N_TRAJ,
             'trajectories_per_gpu': N_TRAJ, 'chunk': CHUNK, 'n_updates_per_chunk': 100,
             'minibatch': 100, 'posterior_samples': N_POSTERIOR_SAMPLES,
+            'posterior_sampler': 'device RNG (MoG.gen(method="philox")); the reference arm draws with numpy',
             'parallelism': 'dp%d' % n_gpus,
             'gradient_exchange': ('none' if n_gpus == 1 else
                                   os.environ.get('BSIG_DP_EXCHANGE', 'p2p') +
@@ -583,6 +584,201 @@ def extra_signature_mdrff(dev):
     return res
 
 
+# ----------------------------------------------------------------- multi-GPU extras / checks
+def _max_over_ranks(ms, dev, world):
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def dp_parity_check(world, rank, dev):
+    """Data-parallel parity where the driver can see it (runs inside `bench.py --gpus N`):
+    G ranks x minibatch 16 with injected rows / noise must (a) leave bit-identical replicas
+    and (b) reproduce, within 3e-5 absolute at lr 1e-3, the parameters of ONE process that
+    trains on the concatenated G*16 minibatch (the only semantic difference is
+    the rank-local mean inside the 1e-5 eps-noise term).  Bench-shape model (F=302,
+    128x128, P=13, K=10: the fused peer-memory exchange path), three updates."""
+    import torch.distributed as dist
+    from bayes_sim_ig.models.mdnn import MDNN
+    from bayes_sim_ig_b200 import data_parallel
+    from bayes_sim_ig_b200.models.train_engine import run_training_captured
+    import contextlib
+    import io
+    f, p, k, bg, n_upd = 302, 13, 10, 16, 3
+    rs = np.random.RandomState(99)                   # identical on every rank
+    n_rows = bg * world
+    x = rs.randn(n_rows, f).astype(np.float32)
+    y = (0.1 + 1.9 * rs.rand(n_rows, p)).astype(np.float32)
+    noise = rs.rand(n_upd, n_rows, p, k).astype(np.float32)
+    lows, highs = np.full(p, 0.1), np.full(p, 2.0)
+
+    def make():
+        torch.manual_seed(1234)
+        return MDNN(f, p, lows, highs, k, False, (128, 128), torch.nn.Tanh, 1e-3, device=str(dev))
+    out = {}
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = make()
+        data_parallel.enable(model)
+        lo, hi = rank * bg, (rank + 1) * bg
+        inj = dict(idx=np.tile(np.arange(bg), (n_upd, 1)), noise_train=noise[:, lo:hi],
+                   noise_test=None)
+        logs = run_training_captured(model, torch.from_numpy(x[lo:hi]).to(dev),
+                                     torch.from_numpy(y[lo:hi]).to(dev), n_upd, bg, 0.0,
+                                     injected=inj)
+        plan = list(model._plans.values())[0]
+        out['exchange'] = 'p2p' if plan.p2p is not None else 'nccl'
+        bits = model.flat_params.view(torch.int32).to(torch.int64)
+        h = torch.stack([bits.sum(), (bits * torch.arange(1, bits.numel() + 1, device=dev)).sum()])
+        hmin, hmax = h.clone(), h.clone()
+        dist.all_reduce(hmin, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hmax, op=dist.ReduceOp.MAX)
+        out['replicas_bit_identical'] = bool(torch.equal(hmin, hmax))
+        loss = torch.tensor(logs['train_loss'], device=dev, dtype=torch.float64)
+        dist.all_reduce(loss)
+        loss /= world
+        if rank == 0:
+            single = make()                          # one process, concatenated minibatch
+            inj1 = dict(idx=np.tile(np.arange(n_rows), (n_upd, 1)), noise_train=noise,
+                        noise_test=None)
+            logs1 = run_training_captured(single, torch.from_numpy(x).to(dev),
+                                          torch.from_numpy(y).to(dev), n_upd, n_rows, 0.0,
+                                          injected=inj1)
+            err = float((single.flat_params - model.flat_params).abs().max().item())
+            lerr = float(np.abs(np.asarray(logs1['train_loss']) - loss.cpu().numpy()).max())
+            out['max_abs_param_diff_vs_single_process'] = err
+            out['max_abs_loss_diff_vs_single_process'] = lerr
+            out['ok'] = bool(out['replicas_bit_identical'] and err <= 3e-5 and lerr <= 1e-4)
+    ok = torch.tensor([1 if out.get('ok', True) and out['replicas_bit_identical'] else 0], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    assert int(ok.item()) == 1, 'data-parallel parity check failed: %r' % (out,)
+    return out
+
+
+def multi_gpu_extras(world, rank, dev, flush, peak_gbs):
+    """BASELINE.json's multi-GPU configurations at N GPUs (weak scaling, every rank the same
+    amount of work, device time = max over ranks):
+      * sharded summarizers (no collective): corrdiff and depth-3 signature on Cartpole-shaped
+        rollouts, 2^20 trajectories per GPU -> aggregate algorithmic GB/s;
+      * configs[3]: ShadowHand-shaped rollouts, 1000 trajectories per GPU and call,
+        summary_corrdiff (F = 105 002) + MDNN[128,128] (13.5 M parameters) data parallel
+        with an NCCL all-reduce of the 54 MB gradient per update;
+      * configs[4]: depth-3 signature + MDRFF fit, 4096 trajectories per GPU, data parallel
+        over the fused peer-memory exchange."""
+    import contextlib
+    import io
+    import torch.distributed as dist
+    from bayes_sim_ig.bayes_sim import BayesSim
+    from bayes_sim_ig_b200 import _lib, data_parallel
+    out = {}
+    st = lambda: _lib.stream_ptr(dev)
+
+    def timed_kernel(fn, reps=10):
+        for _ in range(3):
+            fn()
+        tot = 0.0
+        for _ in range(reps):
+            flush()
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            tot += _max_over_ranks(e0.elapsed_time(e1), dev, world)
+        return tot / reps
+    # ---- sharded summarizers
+    n, t1, d, a = 1 << 20, 21, 4, 1
+    g = torch.Generator('cpu').manual_seed(500 + rank)
+    s = torch.randn(n, t1, d, generator=g).to(dev) * 0.3
+    ac = torch.rand(n, t1, a, generator=g).to(dev)
+    feats = torch.empty((n, 302), device=dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    ms = timed_kernel(lambda: _lib.call('bsig_summary_crosscorr', s.data_ptr(), ac.data_ptr(),
+                                        feats.data_ptr(), n, t1, t1, d, a, 10, 1, flag.data_ptr(), st()))
+    by = n * 4 * (10 * (d + a) + 302)
+    out['summary_corrdiff_cartpole_sharded'] = {
+        'trajectories_per_gpu': n, 'ms': ms, 'aggregate_GBps': world * by / (ms * 1e-3) / 1e9,
+        'per_gpu_frac_of_hbm_peak': by / (ms * 1e-3) / 1e9 / peak_gbs}
+    del feats
+    sig = torch.empty((n, 258), device=dev)
+    ms = timed_kernel(lambda: _lib.call('bsig_signature_fwd', s.data_ptr(), ac.data_ptr(),
+                                        sig.data_ptr(), n, t1, t1, t1, d, a, 3, st()))
+    by = n * 4 * (t1 * (d + a) + 258)
+    out['signature_depth3_cartpole_sharded'] = {
+        'trajectories_per_gpu': n, 'ms': ms, 'aggregate_GBps': world * by / (ms * 1e-3) / 1e9,
+        'per_gpu_frac_of_hbm_peak': by / (ms * 1e-3) / 1e9 / peak_gbs}
+    del s, ac, sig
+    torch.cuda.empty_cache()
+
+    def timed_fit(bsim, params, states, actions, n_traj, reps=3):
+        chunks = range(0, n_traj, CHUNK)
+
+        def fit():
+            for lo in chunks:
+                bsim.run_training(params[lo:lo + CHUNK], states[lo:lo + CHUNK], actions[lo:lo + CHUNK])
+        with contextlib.redirect_stdout(io.StringIO()):
+            fit()
+            fit()
+            tot = 0.0
+            for _ in range(reps):
+                dist.barrier()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fit()
+                e1.record()
+                e1.synchronize()
+                tot += _max_over_ranks(e0.elapsed_time(e1), dev, world)
+        return tot / reps
+    # ---- configs[3]: ShadowHand corrdiff + 13.5 M-parameter MDNN, data parallel
+    task = dict(name='shadowhand', D=211, A=20, T1=51, P=32, K=10)
+    states, actions, params, lows, highs = synth(2000 + rank, 1000, task)
+    states, actions, params = states.to(dev), actions.to(dev), params.to(dev)
+    cfg = {'modelClass': 'MDNN', 'summarizerFxn': 'summary_corrdiff', 'trainTrajLen': 50,
+           'components': 10, 'hiddenLayers': [128, 128], 'lr': 1e-4}
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        bsim = BayesSim(cfg, task['D'], task['A'], task['P'], lows, highs, prior=None,
+                        proposal=None, device=str(dev))
+    data_parallel.enable(bsim.model)
+    ms = timed_fit(bsim, params, states, actions, 1000)
+    plan = list(bsim.model._plans.values())[0]
+    out['shadowhand_corrdiff_mdnn_dp'] = {
+        'config': 'configs[3]: ShadowHand-shaped 1000 trajectories per GPU and call, '
+                  'summary_corrdiff(F=105002) + MDNN[128,128] K=10 (13.5 M parameters), 100 Adam '
+                  'updates x minibatch 100 per GPU + 6 test evals, data parallel',
+        'gradient_exchange': 'p2p' if plan.p2p is not None else
+                             'nccl all-reduce (54 MB) between two CUDA graphs per update',
+        'ms_per_call': ms, 'ms_per_update': ms / 100,
+        'fit_trajectories_per_s': world * 1000 / (ms * 1e-3),
+        'parameters': int(bsim.model.flat_params.numel())}
+    del bsim, states, actions, params
+    torch.cuda.empty_cache()
+    # ---- configs[4]: depth-3 signature + MDRFF, data parallel
+    n4 = 4096
+    states, actions, params, lows, highs = synth(3000 + rank, n4, TASK)
+    states, actions, params = (states * 0.3).to(dev), actions.to(dev), params.to(dev)
+    cfg = {'modelClass': 'MDRFF', 'summarizerFxn': 'summary_signatory', 'trainTrajLen': 20,
+           'components': 10, 'hiddenLayers': [128, 128], 'lr': 1e-4}
+    torch.manual_seed(0)
+    np.random.seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        bsim = BayesSim(cfg, TASK['D'], TASK['A'], TASK['P'], lows, highs, prior=None,
+                        proposal=None, device=str(dev))
+    data_parallel.enable(bsim.model)
+    ms = timed_fit(bsim, params, states, actions, n4)
+    out['signature_mdrff_dp'] = {
+        'config': 'configs[4]: Cartpole-shaped 4096 trajectories per GPU, summary_signatory '
+                  '(depth 3, 258 features) + MDRFF fit, reference constants, data parallel',
+        'ms_per_step': ms, 'fit_trajectories_per_s': world * n4 / (ms * 1e-3)}
+    del bsim, states, actions, params
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_b200(args):
     import contextlib
     import io
@@ -622,7 +818,7 @@ def run_b200(args):
                 logs = bsim.run_training(params[lo:lo + CHUNK], states[lo:lo + CHUNK],
                                          actions[lo:lo + CHUNK])
             post = bsim.predict(states[:1], actions[:1])
-            smp = post.gen(N_POSTERIOR_SAMPLES)
+            smp = post.gen(N_POSTERIOR_SAMPLES, method='philox')   # device RNG (Philox)
         return logs, smp
 
     flush_buf = torch.zeros(64 * 1024 * 1024, device=dev)     # 256 MiB > 126 MB L2
@@ -654,6 +850,8 @@ def run_b200(args):
     for _ in range(max(args.warmup, 3)):
         step(states_d, actions_d, params_d)
     barrier()
+    dp_check = dp_parity_check(world, rank, dev) if world > 1 else None
+    barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = _lib.load().bsig_launch_count() + train_engine.replayed_launches()
@@ -665,7 +863,7 @@ def run_b200(args):
     e2e_value = world * N_TRAJ * args.steps / (ms_e2e * 1e-3)
     h2d = int(states_h.numel() + actions_h.numel() + params_h.numel()) * 4 + \
         2 * (N_TRAJ // CHUNK + 1) * 100 * 100 * 8
-    d2h = (N_TRAJ // CHUNK + 1) * 13 * 4 + N_POSTERIOR_SAMPLES * TASK['P'] * 8 + \
+    d2h = (N_TRAJ // CHUNK + 1) * 13 * 4 + N_POSTERIOR_SAMPLES * TASK['P'] * 4 + \
         TASK['K'] * (1 + 2 * TASK['P']) * 4
 
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
@@ -675,10 +873,20 @@ def run_b200(args):
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': int(launches)}
+    if dp_check is not None:
+        line['dp_check'] = dp_check
+    if world > 1:
+        peak, src = measured_peaks()
+        try:
+            extra = multi_gpu_extras(world, rank, dev, flush, peak)
+        except Exception as exc:                  # an extra must never take the headline down
+            extra = {'error': repr(exc)[:300]}
+        line['extra'] = extra
     if rank == 0 and world == 1:
         peak, src = measured_peaks()
         roofs = kernel_rooflines(dev, flush, peak, src)
         line['roofline'] = dominant_kernel_roofline(dev, peak, src)
+        line['roofline']['kernels'] = roofs     # per-kernel table, under the key the driver keeps
         line['rooflines'] = roofs
         line['extra'] = extra_configs(dev)
         threads = os.cpu_count() or 1

@@ -203,7 +203,12 @@ int bsig_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
 int bsig_p2p_alloc(void** ptr, int64_t bytes, unsigned char* handle64);   /* host call */
 int bsig_p2p_open(const unsigned char* handle64, void** ptr);             /* host call */
 int bsig_p2p_close(void* ptr);
-int bsig_p2p_read(const void* dev_ptr, void* host_ptr, int64_t bytes);   /* blocking D2H copy */
+int bsig_p2p_read(const void* dev_ptr, void* host_ptr, int64_t bytes);   /* Watchdog of the fused exchange: a peer that never publishes its epoch (dead rank) makes
+ * the waiting kernel give up after this many milliseconds (default 20000, env
+ * BSIG_P2P_TIMEOUT_MS), store 1 + peer index in the sticky error word ctrl[2] (read it with
+ * bsig_p2p_read(ctrl + 8 bytes, ...)) and let every later launch skip its wait. */
+int bsig_p2p_set_timeout_ms(int64_t ms);
+/* blocking D2H copy */
 int bsig_p2p_free(void* ptr);
 int bsig_adam_allreduce_step(float* param, const void* const* peer_grads,
                              void* const* peer_flags, void* ctrl, int rank, int world,

@@ -17,12 +17,21 @@ def pytest_configure(config):
 
 
 def pytest_sessionstart(session):
-    """Build libbsig_b200.so when the tree has none yet (a fresh checkout: built artefacts
-    are git-ignored); nvcc cross-compiles without a GPU.  An existing library is left alone
-    (bayes_sim_ig_b200.build only recompiles stale objects)."""
+    """(Re)build libbsig_b200.so whenever nvcc is available: the build is incremental (only
+    objects older than their source or a header are recompiled), so an up-to-date tree costs
+    nothing and a stale git-ignored library is never tested silently.  Without nvcc (the GPU
+    box receives the library prebuilt) an existing library is used as is."""
     try:
+        import shutil
         from bayes_sim_ig_b200 import build as _build
-        if not os.path.exists(_build.LIB_PATH):
+        have_nvcc = shutil.which('nvcc') or os.path.exists('/usr/local/cuda/bin/nvcc')
+        on_gpu_box = False
+        try:
+            import torch
+            on_gpu_box = torch.cuda.is_available()   # snapshot copies may not keep mtimes:
+        except Exception:                           # never spend GPU time recompiling
+            pass
+        if not os.path.exists(_build.LIB_PATH) or (have_nvcc and not on_gpu_box):
             _build.build()
     except Exception as exc:          # tests that need the library report the real problem
         sys.stderr.write('could not build libbsig_b200.so: %r\n' % (exc,))

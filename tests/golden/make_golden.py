@@ -469,6 +469,86 @@ def golden_bayessim():
     print('bayessim.npz', len(out), 'arrays')
 
 
+def seeded_uniforms(call_index, shape):
+    """The i-th torch.rand_like draw of a replayed run (shared with the GPU test)."""
+    g = torch.Generator('cpu').manual_seed(424242 + int(call_index))
+    return torch.rand(tuple(shape), generator=g)
+
+
+def golden_predict_multi():
+    """BayesSim.predict with R = 2 real trajectories (reference bayes_sim.py:148-179): the
+    per-trajectory mixtures are resampled (numpy RNG) and ONE unconditional MDNN is refitted
+    to the 10 000 pooled samples with 500 Adam updates.  Too many draws to store, so they are
+    made reproducible instead: numpy is seeded, torch.rand_like is replaced by
+    seeded_uniforms(call index), and the refit network's initial weights are recorded."""
+    out = {}
+    gb = np.load(os.path.join(HERE, 'bayessim.npz'))
+    lows, highs = np.array([0.01] * 2), np.array([2.0] * 2)
+    cfg = {'modelClass': 'MDNN', 'summarizerFxn': 'summary_start', 'trainTrajLen': 10,
+           'components': 10, 'hiddenLayers': (24, 24), 'lr': 5e-4}
+    with quiet():
+        bsim = ref_bs.BayesSim(model_cfg=cfg, obs_dim=3, act_dim=1, params_dim=2,
+                               params_lows=lows, params_highs=highs, prior=None,
+                               proposal=None, device='cpu')
+    trained = {k[len('mdnn_start.after.'):]: torch.from_numpy(gb[k])
+               for k in gb.files if k.startswith('mdnn_start.after.')}
+    bsim.model.load_state_dict(trained)
+    data = gb['pendulum.data']
+    sa = torch.from_numpy(data[:2]).float().reshape(2, -1, 4)
+    out['states'], out['actions'] = sa[:, :, :3].numpy(), sa[:, :, 3:].numpy()
+    recorded = {}
+    orig_mdnn = ref_bs.MDNN
+
+    class RecMDNN(orig_mdnn):
+        def __init__(self, *a, **k):
+            super().__init__(*a, **k)
+            recorded['init'] = state_to_np(self)
+
+        def run_training(self, x_data, y_data, n_updates, batch_size, test_frac=0.2):
+            recorded['pool'] = y_data.detach().numpy().copy()
+            recorded['n_updates'] = n_updates
+            logs = super().run_training(x_data, y_data, n_updates, batch_size, test_frac)
+            recorded['logs'] = logs
+            return logs
+    calls = {'n': 0}
+    orig_rand_like = torch.rand_like
+
+    def fake_rand_like(t, *a, **k):
+        u = seeded_uniforms(calls['n'], t.shape).to(t.dtype)
+        calls['n'] += 1
+        return u
+    ref_bs.MDNN = RecMDNN
+    torch.rand_like = fake_rand_like
+    try:
+        np.random.seed(77)
+        torch.manual_seed(78)
+        with quiet():
+            post = bsim.predict(sa[:, :, :3], sa[:, :, 3:])
+    finally:
+        ref_bs.MDNN = orig_mdnn
+        torch.rand_like = orig_rand_like
+    out['n_rand_like_calls'] = np.array(calls['n'])
+    out['n_updates'] = np.array(recorded['n_updates'])
+    for key, val in recorded['init'].items():
+        out['refit.init.' + key] = val
+    pool = recorded['pool']
+    out['pool.shape'] = np.array(pool.shape)
+    out['pool.head'] = pool[:16]
+    out['pool.tail'] = pool[-16:]
+    out['pool.mean'] = pool.astype(np.float64).mean(axis=0)
+    out['pool.cov'] = np.cov(pool.astype(np.float64).T)
+    out['refit.train_loss'] = np.array(recorded['logs']['train_loss'])
+    out['refit.test_loss'] = np.array(recorded['logs']['test_loss'])
+    out['post.a'] = post.a
+    out['post.m'] = np.stack([g.m for g in post.xs])
+    out['post.S'] = np.stack([g.S for g in post.xs])
+    xs_eval = np.random.RandomState(5).rand(64, 2) * 2.0
+    out['post.eval_x'] = xs_eval
+    out['post.eval_logp'] = post.eval(xs_eval.astype(np.float32))
+    np.savez_compressed(os.path.join(HERE, 'predict_multi.npz'), **out)
+    print('predict_multi.npz', len(out), 'arrays;', calls['n'], 'rand_like calls')
+
+
 if __name__ == '__main__':
     torch.set_num_threads(1)   # reproducible reduction order
     golden_summarizers()
@@ -479,3 +559,4 @@ if __name__ == '__main__':
     golden_pdf_host()
     golden_rff_host()
     golden_bayessim()
+    golden_predict_multi()

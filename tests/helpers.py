@@ -49,3 +49,10 @@ def synth_rollouts(seed, n, t1, d, a, device=None):
     if device is not None:
         states, actions = states.to(device), actions.to(device)
     return states, actions
+
+
+def seeded_uniforms(call_index, shape):
+    """The i-th torch.rand_like draw of a replayed run: same generator as
+    tests/golden/make_golden.py::seeded_uniforms (golden_predict_multi)."""
+    g = torch.Generator('cpu').manual_seed(424242 + int(call_index))
+    return torch.rand(tuple(shape), generator=g)

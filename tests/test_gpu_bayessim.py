@@ -91,3 +91,96 @@ def test_public_run_training_and_multi_trajectory_predict(golden, capsys):
     assert post.n_components == 4 and post.ndim == 2
     assert np.isfinite(post.eval(g['pendulum.true_params'])).all()
     assert post.gen(5).shape == (5, 2)
+
+
+def test_multi_trajectory_predict_matches_reference(golden, monkeypatch):
+    """BayesSim.predict with R = 2 real trajectories (reference bayes_sim.py:148-179):
+    resample the two per-trajectory mixtures, refit ONE unconditional MDNN with 500 Adam
+    updates, return its mixture.  Replayed draw for draw against the live reference
+    (tests/golden/predict_multi.npz, make_golden.py::golden_predict_multi): numpy is seeded
+    identically, the 508 torch.rand_like draws come from the same per-call generator, the
+    refit network starts from the recorded initial weights.
+
+    Tolerances: the pooled samples are a float64 affine map cast to float32 (1e-6); the
+    refit is 500 chained fp32 updates on two different machines, so its losses are held to
+    1e-3 and the fitted mixture to 2e-2 of each quantity's scale (measured: see the assert
+    messages; agreement degrades gracefully with the number of updates, not by a jump)."""
+    import bayes_sim_ig_b200.bayes_sim as bs_mod
+    import bayes_sim_ig_b200.models.train_engine as te
+    from bayes_sim_ig.bayes_sim import BayesSim
+    from helpers import seeded_uniforms
+    g = golden('predict_multi')
+    gb = golden('bayessim')
+    lows, highs = np.array([0.01] * 2), np.array([2.0] * 2)
+    cfg = {'modelClass': 'MDNN', 'summarizerFxn': 'summary_start', 'trainTrajLen': 10,
+           'components': 10, 'hiddenLayers': (24, 24), 'lr': 5e-4}
+    bsim = BayesSim(model_cfg=cfg, obs_dim=3, act_dim=1, params_dim=2, params_lows=lows,
+                    params_highs=highs, prior=None, proposal=None, device=DEV)
+    load_state(bsim.model, gb.sub('mdnn_start.after.'))
+    n_updates = int(g['n_updates'])
+    n_calls = int(g['n_rand_like_calls'])
+    logs = te.log_steps(n_updates)
+    assert n_calls == 2 + n_updates + len(logs)
+
+    # the refit network starts from the reference's recorded initial weights
+    captured = {}
+
+    class ReplayMDNN(bs_mod.MDNN):
+        def __init__(self, *a, **k):
+            super().__init__(*a, **k)
+            load_state(self, g.sub('refit.init.'))
+
+        def run_training(self, x_data, y_data, n_updates, batch_size, test_frac=0.2):
+            captured['pool'] = y_data.detach().cpu().numpy().copy()
+            captured['pool_device'] = y_data.device.type
+            out = super().run_training(x_data, y_data, n_updates, batch_size, test_frac)
+            captured['logs'] = out
+            return out
+    monkeypatch.setattr(bs_mod, 'MDNN', ReplayMDNN)
+
+    # reference call order of torch.rand_like: 0 = predict_MoGs of the R rows; then per
+    # update one training draw and, on logging steps, one held-out draw; last = the refit
+    # network's predict_MoGs
+    def hook(plan):
+        p, k = plan.p, plan.k
+        tr = torch.empty((plan.n_updates, plan.batch, p, k))
+        te_ = torch.empty((len(plan.logs), max(plan.n_test, 1), p, k))
+        call = 1
+        for e in range(plan.n_updates):
+            tr[e] = seeded_uniforms(call, (plan.batch, p, k))
+            call += 1
+            if e in plan.logs:
+                te_[plan.logs.index(e)] = seeded_uniforms(call, (plan.n_test, p, k))
+                call += 1
+        assert call == n_calls - 1
+        return tr, te_
+    monkeypatch.setattr(te, 'NOISE_HOOK', hook)
+    forward_calls = iter([0, n_calls - 1])
+
+    def fake_rand_like(t, *a, **k):
+        return seeded_uniforms(next(forward_calls), t.shape).to(device=t.device, dtype=t.dtype)
+    monkeypatch.setattr(torch, 'rand_like', fake_rand_like)
+
+    np.random.seed(77)
+    states = torch.from_numpy(g['states']).to(DEV)
+    actions = torch.from_numpy(g['actions']).to(DEV)
+    post = bsim.predict(states, actions)
+
+    pool = captured['pool']
+    assert captured['pool_device'] == 'cuda'          # the pool never left the device
+    assert list(pool.shape) == list(g['pool.shape'])
+    np.testing.assert_allclose(pool[:16], g['pool.head'], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(pool[-16:], g['pool.tail'], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(pool.astype(np.float64).mean(axis=0), g['pool.mean'], rtol=1e-5)
+    np.testing.assert_allclose(np.cov(pool.astype(np.float64).T), g['pool.cov'], rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(captured['logs']['train_loss'], g['refit.train_loss'], rtol=1e-3)
+    np.testing.assert_allclose(captured['logs']['test_loss'], g['refit.test_loss'], rtol=1e-3)
+    assert post.n_components == 10 and post.ndim == 2
+    got_m = np.stack([c.m for c in post.xs])
+    got_s = np.stack([c.S for c in post.xs])
+    assert np.abs(post.a - g['post.a']).max() <= 2e-2 * np.abs(g['post.a']).max(), \
+        np.abs(post.a - g['post.a']).max()
+    assert rel_err(got_m, g['post.m']) < 2e-2, rel_err(got_m, g['post.m'])
+    assert rel_err(got_s, g['post.S']) < 2e-2, rel_err(got_s, g['post.S'])
+    logp = post.eval(g['post.eval_x'].astype(np.float32))
+    np.testing.assert_allclose(logp, g['post.eval_logp'], rtol=2e-2, atol=2e-2)

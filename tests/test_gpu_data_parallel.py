@@ -86,3 +86,48 @@ def test_two_rank_training_matches_single_process_reference(golden, tmp_path):
         # the two exchange implementations differ only in summation order
         a, b = ranks[0][case + '.p2p.1.flat'], ranks[0][case + '.nccl.1.flat']
         assert np.abs(a - b).max() <= 1e-6, case
+
+
+def test_exchange_watchdog_reports_a_missing_peer():
+    """A peer that never publishes its epoch (dead rank) must not hang the exchange kernel:
+    after the time-out it records 1 + peer index in the sticky error word, later launches
+    return at once.  One GPU is enough: 'rank 1' is a second set of local buffers whose
+    flag nobody writes."""
+    import ctypes
+    import time
+    from bayes_sim_ig_b200 import _lib
+    lib = _lib.load()
+    n = 4096
+    dev = torch.device('cuda', 0)
+    torch.cuda.set_device(dev)
+
+    def alloc(nbytes):
+        ptr, buf = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+        assert lib.bsig_p2p_alloc(ctypes.byref(ptr), nbytes, buf) == 0, _lib.last_error()
+        return ptr.value
+    grads = [alloc(4 * n), alloc(4 * n)]
+    flags = [alloc(256), alloc(256)]
+    ctrl = alloc(256)
+    arr = ctypes.c_void_p * 2
+    param = torch.ones(n, device=dev)
+    m, v = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    _lib.call('bsig_p2p_set_timeout_ms', 50)
+    try:
+        t0 = time.perf_counter()
+        _lib.call('bsig_adam_allreduce_step', param.data_ptr(), arr(*grads), arr(*flags), ctrl, 0, 2,
+                  m.data_ptr(), v.data_ptr(), n, 1, 1e-3, 0.9, 0.999, 1e-8, _lib.stream_ptr(dev))
+        torch.cuda.synchronize()
+        first = time.perf_counter() - t0
+        word = ctypes.c_uint32(0)
+        _lib.call('bsig_p2p_read', ctrl + 8, ctypes.addressof(word), 4)
+        assert word.value == 2                      # 1 + index of the missing peer
+        assert 0.04 <= first < 2.0, first
+        t0 = time.perf_counter()
+        _lib.call('bsig_adam_allreduce_step', param.data_ptr(), arr(*grads), arr(*flags), ctrl, 0, 2,
+                  m.data_ptr(), v.data_ptr(), n, 2, 1e-3, 0.9, 0.999, 1e-8, _lib.stream_ptr(dev))
+        torch.cuda.synchronize()
+        assert time.perf_counter() - t0 < 0.04      # sticky: no second time-out
+    finally:
+        _lib.call('bsig_p2p_set_timeout_ms', 20000)
+        for ptr in grads + flags + [ctrl]:
+            lib.bsig_p2p_free(ptr)

@@ -51,6 +51,29 @@ def test_eval_matches_reference(golden, case):
     np.testing.assert_allclose(one, solo.eval(x64), rtol=1e-12)
 
 
+def test_eval_with_zero_weight_components():
+    """A component with weight exactly 0 (log a = -inf; arises when MoG.__mul__ /
+    __truediv__ underflow a float32 weight) must be ignored as scipy's logsumexp does
+    (pdf.py:489), wherever it sits in the mixture -- a leading one used to give NaN."""
+    from bayes_sim_ig.utils import pdf
+    from oracle import pdf_np
+    rs = np.random.RandomState(5)
+    p, k = 3, 4
+    ms = [rs.randn(p) for _ in range(k)]
+    ls = [np.concatenate([0.5 + rs.rand(p), 0.1 * rs.randn(p * (p - 1) // 2)]) for _ in range(k)]
+    x = rs.randn(64, p)
+    for a in ([0.0, 0.2, 0.3, 0.5], [0.4, 0.0, 0.6, 0.0], [0.0, 0.0, 0.0, 1.0]):
+        mog = pdf.MoG(a=np.array(a), ms=ms, Ls=ls)
+        precs = np.stack([g.P for g in mog.xs])
+        logdets = np.array([g.logdetP for g in mog.xs])
+        with np.errstate(divide='ignore'):
+            ref = pdf_np.mog_logpdf(x, np.array(a), np.stack(ms), precs, logdets, log=True)
+        got = mog.eval(x, log=True)
+        assert np.isfinite(got).all()
+        np.testing.assert_allclose(got, ref, rtol=1e-10, atol=1e-10)
+        np.testing.assert_allclose(mog.eval(x, log=False), np.exp(ref), rtol=1e-9)
+
+
 def test_sampling_moments_large_n(golden):
     """Size-independent property: 200k samples reproduce mixture mean/cov."""
     g = golden('pdf')

@@ -42,7 +42,6 @@ SIGNATURES = {
     'bsig_version': (_int, []),
     'bsig_launch_count': (_i64, []),
     'bsig_set_pdl': (_int, [_int]),
-    'bsig_bulk_copy_probe': (_int, [_c_ptr, _c_ptr, _i64, _i64, _int, _int, _c_ptr]),
     'bsig_device_info': (_int, [ctypes.POINTER(_int)] * 3),
     'bsig_summary_start': (_int, [_c_ptr, _c_ptr, _c_ptr] + [_i64] * 6 + [_c_ptr]),
     'bsig_summary_start_tm': (_int, [_c_ptr, _c_ptr, _c_ptr] + [_i64] * 6 + [_c_ptr]),
@@ -79,8 +78,6 @@ SIGNATURES = {
     'bsig_adam_allreduce_step': (_int, [_c_ptr, ctypes.POINTER(_c_ptr), ctypes.POINTER(_c_ptr),
                                         _c_ptr, _int, _int, _c_ptr, _c_ptr, _i64, _i64,
                                         _f32, _f32, _f32, _f32, _c_ptr]),
-    'bsig_mlp_chain_supported': (_int, [_c_ptr] * 3 + [_i64] * 6 + [_int]),
-    'bsig_mlp_chain_step': (_int, [_c_ptr, _i64] + [_c_ptr] * 16 + [_i64] * 6 + [_int, _c_ptr]),
     'bsig_wgrad3_adam_step': (_int, [_c_ptr, _c_ptr, _i64, _c_ptr, _i64, _i64, _i64, _i64,
                                      _c_ptr, _c_ptr, _i64, _i64, _i64, _i64,
                                      _c_ptr, _c_ptr, _i64, _i64, _i64, _i64,
@@ -95,6 +92,7 @@ SIGNATURES = {
     'bsig_mog_sample_philox': (_int, [_c_ptr] * 5 + [_u64, _i64, _i64, _i64, _c_ptr]),
     'bsig_mog_sample_envs': (_int, [_c_ptr, _int] + [_c_ptr] * 8 + [_i64] * 3 + [_c_ptr]),
     'bsig_mog_sample_envs_philox': (_int, [_c_ptr] * 7 + [_u64, _i64, _i64, _i64, _c_ptr]),
+    'bsig_mog_marginal_grid': (_int, [_c_ptr] * 5 + [_i64] * 3 + [_int, _c_ptr]),
     'bsig_mog_logpdf': (_int, [_c_ptr, _int] + [_c_ptr] * 6 + [_i64] * 3 + [_int, _c_ptr]),
 }
 

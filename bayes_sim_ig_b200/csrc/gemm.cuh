@@ -47,7 +47,9 @@ int64_t gemm_simt_ws_bytes(int64_t M, int64_t N, int64_t K);
 int colsum(const float* dy, float* db, int64_t M, int64_t N, cudaStream_t st);
 bool gemm_small_applicable(const GemmArgs& g);
 bool gemm_tc_applicable(const GemmArgs& g);
-int gemm_tc(const GemmArgs& g, bool x3, cudaStream_t st);
+int gemm_tc(const GemmArgs& g, bool x3, void* ws, int64_t ws_bytes, cudaStream_t st);
+int64_t gemm_tc_ws_bytes(int64_t M, int64_t N, int64_t K);
+int gemm_splitk_reduce(const GemmArgs& g, int splits, cudaStream_t st);
 int gemm_small(GemmArgs g, cudaStream_t st);
 
 }  // namespace bsig

@@ -229,6 +229,16 @@ int gemm_simt(GemmArgs g, void* ws, int64_t ws_bytes, cudaStream_t st) {
   return 0;
 }
 
+// fixed-order sum of `splits` partial results [splits][M][N] (g.partial) + epilogue; shared
+// with the tcgen05 engine's split-K
+int gemm_splitk_reduce(const GemmArgs& g, int splits, cudaStream_t st) {
+  const int64_t total = (int64_t)g.M * g.N;
+  const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 8);
+  splitk_reduce_kernel<<<blocks, 256, 0, st>>>(g, splits);
+  BSIG_LAUNCH_CHECK();
+  return 0;
+}
+
 int colsum(const float* dy, float* db, int64_t M, int64_t N, cudaStream_t st) {
   colsum_kernel<<<(unsigned)ceil_div(N, 32), 256, 0, st>>>(dy, db, (int)M, (int)N);
   BSIG_LAUNCH_CHECK();

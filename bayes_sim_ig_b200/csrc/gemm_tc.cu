@@ -2,7 +2,11 @@
 // the dense contractions of the path: the RFF projection (models/rff.py:128-132)
 // and the MLP / head layers at large batch (models/mdnn.py:108-119).
 //
-//   C[M,N] = epi( A[M,K] * B[N,K]^T ),  A and B row-major with K contiguous
+//   C[M,N] = epi( sum_r A(i,r) * B(r,j) ),  every operand row-major in EITHER orientation:
+//   K-major (the reduction index contiguous: x . W^T forward layers, the RFF projection) or
+//   MN-major (the output index contiguous: dgrad reads W[n][k] along k, wgrad reads
+//   dY[b][n] / X[b][k] along n / k) -- so forward, dgrad and wgrad all run on tcgen05
+//   straight from the natural row-major tensors (UMMA descriptors carry the major-ness).
 //
 // Blackwell-native structure: TMA (cp.async.bulk.tensor, 128B swizzle) stages
 // 128x32 fp32 operand tiles in shared memory, ONE elected thread issues
@@ -15,9 +19,16 @@
 // three MMAs (hi*hi + hi*lo + lo*hi): the dropped lo*lo term is 2^-22 relative,
 // so the result matches an fp32 FFMA GEMM to ~1e-6.  Plain TF32 issues one MMA.
 //
-// Requirements: K % 4 == 0 and 16-byte aligned operand rows (TMA global strides),
-// no row gather.  Other shapes use the SIMT engines.
+// TMA needs 16-byte aligned bases and row pitches and cannot gather rows: operands that
+// do not qualify (feature widths = 2 mod 4 such as 302 / 11 802 / 105 002, the 270-wide head
+// output, minibatch row gathers) are first copied into a padded staging buffer in the
+// caller's workspace (stage_rows_kernel).  Skinny outputs with a long reduction (weight
+// gradients at large batch, the ShadowHand first layer) split K over the CTAs; the fp32
+// partials are reduced in fixed order by splitk_reduce_kernel (gemm_simt.cu), which also
+// applies the epilogue.
 #include <cuda.h>
+
+#include <algorithm>
 
 #include "common.cuh"
 #include "gemm.cuh"
@@ -76,6 +87,22 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
   return d;
 }
+// MN-major operand tile as four TMA boxes of [32 (MN, contiguous: 128 B) x BK (K rows)].
+// For 32-bit operands the ONLY MN-major layout the tensor core accepts is
+// SWIZZLE_128B_BASE32B (cute: Layout_MN_SW128_32B_Atom = Swizzle<2,5,2> over 32 MN x 4 K):
+// 32-byte chunks of a 128-byte row are XOR-ed with (row mod 4) -- the TMA counterpart is
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  Atoms (4 K-rows = 512 B) follow each other along K
+// every 512 B (SBO) and along MN every BK * 128 B (LBO = one box); an MMA (K = 8) consumes
+// two K-atoms.
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);           // start address
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16; // leading byte offset: next 32 MN elements
+  d |= (uint64_t)(512 >> 4) << 32;                  // stride byte offset: next 4 K rows
+  d |= (uint64_t)1 << 46;                           // descriptor version (sm_100)
+  d |= (uint64_t)1 << 61;                           // SWIZZLE_128B_BASE32B
+  return d;
+}
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                           uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -97,9 +124,15 @@ struct TcArgs {
   float* C;
   int64_t ldc;
   const float* bias;
+  const float* aux;        // EPI_MUL_DTANH: h of the previous layer [M, ld_aux]
+  int64_t ld_aux;
   int M, N, K;
   int epi;
   float scale;
+  int a_mn, b_mn;          // operand orientation: 0 = K-major, 1 = MN-major
+  int splits;              // K split over this many work items per output tile
+  int kb_per_split;        // BK-blocks per split
+  float* partial;          // splits > 1: raw accumulators [splits][M][N]
 };
 
 // Persistent, warp-specialised kernel: one CTA per SM walks the output tiles.
@@ -126,6 +159,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int num_kb = (g.K + BK - 1) / BK;
   const int n_tiles = (g.N + BN - 1) / BN;
   const int num_tiles = ((g.M + BM - 1) / BM) * n_tiles;
+  const int num_items = num_tiles * g.splits;      // work item = (output tile, K split)
+  constexpr uint32_t MN_BOX = (uint32_t)BK * 128u;   // bytes of one [32 x BK] MN-major box
 
   auto tile_a = [&](int s) { return smem + (size_t)s * TILES_PER_STAGE * TILE_BYTES; };
   auto tile_b = [&](int s) { return tile_a(s) + TILE_BYTES; };
@@ -161,14 +196,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int tile = item / g.splits, split = item - tile * g.splits;
         const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int kb0 = split * g.kb_per_split, kb1 = min(num_kb, kb0 + g.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
           mbar_expect_tx(&full_bar[s], 2 * TILE_BYTES);
-          tma_load_2d(tile_a(s), &map_a, &full_bar[s], kb * BK, m0);
-          tma_load_2d(tile_b(s), &map_b, &full_bar[s], kb * BK, n0);
+          if (!g.a_mn) {
+            tma_load_2d(tile_a(s), &map_a, &full_bar[s], kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int blk = 0; blk < BM / 32; ++blk)
+              tma_load_2d(tile_a(s) + blk * MN_BOX, &map_a, &full_bar[s], m0 + 32 * blk, kb * BK);
+          }
+          if (!g.b_mn) {
+            tma_load_2d(tile_b(s), &map_b, &full_bar[s], kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int blk = 0; blk < BN / 32; ++blk)
+              tma_load_2d(tile_b(s) + blk * MN_BOX, &map_b, &full_bar[s], n0 + 32 * blk, kb * BK);
+          }
         }
       }
     }
@@ -176,15 +225,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // -------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=tf32, K-major both, N=128, M=128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+      // (bits 15 / 16: A / B are MN-major)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.a_mn & 1) << 15) |
+                             ((uint32_t)(g.b_mn & 1) << 16) | ((uint32_t)(BN >> 3) << 17) |
                              ((uint32_t)(BM >> 4) << 24);
       int it = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++tcount) {
+        const int split = item % g.splits;
+        const int kb0 = split * g.kb_per_split, kb1 = min(num_kb, kb0 + g.kb_per_split);
         const int buf = tcount & 1;
         mbar_wait(&tmem_empty_bar[buf], ((tcount >> 1) & 1) ^ 1);   // epilogue drained it
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t parity = (it / STAGES) & 1;
           if (X3) mbar_wait(&conv_bar[s], parity);
@@ -193,13 +246,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint32_t a_hi = smem_u32(tile_a(s)), b_hi = smem_u32(tile_b(s));
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {
-            const uint32_t off = k * 32;        // 8 tf32 = 32 bytes along the swizzled row
-            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-            umma_tf32(d_tmem, umma_desc(a_hi + off), umma_desc(b_hi + off), idesc, acc);
+            // one MMA = 8 reduction steps: 32 bytes along a K-major swizzled row, or one
+            // 8-row (1024-byte) atom of an MN-major tile
+            const uint32_t a_off = g.a_mn ? k * 1024 : k * 32;
+            const uint32_t b_off = g.b_mn ? k * 1024 : k * 32;
+            const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+            auto da = [&](uint32_t base) {
+              return g.a_mn ? umma_desc_mn(base + a_off, MN_BOX) : umma_desc(base + a_off);
+            };
+            auto db = [&](uint32_t base) {
+              return g.b_mn ? umma_desc_mn(base + b_off, MN_BOX) : umma_desc(base + b_off);
+            };
+            umma_tf32(d_tmem, da(a_hi), db(b_hi), idesc, acc);
             if (X3) {
               const uint32_t a_lo = smem_u32(tile_alo(s)), b_lo = smem_u32(tile_blo(s));
-              umma_tf32(d_tmem, umma_desc(a_hi + off), umma_desc(b_lo + off), idesc, 1u);
-              umma_tf32(d_tmem, umma_desc(a_lo + off), umma_desc(b_hi + off), idesc, 1u);
+              umma_tf32(d_tmem, da(a_hi), db(b_lo), idesc, 1u);
+              umma_tf32(d_tmem, da(a_lo), db(b_hi), idesc, 1u);
             }
           }
           umma_commit(&empty_bar[s]);           // stage reusable once these MMAs retire
@@ -211,8 +273,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ------------------------------------------------- hi/lo converters (X3 only)
     const int t = threadIdx.x - 64;             // 0..127
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int split = item % g.splits;
+      const int kb0 = split * g.kb_per_split, kb1 = min(num_kb, kb0 + g.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % STAGES;
         mbar_wait(&full_bar[s], (it / STAGES) & 1);
         float4* a = reinterpret_cast<float4*>(tile_a(s));
@@ -250,7 +314,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const bool vec_ok = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) &&
                         (g.epi != EPI_SINCOS || (g.N & 3) == 0);
     int tcount = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++tcount) {
+      const int tile = item / g.splits, split = item - tile * g.splits;
       const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
       const int buf = tcount & 1;
       mbar_wait(&tmem_full_bar[buf], (tcount >> 1) & 1);
@@ -258,6 +323,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < g.M;
       float* crow = g.C + (int64_t)(row_ok ? row : 0) * g.ldc;
+      const float* auxrow = g.aux + (int64_t)(row_ok ? row : 0) * g.ld_aux;
+      float* prow = g.partial + ((int64_t)split * g.M + (row_ok ? row : 0)) * g.N;
 #pragma unroll 1
       for (int cb = half; cb < BN / 32; cb += CB_STEP) {
         const int jbase = n0 + cb * 32;
@@ -278,6 +345,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (!row_ok) continue;
+        if (g.splits > 1) {
+          // raw accumulators: the fixed-order reduction + epilogue run in a second kernel
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (jbase + c < g.N) prow[jbase + c] = __uint_as_float(r[c]);
+          continue;
+        }
         const bool full_block = jbase + 32 <= g.N;
         // four columns at a time, everything statically indexed (stays in registers)
 #pragma unroll
@@ -290,6 +364,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             w2[u] = 0.f;
             if (g.epi == EPI_BIAS || g.epi == EPI_BIAS_TANH) acc += __ldg(g.bias + j);
             if (g.epi == EPI_BIAS_TANH) acc = tanhf(acc);
+            if (g.epi == EPI_MUL_DTANH) {
+              const float h = __ldg(auxrow + j);
+              acc *= (1.0f - h * h);
+            }
             if (g.epi == EPI_SINCOS) {
               // two-term Cody-Waite reduction to [-pi, pi], then the SFU sin/cos
               // (abs error ~5e-7 on features of magnitude `scale`)
@@ -349,56 +427,158 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// [rows, K] fp32 row-major, row stride ld floats; box = BK x 128 rows, 128B swizzle
-static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t K, int64_t ld) {
+// Row-major operand [outer][inner] with row pitch ld floats.  K-major: inner = K, box =
+// BK x 128 rows; MN-major: inner = the M (or N) index, box = 32 x BK rows.  128B swizzle.
+static int make_map(CUtensorMap* map, const float* base, int64_t outer, int64_t inner, int64_t ld,
+                    bool mn_major) {
   EncodeTiledFn fn = encode_fn();
   BSIG_REQUIRE(fn != nullptr, "gemm_tc: cuTensorMapEncodeTiled is not available");
-  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
   const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  const cuuint32_t box[2] = {(cuuint32_t)(mn_major ? 32 : BK), (cuuint32_t)(mn_major ? BK : BM)};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims,
                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   BSIG_REQUIRE(r == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
   return 0;
+}
+
+// dst[r][c] = src[(rows ? rows[r] : r) * src_ld + c] for c < width, zero up to dst_ld:
+// the padded / gathered staging copy of an operand TMA cannot address directly.
+__global__ void __launch_bounds__(256)
+stage_rows_kernel(const float* __restrict__ src, int64_t src_ld, const int64_t* __restrict__ rows,
+                  float* __restrict__ dst, int64_t dst_ld, int64_t n_rows, int64_t width) {
+  const int64_t q4 = dst_ld >> 2;                    // dst_ld % 4 == 0
+  const int64_t total = n_rows * q4;
+  const bool vec = ((src_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / q4, c = 4 * (e - r * q4);
+    const float* sp = src + (rows ? __ldg(rows + r) : r) * src_ld + c;
+    float4 v;
+    if (vec && c + 4 <= width) {
+      v = __ldg(reinterpret_cast<const float4*>(sp));
+    } else {
+      v.x = c + 0 < width ? __ldg(sp + 0) : 0.f;
+      v.y = c + 1 < width ? __ldg(sp + 1) : 0.f;
+      v.z = c + 2 < width ? __ldg(sp + 2) : 0.f;
+      v.w = c + 3 < width ? __ldg(sp + 3) : 0.f;
+    }
+    *reinterpret_cast<float4*>(dst + r * dst_ld + c) = v;
+  }
+}
+
+// How one operand reaches TMA: orientation, extent of the two row-major indices, pitch,
+// gather of the outer index, and whether it must be staged first.
+struct TcOperand {
+  bool ok, mn_major, stage;
+  const float* base;
+  int64_t outer, inner, ld;
+  const int64_t* gather;
+};
+
+static TcOperand classify(const float* base, int64_t mn_extent, int64_t K, int64_t s_mn, int64_t s_k,
+                          const int64_t* gather_mn, const int64_t* gather_k) {
+  TcOperand o = {};
+  o.base = base;
+  if (s_k == 1 && gather_k == nullptr) {             // K contiguous: rows = the M / N index
+    o.ok = true; o.mn_major = false; o.outer = mn_extent; o.inner = K; o.ld = s_mn;
+    o.gather = gather_mn;
+  } else if (s_mn == 1 && gather_mn == nullptr) {    // M / N contiguous: rows = the K index
+    o.ok = true; o.mn_major = true; o.outer = K; o.inner = mn_extent; o.ld = s_k;
+    o.gather = gather_k;
+  }
+  if (o.ok)
+    o.stage = o.gather != nullptr || (o.ld & 3) != 0 || o.ld < o.inner ||
+              (reinterpret_cast<uintptr_t>(base) & 15) != 0;
+  return o;
+}
+
+static int64_t staged_floats(int64_t outer, int64_t inner) { return outer * ((inner + 3) & ~(int64_t)3) + 64; }
+
+// K split of a skinny problem: enough work items for one wave, at least four BK-blocks each
+static int tc_splits(int64_t M, int64_t N, int64_t K) {
+  const int64_t tiles = ceil_div(M, BM) * ceil_div(N, BN);
+  const int64_t num_kb = ceil_div(K, BK);
+  const int64_t sms = sm_count();
+  if (tiles * 2 > sms || num_kb < 8) return 1;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(sms / tiles, num_kb / 4));
 }
 
 }  // namespace tc
 
 bool gemm_tc_applicable(const GemmArgs& g) {
-  const bool fwd_form = g.a_sr == 1 && g.b_sr == 1 && g.b_sj >= g.K && g.a_si >= g.K;
-  const bool aligned = (g.K % 4 == 0) && (g.a_si % 4 == 0) && (g.b_sj % 4 == 0) &&
-                       ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0) &&
-                       ((reinterpret_cast<uintptr_t>(g.B) & 15) == 0);
+  const tc::TcOperand a = tc::classify(g.A, g.M, g.K, g.a_si, g.a_sr, g.a_rows, nullptr);
+  const tc::TcOperand b = tc::classify(g.B, g.N, g.K, g.b_sj, g.b_sr, nullptr, g.b_rows);
   const bool epi_ok = g.epi == EPI_STORE || g.epi == EPI_BIAS || g.epi == EPI_BIAS_TANH ||
-                      g.epi == EPI_SINCOS;
-  return fwd_form && aligned && epi_ok && g.a_rows == nullptr && g.b_rows == nullptr &&
-         g.rowsum == nullptr && g.M >= 1 && g.N >= 1 && g.K >= 4;
+                      g.epi == EPI_MUL_DTANH || g.epi == EPI_SINCOS;
+  return a.ok && b.ok && epi_ok && g.rowsum == nullptr && g.M >= 1 && g.N >= 1 && g.K >= 1;
 }
 
-int gemm_tc(const GemmArgs& g, bool x3, cudaStream_t st) {
+// workspace: staging copies of both operands (worst case) + split-K partials
+int64_t gemm_tc_ws_bytes(int64_t M, int64_t N, int64_t K) {
+  const int64_t stage = std::max(tc::staged_floats(M, K), tc::staged_floats(K, M)) +
+                        std::max(tc::staged_floats(N, K), tc::staged_floats(K, N));
+  const int s = tc::tc_splits(M, N, K);
+  return 4 * (stage + (s > 1 ? (int64_t)s * M * N : 0)) + 1024;
+}
+
+int gemm_tc(const GemmArgs& g, bool x3, void* ws, int64_t ws_bytes, cudaStream_t st) {
   using namespace tc;
+  TcOperand a = classify(g.A, g.M, g.K, g.a_si, g.a_sr, g.a_rows, nullptr);
+  TcOperand b = classify(g.B, g.N, g.K, g.b_sj, g.b_sr, nullptr, g.b_rows);
+  BSIG_REQUIRE(a.ok && b.ok, "gemm_tc: operand layout not supported");
+  float* wsp = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  int64_t ws_left = ws == nullptr ? 0 : (ws_bytes - (reinterpret_cast<char*>(wsp) - (char*)ws)) / 4;
+  auto stage = [&](TcOperand& o) -> int {
+    if (!o.stage) return 0;
+    const int64_t dst_ld = (o.inner + 3) & ~(int64_t)3;
+    const int64_t need = staged_floats(o.outer, o.inner);
+    BSIG_REQUIRE(ws_left >= need, "gemm_tc: workspace too small for the staging copy");
+    const int64_t work = o.outer * (dst_ld >> 2);
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(work, 256), (int64_t)sm_count() * 8));
+    stage_rows_kernel<<<blocks, 256, 0, st>>>(o.base, o.ld, o.gather, wsp, dst_ld, o.outer, o.inner);
+    BSIG_LAUNCH_CHECK();
+    o.base = wsp; o.ld = dst_ld; o.gather = nullptr; o.stage = false;
+    wsp += need & ~(int64_t)63; ws_left -= need & ~(int64_t)63;
+    return 0;
+  };
+  if (stage(a)) return 1;
+  if (stage(b)) return 1;
   CUtensorMap map_a, map_b;
-  if (make_map(&map_a, g.A, g.M, g.K, g.a_si)) return 1;
-  if (make_map(&map_b, g.B, g.N, g.K, g.b_sj)) return 1;
-  TcArgs a;
-  a.C = g.C; a.ldc = g.ldc; a.bias = g.bias; a.M = g.M; a.N = g.N; a.K = g.K; a.epi = g.epi;
-  a.scale = g.scale;
-  const int64_t num_tiles = ceil_div(g.M, BM) * ceil_div(g.N, BN);
-  const dim3 grid((unsigned)std::min<int64_t>(num_tiles, sm_count()));
+  if (make_map(&map_a, a.base, a.outer, a.inner, a.ld, a.mn_major)) return 1;
+  if (make_map(&map_b, b.base, b.outer, b.inner, b.ld, b.mn_major)) return 1;
+  TcArgs t;
+  t.C = g.C; t.ldc = g.ldc; t.bias = g.bias; t.aux = g.aux; t.ld_aux = g.ld_aux;
+  t.M = g.M; t.N = g.N; t.K = g.K; t.epi = g.epi; t.scale = g.scale;
+  t.a_mn = a.mn_major ? 1 : 0; t.b_mn = b.mn_major ? 1 : 0;
+  int splits = tc_splits(g.M, g.N, g.K);
+  if (splits > 1 && ws_left < (int64_t)splits * g.M * g.N) splits = 1;
+  const int64_t num_kb = ceil_div(g.K, BK);
+  t.kb_per_split = (int)ceil_div(num_kb, splits);
+  splits = (int)ceil_div(num_kb, t.kb_per_split);
+  t.splits = splits;
+  t.partial = splits > 1 ? wsp : nullptr;
+  const int64_t num_items = ceil_div(g.M, BM) * ceil_div(g.N, BN) * splits;
+  const dim3 grid((unsigned)std::min<int64_t>(num_items, sm_count()));
   const size_t smem = (size_t)(x3 ? STAGES_X3 * 4 : STAGES_X1 * 2) * TILE_BYTES + 1024;
   if (x3) {
     BSIG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
-    gemm_tc_kernel<true><<<grid, NUM_THREADS, smem, st>>>(map_a, map_b, a);
+    gemm_tc_kernel<true><<<grid, NUM_THREADS, smem, st>>>(map_a, map_b, t);
   } else {
     BSIG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gemm_tc_kernel<false><<<grid, NUM_THREADS, smem, st>>>(map_a, map_b, a);
+    gemm_tc_kernel<false><<<grid, NUM_THREADS, smem, st>>>(map_a, map_b, t);
   }
   BSIG_LAUNCH_CHECK();
+  if (splits > 1) {
+    GemmArgs r = g;
+    r.partial = t.partial;
+    return gemm_splitk_reduce(r, splits, st);
+  }
   return 0;
 }
 

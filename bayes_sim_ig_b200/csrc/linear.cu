@@ -8,11 +8,13 @@ using namespace bsig;
 static int run_gemm(const GemmArgs& g, int engine, void* ws, int64_t ws_bytes, cudaStream_t st) {
   // tensor-core engines take the GEMMs they can express (K-contiguous operands,
   // 16-byte aligned rows, no gather); everything else runs on the SIMT engines
+  // (forward, dgrad and wgrad alike: >= 2^26 multiply-adds, e.g. every layer of a
+  // 4096-row minibatch at the Cartpole widths and the ShadowHand first layer at 100 rows)
   if (engine == BSIG_GEMM_AUTO)   // tensor cores once the problem is big enough to feed them
-    engine = ((int64_t)g.M * g.N * g.K >= (1ll << 26) && g.M >= 1024) ? BSIG_GEMM_TC_TF32X3
-                                                                       : BSIG_GEMM_SIMT;
-  if ((engine == BSIG_GEMM_TC_TF32 || engine == BSIG_GEMM_TC_TF32X3) && gemm_tc_applicable(g))
-    return gemm_tc(g, engine == BSIG_GEMM_TC_TF32X3, st);
+    engine = ((int64_t)g.M * g.N * g.K >= (1ll << 26)) ? BSIG_GEMM_TC_TF32X3 : BSIG_GEMM_SIMT;
+  if ((engine == BSIG_GEMM_TC_TF32 || engine == BSIG_GEMM_TC_TF32X3) && gemm_tc_applicable(g) &&
+      ws != nullptr && ws_bytes >= gemm_tc_ws_bytes(g.M, g.N, g.K))
+    return gemm_tc(g, engine == BSIG_GEMM_TC_TF32X3, ws, ws_bytes, st);
   if (gemm_small_applicable(g)) return gemm_small(g, st);
   return gemm_simt(g, ws, ws_bytes, st);
 }
@@ -24,6 +26,12 @@ extern "C" int64_t bsig_linear_ws_bytes(int64_t m, int64_t n, int64_t k) {
   int64_t c = gemm_simt_ws_bytes(n, k, m);
   int64_t r = a > b ? a : b;
   r = r > c ? r : c;
+  // tensor-core engine: staging copies of operands TMA cannot address + split-K partials
+  const int64_t ta = gemm_tc_ws_bytes(m, n, k), tb = gemm_tc_ws_bytes(m, k, n),
+                tcc = gemm_tc_ws_bytes(n, k, m);
+  r = r > ta ? r : ta;
+  r = r > tb ? r : tb;
+  r = r > tcc ? r : tcc;
   return r + 256;
 }
 
@@ -65,7 +73,10 @@ extern "C" int bsig_linear_wgrad(const float* dy, const float* x, int64_t ldx,
   g.A = dy; g.a_si = 1; g.a_sr = n;         // A(i,r) = dy[r,i]
   g.B = x; g.b_sr = ldx; g.b_sj = 1; g.b_rows = x_rows;   // B(r,j) = x[rows[r], j]
   g.C = dw; g.ldc = k; g.M = (int)n; g.N = (int)k; g.K = (int)m;
-  const bool fused_bias = db != nullptr && gemm_small_applicable(g);
+  // the small engine forms the bias gradient on the side; the other engines use colsum
+  const bool wants_tc = engine == BSIG_GEMM_TC_TF32 || engine == BSIG_GEMM_TC_TF32X3 ||
+                        (engine == BSIG_GEMM_AUTO && (int64_t)g.M * g.N * g.K >= (1ll << 26));
+  const bool fused_bias = db != nullptr && gemm_small_applicable(g) && !wants_tc;
   if (fused_bias) g.rowsum = db;            // db[i] = sum_r dy[r,i] rides along in the GEMM
   if (run_gemm(g, engine, ws, ws_bytes, (cudaStream_t)stream)) return 1;
   if (db != nullptr && !fused_bias) return colsum(dy, db, m, n, (cudaStream_t)stream);

@@ -530,312 +530,6 @@ __global__ void __launch_bounds__(512) nll_small_kernel(NllArgs a) {
   cluster.sync();       // keep red[] alive until every CTA has read it
 }
 
-// =====================================================================================
-// EXPERIMENTAL (opt-in, BSIG_CHAIN=1; written and compiled in round 1, NOT yet validated on
-// hardware): the dependent chain of a minibatch update in ONE launch.
-//
-// Rows of a minibatch are independent through the whole MLP, so a thread-block cluster of
-// NC <= 16 CTAs splits the B rows (rpc = ceil(B / NC) <= 8 per CTA) and every CTA carries
-// ITS rows through  gather x -> L0 -> L1 -> heads -> fused head epilogue + mixture NLL
-// (forward and backward) -> dgrad heads -> dgrad L1  with all activations in its own shared
-// memory.  Only the three batch-wide sums of the NLL (exp-sum for eps, loss, eps gradient)
-// cross CTAs, through DSMEM.  The weights (360 KB for the Cartpole model) stay in L2 and
-// stream through a double-buffered shared-memory tile ring with cp.async.bulk, two tiles
-// ahead of the arithmetic, across phase boundaries.  This replaces six launches
-// (3 forward GEMMs, NLL, 2 dgrad GEMMs: ~32 of the ~47 us of an update) by one; the
-// weight-gradient GEMMs (a reduction over the batch) and Adam stay separate kernels.
-//
-//   forward tile  = 32 output columns x K (rows of W[N][K], K contiguous):
-//                   lane <-> column, warp <-> K slice, V = 4 (K % 4 == 0: rows copied one
-//                   by one to a padded pitch, LDS.128) or V = 2 (K % 4 == 2: one dense
-//                   copy, LDS.64; K/2 odd => conflict-free); partial sums of the 8 warps
-//                   are combined through shared memory;
-//   dgrad tile    = 32 reduction rows x N (rows of W[K][N], N contiguous, N <= 128):
-//                   lane <-> 4 columns, warp <-> 4 reduction rows, accumulators live in
-//                   registers across all tiles of the phase.
-struct ChainArgs {
-  const float* x; int64_t ldx; const int64_t* rows;   // training set, minibatch row indices [B]
-  const float* y;                                     // targets [*, P], gathered with rows
-  const float* noise;                                 // eps-noise uniforms [B, P, K]
-  const float* w0; const float* b0;                   // [H1, F], [H1]
-  const float* w1; const float* b1;                   // [H2, H1], [H2]
-  const float* wh; const float* bh;                   // [NH, H2], [NH]
-  float* h1; float* h2; float* dz; float* dh2; float* dh1;   // [B, H1], [B, H2], [B, NH], ...
-  float* loss; int* flag;
-  int B, F, H1, H2, NH, P, K, L;
-  int rpc;                                            // rows per CTA (<= 8)
-  int pitch[3];                                       // smem pitch of forward tiles (floats)
-  int vec[3];                                         // 4 or 2 (see above)
-  int tile_floats;                                    // floats per ring slot
-};
-
-constexpr int kChainRows = 8;      // max rows per CTA
-constexpr int kChainThreads = 256;
-
-template <int GW, bool FULL>
-__global__ void __launch_bounds__(kChainThreads) mlp_chain_kernel(ChainArgs c) {
-  extern __shared__ __align__(16) float dyn[];
-  __shared__ float scratch[33];
-  __shared__ float red3[3], bc3[3];
-  __shared__ __align__(8) uint64_t full[2];
-  cg::cluster_group cluster = cg::this_cluster();
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int NC = gridDim.x, rank = blockIdx.x;
-  const int B = c.B, F = c.F, H1 = c.H1, H2 = c.H2, NH = c.NH, P = c.P, K = c.K, PK = P * K;
-  const int F4 = (F + 3) & ~3, NH4 = (NH + 3) & ~3;
-  const int row0 = rank * c.rpc;
-  const int nrow = max(0, min(c.rpc, B - row0));
-  pdl_wait_then_release();
-
-  // ---- shared memory carve-up (all offsets multiples of 4 floats)
-  float* xs = dyn;                                   // [8][F4]
-  float* h1s = xs + kChainRows * F4;                 // [8][H1]
-  float* h2s = h1s + kChainRows * H1;                // [8][H2]
-  float* zs = h2s + kChainRows * H2;                 // [8][NH4]
-  float* dzs = zs + kChainRows * NH4;                // [8][NH4]
-  float* dh2s = dzs + kChainRows * NH4;              // [8][H2]
-  float* ys = dh2s + kChainRows * H2;                // [8][P] (padded to 4)
-  float* ns = ys + ((kChainRows * P + 3) & ~3);      // [8][PK] (padded to 4)
-  float* red = ns + ((kChainRows * PK + 3) & ~3);    // forward: [8 warps][8 rows][32]
-  float* dred = red + 8 * kChainRows * 32;           // dgrad:   [8 warps][8 rows][128]
-  float* ring = dred + 8 * kChainRows * 128;         // 2 x tile_floats
-  float* fs = ring + 2 * (size_t)c.tile_floats;      // FULL: zs/vs scratch of nll_samples
-
-  // ---- weight-tile schedule: L0 | L1 | heads | dgrad heads | dgrad L1
-  const int n0 = (H1 + 31) >> 5, n1 = (H2 + 31) >> 5, n2 = (NH + 31) >> 5;
-  const int seg_end[5] = {n0, n0 + n1, n0 + n1 + n2, n0 + n1 + 2 * n2, n0 + 2 * n1 + 2 * n2};
-  const int NT = seg_end[4];
-  auto issue = [&](int T) {                          // one thread
-    int seg = 0;
-    while (T >= seg_end[seg]) ++seg;
-    const int t = T - (seg ? seg_end[seg - 1] : 0);
-    float* dst = ring + (size_t)(T & 1) * c.tile_floats;
-    uint64_t* bar = &full[T & 1];
-    if (seg < 3) {                                   // forward tile: 32 rows of W[N][Kd]
-      const float* w = seg == 0 ? c.w0 : (seg == 1 ? c.w1 : c.wh);
-      const int N = seg == 0 ? H1 : (seg == 1 ? H2 : NH);
-      const int Kd = seg == 0 ? F : (seg == 1 ? H1 : H2);
-      const int rows = min(32, N - 32 * t);
-      const float* src = w + (size_t)32 * t * Kd;
-      ac::mbar_expect_tx(bar, (uint32_t)rows * Kd * 4u);
-      if (c.vec[seg] == 4) {
-        for (int j = 0; j < rows; ++j)
-          ac::bulk_g2s(dst + (size_t)j * c.pitch[seg], src + (size_t)j * Kd, (uint32_t)Kd * 4u, bar);
-      } else {
-        ac::bulk_g2s(dst, src, (uint32_t)rows * Kd * 4u, bar);
-      }
-    } else {                                         // dgrad tile: 32 reduction rows of W[Kr][N]
-      const float* w = seg == 3 ? c.wh : c.w1;
-      const int Kr = seg == 3 ? NH : H2;
-      const int N = seg == 3 ? H2 : H1;
-      const int rows = min(32, Kr - 32 * t);
-      ac::mbar_expect_tx(bar, (uint32_t)rows * N * 4u);
-      ac::bulk_g2s(dst, w + (size_t)32 * t * N, (uint32_t)rows * N * 4u, bar);
-    }
-  };
-  if (tid == 0) {
-    ac::mbar_init(&full[0], 1);
-    ac::mbar_init(&full[1], 1);
-    ac::fence_barrier_init();
-    issue(0);
-    if (NT > 1) issue(1);
-  }
-
-  // ---- phase A: gather this CTA's rows of x, y and the noise
-  for (int e = tid; e < kChainRows * F4; e += kChainThreads) {
-    const int r = e / F4, k = e - r * F4;
-    float v = 0.f;
-    if (r < nrow && k < F) v = __ldg(c.x + __ldg(c.rows + row0 + r) * c.ldx + k);
-    xs[e] = v;
-  }
-  for (int e = tid; e < nrow * P; e += kChainThreads) {
-    const int r = e / P, i = e - r * P;
-    ys[e] = __ldg(c.y + __ldg(c.rows + row0 + r) * P + i);
-  }
-  for (int e = tid; e < nrow * PK; e += kChainThreads)
-    ns[e] = __ldg(c.noise + (size_t)row0 * PK + e);
-  __syncthreads();
-
-  int T = 0;                                         // next tile to consume
-  // forward layer: out[r][n] = act(sum_k in[r][k] * W[n][k] + b[n]) for this CTA's rows
-  auto forward_layer = [&](int seg, const float* in, int in_pitch, int Kd, int N,
-                           const float* bias, bool tanh_act, float* out_s, int out_pitch,
-                           float* out_g, int out_ld) {
-    const int ntile = (N + 31) >> 5;
-    const int V = c.vec[seg], pitch = c.pitch[seg];
-    const int units = Kd / V;                        // V consecutive k per unit
-    const int upw = (units + 7) >> 3;                // units per warp
-    for (int t = 0; t < ntile; ++t, ++T) {
-      const float* wt = ring + (size_t)(T & 1) * c.tile_floats;
-      ac::mbar_wait(&full[T & 1], (uint32_t)(T >> 1) & 1u);
-      const int ncol = min(32, N - 32 * t);
-      float acc[kChainRows];
-#pragma unroll
-      for (int r = 0; r < kChainRows; ++r) acc[r] = 0.f;
-      if (lane < ncol) {
-        const float* wrow = wt + (size_t)lane * pitch;
-        const int u1 = min(units, (warp + 1) * upw);
-        if (V == 4) {
-          for (int u = warp * upw; u < u1; ++u) {
-            const float4 w4 = *reinterpret_cast<const float4*>(wrow + 4 * u);
-#pragma unroll
-            for (int r = 0; r < kChainRows; ++r) {
-              const float4 a4 = *reinterpret_cast<const float4*>(in + r * in_pitch + 4 * u);
-              acc[r] = fmaf(a4.x, w4.x, acc[r]);
-              acc[r] = fmaf(a4.y, w4.y, acc[r]);
-              acc[r] = fmaf(a4.z, w4.z, acc[r]);
-              acc[r] = fmaf(a4.w, w4.w, acc[r]);
-            }
-          }
-        } else {
-          for (int u = warp * upw; u < u1; ++u) {
-            const float2 w2 = *reinterpret_cast<const float2*>(wrow + 2 * u);
-#pragma unroll
-            for (int r = 0; r < kChainRows; ++r) {
-              const float2 a2 = *reinterpret_cast<const float2*>(in + r * in_pitch + 2 * u);
-              acc[r] = fmaf(a2.x, w2.x, acc[r]);
-              acc[r] = fmaf(a2.y, w2.y, acc[r]);
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < kChainRows; ++r) red[(warp * kChainRows + r) * 32 + lane] = acc[r];
-      __syncthreads();                               // tile consumed, partials visible
-      if (tid == 0 && T + 2 < NT) issue(T + 2);
-      {
-        const int r = warp, n = 32 * t + lane;       // thread (r, lane): one output
-        float sum = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) sum += red[(w * kChainRows + r) * 32 + lane];
-        if (lane < ncol) {
-          sum += __ldg(bias + n);
-          if (tanh_act) sum = tanhf(sum);
-          out_s[r * out_pitch + n] = (r < nrow) ? sum : 0.f;
-          if (out_g != nullptr && r < nrow) out_g[(size_t)(row0 + r) * out_ld + n] = sum;
-        }
-      }
-      __syncthreads();                               // red[] free again, outputs visible
-    }
-  };
-  // dgrad layer: out[r][n] = (sum_j in[r][j] * W[j][n]) * (1 - h[r][n]^2), N <= 128, N % 4 == 0
-  auto dgrad_layer = [&](const float* in, int in_pitch, int Kr, int N, const float* h_s,
-                         int h_pitch, float* out_s, float* out_g) {
-    const int ntile = (Kr + 31) >> 5;
-    float acc[kChainRows][4];
-#pragma unroll
-    for (int r = 0; r < kChainRows; ++r)
-#pragma unroll
-      for (int v = 0; v < 4; ++v) acc[r][v] = 0.f;
-    const bool col_ok = 4 * lane < N;
-    for (int t = 0; t < ntile; ++t, ++T) {
-      const float* wt = ring + (size_t)(T & 1) * c.tile_floats;
-      ac::mbar_wait(&full[T & 1], (uint32_t)(T >> 1) & 1u);
-      const int nj = min(32, Kr - 32 * t);
-      if (col_ok) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int jl = warp * 4 + q;               // reduction row inside the tile
-          if (jl < nj) {
-            const float4 w4 = *reinterpret_cast<const float4*>(wt + (size_t)jl * N + 4 * lane);
-            const int j = 32 * t + jl;
-#pragma unroll
-            for (int r = 0; r < kChainRows; ++r) {
-              const float a = in[r * in_pitch + j];
-              acc[r][0] = fmaf(a, w4.x, acc[r][0]);
-              acc[r][1] = fmaf(a, w4.y, acc[r][1]);
-              acc[r][2] = fmaf(a, w4.z, acc[r][2]);
-              acc[r][3] = fmaf(a, w4.w, acc[r][3]);
-            }
-          }
-        }
-      }
-      __syncthreads();                               // tile consumed
-      if (tid == 0 && T + 2 < NT) issue(T + 2);
-    }
-#pragma unroll
-    for (int r = 0; r < kChainRows; ++r)
-      *reinterpret_cast<float4*>(dred + ((size_t)(warp * kChainRows + r) * 128 + 4 * lane)) =
-          make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
-    __syncthreads();
-    for (int e = tid; e < kChainRows * N; e += kChainThreads) {
-      const int r = e / N, n = e - r * N;
-      float sum = 0.f;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) sum += dred[(size_t)(w * kChainRows + r) * 128 + n];
-      const float h = h_s[r * h_pitch + n];
-      sum *= (1.0f - h * h);
-      if (out_s != nullptr) out_s[r * N + n] = (r < nrow) ? sum : 0.f;
-      if (r < nrow) out_g[(size_t)(row0 + r) * N + n] = sum;
-    }
-    __syncthreads();
-  };
-
-  // ---- phases B-D: forward
-  forward_layer(0, xs, F4, F, H1, c.b0, true, h1s, H1, c.h1, H1);
-  forward_layer(1, h1s, H1, H1, H2, c.b1, true, h2s, H2, c.h2, H2);
-  forward_layer(2, h2s, H2, H2, NH, c.bh, false, zs, NH4, nullptr, 0);
-
-  // ---- phase E: fused head epilogue + mixture NLL, forward and backward, on zs -> dzs
-  {
-    float acc = 0.f;
-    for (int e = tid; e < nrow * PK; e += kChainThreads) {
-      const int r = e / PK, col = e - r * PK;
-      acc += expf(zs[r * NH4 + K + PK + col]);
-    }
-    acc = block_sum(acc, scratch);
-    if (tid == 0) red3[0] = acc;
-  }
-  cluster.sync();
-  const float etot = cluster_sum(cluster, &red3[0], NC, &bc3[0]);
-  const float eps = kEpsNoise * (etot / (float)((int64_t)B * PK));
-  NllArgs t;
-  t.B = nrow; t.P = P; t.K = K; t.L = c.L;
-  t.z_pi = zs; t.ld_pi = NH4;
-  t.mu = zs + K; t.ld_mu = NH4;
-  t.zd = zs + K + PK; t.ld_zd = NH4;
-  t.low = FULL ? zs + K + 2 * PK : nullptr; t.ld_low = NH4;
-  t.noise = ns;
-  t.y = ys; t.y_rows = nullptr;
-  t.grad_scale = nullptr; t.loss = nullptr; t.ws = nullptr; t.flag = c.flag; t.nparts_e = 0;
-  t.d_pi = dzs; t.ldo_pi = NH4;
-  t.d_mu = dzs + K; t.ldo_mu = NH4;
-  t.d_zd = dzs + K + PK; t.ldo_zd = NH4;
-  t.d_low = FULL ? dzs + K + 2 * PK : nullptr; t.ldo_low = NH4;
-  float loss_acc = 0.f, s_acc = 0.f;
-  bool bad = false;
-  nll_samples<GW, 1, true, FULL, true, true, false>(t, eps, 1.0f / (float)B, 0, kChainThreads / GW,
-                                             kChainThreads, fs + tid, fs + (size_t)P * kChainThreads + tid,
-                                             loss_acc, s_acc, bad);
-  if (bad) atomicOr(c.flag, 1);
-  const float lsum = block_sum(loss_acc, scratch);
-  const float ssum = block_sum(s_acc, scratch);
-  if (tid == 0) { red3[1] = lsum; red3[2] = ssum; }
-  cluster.sync();
-  const float ltot = cluster_sum(cluster, &red3[1], NC, &bc3[1]);
-  const float S = cluster_sum(cluster, &red3[2], NC, &bc3[2]);
-  if (rank == 0 && tid == 0) c.loss[0] = ltot / (float)B;
-  {
-    const float cfix = kEpsNoise * S / (float)((int64_t)B * PK);
-    for (int e = tid; e < nrow * PK; e += kChainThreads) {
-      const int r = e / PK, col = e - r * PK;
-      dzs[r * NH4 + K + PK + col] += expf(zs[r * NH4 + K + PK + col]) * cfix;
-    }
-    __syncthreads();
-    for (int e = tid; e < kChainRows * NH; e += kChainThreads) {
-      const int r = e / NH, n = e - r * NH;
-      if (r < nrow) c.dz[(size_t)(row0 + r) * NH + n] = dzs[r * NH4 + n];
-      else dzs[r * NH4 + n] = 0.f;                   // idle rows contribute nothing below
-    }
-    __syncthreads();
-  }
-
-  // ---- phases F-G: dgrad through the heads and the second hidden layer
-  dgrad_layer(dzs, NH4, NH, H2, h2s, H2, dh2s, c.dh2);
-  dgrad_layer(dh2s, H2, H2, H1, h1s, H1, nullptr, c.dh1);
-  cluster.sync();                                    // red3[] stays alive until every CTA has read it
-}
-
 // eps-term fix-up of the fused backward: dzd += exp(zd) * (1e-5/M) * S
 __global__ void __launch_bounds__(256)
 eps_fixup_kernel(const float* __restrict__ zd, int64_t ld_zd, float* dzd, int64_t ldo_zd,
@@ -1345,119 +1039,4 @@ extern "C" int bsig_mdn_nll_fused(const float* z, const float* noise, const floa
     BSIG_LAUNCH_CHECK();
   }
   return 0;
-}
-
-// ------------------------------------------------------------------ chain kernel (opt-in)
-namespace bsig {
-
-// Fills the launch geometry; returns false if the shape is outside the chain kernel's
-// envelope (the caller then keeps the one-kernel-per-GEMM path).
-static bool chain_plan(ChainArgs& c, int* nc_out, size_t* smem_out) {
-  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  if (c.B < 1 || c.B > 16 * kChainRows) return false;
-  if (c.K < 1 || c.K > 32 || c.P < 1 || c.P > 64) return false;
-  if (c.H1 % 4 || c.H2 % 4 || c.H1 > 128 || c.H2 > 128 || c.H1 < 4 || c.H2 < 4) return false;
-  if (c.F < 2 || c.F > 1024 || (c.F & 1)) return false;
-  if (!al16(c.w0) || !al16(c.w1) || !al16(c.wh)) return false;
-  const int kd[3] = {c.F, c.H1, c.H2};
-  const int nn[3] = {c.H1, c.H2, c.NH};
-  int tile = 32 * 128;                                   // dgrad tiles: 32 x N, N <= 128
-  for (int s = 0; s < 3; ++s) {
-    if (kd[s] % 4 == 0) {                                // per-row copies, LDS.128: pitch/4 odd
-      c.vec[s] = 4;
-      c.pitch[s] = ((kd[s] / 4) & 1) ? kd[s] : kd[s] + 4;
-    } else {                                             // K % 4 == 2: dense copy, LDS.64
-      c.vec[s] = 2;
-      c.pitch[s] = kd[s];
-      const int tail = nn[s] % 32;                       // bulk size must be a multiple of 16 B
-      if (tail && ((int64_t)tail * kd[s]) % 4) return false;
-    }
-    tile = std::max(tile, 32 * c.pitch[s]);
-  }
-  c.tile_floats = (tile + 3) & ~3;
-  int nc = (int)ceil_div(c.B, kChainRows);
-  nc = std::max(nc, std::min(16, c.B));                  // as many CTAs as rows allow, <= 16
-  c.rpc = (int)ceil_div(c.B, nc);
-  nc = (int)ceil_div(c.B, c.rpc);
-  const int F4 = (c.F + 3) & ~3, NH4 = (c.NH + 3) & ~3, PK = c.P * c.K;
-  size_t fl = (size_t)kChainRows * (F4 + c.H1 + 2 * c.H2 + 2 * NH4) +
-              ((kChainRows * c.P + 3) & ~3) + ((kChainRows * PK + 3) & ~3) +
-              8 * kChainRows * 32 + 8 * kChainRows * 128 + 2 * (size_t)c.tile_floats;
-  if (c.L > 0) fl += 2 * (size_t)c.P * kChainThreads;
-  *smem_out = fl * sizeof(float);
-  *nc_out = nc;
-  return *smem_out <= 220 * 1024;
-}
-
-template <int GW, bool FULL>
-static int launch_chain_t(const ChainArgs& c, int nc, size_t smem, cudaStream_t st) {
-  auto kern = mlp_chain_kernel<GW, FULL>;
-  BSIG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (nc > 8) BSIG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)nc);
-  cfg.blockDim = dim3(kChainThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)nc;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = add_pdl_attr(attr, 1);
-  BSIG_CUDA(cudaLaunchKernelEx(&cfg, kern, c));
-  BSIG_LAUNCH_CHECK();
-  return 0;
-}
-
-}  // namespace bsig
-
-static void chain_fill(ChainArgs& c, int64_t b, int64_t f, int64_t h1, int64_t h2, int64_t p,
-                       int64_t k, int full_cov) {
-  c.B = (int)b; c.F = (int)f; c.H1 = (int)h1; c.H2 = (int)h2; c.P = (int)p; c.K = (int)k;
-  c.L = (full_cov && p > 1) ? (int)(p * (p - 1) / 2) : 0;
-  c.NH = (int)(k + 2 * p * k + (int64_t)c.L * k);
-}
-
-extern "C" int bsig_mlp_chain_supported(const float* w0, const float* w1, const float* wh,
-                                        int64_t b, int64_t f, int64_t h1, int64_t h2, int64_t p,
-                                        int64_t k, int full_cov) {
-  ChainArgs c = {};
-  chain_fill(c, b, f, h1, h2, p, k, full_cov);
-  c.w0 = w0; c.w1 = w1; c.wh = wh;
-  int nc = 0;
-  size_t smem = 0;
-  return chain_plan(c, &nc, &smem) ? 1 : 0;
-}
-
-extern "C" int bsig_mlp_chain_step(const float* x, int64_t ldx, const int64_t* rows, const float* y,
-                                   const float* noise, const float* w0, const float* b0,
-                                   const float* w1, const float* b1, const float* wh,
-                                   const float* bh, float* h1_out, float* h2_out, float* dz,
-                                   float* dh2, float* dh1, float* loss, int* flag, int64_t b,
-                                   int64_t f, int64_t h1, int64_t h2, int64_t p, int64_t k,
-                                   int full_cov, void* stream) {
-  BSIG_REQUIRE(rows != nullptr && flag != nullptr && loss != nullptr, "mlp_chain_step: null argument");
-  ChainArgs c = {};
-  chain_fill(c, b, f, h1, h2, p, k, full_cov);
-  c.x = x; c.ldx = ldx; c.rows = rows; c.y = y; c.noise = noise;
-  c.w0 = w0; c.b0 = b0; c.w1 = w1; c.b1 = b1; c.wh = wh; c.bh = bh;
-  c.h1 = h1_out; c.h2 = h2_out; c.dz = dz; c.dh2 = dh2; c.dh1 = dh1; c.loss = loss; c.flag = flag;
-  int nc = 0;
-  size_t smem = 0;
-  BSIG_REQUIRE(chain_plan(c, &nc, &smem), "mlp_chain_step: shape outside the chain kernel's envelope "
-               "(query bsig_mlp_chain_supported first)");
-  int gw = 1;
-  while (gw < c.K) gw <<= 1;
-  cudaStream_t st = (cudaStream_t)stream;
-#define BSIG_CH(GWV)                                                           \
-  case GWV:                                                                    \
-    return c.L > 0 ? launch_chain_t<GWV, true>(c, nc, smem, st)                \
-                   : launch_chain_t<GWV, false>(c, nc, smem, st);
-  switch (gw) {
-    BSIG_CH(1) BSIG_CH(2) BSIG_CH(4) BSIG_CH(8) BSIG_CH(16) BSIG_CH(32)
-  }
-#undef BSIG_CH
-  return 1;
 }

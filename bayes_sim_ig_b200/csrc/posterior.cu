@@ -231,6 +231,54 @@ mog_logpdf_kernel(const X_T* __restrict__ x, const double* __restrict__ a,
   }
 }
 
+// ------------------------------------------------- pairwise marginal densities on grids
+// All 2-D marginals a posterior plot needs (utils/plot.py:38-44, 131-149: for every pair of
+// parameters, MoG.eval(grid, ii=pair, log=False) on a 100 x 100 np.mgrid) in ONE launch.
+// params [NP][K][6] = {m0, m1, p00, p01, p11, logdetP} of each component's 2-D marginal
+// (precision of the jittered 2 x 2 covariance block, built on the host); lims [NP][4] =
+// {xmin, xmax, ymin, ymax}; grid point (i, j) of pair q is (xmin + i dx, ymin + j dy) with
+// dx = (xmax - xmin) / (nbins - 1) -- np.mgrid[xmin:xmax:nbins*1j] -- and lands at
+// out[q][i][j].
+__global__ void __launch_bounds__(256)
+mog_marginal_grid_kernel(const double* __restrict__ a, const double* __restrict__ log_a,
+                         const double* __restrict__ params, const double* __restrict__ lims,
+                         double* __restrict__ out, int64_t n_pairs, int K, int nbins,
+                         int log_space) {
+  const double log2pi = 1.8378770664093454835606594728112;
+  const int64_t per = (int64_t)nbins * nbins;
+  const int64_t total = n_pairs * per;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t q = e / per;
+    const int r = (int)(e - q * per);
+    const int i = r / nbins, j = r - i * nbins;
+    const double* lm = lims + q * 4;
+    const double den = (double)(nbins > 1 ? nbins - 1 : 1);
+    const double x0 = __ldg(lm + 0) + (double)i * ((__ldg(lm + 1) - __ldg(lm + 0)) / den);
+    const double x1 = __ldg(lm + 2) + (double)j * ((__ldg(lm + 3) - __ldg(lm + 2)) / den);
+    double run_max = -INFINITY, run_sum = 0.0, lin = 0.0;
+    for (int k = 0; k < K; ++k) {
+      const double* pk = params + (q * K + k) * 6;
+      const double d0 = x0 - __ldg(pk + 0), d1 = x1 - __ldg(pk + 1);
+      const double quad = d0 * d0 * __ldg(pk + 2) + 2.0 * d0 * d1 * __ldg(pk + 3) + d1 * d1 * __ldg(pk + 4);
+      const double lp = 0.5 * (-quad + __ldg(pk + 5) - 2.0 * log2pi);
+      if (log_space) {
+        const double t = lp + __ldg(log_a + k);
+        if (t == -INFINITY) continue;
+        if (t > run_max) {
+          run_sum = run_sum * exp(run_max - t) + 1.0;
+          run_max = t;
+        } else {
+          run_sum += exp(t - run_max);
+        }
+      } else {
+        lin += __ldg(a + k) * exp(lp);
+      }
+    }
+    out[e] = log_space ? run_max + log(run_sum) : lin;
+  }
+}
+
 static int grid_for(int64_t work, int threads) {
   return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(work, threads), (int64_t)sm_count() * 8));
 }
@@ -333,6 +381,17 @@ extern "C" int bsig_mog_sample_envs_philox(const float* a, const float* means, c
   if (n == 0) return 0;
   mog_sample_philox_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
       a, means, cmats, comp_idx, samples, seed, n, (int)p, (int)k, lows, highs);
+  BSIG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int bsig_mog_marginal_grid(const double* a, const double* log_a, const double* params,
+                                      const double* lims, double* out, int64_t n_pairs, int64_t k,
+                                      int64_t nbins, int log_space, void* stream) {
+  BSIG_REQUIRE(n_pairs >= 0 && k >= 1 && nbins >= 1, "mog_marginal_grid: bad sizes");
+  if (n_pairs == 0) return 0;
+  mog_marginal_grid_kernel<<<grid_for(n_pairs * nbins * nbins, 256), 256, 0, (cudaStream_t)stream>>>(
+      a, log_a, params, lims, out, n_pairs, (int)k, (int)nbins, log_space);
   BSIG_LAUNCH_CHECK();
   return 0;
 }

@@ -131,22 +131,11 @@ class TrainPlan(object):
         self.loss_buf = torch.zeros(2 * n_log + 1, **f32)   # [train..., test..., scratch]
         self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
         self.graph = None
-        # EXPERIMENTAL, opt-in: forward + NLL + dgrad of an update as ONE cluster kernel
-        # (csrc/mdn.cu: mlp_chain_kernel; not yet validated on hardware, default off)
-        self.chain = False
-        if os.environ.get('BSIG_CHAIN') == '1' and self.rff is None and len(trunk) == 2:
-            layers, head = self._views()
-            self.chain = bool(lib.bsig_mlp_chain_supported(
-                layers[0]['w'].data_ptr(), layers[1]['w'].data_ptr(), head['w'].data_ptr(),
-                batch, in_dim, widths[0], widths[1], p, k, 1 if model.full_covariance else 0))
-        # ... and, on a single GPU, the weight gradients + Adam as one more launch
-        self.chain_fused_adam = (self.chain and self.p2p is None and batch <= 128 and
-                                 data_parallel.world_of(model) == 1)
         # single GPU, two hidden layers: the three weight-gradient GEMMs and Adam are ONE
         # launch (csrc/optim.cu: wgrad3_adam_kernel) on the critical path instead of three
         # side-stream launches + the Adam launch.  Opt-in (BSIG_FUSED_WGRAD=1): measured equal to the default
         # (4.80 vs 4.75 ms per 100 updates, profiles/r2/), it only lowers the launch count
-        self.fused_wgrad_adam = (not self.chain and self.rff is None and len(trunk) == 2 and
+        self.fused_wgrad_adam = (self.rff is None and len(trunk) == 2 and
                                  self.p2p is None and batch <= 128 and
                                  data_parallel.world_of(model) == 1 and
                                  os.environ.get('BSIG_FUSED_WGRAD', '0') == '1')
@@ -279,58 +268,7 @@ class TrainPlan(object):
                   ACT_NONE, eng, wsp, wsn, st)
         return cur, ld, rows_p
 
-    def _enqueue_step_chain(self, step, st):
-        """Opt-in form of _enqueue_step: one cluster kernel for gather + forward + NLL +
-        dgrad, then the three weight-gradient GEMMs."""
-        m = self.model
-        eng = int(m.gemm_engine)
-        wsp, wsn = self.ws_gemm.data_ptr(), self.ws_gemm.numel()
-        b, p, k = self.batch, self.p, self.k
-        rows = self.idx[step]
-        layers, head = self._views(self.p2p.local_grads(step) if self.p2p is not None else None)
-        slot = self.logs.index(step) if step in self.logs else None
-        n_log = len(self.logs)
-        loss_ptr = self.loss_buf.data_ptr() + 4 * (slot if slot is not None else 2 * n_log)
-        h1, h2 = self.tr['h']
-        _lib.call('bsig_mlp_chain_step', self.x_train_buf.data_ptr(), self.x_ld, rows.data_ptr(),
-                  self.y_train.data_ptr(), self.noise_train[step].data_ptr(),
-                  layers[0]['w'].data_ptr(), layers[0]['b'].data_ptr(),
-                  layers[1]['w'].data_ptr(), layers[1]['b'].data_ptr(),
-                  head['w'].data_ptr(), head['b'].data_ptr(), h1.data_ptr(), h2.data_ptr(),
-                  self.dz.data_ptr(), self.dh[1].data_ptr(), self.dh[0].data_ptr(), loss_ptr,
-                  self.flag.data_ptr(), b, self.in_dim, layers[0]['n'], layers[1]['n'], p, k,
-                  1 if m.full_covariance else 0, st)
-        if self.chain_fused_adam:
-            # single GPU: the three weight-gradient GEMMs and Adam in one more launch
-            nw0, nw1 = layers[0]['n'] * layers[0]['k'], layers[1]['n'] * layers[1]['k']
-            off1 = nw0 + layers[0]['n']
-            _lib.call('bsig_wgrad3_adam_step',
-                      self.dh[0].data_ptr(), self.x_train_buf.data_ptr(), self.x_ld, rows.data_ptr(),
-                      layers[0]['n'], layers[0]['k'], 0, nw0,
-                      self.dh[1].data_ptr(), h1.data_ptr(), layers[1]['n'], layers[1]['k'],
-                      off1, off1 + nw1,
-                      self.dz.data_ptr(), h2.data_ptr(), head['n'], head['k'],
-                      m._head_w_off, m._head_b_off,
-                      m.flat_params.data_ptr(), self.exp_avg.data_ptr(),
-                      self.exp_avg_sq.data_ptr(), b, step + 1, float(m.lr), 0.9, 0.999, 1e-8, st)
-            return
-        main = torch.cuda.current_stream(self.dev)
-        side = self.side if self.fork_wgrad else None
-        if side is not None:
-            side.wait_stream(main)
-        wst = side.cuda_stream if side is not None else st
-        for dy, xin, xld, xrows, lay in (
-                (self.dz, h2, layers[1]['n'], None, head),
-                (self.dh[1], h1, layers[0]['n'], None, layers[1]),
-                (self.dh[0], self.x_train_buf, self.x_ld, rows.data_ptr(), layers[0])):
-            _lib.call('bsig_linear_wgrad', dy.data_ptr(), xin.data_ptr(), xld, xrows, lay['dw'],
-                      lay['db'], b, lay['n'], lay['k'], eng, wsp, wsn, wst)
-        if side is not None:
-            main.wait_stream(side)
-
     def _enqueue_step(self, step, st):
-        if self.chain:
-            return self._enqueue_step_chain(step, st)
         m = self.model
         eng = int(m.gemm_engine)
         wsp, wsn = self.ws_gemm.data_ptr(), self.ws_gemm.numel()
@@ -390,9 +328,7 @@ class TrainPlan(object):
         slot = self.logs.index(step) if step in self.logs else None
         n_log = len(self.logs)
         world = data_parallel.world_of(m)
-        if self.chain_fused_adam:
-            pass                                  # Adam ran in the epilogue of bsig_wgrad3_adam_step
-        elif self.fused_wgrad_adam:
+        if self.fused_wgrad_adam:
             layers, head = self._views()
             h1, h2 = self.tr['h']
             nw0, nw1 = layers[0]['n'] * layers[0]['k'], layers[1]['n'] * layers[1]['k']

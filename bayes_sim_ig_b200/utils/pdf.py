@@ -445,6 +445,40 @@ class MoG:
             print('weights\n', self.a, '\nres\n', res)
         return res
 
+    def eval_marginal_grids(self, pairs, lims, nbins=100, log=False):
+        """All pairwise 2-D marginals on regular grids in ONE device launch -- the batched
+        form of what ``plot_posterior`` does pair by pair (reference utils/plot.py:38-44:
+        ``posterior.eval(X.T, ii=dims, log=False)`` on ``np.mgrid[xmin:xmax:nbins*1j,
+        ymin:ymax:nbins*1j]``).  ``pairs``: sequence of (i, j) parameter indices; ``lims``:
+        one (xmin, xmax, ymin, ymax) for all pairs or one per pair.  Returns
+        [len(pairs), nbins, nbins] float64, entry [q, i, j] = density at grid point (i, j).
+        The covariance jitter of the marginal branch (pdf.py:336) is drawn from numpy's global
+        RNG pair by pair, component by component -- the order a loop of reference calls uses."""
+        pairs = [tuple(int(v) for v in pr) for pr in pairs]
+        n_pairs, k = len(pairs), self.n_components
+        lims = np.asarray(lims, dtype=np.float64)
+        if lims.ndim == 1:
+            lims = np.tile(lims, (n_pairs, 1))
+        assert lims.shape == (n_pairs, 4)
+        prm = np.empty((n_pairs, k, 6), dtype=np.float64)
+        for q, pr in enumerate(pairs):
+            for c, g in enumerate(self.xs):
+                mean, cov = g._marginal(list(pr))
+                prec = np.linalg.inv(cov)
+                prm[q, c] = (mean[0], mean[1], prec[0, 0], 0.5 * (prec[0, 1] + prec[1, 0]),
+                             prec[1, 1], -np.linalg.slogdet(cov)[1])
+        if n_pairs == 0:
+            return np.zeros((0, nbins, nbins))
+        dev = _device()
+        with np.errstate(divide='ignore'):
+            log_a = np.log(np.asarray(self.a))
+        a_d, la_d, p_d, l_d = (_dev64(t, dev) for t in (self.a, log_a, prm, lims))
+        out = torch.empty((n_pairs, nbins, nbins), dtype=torch.float64, device=dev)
+        _lib.call('bsig_mog_marginal_grid', a_d.data_ptr(), la_d.data_ptr(), p_d.data_ptr(),
+                  l_d.data_ptr(), out.data_ptr(), n_pairs, k, int(nbins), 1 if log else 0,
+                  _lib.stream_ptr(dev))
+        return out.cpu().numpy()
+
     def __str__(self):
         mus = np.array([g.m.tolist() for g in self.xs])
         diag_s = np.array([np.diagonal(g.S).tolist() for g in self.xs])

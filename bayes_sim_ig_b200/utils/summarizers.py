@@ -194,9 +194,15 @@ class _SignatureFn(torch.autograd.Function):
         return d_states, d_actions, None
 
 
-def summary_signatory(states, actions):
+def summary_signatory(states, actions, time_major=False):
     """Reference summarizers.py:144-168: signature of the time-augmented path
-    [t | s_t | a_t] truncated at signature_depth(1 + D + A)."""
+    [t | s_t | a_t] truncated at signature_depth(1 + D + A).
+    ``time_major=True``: ``states`` [T, N, D] / ``actions`` [T', N, A] as a
+    vectorised simulator writes them.  The signature kernel streams whole trajectories with
+    bulk copies, so time-major buffers are transposed on the device first (one extra pass
+    over the rollouts; the other summarizers read time-major buffers in place)."""
+    if time_major:
+        states, actions = states.transpose(0, 1), actions.transpose(0, 1)
     assert (len(states.shape) == 3), 'states should be batch x time x state_dim'
     bsz, path_len, state_dim = states.shape
     assert actions.shape[0] == bsz and actions.shape[1] >= path_len

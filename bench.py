@@ -278,7 +278,7 @@ def kernel_rooflines(dev, flush, peak_gbs, peak_src):
                      'algorithmic_bytes': int(algo_bytes), 'shape': note, 'peak_source': peak_src}
 
     # summary_corrdiff, ShadowHand-shaped (F = 105002): 4*[W(D+A) + F] B/traj
-    n, t1, d, a = 1024, 51, 211, 20
+    n, t1, d, a = 4096, 51, 211, 20          # 1.7 GB of summaries: far beyond the 126 MB L2
     s = torch.randn(n, t1, d, device=dev)
     ac = torch.rand(n, t1, a, device=dev)
     width = 5 * (d - 1) * 5 * a + 2
@@ -477,21 +477,28 @@ def extra_configs(dev):
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         feats = bsim.summarizer_fxn(states, actions)
+        mogs_in = bsim.model.rff.to_features(feats)      # 65536 x 680 -> 200 on tcgen05 (warm-up)
         torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        mogs_in = bsim.model.rff.to_features(feats)      # 65536 x 680 -> 200 on tcgen05
-        torch.cuda.synchronize()
-        t_rff = time.perf_counter() - t1
+        reps = []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            mogs_in = bsim.model.rff.to_features(feats)
+            e1.record()
+            e1.synchronize()
+            reps.append(e0.elapsed_time(e1))
+        t_rff = 1e-3 * float(np.median(reps))
     out['mdrff_ant_64k'] = {
         'config': 'configs[2]: Ant-shaped 65536 trajectories [T1=51,D=60,A=8,P=17], '
                   'summary_start(F=680) + MDRFF(n_feat=200, sigma=4, RBF) fit, reference constants',
         'fit_trajectories_per_s': n / dt, 'seconds': dt, 'final_test_loss': logs['test_loss'][-1],
-        'rff_features_whole_batch_ms': 1e3 * t_rff, 'features_shape': list(mogs_in.shape)}
+        'rff_features_whole_batch_ms': 1e3 * t_rff, 'rff_timing': 'median of 5 warm calls, CUDA events',
+        'features_shape': list(mogs_in.shape)}
     del bsim, states, actions, params, feats, mogs_in
     import gc
     gc.collect()
     torch.cuda.empty_cache()
-    for fn in (extra_shadowhand, extra_signature_mdrff):
+    for fn in (extra_shadowhand, extra_signature_mdrff, extra_scaled_mode):
         try:
             out.update(fn(dev))
         except Exception as exc:          # an extra must never take the headline line down
@@ -536,6 +543,55 @@ def extra_shadowhand(dev):
     return res
 
 
+def extra_scaled_mode(dev):
+    """SURVEY 8.d "scaled mode": the reference's 10 passes over the data, but with a large
+    per-GPU minibatch B_g and n_updates = 10 N / B_g in ONE run_training call over all N
+    trajectories (the class constants are overridable; `model.run_training` takes them as
+    arguments).  At these sizes every layer GEMM (forward, dgrad, wgrad: >= 2^26 MACs) runs
+    on the tcgen05 engine (TF32x3, MN-major operands for the backward); the same call on the
+    fp32 SIMT engine is timed beside it."""
+    import contextlib
+    import io
+    from bayes_sim_ig.bayes_sim import BayesSim
+    res = {}
+    n = 1 << 18
+    states, actions, params, lows, highs = synth(21, n, TASK)
+    states, actions, params = states.to(dev), actions.to(dev), params.to(dev)
+    cfg = {'modelClass': 'MDNN', 'summarizerFxn': SUMMARIZER, 'trainTrajLen': TASK['T1'] - 1,
+           'components': TASK['K'], 'hiddenLayers': list(HIDDEN), 'lr': LR}
+    with contextlib.redirect_stdout(io.StringIO()):
+        bsim = BayesSim(cfg, TASK['D'], TASK['A'], TASK['P'], lows, highs, prior=None,
+                        proposal=None, device=str(dev))
+        feats = bsim.summarizer_fxn(states, actions)
+        for b_g in (4096, 16384):
+            n_updates = 10 * int(n * 0.8) // b_g
+            entry = {}
+            for tag, engine in (('tcgen05_tf32x3', -1), ('simt_fp32', 0)):
+                bsim.model.gemm_engine = engine
+                bsim.model.run_training(feats, params, n_updates, b_g, 0.2)     # capture + warm up
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                logs = bsim.model.run_training(feats, params, n_updates, b_g, 0.2)
+                e1.record()
+                e1.synchronize()
+                ms = e0.elapsed_time(e1)
+                entry[tag] = {'ms_per_call': ms, 'ms_per_update': ms / n_updates,
+                              'fit_trajectories_per_s': n / (ms * 1e-3),
+                              'final_test_loss': logs['test_loss'][-1]}
+                bsim.model._plans = {}
+                torch.cuda.empty_cache()
+            entry['n_updates'] = n_updates
+            entry['speedup_tensor_core_vs_simt'] = (entry['simt_fp32']['ms_per_call'] /
+                                                    entry['tcgen05_tf32x3']['ms_per_call'])
+            res['scaled_mode_B%d' % b_g] = entry
+    res['scaled_mode_config'] = ('Cartpole-shaped %d trajectories on one GPU, summary_corrdiff(F=302) '
+                                 '+ MDNN[128,128] K=10, 10 passes, minibatch B_g, one call' % n)
+    del bsim, states, actions, params, feats
+    torch.cuda.empty_cache()
+    return res
+
+
 def extra_signature_mdrff(dev):
     """configs[4], single-GPU slice: depth-3 path-signature summarizer on Cartpole-shaped
     rollouts (C = 6 -> 258 features) + MDRFF fit (reference constants, chunks of 1000) and a
@@ -569,9 +625,12 @@ def extra_signature_mdrff(dev):
             for ns in (10000, 1000000):
                 post.gen(ns, method='philox')
                 torch.cuda.synchronize()
-                t1 = time.perf_counter()
-                smp = post.gen(ns, method='philox')
-                sweep[str(ns)] = ns / (time.perf_counter() - t1)
+                reps = []
+                for _ in range(5):
+                    t1 = time.perf_counter()
+                    smp = post.gen(ns, method='philox')
+                    reps.append(time.perf_counter() - t1)
+                sweep[str(ns)] = ns / float(np.median(reps))     # median of 5 warm calls
         res['signature_mdrff_%d' % n] = {
             'config': 'configs[4] (one GPU): Cartpole-shaped %d trajectories, summary_signatory '
                       '(depth 3, 258 features) + MDRFF fit, reference constants; posterior sampling '

@@ -50,10 +50,6 @@ int64_t bsig_launch_count(void);
 /* Programmatic dependent launch of the training-step kernels (default on; env BSIG_PDL=0
  * or bsig_set_pdl(0) turns it off).  No reference counterpart (launch plumbing). */
 int bsig_set_pdl(int enabled);
-/* Profiling aid (no reference counterpart): persistent copy through the same cp.async.bulk
- * double-buffer pipeline the streaming kernels use; measures what the 1-D bulk path sustains. */
-int bsig_bulk_copy_probe(const void* src, void* dst, int64_t bytes, int64_t tile_bytes,
-                         int stages, int ctas_per_sm, void* stream);
 /* host query: SM count and compute capability of the current device */
 int bsig_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
@@ -214,25 +210,6 @@ int bsig_adam_allreduce_step(float* param, const void* const* peer_grads,
                              void* const* peer_flags, void* ctrl, int rank, int world,
                              float* exp_avg, float* exp_avg_sq, int64_t count, int64_t step,
                              float lr, float beta1, float beta2, float eps, void* stream);
-/* EXPERIMENTAL, opt-in (BSIG_CHAIN=1 in the Python engine): the dependent chain of one
- * minibatch update of a two-hidden-layer tanh MDNN -- gather, three forward layers
- * (mdnn.py:108-119), fused head epilogue + mixture NLL forward/backward (mdnn.py:109-178),
- * dgrad through the heads and the second hidden layer -- in ONE thread-block-cluster launch
- * (rows are independent through the MLP; only the NLL's three batch-wide sums cross CTAs).
- * Written and compiled in round 1, not yet validated on hardware; nothing calls it unless
- * BSIG_CHAIN=1.  x [*, f] (ld ldx) and y [*, p] are gathered with rows [b]; noise [b,p,k];
- * w0 [h1,f], w1 [h2,h1], wh [n_head,h2] 16-byte aligned; outputs h1_out [b,h1], h2_out [b,h2],
- * dz [b,n_head], dh2 [b,h2], dh1 [b,h1] (pre-activation gradients), loss [1].
- * bsig_mlp_chain_supported returns 1 if the shape is inside the kernel's envelope. */
-int bsig_mlp_chain_supported(const float* w0, const float* w1, const float* wh, int64_t b,
-                             int64_t f, int64_t h1, int64_t h2, int64_t p, int64_t k,
-                             int full_cov);
-int bsig_mlp_chain_step(const float* x, int64_t ldx, const int64_t* rows, const float* y,
-                        const float* noise, const float* w0, const float* b0, const float* w1,
-                        const float* b1, const float* wh, const float* bh, float* h1_out,
-                        float* h2_out, float* dz, float* dh2, float* dh1, float* loss, int* flag,
-                        int64_t b, int64_t f, int64_t h1, int64_t h2, int64_t p, int64_t k,
-                        int full_cov, void* stream);
 /* ---------------------------------------------------------------- persistent training
  * ALL Adam updates [step0, step1) of MDNN.run_training's loop (models/mdnn.py:217-234:
  * np.random.randint rows -> gather -> forward (mdnn.py:89-125) -> mdn_loss_fn (mdnn.py:127-178)
@@ -279,11 +256,13 @@ int bsig_train_persistent_query(const bsig_tp_desc* desc, int64_t* scratch_float
                                 int64_t* smem_bytes);
 int bsig_train_persistent(const bsig_tp_desc* desc, int64_t step0, int64_t step1, void* stream);
 
-/* EXPERIMENTAL, opt-in companion of bsig_mlp_chain_step (single GPU; not yet validated on
- * hardware): the weight-gradient GEMMs of the three layers of an update (dW_l = dY_l^T X_l,
- * db_l = column sums of dY_l; mdnn.py:233) and torch.optim.Adam (mdnn.py:234) in one launch.
- * Layer l: dy_l [b, n_l], x_l [*, k_l] (layer 0 gathered with x0_rows, ld ld_x0), weight at
- * param + w_off_l ([n_l, k_l]) and bias at param + b_off_l inside the flat buffers. */
+/* Opt-in (BSIG_FUSED_WGRAD=1 in the Python engine; single GPU, minibatch <= 128): the three
+ * weight-gradient GEMMs of a two-hidden-layer MDNN update (autograd of mdnn.py:108-119) and
+ * torch.optim.Adam.step (mdnn.py:234) in ONE launch: one 32 x 32 tile of one dW_l = dY_l^T X_l
+ * per CTA, Adam applied to those parameters in the epilogue (no gradient buffer).  Validated
+ * on hardware (round 2); measured equal to the default three GEMMs + Adam (profiles/r2/).
+ * Layer l: dy_l [b, n_l], x_l [*, k_l] (x_0 gathered with x0_rows, pitch ld_x0), weight /
+ * bias at float offsets w_off_l / b_off_l of param. */
 int bsig_wgrad3_adam_step(const float* dy0, const float* x0, int64_t ld_x0, const int64_t* x0_rows,
                           int64_t n0, int64_t k0, int64_t w_off0, int64_t b_off0,
                           const float* dy1, const float* x1, int64_t n1, int64_t k1,
@@ -352,6 +331,17 @@ int bsig_mog_sample_envs_philox(const float* a, const float* means, const float*
 int bsig_mog_logpdf(const void* x, int x_is_f32, const double* a, const double* log_a,
                     const double* means, const double* precs, const double* logdet_p, double* out,
                     int64_t m, int64_t p, int64_t k, int log_space, void* stream);
+
+/* Every pairwise 2-D marginal density a posterior plot evaluates, in one launch: the batched
+ * form of utils/plot.py:38-44 (get_2d_posterior_data: posterior.eval(np.mgrid grid, ii=dims,
+ * log=False) -> MoG.eval / Gaussian.eval marginal branch, utils/pdf.py:334-339, 474-491),
+ * which the reference runs once per parameter pair (P(P-1)/2 times 100 x 100 points).
+ * a, log_a [K]; params [n_pairs][K][6] = mean (2), precision p00 p01 p11 and log det
+ * precision of each component's jittered 2 x 2 marginal (host, float64); lims [n_pairs][4]
+ * = xmin, xmax, ymin, ymax; out [n_pairs][nbins][nbins] float64 in np.mgrid order. */
+int bsig_mog_marginal_grid(const double* a, const double* log_a, const double* params,
+                           const double* lims, double* out, int64_t n_pairs, int64_t k,
+                           int64_t nbins, int log_space, void* stream);
 
 #ifdef __cplusplus
 }

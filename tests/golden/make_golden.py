@@ -304,6 +304,41 @@ def golden_pdf():
     print('pdf.npz', len(out), 'arrays')
 
 
+def golden_pdf_marginal():
+    """Pairwise 2-D marginal densities on regular grids as utils/plot.py:38-44 evaluates them
+    (get_2d_posterior_data: posterior.eval(X.T, ii=dims, log=False) on an np.mgrid), pair by
+    pair through the LIVE reference (MoG.eval -> Gaussian.eval marginal branch,
+    pdf.py:334-339, which jitters the covariance with numpy's global RNG)."""
+    out = {}
+    rs = np.random.RandomState(11)
+    p, k, nbins = 5, 6, 32
+    a = rs.rand(k) + 0.05
+    a = a / a.sum()
+    ms = [0.3 + rs.rand(p) for _ in range(k)]
+    nl = p * (p - 1) // 2
+    ls = [np.concatenate([0.2 + 0.3 * rs.rand(p), 0.1 * rs.randn(nl)]) for _ in range(k)]
+    mog = ref_pdf.MoG(a=a, ms=ms, Ls=ls)
+    out['a'], out['ms'], out['Ls'] = a, np.stack(ms), np.stack(ls)
+    pairs = [(i, j) for i in range(p) for j in range(i + 1, p)]
+    lims = np.array([[-0.2 + 0.05 * q, 1.6, 0.0, 1.8 - 0.03 * q] for q in range(len(pairs))])
+    out['pairs'], out['lims'], out['nbins'] = np.array(pairs), lims, np.array(nbins)
+    np.random.seed(91)
+    grids, logs = [], []
+    for (i, j), (xmin, xmax, ymin, ymax) in zip(pairs, lims):
+        xi, yi = np.mgrid[xmin:xmax:nbins * 1j, ymin:ymax:nbins * 1j]
+        X = np.concatenate((xi.reshape(1, nbins * nbins), yi.reshape(1, nbins * nbins)), axis=0)
+        grids.append(mog.eval(X.T, ii=[i, j], log=False).reshape(nbins, nbins))
+    out['density'] = np.stack(grids)
+    np.random.seed(92)
+    for (i, j), (xmin, xmax, ymin, ymax) in zip(pairs, lims):
+        xi, yi = np.mgrid[xmin:xmax:nbins * 1j, ymin:ymax:nbins * 1j]
+        X = np.concatenate((xi.reshape(1, nbins * nbins), yi.reshape(1, nbins * nbins)), axis=0)
+        logs.append(mog.eval(X.T, ii=[i, j], log=True).reshape(nbins, nbins))
+    out['logdensity'] = np.stack(logs)
+    np.savez_compressed(os.path.join(HERE, 'pdf_marginal.npz'), **out)
+    print('pdf_marginal.npz', len(out), 'arrays')
+
+
 def golden_pdf_host():
     """Host-side pdf surface that is not on the device path (SURVEY 8.b list): Uniform,
     Gaussian algebra / KL, MoG moments / projection / sampled KL, fit_mog.  Every value
@@ -556,6 +591,7 @@ if __name__ == '__main__':
     if 'bench' in sys.argv[1:] or len(sys.argv) == 1:
         golden_mdn_bench()
     golden_pdf()
+    golden_pdf_marginal()
     golden_pdf_host()
     golden_rff_host()
     golden_bayessim()

@@ -203,27 +203,6 @@ def test_capture_guard_restores_gc_state():
         gc.enable()
 
 
-def test_chain_kernel_envelope_is_a_pure_host_decision():
-    """bsig_mlp_chain_supported (experimental path, off by default) only inspects shapes and
-    pointer alignment: it can be exercised without a GPU."""
-    from bayes_sim_ig_b200 import _lib
-    lib = _lib.load()
-    ok = lambda w0, w1, wh, b, f, h1, h2, p, k, full: lib.bsig_mlp_chain_supported(
-        w0, w1, wh, b, f, h1, h2, p, k, full)
-    base = 1 << 20                                            # any 16-byte aligned address
-    # the bench shape (Cartpole corrdiff, 128/128, P=13, K=10, minibatch 100) and its test split
-    assert ok(base, base + 16, base + 32, 100, 302, 128, 128, 13, 10, 0) == 1
-    assert ok(base, base + 16, base + 32, 128, 302, 128, 128, 4, 10, 1) == 1
-    # full covariance at P = 13: z and dz rows (1050 wide) no longer fit next to the tile ring
-    assert ok(base, base + 16, base + 32, 100, 302, 128, 128, 13, 10, 1) == 0
-    assert ok(base, base + 16, base + 32, 200, 302, 128, 128, 13, 10, 0) == 0   # > 16 x 8 rows
-    assert ok(base, base + 16, base + 32, 100, 301, 128, 128, 13, 10, 0) == 0   # odd width
-    assert ok(base, base + 16, base + 32, 100, 302, 256, 128, 13, 10, 0) == 0   # hidden > 128
-    assert ok(base + 4, base + 16, base + 32, 100, 302, 128, 128, 13, 10, 0) == 0   # misaligned
-    assert ok(base, base + 16, base + 32, 100, 302, 128, 128, 13, 40, 0) == 0   # K > 32
-    # ShadowHand-sized first layer does not fit the tile ring
-    assert ok(base, base + 16, base + 32, 100, 105002, 128, 128, 32, 10, 0) == 0
-
 
 def test_host_pdf_surface_matches_live_reference(golden):
     """Uniform, Gaussian algebra / KL, MoG x Gaussian product and quotient, fit_mog: host
@@ -337,39 +316,3 @@ def test_packed_lane_group_reduction_scheme_for_every_width():
             np.testing.assert_allclose(tot[g * k:(g + 1) * k], grp.sum(), rtol=1e-12, atol=1e-12)
             assert len(set(tot[g * k:(g + 1) * k].tolist())) == 1      # identical bits per group
             np.testing.assert_array_equal(mx[g * k:(g + 1) * k], grp.max())
-
-
-def test_chain_kernel_schedule_arithmetic_replayed_on_the_host():
-    """Index arithmetic of the experimental mlp_chain_kernel (csrc/mdn.cu), replayed: the flat
-    weight-tile schedule visits every 32-row tile of W0, W1, Wh (forward) and Wh, W1 (dgrad)
-    exactly once and in order, the 8 K-slices of a forward tile partition the reduction, and
-    the row split covers the minibatch."""
-    for (b, f, h1, h2, nh) in ((100, 302, 128, 128, 270), (9, 12, 16, 16, 28), (128, 10, 32, 32, 1050)):
-        n0, n1, n2 = (h1 + 31) // 32, (h2 + 31) // 32, (nh + 31) // 32
-        seg_end = [n0, n0 + n1, n0 + n1 + n2, n0 + n1 + 2 * n2, n0 + 2 * n1 + 2 * n2]
-        seen = []
-        for t_flat in range(seg_end[4]):
-            seg = 0
-            while t_flat >= seg_end[seg]:
-                seg += 1
-            seen.append((seg, t_flat - (seg_end[seg - 1] if seg else 0)))
-        expect = [(0, t) for t in range(n0)] + [(1, t) for t in range(n1)] + \
-                 [(2, t) for t in range(n2)] + [(3, t) for t in range(n2)] + [(4, t) for t in range(n1)]
-        assert seen == expect
-        for kd in (f, h1, h2):
-            v = 4 if kd % 4 == 0 else 2
-            units = kd // v
-            upw = (units + 7) // 8
-            covered = []
-            for warp in range(8):
-                covered += list(range(warp * upw, min(units, (warp + 1) * upw)))
-            assert covered == list(range(units)) and units * v == kd
-            pitch = kd if v == 2 else (kd if (kd // 4) % 2 else kd + 4)
-            if v == 4:
-                assert pitch % 4 == 0 and (pitch // 4) % 2 == 1     # conflict-free LDS.128
-            else:
-                assert (kd // 2) % 2 == 1                           # conflict-free LDS.64
-        nc = max((b + 7) // 8, min(16, b))
-        rpc = (b + nc - 1) // nc
-        nc = (b + rpc - 1) // rpc
-        assert rpc <= 8 and nc <= 16 and nc * rpc >= b and (nc - 1) * rpc < b

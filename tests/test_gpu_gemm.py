@@ -107,3 +107,42 @@ def test_dgrad_wgrad_gather(shape):
     lib.call('bsig_linear_fwd', xfull.data_ptr(), k, rows.data_ptr(), w.data_ptr(), b.data_ptr(),
              y.data_ptr(), m, n, k, 0, SIMT, ws.data_ptr(), ws.numel(), st)
     assert _rel(y, xg @ w.double().T) < 1e-5
+
+
+@pytest.mark.parametrize('engine', [TC_TF32, TC_X3])
+@pytest.mark.parametrize('shape', [(4096, 128, 302), (1000, 270, 128), (257, 64, 100),
+                                   (100, 128, 20002), (5000, 128, 128), (384, 270, 128)])
+def test_dgrad_wgrad_gather_on_tensor_cores(engine, shape):
+    """dgrad (MN-major weight operand, fused tanh'), wgrad (both operands MN-major, minibatch
+    gather, split-K for the skinny output) and a gathered forward on the tcgen05 engine,
+    including widths that are 2 mod 4 (302, 270, 20002: staged through a padded copy),
+    against float64.  Same tolerances as the forward engine tests, with the length of the
+    reduction of each GEMM (n for dgrad, the batch for wgrad, k for forward)."""
+    lib = _lib()
+    m, n, k = shape
+    g = torch.Generator('cpu').manual_seed(11 * m + n)
+    xfull = torch.randn(m + 50, k, generator=g).to(DEV)
+    rows = torch.randint(0, m + 50, (m,), generator=g).to(DEV)
+    w = (torch.randn(n, k, generator=g) / np.sqrt(k)).to(DEV)
+    dy = torch.randn(m, n, generator=g).to(DEV)
+    h = torch.tanh(torch.randn(m, k, generator=g)).to(DEV)
+    dx = torch.empty(m, k, device=DEV)
+    dw = torch.empty(n, k, device=DEV)
+    db = torch.empty(n, device=DEV)
+    ws = _ws(m, n, k)
+    st = lib.stream_ptr(DEV)
+    lib.call('bsig_linear_dgrad', dy.data_ptr(), w.data_ptr(), h.data_ptr(), dx.data_ptr(), m, n, k,
+             1, engine, ws.data_ptr(), ws.numel(), st)
+    ref = (dy.double() @ w.double()) * (1 - h.double() ** 2)
+    assert _rel(dx, ref) < tol_for(engine, n), ('dgrad', _rel(dx, ref))
+    lib.call('bsig_linear_wgrad', dy.data_ptr(), xfull.data_ptr(), k, rows.data_ptr(), dw.data_ptr(),
+             db.data_ptr(), m, n, k, engine, ws.data_ptr(), ws.numel(), st)
+    xg = xfull[rows].double()
+    assert _rel(dw, dy.double().T @ xg) < tol_for(engine, m), ('wgrad', _rel(dw, dy.double().T @ xg))
+    assert _rel(db, dy.double().sum(0)) < 1e-5
+    y = torch.empty(m, n, device=DEV)
+    b = torch.randn(n, generator=g).to(DEV)
+    lib.call('bsig_linear_fwd', xfull.data_ptr(), k, rows.data_ptr(), w.data_ptr(), b.data_ptr(),
+             y.data_ptr(), m, n, k, 1, engine, ws.data_ptr(), ws.numel(), st)
+    ref = torch.tanh(xg @ w.double().T + b.double())
+    assert _rel(y, ref) < tol_for(engine, k), ('fwd', _rel(y, ref))

@@ -137,3 +137,30 @@ def test_batched_params_sampling_matches_per_env_reference(golden, case):
     mean, cov = mog.calc_mean_and_cov()
     assert np.abs(big.mean(0) - mean).max() < 0.02
     assert np.abs(np.cov(big.T).reshape(cov.shape) - cov).max() < 0.05
+
+
+def test_batched_pairwise_marginal_grids_match_reference(golden):
+    """every pairwise 2-D marginal a posterior plot evaluates
+    (utils/plot.py:38-44), all pairs in ONE launch, against the live reference called pair by
+    pair (tests/golden/pdf_marginal.npz): same jitter draws (numpy seeded as the reference
+    loop was), densities and log densities to 1e-9."""
+    from bayes_sim_ig.utils import pdf
+    g = golden('pdf_marginal')
+    mog = pdf.MoG(a=g['a'], ms=list(g['ms']), Ls=list(g['Ls']))
+    pairs, lims, nbins = [tuple(pr) for pr in g['pairs']], g['lims'], int(g['nbins'])
+    np.random.seed(91)
+    dens = mog.eval_marginal_grids(pairs, lims, nbins=nbins, log=False)
+    assert dens.shape == g['density'].shape and dens.dtype == np.float64
+    np.testing.assert_allclose(dens, g['density'], rtol=1e-9, atol=1e-300)
+    np.random.seed(92)
+    logd = mog.eval_marginal_grids(pairs, lims, nbins=nbins, log=True)
+    np.testing.assert_allclose(logd, g['logdensity'], rtol=1e-9, atol=1e-9)
+    # one limit tuple for all pairs; the pair-by-pair path of MoG.eval gives the same grid
+    np.random.seed(5)
+    one = mog.eval_marginal_grids(pairs[:2], (0.0, 1.5, 0.0, 1.5), nbins=8)
+    np.random.seed(5)
+    xi, yi = np.mgrid[0.0:1.5:8j, 0.0:1.5:8j]
+    pts = np.stack([xi.ravel(), yi.ravel()], axis=1)
+    for q in range(2):
+        np.testing.assert_allclose(one[q].ravel(), mog.eval(pts, ii=list(pairs[q]), log=False),
+                                   rtol=1e-9)

@@ -230,3 +230,30 @@ def test_time_major_ingestion_is_bit_identical(shape, capsys):
     # actions stored with extra steps
     longer = torch.cat([a_tm, a_tm[:2]], 0).contiguous()
     assert torch.equal(S.summary_corrdiff(s_tm, longer, time_major=True), S.summary_corrdiff(s, ac))
+
+
+@pytest.mark.parametrize('shape', [(37, 21, 4, 1), (5, 11, 108, 21), (64, 51, 60, 8), (3, 7, 3, 2)])
+def test_time_major_ingestion_matches_the_oracle(shape, capsys):
+    """Time-major ingestion against the CPU oracle (oracle/summarizers_np.py, pinned to the
+    live reference) evaluated on the trajectory-major rollouts: copies and the corr product
+    block bit-exact, mean / std to 2e-6, signature to 2e-5 of the largest term."""
+    from bayes_sim_ig.utils import summarizers as S
+    n, t1, d, a = shape
+    s, ac = synth_rollouts(4, n, t1, d, a, DEV)
+    s = s * 0.3                                      # keeps the depth-3 signature terms O(1)
+    s_np, a_np = s.cpu().numpy(), ac.cpu().numpy()
+    s_tm, a_tm = s.transpose(0, 1).contiguous(), ac.transpose(0, 1).contiguous()
+    if t1 >= 10:
+        for name in ('summary_start', 'summary_waypts'):
+            got = getattr(S, name)(s_tm, a_tm, time_major=True).cpu().numpy()
+            assert np.array_equal(got, getattr(osum, name)(s_np, a_np)), name
+    for name in ('summary_corr', 'summary_corrdiff'):
+        got = getattr(S, name)(s_tm, a_tm, time_major=True).cpu().numpy()
+        ref = getattr(osum, name)(s_np, a_np)
+        assert np.array_equal(got[:, :-2], ref[:, :-2]), name
+        np.testing.assert_allclose(got[:, -2:], ref[:, -2:], rtol=2e-6, atol=1e-6)
+    if S.signature_depth(1 + d + a) > 0:
+        got = S.summary_signatory(s_tm, a_tm, time_major=True).cpu().numpy()
+        ref = osum.summary_signatory(s_np, a_np)
+        assert got.shape == ref.shape
+        assert np.abs(got - ref).max() <= 2e-5 * max(np.abs(ref).max(), 1.0)

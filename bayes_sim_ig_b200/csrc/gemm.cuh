@@ -44,7 +44,8 @@ inline GemmArgs gemm_args_zero() {
 
 int gemm_simt(GemmArgs g, void* ws, int64_t ws_bytes, cudaStream_t st);
 int64_t gemm_simt_ws_bytes(int64_t M, int64_t N, int64_t K);
-int colsum(const float* dy, float* db, int64_t M, int64_t N, cudaStream_t st);
+int colsum(const float* dy, float* db, int64_t M, int64_t N, void* ws, int64_t ws_bytes,
+           cudaStream_t st);
 bool gemm_small_applicable(const GemmArgs& g);
 bool gemm_tc_applicable(const GemmArgs& g);
 int gemm_tc(const GemmArgs& g, bool x3, void* ws, int64_t ws_bytes, cudaStream_t st);

@@ -239,8 +239,53 @@ int gemm_splitk_reduce(const GemmArgs& g, int splits, cudaStream_t st) {
   return 0;
 }
 
-int colsum(const float* dy, float* db, int64_t M, int64_t N, cudaStream_t st) {
-  colsum_kernel<<<(unsigned)ceil_div(N, 32), 256, 0, st>>>(dy, db, (int)M, (int)N);
+// Large batches: the rows are split over gridDim.y CTAs per 32-column block (partial sums
+// [splits][N] in the workspace), a second launch adds the partials in split order --
+// deterministic, and the first pass streams dy at HBM speed instead of on ceil(N/32) CTAs.
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const float* __restrict__ dy, float* __restrict__ part, int M, int N,
+                      int rows_per_split) {
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + cx;
+  const int r0 = blockIdx.y * rows_per_split, r1 = min(M, r0 + rows_per_split);
+  float acc = 0.f;
+  if (j < N)
+    for (int i = r0 + ry; i < r1; i += 8) acc += __ldg(dy + (int64_t)i * N + j);
+  red[ry][cx] = acc;
+  __syncthreads();
+  if (ry == 0 && j < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += red[q][cx];
+    part[(int64_t)blockIdx.y * N + j] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+colsum_final_kernel(const float* __restrict__ part, float* __restrict__ db, int splits, int N) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  float t = 0.f;
+  for (int s = 0; s < splits; ++s) t += __ldcg(part + (int64_t)s * N + j);
+  db[j] = t;
+}
+
+int colsum(const float* dy, float* db, int64_t M, int64_t N, void* ws, int64_t ws_bytes,
+           cudaStream_t st) {
+  const int64_t col_blocks = ceil_div(N, 32);
+  int64_t splits = std::min<int64_t>(ceil_div(M, 256), std::max<int64_t>(1, (4 * (int64_t)sm_count()) / col_blocks));
+  if (M >= 2048 && splits > 1 && ws != nullptr && ws_bytes >= splits * N * (int64_t)sizeof(float)) {
+    const int rps = (int)ceil_div(M, splits);
+    splits = ceil_div(M, rps);
+    const dim3 grid((unsigned)col_blocks, (unsigned)splits);
+    colsum_partial_kernel<<<grid, 256, 0, st>>>(dy, (float*)ws, (int)M, (int)N, rps);
+    BSIG_LAUNCH_CHECK();
+    colsum_final_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>((const float*)ws, db, (int)splits, (int)N);
+    BSIG_LAUNCH_CHECK();
+    return 0;
+  }
+  colsum_kernel<<<(unsigned)col_blocks, 256, 0, st>>>(dy, db, (int)M, (int)N);
   BSIG_LAUNCH_CHECK();
   return 0;
 }

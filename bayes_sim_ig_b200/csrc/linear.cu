@@ -79,7 +79,8 @@ extern "C" int bsig_linear_wgrad(const float* dy, const float* x, int64_t ldx,
   const bool fused_bias = db != nullptr && gemm_small_applicable(g) && !wants_tc;
   if (fused_bias) g.rowsum = db;            // db[i] = sum_r dy[r,i] rides along in the GEMM
   if (run_gemm(g, engine, ws, ws_bytes, (cudaStream_t)stream)) return 1;
-  if (db != nullptr && !fused_bias) return colsum(dy, db, m, n, (cudaStream_t)stream);
+  // (after the GEMM in stream order: its workspace is free again)
+  if (db != nullptr && !fused_bias) return colsum(dy, db, m, n, ws, ws_bytes, (cudaStream_t)stream);
   return 0;
 }
 

@@ -634,6 +634,98 @@ __global__ void __launch_bounds__(256) signature3_bwd_small_kernel(SigBwdArgs p)
   if (active) store_path_grad(p, traj, 0, i, -dd_next);
 }
 
+// depth 3, 9 <= C <= 22 (the widest path that still gets depth 3): one CTA per trajectory,
+// thread (i, j) owns entry (i, j) of the level-2 adjoint G2 and of S2; the C^3 level-3
+// adjoint G3 (constant through the sweep) sits in shared memory.  Per reverse step
+//   A_ij = sum_k G3[i,j,k] d_k                      (thread (i,j), C FMAs)
+//   T_ij = S2_ij + (S1_i/2 + d_i/6) d_j             (before the step)
+//   dd[a] = G1'[a] + sum_j (G2'[a,j]/2 + A_aj/6) d_j                                (row a)
+//         + sum_i { G2'[i,a] (S1_i + d_i/2) + (S1_i/2 + d_i/6) A_ia }               (column a)
+//         + sum_ij G3[i,j,a] T_ij                  (thread (i,a): sum over j, then over i)
+//   G2 = G2' + A,   G1[i] = G1'[i] + sum_j (G2'[i,j] + A_ij/2) d_j.
+// Same formulas as signature3_bwd_small_kernel, with the row / column sums going through
+// shared memory instead of registers.
+__global__ void __launch_bounds__(512) signature3_bwd_kernel(SigBwdArgs p) {
+  extern __shared__ __align__(16) float smem[];
+  const int C = p.C, L = p.L, steps = L - 1, CC = C * C;
+  float* x = smem;                              // [L][C] path points
+  float* g3 = x + (size_t)L * C;                // [C][C][C]
+  float* tm = g3 + (size_t)CC * C;              // [C][C]  T_ij
+  float* rw = tm + CC;                          // [C][C]  row terms of dd
+  float* rg = rw + CC;                          // [C][C]  row terms of the G1 update
+  float* cl = rg + CC;                          // [C][C]  column terms of dd
+  float* p3 = cl + CC;                          // [C][C]  p3[i][a] = sum_j G3[i,j,a] T_ij
+  float* g1s = p3 + CC;                         // [C]
+  float* dv = g1s + C;                          // [C] increment of the current step
+  const int64_t traj = blockIdx.x;
+  const int tid = threadIdx.x;
+  SigArgs q;
+  q.states = p.states; q.actions = p.actions; q.out = nullptr; q.n = p.n;
+  q.s_stride = p.s_stride; q.a_stride = p.a_stride; q.L = L; q.D = p.D; q.A = p.A; q.C = C;
+  q.tpb = 1; q.siglen = p.siglen;
+  load_paths(q, x, traj, 1);
+  const float* gr = p.grad + traj * p.siglen;
+  for (int e = tid; e < CC * C; e += blockDim.x) g3[e] = __ldg(gr + C + CC + e);
+  for (int e = tid; e < C; e += blockDim.x) g1s[e] = __ldg(gr + e);
+  const bool live = tid < CC;
+  const int i = live ? tid / C : 0, j = live ? tid - i * C : 0;
+  float g2 = live ? __ldg(gr + C + tid) : 0.f;
+  __syncthreads();
+  // forward sweep: S2_ij and S1_i after the last step
+  float s1 = 0.f, s2 = 0.f;
+  for (int t = 0; t < steps; ++t) {
+    const float di = x[(t + 1) * C + i] - x[t * C + i];
+    const float dj = x[(t + 1) * C + j] - x[t * C + j];
+    s2 = fmaf(s1 + 0.5f * di, dj, s2);
+    s1 += di;
+  }
+  float dd_next = 0.f;
+  for (int t = steps - 1; t >= 0; --t) {
+    if (tid < C) dv[tid] = x[(t + 1) * C + tid] - x[t * C + tid];
+    __syncthreads();
+    if (live) {
+      const float di = dv[i], dj = dv[j];
+      s1 -= di;                                           // S1_i before this step
+      const float a2 = s1 + 0.5f * di;
+      const float u = 0.5f * s1 + di * (1.0f / 6.0f);
+      s2 = fmaf(-a2, dj, s2);                             // S2_ij before this step
+      const float* row = g3 + (size_t)tid * C;
+      float aij = 0.f;
+      for (int k = 0; k < C; ++k) aij = fmaf(row[k], dv[k], aij);
+      tm[tid] = fmaf(u, dj, s2);
+      rw[tid] = (0.5f * g2 + aij * (1.0f / 6.0f)) * dj;
+      rg[tid] = (g2 + 0.5f * aij) * dj;
+      cl[tid] = fmaf(g2, a2, u * aij);
+      g2 += aij;
+    }
+    __syncthreads();
+    if (live) {                                           // thread (i, a = j)
+      float acc = 0.f;
+      const float* g3i = g3 + (size_t)i * CC + j;
+      const float* ti = tm + i * C;
+      for (int jj = 0; jj < C; ++jj) acc = fmaf(g3i[jj * C], ti[jj], acc);
+      p3[tid] = acc;
+    }
+    __syncthreads();
+    if (tid < C) {
+      const int a = tid;
+      float own = g1s[a], upd = 0.f, col = 0.f;
+      for (int q2 = 0; q2 < C; ++q2) {
+        own += rw[a * C + q2];
+        upd += rg[a * C + q2];
+        col += cl[q2 * C + a] + p3[q2 * C + a];
+      }
+      const float dd = own + col;
+      g1s[a] += upd;
+      store_path_grad(p, traj, t + 1, a, dd - dd_next);
+      dd_next = dd;
+    }
+    // the next step's dv write happens after its own barrier; tm / rw / rg / cl / p3 are
+    // rewritten only after that barrier as well
+  }
+  if (tid < C) store_path_grad(p, traj, 0, tid, -dd_next);
+}
+
 // depth 1 and 2, any C: one CTA per trajectory.  At depth 2 the level-2 adjoint is
 // constant (G2) and G1 before step t is G1 + G2 (x_{L-1} - x_{t+1}).
 __global__ void __launch_bounds__(256) signature12_bwd_kernel(SigBwdArgs p, int depth) {
@@ -696,8 +788,20 @@ extern "C" int bsig_signature_bwd(const float* states, const float* actions, con
   p.siglen = C + (depth >= 2 ? C * C : 0) + (depth >= 3 ? C * C * C : 0);
   cudaStream_t st = (cudaStream_t)stream;
   if (depth == 3) {
-    BSIG_REQUIRE(C <= 8, "signature_bwd: depth-3 gradients are implemented for <= 8 channels "
-                         "(got %d)", (int)C);
+    BSIG_REQUIRE(C <= 22, "signature_bwd: depth 3 supports at most 22 channels (got %d)", (int)C);
+    if (C > 8) {
+      // wide paths: one CTA per trajectory, G3 in shared memory
+      p.tpb = 1;
+      const size_t smem = ((size_t)len * C + (size_t)C * C * C + 5 * (size_t)C * C + 2 * (size_t)C) * 4;
+      BSIG_REQUIRE(smem <= 200 * 1024, "signature_bwd: path too long for shared memory");
+      if (smem > 48 * 1024)
+        BSIG_CUDA(cudaFuncSetAttribute(signature3_bwd_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const int threads = (int)((C * C + 31) / 32 * 32);
+      signature3_bwd_kernel<<<(unsigned)n, threads, smem, st>>>(p);
+      BSIG_LAUNCH_CHECK();
+      return 0;
+    }
     const int tpw = 32 / (int)C, nwarp = 8;
     p.tpb = tpw * nwarp;
     const int64_t steps = len - 1;

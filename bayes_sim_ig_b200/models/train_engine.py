@@ -128,6 +128,14 @@ class TrainPlan(object):
         self.fork_wgrad = all(single_launch(batch, n_out, k_in) and single_launch(batch, k_in, n_out)
                               and single_launch(n_out, k_in, batch) for n_out, k_in in shapes)
         self.side = torch.cuda.Stream(device=dev) if self.fork_wgrad else None
+        # large first layers (>= 2^26 multiply-adds: they run on the tcgen05 engine, which
+        # cannot gather rows through TMA): the minibatch rows are gathered ONCE per update
+        # into a dense, 16-byte aligned buffer that both the forward and the weight-gradient
+        # GEMM read, instead of being staged inside each of them
+        self.xg = None
+        if (self.rff is None and trunk and int(model.gemm_engine) != 0 and
+                batch * widths[0] * in_dim >= (1 << 26)):
+            self.xg = torch.zeros((batch, self.x_ld), **f32)
         self.loss_buf = torch.zeros(2 * n_log + 1, **f32)   # [train..., test..., scratch]
         self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
         self.graph = None
@@ -278,7 +286,13 @@ class TrainPlan(object):
         slot = self.logs.index(step) if step in self.logs else None
         n_log = len(self.logs)
         loss_ptr = self.loss_buf.data_ptr() + 4 * (slot if slot is not None else 2 * n_log)
-        hin, hin_ld, hin_rows = self._forward(self.tr, self.x_train_buf, rows, b, st, ld=self.x_ld)
+        if self.xg is not None:
+            _lib.call('bsig_gather_rows', self.x_train_buf.data_ptr(), self.x_ld, rows.data_ptr(),
+                      self.xg.data_ptr(), b, self.x_ld, st)
+            x0, x0_rows = self.xg, None
+        else:
+            x0, x0_rows = self.x_train_buf, rows
+        hin, hin_ld, hin_rows = self._forward(self.tr, x0, x0_rows, b, st, ld=self.x_ld)
         _lib.call('bsig_mdn_nll_fused', self.tr['z'].data_ptr(), self.noise_train[step].data_ptr(),
                   self.y_train.data_ptr(), rows.data_ptr(), loss_ptr, self.dz.data_ptr(),
                   b, p, k, 1 if m.full_covariance else 0, self.ws_mdn.data_ptr(),
@@ -313,6 +327,8 @@ class TrainPlan(object):
                 xin, xld, xrows = self.tr['h'][li - 1], layers[li - 1]['n'], None
             elif self.rff is not None:
                 xin, xld, xrows = self.tr['feat'], self.feat_dim, None
+            elif self.xg is not None:
+                xin, xld, xrows = self.xg, self.x_ld, None
             else:
                 xin, xld, xrows = self.x_train_buf, self.x_ld, rows.data_ptr()
             wgrad(self.dh[li], xin, xld, xrows, lay, lay['n'], lay['k'])

@@ -114,6 +114,18 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from tensor memory (lane = row of the tile, one 32-bit column per K element)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                    smem_u32(bar))
@@ -148,6 +160,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   constexpr int STAGES = X3 ? STAGES_X3 : STAGES_X1;
   constexpr int TILES_PER_STAGE = X3 ? 4 : 2;      // A, B (+ A_lo, B_lo)
   constexpr int EPI_WARPS = X3 ? 4 : 8;
+  constexpr uint32_t TMEM_COLS = X3 ? 512 : 256;
+  // X3 with a K-major A: the converter warps write hi / lo of A into tensor memory and the
+  // MMA takes A from there -- the tensor core then reads only B from shared memory, whose
+  // bandwidth (128 B/clk: exactly what three SS MMAs per K step consume) was the limit of
+  // the all-shared-memory form
+  const bool a_ts = X3 && !g.a_mn;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
@@ -180,10 +198,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    // two ping-pong accumulators of 128 fp32 columns
+    // two ping-pong accumulators of 128 fp32 columns; X3 additionally stages the hi / lo
+    // halves of the A operand of every pipeline stage in tensor memory (64 columns each)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(&tmem_base_slot)),
-                 "r"(256)
+                 "r"(TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -257,11 +276,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             auto db = [&](uint32_t base) {
               return g.b_mn ? umma_desc_mn(base + b_off, MN_BOX) : umma_desc(base + b_off);
             };
-            umma_tf32(d_tmem, da(a_hi), db(b_hi), idesc, acc);
-            if (X3) {
-              const uint32_t a_lo = smem_u32(tile_alo(s)), b_lo = smem_u32(tile_blo(s));
-              umma_tf32(d_tmem, da(a_hi), db(b_lo), idesc, 1u);
-              umma_tf32(d_tmem, da(a_lo), db(b_hi), idesc, 1u);
+            if (a_ts) {
+              const uint32_t a_tm = tmem_base + 256u + (uint32_t)(s * 64 + k * 8);
+              const uint32_t b_lo = smem_u32(tile_blo(s));
+              umma_tf32_ts(d_tmem, a_tm, db(b_hi), idesc, acc);
+              umma_tf32_ts(d_tmem, a_tm, db(b_lo), idesc, 1u);
+              umma_tf32_ts(d_tmem, a_tm + 32u, db(b_hi), idesc, 1u);
+            } else {
+              umma_tf32(d_tmem, da(a_hi), db(b_hi), idesc, acc);
+              if (X3) {
+                const uint32_t a_lo = smem_u32(tile_alo(s)), b_lo = smem_u32(tile_blo(s));
+                umma_tf32(d_tmem, da(a_hi), db(b_lo), idesc, 1u);
+                umma_tf32(d_tmem, da(a_lo), db(b_hi), idesc, 1u);
+              }
             }
           }
           umma_commit(&empty_bar[s]);           // stage reusable once these MMAs retire
@@ -279,6 +306,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % STAGES;
         mbar_wait(&full_bar[s], (it / STAGES) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float4* a = reinterpret_cast<float4*>(tile_a(s));
         float4* b = reinterpret_cast<float4*>(tile_b(s));
         float4* alo = reinterpret_cast<float4*>(tile_alo(s));
@@ -294,13 +322,54 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           hi_p[idx] = h;
           lo_p[idx] = l;
         };
+        if (a_ts) {
+          // thread <-> row of the A tile (the TMEM lane quadrant of a warp is warp % 4):
+          // read the row's 32 K values (128 B, 16-byte chunks XOR-swizzled with row % 8),
+          // split, and store hi / lo as 32 + 32 tensor-memory columns of this stage
+          const int m = (warp & 3) * 32 + lane;
+          const uint8_t* arow = tile_a(s) + m * 128;
+          uint32_t hi[32], lo[32];
 #pragma unroll
-        for (int q = 0; q < TILE_BYTES / 16 / 128; ++q) {   // 8 float4 per thread per tile
-          split(a, alo, t + 128 * q);
-          split(b, blo, t + 128 * q);
+          for (int c = 0; c < 8; ++c) {
+            const float4 v = *reinterpret_cast<const float4*>(arow + ((c ^ (m & 7)) << 4));
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const uint32_t h = __float_as_uint(vv[u]) & 0xffffe000u;
+              hi[4 * c + u] = h;
+              lo[4 * c + u] = __float_as_uint(vv[u] - __uint_as_float(h));
+            }
+          }
+          const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 256u + (uint32_t)(s * 64);
+#define BSIG_ST32(ADDR, R)                                                                       \
+  asm volatile(                                                                                  \
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                            \
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "                 \
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(  \
+          ADDR),                                                                                 \
+      "r"(R[0]), "r"(R[1]), "r"(R[2]), "r"(R[3]), "r"(R[4]), "r"(R[5]), "r"(R[6]), "r"(R[7]),    \
+      "r"(R[8]), "r"(R[9]), "r"(R[10]), "r"(R[11]), "r"(R[12]), "r"(R[13]), "r"(R[14]),          \
+      "r"(R[15]), "r"(R[16]), "r"(R[17]), "r"(R[18]), "r"(R[19]), "r"(R[20]), "r"(R[21]),        \
+      "r"(R[22]), "r"(R[23]), "r"(R[24]), "r"(R[25]), "r"(R[26]), "r"(R[27]), "r"(R[28]),        \
+      "r"(R[29]), "r"(R[30]), "r"(R[31])                                                         \
+      : "memory")
+          BSIG_ST32(taddr, hi);
+          BSIG_ST32(taddr + 32u, lo);
+#undef BSIG_ST32
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int q = 0; q < TILE_BYTES / 16 / 128; ++q) split(b, blo, t + 128 * q);
+        } else {
+#pragma unroll
+          for (int q = 0; q < TILE_BYTES / 16 / 128; ++q) {   // 8 float4 per thread per tile
+            split(a, alo, t + 128 * q);
+            split(b, blo, t + 128 * q);
+          }
         }
-        // make the generic-proxy writes visible to the tensor core (async proxy)
+        // make the generic-proxy writes visible to the tensor core (async proxy), order the
+        // tensor-memory stores before the MMA warp's reads
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         mbar_arrive(&conv_bar[s]);
       }
     }
@@ -404,7 +473,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
                  : "memory");
   }
 }

@@ -47,6 +47,14 @@ SIGNATURES = {
     'bsig_summary_start_tm': (_int, [_c_ptr, _c_ptr, _c_ptr] + [_i64] * 6 + [_c_ptr]),
     'bsig_summary_crosscorr': (_int, [_c_ptr, _c_ptr, _c_ptr] + [_i64] * 6 + [_int, _c_ptr, _c_ptr]),
     'bsig_summary_crosscorr_tm': (_int, [_c_ptr, _c_ptr, _c_ptr] + [_i64] * 6 + [_int, _c_ptr, _c_ptr]),
+    'bsig_corr_factors': (_int, [_c_ptr, _c_ptr, _c_ptr] + [_i64] * 7 + [_int, _int, _c_ptr, _c_ptr]),
+    'bsig_corr_linear_applicable': (_int, [_i64] * 5),
+    'bsig_corr_linear_ws_bytes': (_i64, [_i64] * 4),
+    'bsig_corr_linear_fwd': (_int, [_c_ptr, _i64, _c_ptr, _i64, _i64, _c_ptr, _c_ptr, _c_ptr, _i64,
+                                    _i64, _int, _c_ptr, _i64, _c_ptr]),
+    'bsig_corr_linear_wgrad': (_int, [_c_ptr, _c_ptr, _i64, _c_ptr, _i64, _i64, _i64, _i64,
+                                      _c_ptr, _c_ptr, _c_ptr, _c_ptr, _i64, _f32, _f32, _f32,
+                                      _f32, _f32, _c_ptr]),
     'bsig_signature_fwd': (_int, [_c_ptr, _c_ptr, _c_ptr] + [_i64] * 6 + [_int, _c_ptr]),
     'bsig_signature_bwd': (_int, [_c_ptr] * 5 + [_i64] * 6 + [_int, _c_ptr]),
     'bsig_linear_ws_bytes': (_i64, [_i64] * 3),
@@ -56,6 +64,7 @@ SIGNATURES = {
                                  _c_ptr, _i64, _c_ptr]),
     'bsig_linear_wgrad': (_int, [_c_ptr, _c_ptr, _i64, _c_ptr, _c_ptr, _c_ptr, _i64, _i64, _i64,
                                  _int, _c_ptr, _i64, _c_ptr]),
+    'bsig_linear_colsum': (_int, [_c_ptr, _c_ptr, _i64, _i64, _c_ptr]),
     'bsig_tanh_bwd': (_int, [_c_ptr, _c_ptr, _c_ptr, _i64, _c_ptr]),
     'bsig_rff_features': (_int, [_c_ptr, _i64, _c_ptr, _c_ptr, _c_ptr, _i64, _i64, _i64, _f32,
                                  _int, _c_ptr, _i64, _c_ptr]),

@@ -4,6 +4,8 @@ Same constructor, class constants, ``run_training`` and ``predict`` as the
 reference; the summarizer and model named in ``model_cfg`` are looked up by name
 among this package's implementations.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -76,7 +78,7 @@ class BayesSim(object):
         steps of MINIBATCH_SIZE on the summaries."""
         dev = self.model.flat_params.device
         with _lib.nvtx_range('bsig.summarize'):
-            traj_summaries = self.summarizer_fxn(traj_states.to(dev), traj_actions.to(dev))
+            traj_summaries = self._training_summaries(traj_states.to(dev), traj_actions.to(dev))
         with _lib.nvtx_range('bsig.run_training'):
             log_dict = self.model.run_training(
                 x_data=traj_summaries, y_data=params,
@@ -84,6 +86,23 @@ class BayesSim(object):
                 batch_size=BayesSim.MINIBATCH_SIZE,
                 test_frac=BayesSim.TEST_FRACTION)
         return log_dict
+
+    # Cross-correlation summaries at least this wide are handed to the MDNN in factored form
+    # (SURVEY 8.f rank 1): the [N, F] tensor is never materialised, the first layer's GEMMs
+    # generate it tile by tile (csrc/corr_layer.cu).  BSIG_FUSED_CORR=0 switches it off.
+    FUSED_CORR_MIN_WIDTH = 4096
+
+    def _training_summaries(self, states, actions):
+        name = self.summarizer_fxn.__name__
+        fused = (name in ('summary_corr', 'summary_corrdiff', 'cross_correlation') and
+                 type(self.model) is MDNN and self.model.net is not None and
+                 self.model.input_dim >= self.FUSED_CORR_MIN_WIDTH and
+                 os.environ.get('BSIG_FUSED_CORR', '1') != '0')
+        if not fused:
+            return self.summarizer_fxn(states, actions)
+        feats = _summarizers.corr_factors(states, actions, use_state_diff=(name == 'summary_corrdiff'))
+        print('cross_corr feats', torch.Size(feats.shape), feats.device)   # as the summarizer prints
+        return feats
 
     def predict(self, states, actions, threshold=0.005):
         """Reference bayes_sim.py:116-179 -> host ``pdf.MoG`` posterior."""

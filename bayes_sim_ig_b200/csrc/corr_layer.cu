@@ -1,0 +1,904 @@
+// Fused cross-correlation summarizer -> first dense layer.
+//
+// The reference materialises  x[n, p*Q + q] = sf[n,p] * af[n,q]  (+ mean, std of sf) per
+// trajectory (utils/summarizers.py:106-119: 420 KB per ShadowHand trajectory) and feeds it to
+// the first nn.Linear of the MDNN (models/mdnn.py:108).  x is a rank-one outer product, so
+// nothing but its two factors ever has to exist in memory:
+//
+//   corr_factors_kernel   rollouts -> fac[n] = [ sf (S) | af (Q) | mean | std ]   (~4.6 KB)
+//   corr_fwd_kernel       y = act(x W^T + b): split-K over the SMs; every CTA GENERATES its
+//                         128 x 32 tiles of x (as tf32 hi / lo halves, straight into tensor
+//                         memory) from the factors in shared memory, W tiles arrive by 8-byte
+//                         cp.async into the swizzled operand layout (rows are 8-byte aligned),
+//                         tcgen05.mma (TS form, TF32x3) accumulates in tensor memory
+//   corr_wgrad_kernel     dW[j, k] = sum_n dy[n, j] x[n, k]: dy^T lives in tensor memory for the
+//                         whole launch, the x tiles are generated into swizzled shared memory,
+//                         and the epilogue applies Adam to W / exp_avg / exp_avg_sq in place
+//                         (or stores dW for the data-parallel exchange) -- the 13.4 M-parameter
+//                         ShadowHand weight gradient never touches HBM
+//
+// x values are the same fp32 products the summarizer kernel would have stored (one rounding),
+// the TF32x3 split recovers the fp32 mantissas of both operands, accumulation is fp32 in TMEM.
+#include <cuda.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "gemm.cuh"
+#include "tc_ptx.cuh"
+
+namespace bsig {
+namespace corr {
+
+using namespace tc;
+
+// exact n / d for n, d < 2^20 (m = ceil(2^40 / d))
+struct FastDiv {
+  uint32_t d;
+  uint64_t m;
+};
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+  return (uint32_t)(((uint64_t)n * f.m) >> 40);
+}
+static FastDiv mk_div(uint64_t d) {
+  FastDiv f;
+  f.d = (uint32_t)d;
+  f.m = ((1ull << 40) + d - 1) / d;
+  return f;
+}
+
+// ------------------------------------------------------------------ factors
+struct FactorArgs {
+  const float* states;
+  const float* actions;
+  float* fac;
+  int64_t ldf;
+  int* flag;
+  int64_t n;
+  int64_t s_stride, a_stride, s_tstride, a_tstride;
+  int D, A, Pn, Qn, use_diff;
+};
+
+// One warp per trajectory.  mean / unbiased std of sf are formed exactly as crosscorr_kernel
+// (summarizers.cu) forms them -- fp64, two passes, sequential for Pn <= 64 and lane-strided +
+// butterfly otherwise -- so the two statistics are bit-identical to the materialised summary.
+__global__ void __launch_bounds__(256) corr_factors_kernel(FactorArgs p, FastDiv divD, FastDiv divA) {
+  extern __shared__ float fsm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t traj = (int64_t)blockIdx.x * 8 + warp;
+  if (traj >= p.n) return;
+  float* v = fsm + (size_t)warp * p.Pn;
+  float* out = p.fac + traj * p.ldf;
+  const int Dm1 = p.D - 1;
+  bool bad = false;
+  float smax = 0.f, amax = 0.f;
+  for (int i = lane; i < p.Pn; i += 32) {
+    const uint32_t t = fdiv((uint32_t)i, divD), j = (uint32_t)i - t * (uint32_t)Dm1;
+    const float* s = p.states + traj * p.s_stride + t * p.s_tstride + j;
+    const float lo = __ldg(s);
+    const float x = p.use_diff ? (__ldg(s + 1) - lo) : lo;
+    bad |= !finite_f(x);
+    smax = fmaxf(smax, fabsf(x));
+    v[i] = x;
+    out[i] = x;
+  }
+  for (int q = lane; q < p.Qn; q += 32) {
+    const uint32_t tq = fdiv((uint32_t)q, divA);
+    const float x = __ldg(p.actions + traj * p.a_stride + tq * p.a_tstride +
+                          ((uint32_t)q - tq * (uint32_t)p.A));
+    bad |= !finite_f(x);
+    amax = fmaxf(amax, fabsf(x));
+    out[p.Pn + q] = x;
+  }
+  __syncwarp();
+  float mean_f, sd_f;
+  if (p.Pn <= 64) {
+    double acc = 0.0;
+    for (int i = 0; i < p.Pn; ++i) acc += (double)v[i];
+    const double mean = acc / (double)p.Pn;
+    double sq = 0.0;
+    for (int i = 0; i < p.Pn; ++i) {
+      const double dlt = (double)v[i] - mean;
+      sq += dlt * dlt;
+    }
+    mean_f = (float)mean;
+    sd_f = p.Pn < 2 ? 0.f : (float)sqrt(sq / (double)(p.Pn - 1));
+  } else {
+    double acc = 0.0;
+    for (int i = lane; i < p.Pn; i += 32) acc += (double)v[i];
+    acc = warp_sum(acc);
+    const double mean = acc / (double)p.Pn;
+    double sq = 0.0;
+    for (int i = lane; i < p.Pn; i += 32) {
+      const double dlt = (double)v[i] - mean;
+      sq += dlt * dlt;
+    }
+    sq = warp_sum(sq);
+    mean_f = (float)mean;
+    sd_f = (float)sqrt(sq / (double)(p.Pn - 1));
+  }
+  // torch.isfinite(feats).all(): with finite factors a product can only overflow, and the
+  // largest product of a row is max|sf| * max|af| (rounding is monotonic)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, o));
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  }
+  bad |= !finite_f(sd_f) || !finite_f(mean_f) || !(smax * amax <= 3.402823466e38f);
+  if (lane == 0) {
+    out[p.Pn + p.Qn] = mean_f;
+    out[p.Pn + p.Qn + 1] = sd_f;
+    for (int64_t c = p.Pn + p.Qn + 2; c < p.ldf; ++c) out[c] = 0.f;
+  }
+  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(p.flag, 1);
+}
+
+// ------------------------------------------------------------------ forward
+constexpr int BM = 128, BN = 128, BK = 32;
+constexpr int TILE_BYTES = BM * BK * 4;           // 16 KB
+// warps 0-3 stream W (cp.async), warp 4 issues the MMAs, warps 5-12 generate x / split W,
+// warps 13-16 drain the accumulator.  Every role is a chain of dependent instructions, so a
+// warp issues one instruction every ~5 cycles: the work of a stage is spread over enough warps
+// that none of them needs more than the ~800 cycles the three TF32 MMAs of a stage take.
+constexpr int FWD_THREADS = 17 * 32;
+constexpr int FWD_MAX_STAGES = 4;
+constexpr int FWD_PREFETCH = 8;                   // L2 prefetch distance of the W stream (stages)
+
+struct FwdArgs {
+  const float* fac;
+  int64_t ldf;
+  const int64_t* rows;
+  const float* w;          // [N][F]
+  int S, Q, F;             // F = S*Q + 2
+  int M, N;                // rows of the batch, output columns (<= 128)
+  int splits, kb_per_split, num_kb;
+  int stages;              // shared-memory / tensor-memory ring depth (<= FWD_MAX_STAGES)
+  int qp, npp;             // odd pitches of the staged af (wrap-extended by 32) / sf rows
+  float* partial;          // [splits][M][N]
+};
+
+__global__ void __launch_bounds__(FWD_THREADS, 1)
+corr_fwd_kernel(FwdArgs g, FastDiv divQ) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[FWD_MAX_STAGES], conv_bar[FWD_MAX_STAGES], empty_bar[FWD_MAX_STAGES];
+  __shared__ uint64_t tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+  const int STAGES = g.stages;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (g.M + BM - 1) / BM;
+  const int num_items = m_tiles * g.splits;
+  auto tile_b = [&](int s) { return smem + (size_t)s * 2 * TILE_BYTES; };
+  auto tile_blo = [&](int s) { return tile_b(s) + TILE_BYTES; };
+  float* af_s = reinterpret_cast<float*>(smem + (size_t)STAGES * 2 * TILE_BYTES);   // [128][qp]
+  float* sf_s = af_s + (size_t)BM * g.qp;                                           // [128][npp]
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 128);              // one cp.async arrival per producer lane
+      mbar_init(&conv_bar[s], 256);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    // 2 x 128 accumulator columns + (hi 32 | lo 32) columns of generated A per stage
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_slot)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp < 4) {
+    // ------------------------------------------------ producers: W tiles by 8-byte cp.async
+    // W [N][F] has rows that are only 8-byte aligned (F = s*q + 2 is even, never a multiple of
+    // four for the reference's windows), which TMA cannot address (16-byte box origins): each
+    // producer warp copies 32 rows of the 128 x 32 tile as 8-byte pieces straight into the
+    // 128B-swizzled layout the tensor core reads; completion arrives on the stage's mbarrier.
+    // lane -> (row parity h, 8-byte piece pc); iteration i -> row 32*warp + 2i + h
+    const int h = lane >> 4, pc = lane & 15;
+    const uint32_t c0 = (uint32_t)((pc >> 1) ^ h);          // 16-byte chunk before the row swizzle
+    const uint32_t dst_lane = (uint32_t)(warp * 32 + h) * 128u + (uint32_t)((pc & 1) << 3);
+    const float* src_lane = g.w + (int64_t)(warp * 32 + h) * g.F + 2 * pc;
+    int it = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int split = item % g.splits;
+      const int kb0 = split * g.kb_per_split, kb1 = min(g.num_kb, kb0 + g.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % STAGES;
+        const int k0 = kb * BK;
+        // warm L2 a few stages ahead: one 128-byte line per lane (row 32*warp + lane)
+        if (kb + FWD_PREFETCH < kb1 && warp * 32 + lane < g.N)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(g.w + (int64_t)(warp * 32 + lane) * g.F +
+                                                       k0 + FWD_PREFETCH * BK));
+        mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+        const uint32_t dst_base = smem_u32(tile_b(s)) + dst_lane;
+        const bool k_ok = k0 + 2 * pc < g.F;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const uint32_t dst = dst_base + (uint32_t)(2 * i) * 128u + ((c0 ^ (uint32_t)((2 * i) & 7)) << 4);
+          const bool valid = k_ok && (warp * 32 + 2 * i + h) < g.N;
+          const float* src = valid ? src_lane + (int64_t)(2 * i) * g.F + k0 : g.w;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src),
+                       "r"(valid ? 8 : 0)
+                       : "memory");
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(
+                         smem_u32(&full_bar[s]))
+                     : "memory");
+      }
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------ MMA issuer (A from tensor memory)
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)(BM >> 4) << 24);
+      int it = 0, tcount = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++tcount) {
+        const int split = item % g.splits;
+        const int kb0 = split * g.kb_per_split, kb1 = min(g.num_kb, kb0 + g.kb_per_split);
+        const int buf = tcount & 1;
+        mbar_wait(&tmem_empty_bar[buf], ((tcount >> 1) & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&conv_bar[s], (it / STAGES) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t b_hi = smem_u32(tile_b(s)), b_lo = smem_u32(tile_blo(s));
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint32_t a_tm = tmem_base + 256u + (uint32_t)(s * 64 + k * 8);
+            const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+            umma_tf32_ts(d_tmem, a_tm, umma_desc(b_hi + k * 32), idesc, acc);
+            umma_tf32_ts(d_tmem, a_tm, umma_desc(b_lo + k * 32), idesc, 1u);
+            umma_tf32_ts(d_tmem, a_tm + 32u, umma_desc(b_hi + k * 32), idesc, 1u);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full_bar[buf]);
+      }
+    }
+  } else if (warp < 13) {
+    // ------------------------------------------------ generators: x tiles -> TMEM, W hi/lo
+    // two warps per TMEM lane quadrant: each generates 16 of the 32 K columns of its rows
+    const int t = threadIdx.x - 5 * 32;         // 0..255
+    const int half = (warp - 5) >> 2;           // K columns [16*half, 16*half + 16) of a block
+    const int m = (warp & 3) * 32 + lane;       // row of the tile = TMEM lane of this thread
+    const uint32_t SQ = (uint32_t)(g.F - 2);
+    int it = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int mt = item / g.splits, split = item - mt * g.splits;
+      const int kb0 = split * g.kb_per_split, kb1 = min(g.num_kb, kb0 + g.kb_per_split);
+      const int m0 = mt * BM;
+      const uint32_t p_base = fdiv((uint32_t)(kb0 * BK), divQ);
+      const uint32_t p_last = min((uint32_t)g.S - 1, fdiv((uint32_t)(min(kb1 * BK, g.F) - 1), divQ));
+      const int np = p_base < (uint32_t)g.S ? (int)(p_last - p_base) + 1 : 0;
+      // stage the factors of this item's rows: af [128][Q + 32] (the first 32 entries repeated
+      // behind the row, so that a block of 32 consecutive q never has to wrap), the sf columns
+      // of the K slice.  Thread pair (t, t+128) shares row t & 127; 4-byte cp.async each.
+      asm volatile("bar.sync 1, 256;" ::: "memory");     // previous item fully generated
+      {
+        const int r = t & 127, part = t >> 7;
+        const bool row_ok = m0 + r < g.M;
+        const int64_t src = row_ok ? (g.rows ? __ldg(g.rows + m0 + r) : (int64_t)(m0 + r)) : 0;
+        const float* frow = g.fac + src * g.ldf;
+        const uint32_t a_dst = smem_u32(af_s + r * g.qp), s_dst = smem_u32(sf_s + r * g.npp);
+        const int sz = row_ok ? 4 : 0;           // rows past the batch: zero fill
+        const int qx = g.Q + 32;
+        for (int q = part; q < qx; q += 2) {
+          int qs = q;
+          while (qs >= g.Q) qs -= g.Q;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(a_dst + 4u * q),
+                       "l"(frow + g.S + qs), "r"(sz)
+                       : "memory");
+        }
+        for (int c = part; c < np; c += 2)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(s_dst + 4u * c),
+                       "l"(frow + p_base + c), "r"(sz)
+                       : "memory");
+      }
+      float mu = 0.f, sd = 0.f;
+      if (m0 + m < g.M) {
+        const int64_t src = g.rows ? __ldg(g.rows + m0 + m) : (int64_t)(m0 + m);
+        mu = __ldg(g.fac + src * g.ldf + g.S + g.Q);
+        sd = __ldg(g.fac + src * g.ldf + g.S + g.Q + 1);
+      }
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float* afr = af_s + m * g.qp;
+      const float* sfr = sf_s + m * g.npp;
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % STAGES;
+        // the x tile does not depend on the W data, but its TMEM slot is only free once the
+        // MMAs of the previous round have retired -- which is what let the producers refill
+        // the stage, i.e. what full_bar certifies
+        mbar_wait(&full_bar[s], (it / STAGES) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t k0 = (uint32_t)kb * BK + 16u * (uint32_t)half;
+        const uint32_t pcur = fdiv(k0, divQ);
+        const uint32_t q0 = k0 - pcur * (uint32_t)g.Q;
+        uint32_t hi[16], lo[16];
+        if (g.Q >= 16 && k0 + 16 <= SQ) {
+          // common case: 16 products from at most two state features, no wrap in af
+          const uint32_t n1 = (uint32_t)g.Q - q0;          // elements left in feature row pcur
+          const float sv0 = sfr[pcur - p_base];
+          const float sv1 = n1 < 16 ? sfr[pcur + 1 - p_base] : 0.f;
+          const float* ap = afr + q0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float xv = ((uint32_t)i < n1 ? sv0 : sv1) * ap[i];
+            const uint32_t hb = __float_as_uint(xv) & 0xffffe000u;
+            hi[i] = hb;
+            lo[i] = __float_as_uint(xv - __uint_as_float(hb));
+          }
+        } else {
+          // narrow action windows (several wraps per block) and the tail block with the two
+          // statistics / the zero padding behind them
+          uint32_t pp = pcur, q = q0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float xv;
+            if (pp < (uint32_t)g.S) {
+              xv = sfr[pp - p_base] * afr[q];
+            } else {
+              const uint32_t tail = k0 + i - SQ;
+              xv = tail == 0 ? mu : (tail == 1 ? sd : 0.f);
+            }
+            const uint32_t hb = __float_as_uint(xv) & 0xffffe000u;
+            hi[i] = hb;
+            lo[i] = __float_as_uint(xv - __uint_as_float(hb));
+            if (++q == (uint32_t)g.Q) {
+              q = 0;
+              ++pp;
+            }
+          }
+        }
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 256u +
+                               (uint32_t)(s * 64 + 16 * half);
+        BSIG_TMEM_ST16(taddr, hi);
+        BSIG_TMEM_ST16(taddr + 32u, lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        // W tile: hi in place, lo beside it
+        float4* b = reinterpret_cast<float4*>(tile_b(s));
+        float4* blo = reinterpret_cast<float4*>(tile_blo(s));
+#pragma unroll
+        for (int u = 0; u < TILE_BYTES / 16 / 256; ++u) {
+          const int idx = t + 256 * u;
+          const float4 v = b[idx];
+          float4 hh, l;
+          hh.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+          hh.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+          hh.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+          hh.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+          l.x = v.x - hh.x; l.y = v.y - hh.y; l.z = v.z - hh.z; l.w = v.w - hh.w;
+          b[idx] = hh;
+          blo[idx] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(&conv_bar[s]);
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue: raw partial accumulators
+    const int qd = warp & 3;
+    int tcount = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++tcount) {
+      const int mt = item / g.splits, split = item - mt * g.splits;
+      const int buf = tcount & 1;
+      mbar_wait(&tmem_full_bar[buf], (tcount >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int row = mt * BM + qd * 32 + lane;
+      const bool row_ok = row < g.M;
+      float* prow = g.partial + ((int64_t)split * g.M + (row_ok ? row : 0)) * g.N;
+#pragma unroll 1
+      for (int cb = 0; cb < BN / 32; ++cb) {
+        if (cb * 32 >= g.N) break;
+        uint32_t r[32];
+        const uint32_t taddr =
+            tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(buf * BN + cb * 32);
+        BSIG_TMEM_LD32(r, taddr);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (!row_ok) continue;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const int j = cb * 32 + c;
+          if (j < g.N) prow[j] = __uint_as_float(r[c]);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&tmem_empty_bar[buf]);
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ weight gradient (+ Adam)
+constexpr int WG_TN = 64;                         // k columns per output tile
+constexpr int WG_EPI_WARPS = 16;
+constexpr int WG_THREADS = (5 + WG_EPI_WARPS) * 32;   // warp0 MMA, 1-4 generate, 5-20 epilogue
+constexpr int WG_STAGE_BYTES = 2 * 4 * WG_TN * 128;   // hi + lo, four [64 x 32] sub-tiles = 64 KB
+constexpr int WG_EP = 65;                         // pitch of the epilogue staging tile
+
+struct WgradArgs {
+  const float* dy;         // [M][N]  (N = n_out, contiguous)
+  const float* fac;
+  int64_t ldf;
+  const int64_t* rows;
+  int S, Q, F;
+  int M, N;                // batch rows (<= 128), n_out (<= 128)
+  int KP;                  // M rounded up to 8
+  int NP;                  // pitch of the transposed factor rows in shared memory
+  int np_max;              // sf columns a CTA can need
+  int num_tiles;
+  float* dw;               // nullable: store the gradient [N][F]
+  float* w;                // Adam in the epilogue when exp_avg != nullptr
+  float* exp_avg;
+  float* exp_avg_sq;
+  float one_minus_b1, b2, one_minus_b2, step_size, inv_bc2_sqrt, eps, gscale;
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1) corr_wgrad_kernel(WgradArgs g, FastDiv divQ) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  __shared__ uint64_t b_full[2], b_empty[2], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* stage_b = smem;                                               // 2 x 64 KB
+  float* ep_s = reinterpret_cast<float*>(smem + 2 * WG_STAGE_BYTES);      // [128][65]
+  float* afT = ep_s + 128 * WG_EP;                                        // [Q][NP]
+  float* sfT = afT + (size_t)g.Q * g.NP;                                  // [np_max][NP]
+  float* mu_s = sfT + (size_t)g.np_max * g.NP;                            // [128]
+  float* sd_s = mu_s + 128;                                               // [128]
+
+  // contiguous tile range of this CTA (its sf columns are contiguous too)
+  const int t_begin = (int)(((int64_t)blockIdx.x * g.num_tiles) / gridDim.x);
+  const int t_end = (int)(((int64_t)(blockIdx.x + 1) * g.num_tiles) / gridDim.x);
+  const uint32_t SQ = (uint32_t)(g.F - 2);
+  const uint32_t k_first = (uint32_t)t_begin * WG_TN;
+  const uint32_t p_base = min(fdiv(min(k_first, SQ - 1), divQ), (uint32_t)g.S - 1);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&b_full[i], 128);
+      mbar_init(&b_empty[i], 1);
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], WG_EPI_WARPS * 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    // columns [0,256): dy^T as tf32 hi (0..) and lo (128..); [256, 384): two accumulators
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_slot)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp >= 1 && warp <= 4) {
+    // ---- one-off: dy^T -> tensor memory (lane = output j, column = batch row n), transposed
+    //      factor rows -> shared memory
+    const int t = threadIdx.x - 32;              // 0..127
+    const int j = (warp & 3) * 32 + lane;        // TMEM lane of this thread
+    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    for (int n0 = 0; n0 < g.KP; n0 += 32) {
+      float v[32];
+#pragma unroll
+      for (int u = 0; u < 32; ++u) {             // 32 independent loads in flight
+        const int n = n0 + u;
+        v[u] = (n < g.M && j < g.N) ? __ldg(g.dy + (int64_t)n * g.N + j) : 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (n0 + 8 * c < g.KP) {                 // warp-uniform
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const uint32_t h = __float_as_uint(v[8 * c + u]) & 0xffffe000u;
+            hi[u] = h;
+            lo[u] = __float_as_uint(v[8 * c + u] - __uint_as_float(h));
+          }
+          BSIG_TMEM_ST8(lane_addr + (uint32_t)(n0 + 8 * c), hi);
+          BSIG_TMEM_ST8(lane_addr + 128u + (uint32_t)(n0 + 8 * c), lo);
+        }
+      }
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    // thread t stages batch row t (transposed: [feature][row]) with 4-byte cp.async
+    if (t < g.KP) {
+      const bool row_ok = t < g.M;
+      const int64_t src = row_ok ? (g.rows ? __ldg(g.rows + t) : (int64_t)t) : 0;
+      const float* frow = g.fac + src * g.ldf;
+      const int sz = row_ok ? 4 : 0;
+      const uint32_t a_dst = smem_u32(afT + t), s_dst = smem_u32(sfT + t);
+      const uint32_t pitch = 4u * (uint32_t)g.NP;
+      for (int q = 0; q < g.Q; ++q)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(a_dst + pitch * q),
+                     "l"(frow + g.S + q), "r"(sz)
+                     : "memory");
+      for (int c = 0; c < g.np_max; ++c) {
+        const bool ok = row_ok && p_base + c < (uint32_t)g.S;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(s_dst + pitch * c),
+                     "l"(ok ? frow + p_base + c : g.fac), "r"(ok ? 4 : 0)
+                     : "memory");
+      }
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(mu_s + t)),
+                   "l"(frow + g.S + g.Q), "r"(sz)
+                   : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(sd_s + t)),
+                   "l"(frow + g.S + g.Q + 1), "r"(sz)
+                   : "memory");
+    } else {
+      mu_s[t] = 0.f;
+      sd_s[t] = 0.f;
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  const int n_chunks = g.KP / 4;                 // 16-byte chunks (4 batch rows) per k row
+  if (warp == 0) {
+    // ------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(WG_TN >> 3) << 17) |
+                             ((uint32_t)(128 >> 4) << 24);
+      int it = 0;
+      for (int tile = t_begin; tile < t_end; ++tile, ++it) {
+        const int s = it & 1;
+        const uint32_t par = (it >> 1) & 1;
+        mbar_wait(&acc_empty[s], par ^ 1);
+        mbar_wait(&b_full[s], par);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + 256u + (uint32_t)(s * WG_TN);
+        const uint32_t b_hi = smem_u32(stage_b + (size_t)s * WG_STAGE_BYTES);
+        const uint32_t b_lo = b_hi + WG_STAGE_BYTES / 2;
+        for (int ks = 0; ks < g.KP / 8; ++ks) {
+          const uint32_t off = (uint32_t)(ks >> 2) * (WG_TN * 128) + (uint32_t)(ks & 3) * 32;
+          const uint32_t a_hi = tmem_base + (uint32_t)(ks * 8), a_lo = a_hi + 128u;
+          umma_tf32_ts(d_tmem, a_hi, umma_desc(b_hi + off), idesc, ks > 0 ? 1u : 0u);
+          umma_tf32_ts(d_tmem, a_hi, umma_desc(b_lo + off), idesc, 1u);
+          umma_tf32_ts(d_tmem, a_lo, umma_desc(b_hi + off), idesc, 1u);
+        }
+        umma_commit(&b_empty[s]);
+        umma_commit(&acc_full[s]);
+      }
+    }
+  } else if (warp <= 4) {
+    // ------------------------------------------------ generators: x^T tiles, K-major, SW128
+    const int t = threadIdx.x - 32;              // 0..127
+    const int r = t & (WG_TN - 1);               // k row of the tile owned by this thread
+    int it = 0;
+    for (int tile = t_begin; tile < t_end; ++tile, ++it) {
+      const int s = it & 1;
+      mbar_wait(&b_empty[s], ((it >> 1) & 1) ^ 1);
+      uint8_t* hi_base = stage_b + (size_t)s * WG_STAGE_BYTES;
+      uint8_t* lo_base = hi_base + WG_STAGE_BYTES / 2;
+      const uint32_t k = (uint32_t)tile * WG_TN + (uint32_t)r;
+      const uint32_t pk = fdiv(min(k, SQ), divQ);
+      const uint32_t qk = k - pk * (uint32_t)g.Q;
+      const bool prod = k < SQ;
+      const float* sfp = sfT + (size_t)(prod ? pk - p_base : 0) * g.NP;
+      const float* afp = afT + (size_t)(prod ? qk : 0) * g.NP;
+      const float* tailp = k == SQ ? mu_s : sd_s;
+      const bool tail = (k == SQ) || (k == SQ + 1);
+      for (int c = t >> 6; c < n_chunks; c += 2) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (prod) {
+          const float4 a = *reinterpret_cast<const float4*>(afp + 4 * c);
+          const float4 sv = *reinterpret_cast<const float4*>(sfp + 4 * c);
+          v.x = sv.x * a.x; v.y = sv.y * a.y; v.z = sv.z * a.z; v.w = sv.w * a.w;
+        } else if (tail) {
+          v = *reinterpret_cast<const float4*>(tailp + 4 * c);
+        }
+        float4 h, l;
+        h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+        h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+        h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+        h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+        l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+        const uint32_t off = (uint32_t)(c >> 3) * (WG_TN * 128) + (uint32_t)r * 128 +
+                             (uint32_t)(((c & 7) ^ (r & 7)) << 4);
+        *reinterpret_cast<float4*>(hi_base + off) = h;
+        *reinterpret_cast<float4*>(lo_base + off) = l;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(&b_full[s]);
+    }
+  } else {
+    // ------------------------------------------------ epilogue: Adam / gradient store
+    // 16 warps: four per TMEM lane quadrant, each drains 16 of the 64 accumulator columns into
+    // the staging tile; then warp ew owns rows ew, ew+16, ... (8 rows) and lane l the column
+    // pair 2l: every row is one coalesced 256-byte access per array.  The HBM stream (read and
+    // write W, exp_avg, exp_avg_sq: 24 B per parameter) is the whole cost of the kernel, so it
+    // is kept in flight across everything else: the lines of tile t+1 are prefetched into L2
+    // while tile t is processed, and the 24 loads of a thread are issued BEFORE it waits for
+    // the accumulator and the staging barriers.
+    const int ew = warp - 5;                      // 0..15
+    const int qd = warp & 3;                      // TMEM lane quadrant
+    const int part = ew >> 2;                     // which 16 of the 64 accumulator columns
+    const int et = threadIdx.x - 5 * 32;          // 0..511
+    const bool adam = g.exp_avg != nullptr;
+    auto prefetch_tile = [&](int tile) {
+      // 128 rows x 3 arrays x 256 B (8-byte aligned: up to three 128-byte lines each)
+      if (!adam) return;
+      const int j = et >> 2, sub = et & 3;        // 4 threads per row
+      if (j >= g.N || sub == 3) return;
+      const float* base = sub == 0 ? g.w : (sub == 1 ? g.exp_avg : g.exp_avg_sq);
+      const int64_t e0 = (int64_t)j * g.F + (int64_t)tile * WG_TN;
+      const int64_t e1 = min(e0 + WG_TN, (int64_t)(j + 1) * g.F);
+      const char* p0 = reinterpret_cast<const char*>(base + e0);
+      const char* p1 = reinterpret_cast<const char*>(base + e1) - 1;
+      for (const char* q = reinterpret_cast<const char*>((uintptr_t)p0 & ~(uintptr_t)127); q <= p1;
+           q += 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+    };
+    if (t_begin < t_end) prefetch_tile(t_begin);
+    int it = 0;
+    for (int tile = t_begin; tile < t_end; ++tile, ++it) {
+      const int s = it & 1;
+      if (tile + 1 < t_end) prefetch_tile(tile + 1);
+      const int64_t kcol = (int64_t)tile * WG_TN + 2 * lane;
+      const bool col_ok = kcol < g.F;
+      float2 pw[8], pm[8], pv[8];
+      if (adam && col_ok) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = ew + 16 * u;
+          if (j < g.N) {
+            const int64_t e = (int64_t)j * g.F + kcol;
+            pw[u] = *reinterpret_cast<const float2*>(g.w + e);
+            pm[u] = *reinterpret_cast<const float2*>(g.exp_avg + e);
+            pv[u] = *reinterpret_cast<const float2*>(g.exp_avg_sq + e);
+          }
+        }
+      }
+      mbar_wait(&acc_full[s], (it >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t r[16];
+      const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + 256u +
+                             (uint32_t)(s * WG_TN + part * 16);
+      BSIG_TMEM_LD16(r, taddr);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&acc_empty[s]);
+      asm volatile("bar.sync 1, 512;" ::: "memory");    // previous tile's staging fully consumed
+      float* erow = ep_s + (qd * 32 + lane) * WG_EP + part * 16;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) erow[c] = __uint_as_float(r[c]);
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      if (col_ok) {
+        if (adam) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int j = ew + 16 * u;
+            if (j < g.N) {
+              const int64_t e = (int64_t)j * g.F + kcol;
+              const float* gs = ep_s + j * WG_EP + 2 * lane;
+              auto upd = [&](float& pp, float gg, float& mm, float& vv) {
+                gg *= g.gscale;
+                mm = mm + (gg - mm) * g.one_minus_b1;
+                vv = vv * g.b2 + g.one_minus_b2 * gg * gg;
+                const float denom = sqrtf(vv) * g.inv_bc2_sqrt + g.eps;
+                pp = pp - g.step_size * (mm / denom);
+              };
+              const float g0 = gs[0], g1 = gs[1];
+              upd(pw[u].x, g0, pm[u].x, pv[u].x);
+              upd(pw[u].y, g1, pm[u].y, pv[u].y);
+              *reinterpret_cast<float2*>(g.w + e) = pw[u];
+              *reinterpret_cast<float2*>(g.exp_avg + e) = pm[u];
+              *reinterpret_cast<float2*>(g.exp_avg_sq + e) = pv[u];
+              if (g.dw != nullptr) *reinterpret_cast<float2*>(g.dw + e) = make_float2(g0, g1);
+            }
+          }
+        } else {
+          for (int j = ew; j < g.N; j += WG_EPI_WARPS) {
+            const float* gs = ep_s + j * WG_EP + 2 * lane;
+            *reinterpret_cast<float2*>(g.dw + (int64_t)j * g.F + kcol) = make_float2(gs[0], gs[1]);
+          }
+        }
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ host side
+struct FwdPlan {
+  bool ok;
+  int splits, kb_per_split, num_kb, stages, qp, npp;
+  size_t smem;
+};
+
+static FwdPlan plan_fwd(int64_t m, int64_t n_out, int64_t s, int64_t q) {
+  FwdPlan p = {};
+  const int64_t F = s * q + 2;
+  if (m < 1 || n_out < 1 || n_out > 128 || s < 1 || q < 1 || F >= (1 << 20)) return p;
+  const int64_t m_tiles = ceil_div(m, BM);
+  p.num_kb = (int)ceil_div(F, BK);
+  int64_t splits = std::max<int64_t>(1, std::min<int64_t>(p.num_kb, sm_count() / m_tiles));
+  p.kb_per_split = (int)ceil_div(p.num_kb, splits);
+  p.splits = (int)ceil_div(p.num_kb, p.kb_per_split);
+  p.qp = (int)((q + 32) | 1);
+  const int64_t np = ((int64_t)p.kb_per_split * BK) / q + 2;
+  p.npp = (int)(np | 1);
+  const size_t factors = (size_t)BM * (p.qp + p.npp) * 4;
+  for (int st = FWD_MAX_STAGES; st >= 2; --st) {
+    const size_t need = (size_t)st * 2 * TILE_BYTES + factors + 1024;
+    if (need <= 220 * 1024) {
+      p.stages = st;
+      p.smem = need;
+      p.ok = true;
+      break;
+    }
+  }
+  return p;
+}
+
+struct WgPlan {
+  bool ok;
+  int KP, NP, np_max, num_tiles, grid;
+  size_t smem;
+};
+
+static WgPlan plan_wgrad(int64_t m, int64_t n_out, int64_t s, int64_t q) {
+  WgPlan p = {};
+  const int64_t F = s * q + 2;
+  if (m < 1 || m > 128 || n_out < 1 || n_out > 128 || s < 1 || q < 1 || F >= (1 << 20)) return p;
+  p.KP = (int)(ceil_div(m, 8) * 8);
+  p.NP = p.KP + 4;
+  p.num_tiles = (int)ceil_div(F, WG_TN);
+  p.grid = (int)std::min<int64_t>(p.num_tiles, sm_count());
+  const int64_t tiles_per_cta = ceil_div(p.num_tiles, p.grid);
+  p.np_max = (int)((tiles_per_cta * WG_TN) / q + 2);
+  p.smem = (size_t)2 * WG_STAGE_BYTES + (size_t)128 * WG_EP * 4 +
+           (size_t)(q + p.np_max) * p.NP * 4 + 2 * 128 * 4 + 1024;
+  p.ok = p.smem <= 225 * 1024;
+  return p;
+}
+
+}  // namespace corr
+}  // namespace bsig
+
+using namespace bsig;
+
+extern "C" int bsig_corr_factors(const float* states, const float* actions, float* fac, int64_t ldf,
+                                 int64_t n, int64_t t_states, int64_t t_actions, int64_t d,
+                                 int64_t a, int64_t w, int use_state_diff, int time_major,
+                                 int* nonfinite_flag, void* stream) {
+  BSIG_REQUIRE(n >= 0 && d >= 2 && a >= 1 && w >= 1, "corr_factors: need d>=2, a>=1, w>=1");
+  BSIG_REQUIRE(t_states >= w && t_actions >= w, "corr_factors: trajectories shorter than w");
+  BSIG_REQUIRE(nonfinite_flag != nullptr, "corr_factors: flag pointer required");
+  const int64_t pn = w * (d - 1), qn = w * a;
+  BSIG_REQUIRE(ldf >= pn + qn + 2, "corr_factors: row pitch too small");
+  BSIG_REQUIRE(pn < (1 << 20) && qn < (1 << 20), "corr_factors: window too wide");
+  if (n == 0) return 0;
+  corr::FactorArgs p;
+  p.states = states; p.actions = actions; p.fac = fac; p.ldf = ldf; p.flag = nonfinite_flag;
+  p.n = n;
+  if (time_major) {
+    p.s_stride = d; p.a_stride = a; p.s_tstride = n * d; p.a_tstride = n * a;
+  } else {
+    p.s_stride = t_states * d; p.a_stride = t_actions * a; p.s_tstride = d; p.a_tstride = a;
+  }
+  p.D = (int)d; p.A = (int)a; p.Pn = (int)pn; p.Qn = (int)qn; p.use_diff = use_state_diff;
+  const size_t smem = (size_t)8 * pn * 4;
+  BSIG_REQUIRE(smem <= 200 * 1024, "corr_factors: window too large for shared memory");
+  if (smem > 48 * 1024)
+    BSIG_CUDA(cudaFuncSetAttribute(corr::corr_factors_kernel,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  corr::corr_factors_kernel<<<(unsigned)ceil_div(n, 8), 256, smem, (cudaStream_t)stream>>>(
+      p, corr::mk_div((uint64_t)(d - 1)), corr::mk_div((uint64_t)a));
+  BSIG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int bsig_corr_linear_applicable(int64_t batch, int64_t rows_max, int64_t n_out,
+                                           int64_t s, int64_t q) {
+  return (corr::plan_fwd(rows_max, n_out, s, q).ok && corr::plan_fwd(batch, n_out, s, q).ok &&
+          corr::plan_wgrad(batch, n_out, s, q).ok) ? 1 : 0;
+}
+
+extern "C" int64_t bsig_corr_linear_ws_bytes(int64_t m, int64_t n_out, int64_t s, int64_t q) {
+  const corr::FwdPlan p = corr::plan_fwd(m, n_out, s, q);
+  if (!p.ok) return 0;
+  return (int64_t)p.splits * m * n_out * 4 + 1024;
+}
+
+extern "C" int bsig_corr_linear_fwd(const float* fac, int64_t ldf, const int64_t* rows, int64_t s,
+                                    int64_t q, const float* w, const float* b, float* y, int64_t m,
+                                    int64_t n_out, int act, void* ws, int64_t ws_bytes,
+                                    void* stream) {
+  using namespace corr;
+  const FwdPlan p = plan_fwd(m, n_out, s, q);
+  BSIG_REQUIRE(p.ok, "corr_linear_fwd: shape outside the fused kernel's envelope "
+               "(n_out <= 128, s*q+2 < 2^20, factors must fit shared memory)");
+  BSIG_REQUIRE(act == BSIG_ACT_NONE || act == BSIG_ACT_TANH, "corr_linear_fwd: unknown activation");
+  BSIG_REQUIRE(!(b == nullptr && act == BSIG_ACT_TANH), "corr_linear_fwd: tanh needs a bias");
+  BSIG_REQUIRE((reinterpret_cast<uintptr_t>(w) & 7) == 0, "corr_linear_fwd: weight must be 8-byte aligned");
+  BSIG_REQUIRE(ws != nullptr && ws_bytes >= bsig_corr_linear_ws_bytes(m, n_out, s, q),
+               "corr_linear_fwd: workspace too small");
+  const int64_t F = s * q + 2;
+  FwdArgs g;
+  g.fac = fac; g.ldf = ldf; g.rows = rows; g.w = w; g.S = (int)s; g.Q = (int)q; g.F = (int)F;
+  g.M = (int)m; g.N = (int)n_out;
+  g.splits = p.splits; g.kb_per_split = p.kb_per_split; g.num_kb = p.num_kb; g.stages = p.stages;
+  g.qp = p.qp; g.npp = p.npp;
+  g.partial = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  const int64_t items = ceil_div(m, BM) * p.splits;
+  BSIG_CUDA(cudaFuncSetAttribute(corr_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)p.smem));
+  corr_fwd_kernel<<<(unsigned)std::min<int64_t>(items, sm_count()), FWD_THREADS, p.smem,
+                    (cudaStream_t)stream>>>(g, mk_div((uint64_t)q));
+  BSIG_LAUNCH_CHECK();
+  GemmArgs r2 = gemm_args_zero();
+  r2.C = y; r2.ldc = n_out; r2.M = (int)m; r2.N = (int)n_out; r2.K = (int)F;
+  r2.bias = b;
+  r2.epi = b == nullptr ? EPI_STORE : (act == BSIG_ACT_TANH ? EPI_BIAS_TANH : EPI_BIAS);
+  r2.partial = g.partial;
+  return gemm_splitk_reduce(r2, p.splits, (cudaStream_t)stream);
+}
+
+extern "C" int bsig_corr_linear_wgrad(const float* dy, const float* fac, int64_t ldf,
+                                      const int64_t* rows, int64_t s, int64_t q, int64_t m,
+                                      int64_t n_out, float* dw, float* w, float* exp_avg,
+                                      float* exp_avg_sq, int64_t step, float lr, float beta1,
+                                      float beta2, float eps, float grad_scale, void* stream) {
+  using namespace corr;
+  const WgPlan p = plan_wgrad(m, n_out, s, q);
+  BSIG_REQUIRE(p.ok, "corr_linear_wgrad: shape outside the fused kernel's envelope "
+               "(batch <= 128, n_out <= 128, s*q+2 < 2^20, factors must fit shared memory)");
+  const bool adam = exp_avg != nullptr;
+  BSIG_REQUIRE(adam || dw != nullptr, "corr_linear_wgrad: nothing to do (no dw, no Adam state)");
+  BSIG_REQUIRE(!adam || (w != nullptr && exp_avg_sq != nullptr && step >= 1),
+               "corr_linear_wgrad: Adam needs w, exp_avg, exp_avg_sq and step >= 1");
+  const uintptr_t al = (uintptr_t)dw | (uintptr_t)w | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq;
+  BSIG_REQUIRE((al & 7) == 0, "corr_linear_wgrad: buffers must be 8-byte aligned");
+  WgradArgs g;
+  g.dy = dy; g.fac = fac; g.ldf = ldf; g.rows = rows;
+  g.S = (int)s; g.Q = (int)q; g.F = (int)(s * q + 2);
+  g.M = (int)m; g.N = (int)n_out; g.KP = p.KP; g.NP = p.NP; g.np_max = p.np_max;
+  g.num_tiles = p.num_tiles;
+  g.dw = dw; g.w = w; g.exp_avg = exp_avg; g.exp_avg_sq = exp_avg_sq;
+  const double bc1 = 1.0 - pow((double)beta1, (double)(adam ? step : 1));
+  const double bc2 = 1.0 - pow((double)beta2, (double)(adam ? step : 1));
+  g.one_minus_b1 = 1.0f - beta1; g.b2 = beta2; g.one_minus_b2 = 1.0f - beta2;
+  g.step_size = (float)((double)lr / bc1);
+  g.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+  g.eps = eps; g.gscale = grad_scale;
+  BSIG_CUDA(cudaFuncSetAttribute(corr_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)p.smem));
+  corr_wgrad_kernel<<<p.grid, WG_THREADS, p.smem, (cudaStream_t)stream>>>(g, mk_div((uint64_t)q));
+  BSIG_LAUNCH_CHECK();
+  return 0;
+}

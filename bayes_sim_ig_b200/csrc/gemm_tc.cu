@@ -32,6 +32,7 @@
 
 #include "common.cuh"
 #include "gemm.cuh"
+#include "tc_ptx.cuh"
 
 namespace bsig {
 
@@ -41,96 +42,6 @@ constexpr int BM = 128, BN = 128, BK = 32;       // BK fp32 = one 128-byte swizz
 constexpr int STAGES_X1 = 6, STAGES_X3 = 3;       // 192 KB of operand stages per (persistent) CTA
 constexpr int TILE_BYTES = BM * BK * 4;           // 16 KB
 constexpr int NUM_THREADS = 320;                  // warp0 TMA, warp1 MMA, warps2-9 convert+epilogue
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar,
-                                            int c_inner, int c_outer) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
-      : "memory");
-}
-// K-major, 128B-swizzled operand tile: 8-row groups are 1024 B apart
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);           // start address
-  d |= (uint64_t)1 << 16;                           // leading byte offset (unused for SW128 K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset
-  d |= (uint64_t)1 << 46;                           // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
-  return d;
-}
-// MN-major operand tile as four TMA boxes of [32 (MN, contiguous: 128 B) x BK (K rows)].
-// For 32-bit operands the ONLY MN-major layout the tensor core accepts is
-// SWIZZLE_128B_BASE32B (cute: Layout_MN_SW128_32B_Atom = Swizzle<2,5,2> over 32 MN x 4 K):
-// 32-byte chunks of a 128-byte row are XOR-ed with (row mod 4) -- the TMA counterpart is
-// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  Atoms (4 K-rows = 512 B) follow each other along K
-// every 512 B (SBO) and along MN every BK * 128 B (LBO = one box); an MMA (K = 8) consumes
-// two K-atoms.
-__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);           // start address
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16; // leading byte offset: next 32 MN elements
-  d |= (uint64_t)(512 >> 4) << 32;                  // stride byte offset: next 4 K rows
-  d |= (uint64_t)1 << 46;                           // descriptor version (sm_100)
-  d |= (uint64_t)1 << 61;                           // SWIZZLE_128B_BASE32B
-  return d;
-}
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                          uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// A operand from tensor memory (lane = row of the tile, one 32-bit column per K element)
-__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
-                                             uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                   smem_u32(bar))
-               : "memory");
-}
 
 struct TcArgs {
   float* C;
@@ -478,12 +389,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
+EncodeTiledFn encode_fn() {
   static EncodeTiledFn fn = nullptr;
   if (fn == nullptr) {
     void* p = nullptr;

@@ -96,3 +96,8 @@ extern "C" int bsig_rff_features(const float* x, int64_t ldx, const int64_t* x_r
   g.epi = EPI_SINCOS; g.scale = scale;
   return run_gemm(g, engine, ws, ws_bytes, (cudaStream_t)stream);
 }
+
+extern "C" int bsig_linear_colsum(const float* dy, float* db, int64_t m, int64_t n, void* stream) {
+  BSIG_REQUIRE(m >= 1 && n >= 1, "linear_colsum: empty problem");
+  return colsum(dy, db, m, n, nullptr, 0, (cudaStream_t)stream);
+}

@@ -66,7 +66,7 @@ def _quiet_gc():
 class TrainPlan(object):
     """Persistent buffers + the captured graph for one problem shape."""
 
-    def __init__(self, model, n_train, n_test, n_updates, batch, in_dim):
+    def __init__(self, model, n_train, n_test, n_updates, batch, in_dim, corr=None):
         self.model = model
         dev = model.flat_params.device
         self.dev = dev
@@ -80,10 +80,19 @@ class TrainPlan(object):
         # training rows live in a zero-padded buffer whose pitch is a multiple of 4 floats, so
         # that the persistent kernel can fetch a minibatch row with one 16-byte aligned bulk copy
         self.x_ld = (in_dim + 3) // 4 * 4
-        self.x_train_buf = torch.zeros((n_train, self.x_ld), **f32)
-        self.x_train = self.x_train_buf[:, :in_dim]
+        # factored cross-correlation summaries (utils.summarizers.CorrFactors):
+        # only the factor rows are stored; the first layer's forward and weight-gradient GEMMs
+        # generate the summary tiles on the fly (csrc/corr_layer.cu)
+        self.corr = corr                     # None or (s, q, ldf)
+        if corr is not None:
+            self.fac_train = torch.zeros((n_train, corr[2]), **f32)
+            self.fac_test = torch.zeros((max(n_test, 1), corr[2]), **f32)
+            self.x_train_buf = self.x_train = self.x_test = None
+        else:
+            self.x_train_buf = torch.zeros((n_train, self.x_ld), **f32)
+            self.x_train = self.x_train_buf[:, :in_dim]
+            self.x_test = torch.empty((max(n_test, 1), in_dim), **f32)
         self.y_train = torch.empty((n_train, p), **f32)
-        self.x_test = torch.empty((max(n_test, 1), in_dim), **f32)
         self.y_test = torch.empty((max(n_test, 1), p), **f32)
         self.y_stage = torch.empty((n_train + n_test, p), **f32)
         self.idx = torch.empty((n_updates, batch), dtype=torch.int64, device=dev)
@@ -121,19 +130,29 @@ class TrainPlan(object):
                        for rows in (batch, rows_max) for n_out, k_in in shapes)
         self.ws_gemm = torch.empty(int(ws_bytes) + 256, dtype=torch.uint8, device=dev)
         self.ws_mdn = torch.zeros(lib.bsig_mdn_ws_bytes(rows_max), dtype=torch.uint8, device=dev)
+        self.corr_adam = False
+        if corr is not None:
+            n0 = widths[0]
+            self.ws_corr = torch.empty(int(lib.bsig_corr_linear_ws_bytes(rows_max, n0, corr[0],
+                                                                         corr[1])) + 256,
+                                       dtype=torch.uint8, device=dev)
+            # single GPU: Adam of the first-layer weight runs in the weight-gradient epilogue
+            # (the gradient never reaches HBM); the flat Adam pass then starts behind that weight
+            self.corr_adam = (data_parallel.world_of(model) == 1 and (n0 * in_dim) % 4 == 0)
         # weight-gradient GEMMs run on a side stream, concurrently with the dgrad chain,
         # when every GEMM of the step is a single-launch (workspace-free) kernel
         def single_launch(m_, n_, k_):
             return m_ * n_ <= 128 * 1024 and k_ <= 8192
-        self.fork_wgrad = all(single_launch(batch, n_out, k_in) and single_launch(batch, k_in, n_out)
-                              and single_launch(n_out, k_in, batch) for n_out, k_in in shapes)
+        self.fork_wgrad = corr is None and all(
+            single_launch(batch, n_out, k_in) and single_launch(batch, k_in, n_out)
+            and single_launch(n_out, k_in, batch) for n_out, k_in in shapes)
         self.side = torch.cuda.Stream(device=dev) if self.fork_wgrad else None
         # large first layers (>= 2^26 multiply-adds: they run on the tcgen05 engine, which
         # cannot gather rows through TMA): the minibatch rows are gathered ONCE per update
         # into a dense, 16-byte aligned buffer that both the forward and the weight-gradient
         # GEMM read, instead of being staged inside each of them
         self.xg = None
-        if (self.rff is None and trunk and int(model.gemm_engine) != 0 and
+        if (corr is None and self.rff is None and trunk and int(model.gemm_engine) != 0 and
                 batch * widths[0] * in_dim >= (1 << 26)):
             self.xg = torch.zeros((batch, self.x_ld), **f32)
         self.loss_buf = torch.zeros(2 * n_log + 1, **f32)   # [train..., test..., scratch]
@@ -143,7 +162,7 @@ class TrainPlan(object):
         # launch (csrc/optim.cu: wgrad3_adam_kernel) on the critical path instead of three
         # side-stream launches + the Adam launch.  Opt-in (BSIG_FUSED_WGRAD=1): measured equal to the default
         # (4.80 vs 4.75 ms per 100 updates, profiles/r2/), it only lowers the launch count
-        self.fused_wgrad_adam = (self.rff is None and len(trunk) == 2 and
+        self.fused_wgrad_adam = (corr is None and self.rff is None and len(trunk) == 2 and
                                  self.p2p is None and batch <= 128 and
                                  data_parallel.world_of(model) == 1 and
                                  os.environ.get('BSIG_FUSED_WGRAD', '0') == '1')
@@ -160,7 +179,7 @@ class TrainPlan(object):
         import ctypes
         self.persistent = False
         m = self.model
-        if os.environ.get('BSIG_PERSISTENT', '0') != '1':
+        if os.environ.get('BSIG_PERSISTENT', '0') != '1' or self.corr is not None:
             return
         if data_parallel.world_of(m) > 1:
             return
@@ -267,6 +286,14 @@ class TrainPlan(object):
                       float(self.rff.a), int(self.rff.gemm_engine), wsp, wsn, st)
             cur, ld, rows_p = acts['feat'], acts['feat'].shape[1], None
         for li, lay in enumerate(layers):
+            if li == 0 and self.corr is not None:
+                cs, cq, cld = self.corr
+                _lib.call('bsig_corr_linear_fwd', cur.data_ptr(), cld, rows_p, cs, cq,
+                          lay['w'].data_ptr(), lay['b'].data_ptr(), acts['h'][0].data_ptr(),
+                          n_rows, lay['n'], ACT_TANH, self.ws_corr.data_ptr(),
+                          self.ws_corr.numel(), st)
+                cur, ld, rows_p = acts['h'][0], lay['n'], None
+                continue
             _lib.call('bsig_linear_fwd', cur.data_ptr(), ld, rows_p, lay['w'].data_ptr(),
                       lay['b'].data_ptr(), acts['h'][li].data_ptr(), n_rows, lay['n'], lay['k'],
                       ACT_TANH, eng, wsp, wsn, st)
@@ -286,7 +313,9 @@ class TrainPlan(object):
         slot = self.logs.index(step) if step in self.logs else None
         n_log = len(self.logs)
         loss_ptr = self.loss_buf.data_ptr() + 4 * (slot if slot is not None else 2 * n_log)
-        if self.xg is not None:
+        if self.corr is not None:
+            x0, x0_rows = self.fac_train, rows
+        elif self.xg is not None:
             _lib.call('bsig_gather_rows', self.x_train_buf.data_ptr(), self.x_ld, rows.data_ptr(),
                       self.xg.data_ptr(), b, self.x_ld, st)
             x0, x0_rows = self.xg, None
@@ -323,6 +352,10 @@ class TrainPlan(object):
             _lib.call('bsig_linear_dgrad', dcur.data_ptr(), nxt['w'].data_ptr(),
                       self.tr['h'][li].data_ptr(), self.dh[li].data_ptr(), b, nxt['n'], nxt['k'],
                       ACT_TANH, eng, wsp, wsn, st)
+            if li == 0 and self.corr is not None:
+                self._enqueue_corr_wgrad(step, lay, rows, st)
+                dcur, nxt = self.dh[li], lay
+                continue
             if li > 0:
                 xin, xld, xrows = self.tr['h'][li - 1], layers[li - 1]['n'], None
             elif self.rff is not None:
@@ -335,6 +368,25 @@ class TrainPlan(object):
             dcur, nxt = self.dh[li], lay
         if side is not None and not self.fused_wgrad_adam:
             main.wait_stream(side)
+
+    def _enqueue_corr_wgrad(self, step, lay, rows, st):
+        """Weight gradient of the first layer from the factored summary rows; single GPU:
+        with Adam of that weight in the epilogue (fresh moments per call, step count as in
+        _enqueue_update); data parallel: the gradient is stored for the exchange."""
+        m = self.model
+        cs, cq, cld = self.corr
+        nw0 = lay['n'] * lay['k']
+        _lib.call('bsig_linear_colsum', self.dh[0].data_ptr(), lay['db'], self.batch, lay['n'], st)
+        if self.corr_adam:
+            _lib.call('bsig_corr_linear_wgrad', self.dh[0].data_ptr(), self.fac_train.data_ptr(),
+                      cld, rows.data_ptr(), cs, cq, self.batch, lay['n'], None,
+                      lay['w'].data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                      step + 1, float(m.lr), 0.9, 0.999, 1e-8, 1.0, st)
+        else:
+            _lib.call('bsig_corr_linear_wgrad', self.dh[0].data_ptr(), self.fac_train.data_ptr(),
+                      cld, rows.data_ptr(), cs, cq, self.batch, lay['n'], lay['dw'],
+                      None, None, None, 1, 0.0, 0.9, 0.999, 1e-8, 1.0, st)
+        assert nw0 == m._offsets[1]       # the first-layer weight opens the flat buffer
 
     def _enqueue_update(self, step, st):
         """Second half of a step: Adam (gradient mean over the replicas folded in) and,
@@ -363,8 +415,11 @@ class TrainPlan(object):
             # one kernel: all-reduce over NVLink peer memory (1/world folded in) + Adam
             self.p2p.adam_allreduce(m, self.exp_avg, self.exp_avg_sq, step, step + 1, st)
         else:
-            _lib.call('bsig_adam_step', m.flat_params.data_ptr(), self.grads.data_ptr(),
-                      self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), m.flat_params.numel(),
+            # (factored first layer, single GPU: its weight was updated in the wgrad epilogue)
+            skip = m._offsets[1] if self.corr_adam else 0
+            _lib.call('bsig_adam_step', m.flat_params.data_ptr() + 4 * skip,
+                      self.grads.data_ptr() + 4 * skip, self.exp_avg.data_ptr() + 4 * skip,
+                      self.exp_avg_sq.data_ptr() + 4 * skip, m.flat_params.numel() - skip,
                       step + 1, float(m.lr), 0.9, 0.999, 1e-8, 1.0 / world, st)
         self._enqueue_eval(step, st)
 
@@ -375,7 +430,8 @@ class TrainPlan(object):
         slot = self.logs.index(step) if step in self.logs else None
         n_log = len(self.logs)
         if slot is not None and self.n_test > 0:
-            self._forward(self.te, self.x_test, None, self.n_test, st)
+            self._forward(self.te, self.fac_test if self.corr is not None else self.x_test,
+                          None, self.n_test, st)
             _lib.call('bsig_mdn_nll_fused', self.te['z'].data_ptr(),
                       self.noise_test[slot].data_ptr(), self.y_test.data_ptr(), None,
                       self.loss_buf.data_ptr() + 4 * (n_log + slot), None, self.n_test, p, k,
@@ -469,11 +525,17 @@ class TrainPlan(object):
 def _stage_inputs(plan, model, x_data, y_data):
     n_train, n_test = plan.n_train, plan.n_test
     dev = plan.dev
-    x_data = x_data.detach()
     y_data = y_data.detach()
-    plan.x_train.copy_(x_data[:n_train], non_blocking=True)
-    if n_test > 0:
-        plan.x_test[:n_test].copy_(x_data[n_train:], non_blocking=True)
+    if plan.corr is not None:
+        fac = x_data.fac.detach()
+        plan.fac_train.copy_(fac[:n_train], non_blocking=True)
+        if n_test > 0:
+            plan.fac_test[:n_test].copy_(fac[n_train:], non_blocking=True)
+    else:
+        x_data = x_data.detach()
+        plan.x_train.copy_(x_data[:n_train], non_blocking=True)
+        if n_test > 0:
+            plan.x_test[:n_test].copy_(x_data[n_train:], non_blocking=True)
     y_dev = y_data.to(device=dev, dtype=torch.float32).contiguous()
     st = _lib.stream_ptr(dev)
     if model.output_lows is not None:
@@ -485,6 +547,21 @@ def _stage_inputs(plan, model, x_data, y_data):
     plan.y_train.copy_(plan.y_stage[:n_train])
     if n_test > 0:
         plan.y_test[:n_test].copy_(plan.y_stage[n_train:])
+
+
+def _corr_layout(model, x_data, batch_size, n_test):
+    """(s, q, ldf) when ``x_data`` is a CorrFactors object the fused first-layer kernels can
+    consume for this model (an MDNN trunk whose first layer is at most 128 wide, minibatch of at
+    most 128 rows, csrc/corr_layer.cu), else None."""
+    if not hasattr(x_data, 'fac') or not hasattr(x_data, 'materialize'):
+        return None
+    trunk = model._trunk_layers()
+    if getattr(model, 'rff', None) is not None or not trunk:
+        return None
+    n0 = trunk[0].weight.shape[0]
+    ok = _lib.load().bsig_corr_linear_applicable(batch_size, max(batch_size, n_test, 1), n0,
+                                                 x_data.s, x_data.q)
+    return (x_data.s, x_data.q, int(x_data.fac.shape[1])) if ok else None
 
 
 def run_training_captured(model, x_data, y_data, n_updates, batch_size, test_frac=0.2,
@@ -501,12 +578,15 @@ def run_training_captured(model, x_data, y_data, n_updates, batch_size, test_fra
     n_test = n_tot - n_train
     in_dim = x_data.shape[1]
     dp = data_parallel.world_of(model) > 1
+    corr = _corr_layout(model, x_data, batch_size, n_test)
+    if corr is None and hasattr(x_data, 'materialize'):
+        x_data = x_data.materialize()          # shape outside the fused kernels' envelope
     key = (n_train, n_test, n_updates, batch_size, in_dim, bool(use_graph), dp,
-           float(model.lr), int(model.gemm_engine))
+           float(model.lr), int(model.gemm_engine), corr)
     with torch.cuda.device(dev):
         plan = model._plans.get(key)
         if plan is None:
-            plan = TrainPlan(model, n_train, n_test, n_updates, batch_size, in_dim)
+            plan = TrainPlan(model, n_train, n_test, n_updates, batch_size, in_dim, corr)
             model._plans[key] = plan
         _stage_inputs(plan, model, x_data, y_data)
         if injected is None:

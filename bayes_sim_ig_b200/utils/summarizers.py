@@ -22,7 +22,7 @@ from .. import _lib
 
 __all__ = ['pad_states_actions', 'summary_start', 'summary_waypts', 'cross_correlation',
            'summary_corrdiff', 'summary_corr', 'signature_depth', 'summary_signatory',
-           'summary_width']
+           'summary_width', 'CorrFactors', 'corr_factors']
 
 
 def _as_kernel_input(t):
@@ -129,6 +129,80 @@ def cross_correlation(states, actions, use_state_diff=False, time_major=False):
     assert (int(flag.item()) == 0)       # torch.isfinite(feats).all() in the reference
     print('cross_corr feats', feats.shape, feats.device)
     return feats
+
+
+class CorrFactors(object):
+    """Cross-correlation summaries in factored form.
+
+    A row of ``cross_correlation`` is ``[outer(sf, af).ravel() | mean(sf) | std(sf)]``
+    (reference summarizers.py:106-119): rank one.  This object holds only the factors,
+    ``fac [N, ldf] = [sf (s) | af (q) | mean | std | 0-pad]`` -- 4.6 KB instead of 420 KB per
+    ShadowHand trajectory -- and stands in for the ``[N, s*q+2]`` summary tensor wherever the
+    consumer is the first dense layer of an MDNN (``MDNN.run_training`` generates the summary
+    tiles inside the layer's tcgen05 GEMMs, csrc/corr_layer.cu).  ``materialize()`` gives the
+    reference's tensor, bit for bit what ``cross_correlation`` returns."""
+
+    def __init__(self, fac, s, q):
+        self.fac, self.s, self.q = fac, int(s), int(q)
+
+    @property
+    def shape(self):
+        return (self.fac.shape[0], self.s * self.q + 2)
+
+    @property
+    def device(self):
+        return self.fac.device
+
+    def __len__(self):
+        return self.fac.shape[0]
+
+    def __getitem__(self, key):
+        """Row selection only (the ordered train / test split of run_training)."""
+        if isinstance(key, tuple):
+            raise TypeError('CorrFactors supports row indexing only; call materialize()')
+        rows = self.fac[key]
+        if rows.dim() == 1:
+            rows = rows.unsqueeze(0)
+        return CorrFactors(rows, self.s, self.q)
+
+    def materialize(self):
+        sf = self.fac[:, :self.s]
+        af = self.fac[:, self.s:self.s + self.q]
+        prod = (sf.unsqueeze(2) * af.unsqueeze(1)).reshape(self.fac.shape[0], -1)
+        return torch.cat([prod, self.fac[:, self.s + self.q:self.s + self.q + 2]], dim=1)
+
+
+def corr_factors(states, actions, use_state_diff=False, time_major=False):
+    """``cross_correlation`` without the outer product: same inputs, same padding and
+    window rules (reference summarizers.py:90-105), same finiteness assertion; returns
+    ``CorrFactors``."""
+    assert (len(states.shape) == 3), 'Need states: ntraj x n_steps x state_dim'
+    assert (len(actions.shape) == 3), 'Need actions: ntraj x n_steps x state_dim'
+    if time_major:
+        traj_len, ntraj, state_dim = states.shape
+        assert actions.shape[0] >= min(traj_len, 10) and actions.shape[1] == ntraj
+        t_states, t_actions = states.shape[0], actions.shape[0]
+    else:
+        ntraj, traj_len, state_dim = states.shape
+        if actions.shape[1] < traj_len:
+            states, actions = pad_states_actions(states, actions)
+        t_states, t_actions = states.shape[1], actions.shape[1]
+    assert (traj_len > 1)
+    max_traj_len = 5 if state_dim > 50 else 10
+    w = min(traj_len, max_traj_len)
+    states, actions = _as_kernel_input(states), _as_kernel_input(actions)
+    act_dim = actions.shape[2]
+    s, q = w * (state_dim - 1), w * act_dim
+    ldf = (s + q + 2 + 3) // 4 * 4
+    fac = torch.empty((ntraj, ldf), dtype=torch.float32, device=states.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=states.device)
+    with torch.cuda.device(states.device):
+        _lib.call('bsig_corr_factors', _lib.ptr(states), _lib.ptr(actions), _lib.ptr(fac), ldf,
+                  ntraj, t_states, t_actions, state_dim, act_dim, w,
+                  1 if use_state_diff else 0, 1 if time_major else 0,
+                  _lib.ptr(flag, torch.int32), _lib.stream_ptr(states.device))
+    assert (int(flag.item()) == 0)       # torch.isfinite(feats).all() in the reference
+    return CorrFactors(fac, s, q)
 
 
 def summary_corrdiff(states, actions, time_major=False):

@@ -88,6 +88,40 @@ int bsig_summary_crosscorr_tm(const float* states, const float* actions, float* 
                               int64_t d, int64_t a, int64_t w, int use_state_diff,
                               int* nonfinite_flag, void* stream);
 
+/* ------------------------------------------------- fused cross-correlation -> first layer
+ * utils/summarizers.py:106-119 (the outer product sf (x) af and its two
+ * statistics) feeding models/mdnn.py:108 (first nn.Linear) through bayes_sim.py:108-113.
+ * The summary row x[i, p*q_n + q] = sf[i,p] * af[i,q] is rank one, so only its factors are
+ * ever stored:  fac [n, ldf] = [ sf (s = w*(d-1)) | af (q = w*a) | mean(sf) | std(sf) | 0.. ]
+ * (ldf >= s+q+2).  mean / std / the non-finite flag are exactly those of
+ * bsig_summary_crosscorr on the same rollouts. */
+int bsig_corr_factors(const float* states, const float* actions, float* fac, int64_t ldf,
+                      int64_t n, int64_t t_states, int64_t t_actions, int64_t d, int64_t a,
+                      int64_t w, int use_state_diff, int time_major, int* nonfinite_flag,
+                      void* stream);
+/* 1 if the fused first-layer kernels take this shape (minibatch `batch` <= 128 rows for the
+ * weight gradient, forward passes of up to rows_max rows, n_out <= 128,
+ * s*q + 2 < 2^20, factor rows within shared memory), else 0: the caller then materialises the
+ * summary and uses bsig_linear_*. */
+int bsig_corr_linear_applicable(int64_t batch, int64_t rows_max, int64_t n_out, int64_t s,
+                                int64_t q);
+int64_t bsig_corr_linear_ws_bytes(int64_t m, int64_t n_out, int64_t s, int64_t q);
+/* y [m, n_out] = act( x w^T + b ) with x [m, s*q+2] generated on the fly from
+ * fac[rows[i]] (rows nullable), w [n_out, s*q+2] row-major (8-byte aligned base):
+ * nn.Linear (+ Tanh) of mdnn.py:108 on the never-materialised summary.  tcgen05, TF32x3. */
+int bsig_corr_linear_fwd(const float* fac, int64_t ldf, const int64_t* rows, int64_t s,
+                         int64_t q, const float* w, const float* b, float* y, int64_t m,
+                         int64_t n_out, int act, void* ws, int64_t ws_bytes, void* stream);
+/* dw [n_out, s*q+2] = dy^T [n_out, m] x [m, s*q+2] (autograd of mdnn.py:108, weight part).
+ * exp_avg != NULL: torch.optim.Adam (mdnn.py:203,234; same arithmetic as bsig_adam_step,
+ * gradient scaled by grad_scale) is applied to w / exp_avg / exp_avg_sq in the epilogue and
+ * the gradient is only stored if dw != NULL; exp_avg == NULL: dw is stored (data-parallel
+ * exchange, external optimisers). */
+int bsig_corr_linear_wgrad(const float* dy, const float* fac, int64_t ldf, const int64_t* rows,
+                           int64_t s, int64_t q, int64_t m, int64_t n_out, float* dw, float* w,
+                           float* exp_avg, float* exp_avg_sq, int64_t step, float lr, float beta1,
+                           float beta2, float eps, float grad_scale, void* stream);
+
 /* summary_signatory (summarizers.py:144-168; arithmetic = signatory.signature):
  * path_t = [t+1 | states[i,t,:] | actions[i,t,:]], t < len; depth in {1,2,3};
  * out [n, sum_{k<=depth} c^k], c = 1+d+a, levels concatenated, each C-order.
@@ -121,6 +155,9 @@ int bsig_linear_fwd(const float* x, int64_t ldx, const int64_t* x_rows,
 int bsig_linear_dgrad(const float* dy, const float* w, const float* h_prev, float* dx,
                       int64_t m, int64_t n, int64_t k, int act_prev, int engine,
                       void* ws, int64_t ws_bytes, void* stream);
+/* db [n] = colsum(dy [m,n]): the bias gradient alone (autograd of mdnn.py:108-119), for layers
+ * whose weight gradient is formed by bsig_corr_linear_wgrad. */
+int bsig_linear_colsum(const float* dy, float* db, int64_t m, int64_t n, void* stream);
 /* dw [n,k] = dy^T [n,m] @ x [m,k] (x optionally row-gathered); db [n] = colsum(dy). */
 int bsig_linear_wgrad(const float* dy, const float* x, int64_t ldx, const int64_t* x_rows,
                       float* dw, float* db, int64_t m, int64_t n, int64_t k, int engine,

@@ -1,0 +1,3 @@
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_corr_layer.py -m gpu -q > gpurun_out/r2b_corr_tests.log 2>&1
+tail -25 gpurun_out/r2b_corr_tests.log

@@ -22,7 +22,7 @@ cfg = {'modelClass': 'MDNN', 'summarizerFxn': 'summary_corrdiff', 'trainTrajLen'
 with contextlib.redirect_stdout(io.StringIO()):
     bsim = BayesSim(cfg, task['D'], task['A'], task['P'], lows, highs, prior=None, proposal=None,
                     device=str(dev))
-    feats = bsim.summarizer_fxn(states, actions)
+    feats = bsim._training_summaries(states, actions)     # factored unless BSIG_FUSED_CORR=0
     for _ in range(2):
         logs = bsim.model.run_training(feats, params, n_updates, 100, 0.2)
 torch.cuda.synchronize()

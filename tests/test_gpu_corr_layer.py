@@ -1,0 +1,292 @@
+"""GPU parity of the fused cross-correlation -> first-layer kernels (SURVEY 8.f rank 1,
+csrc/corr_layer.cu) through the C ABI, against the CPU oracle of the reference's summarizer
+(oracle/summarizers_np.py <- utils/summarizers.py:90-130) followed by the float64 layer
+arithmetic of models/mdnn.py:108 and its autograd / torch.optim.Adam (oracle/mdn_np.adam_step).
+
+Tolerances (max-norm relative): the summary factors and the two statistics are bit-exact /
+2e-6 like the materialised summary; the TF32x3 tensor-core products carry the tolerance of
+tests/test_gpu_gemm.py (2e-5 + 4e-8*K: fp32-grade operands, truncating fp32 accumulator)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import synth_rollouts
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+# (name, D, A, T1): window / widths follow the reference's rule (5 steps when D > 50)
+TASKS = {
+    'cartpole': (4, 1, 21),          # s=30   q=10   F=302
+    'ant': (60, 8, 51),              # s=295  q=40   F=11802
+    'halfcheetah': (17, 6, 31),      # s=160  q=60   F=9602
+    'shadowhand': (211, 20, 51),     # s=1050 q=100  F=105002
+}
+
+
+def _lib():
+    from bayes_sim_ig_b200 import _lib
+    return _lib
+
+
+def _factors(task, n, seed=0, use_diff=True):
+    from bayes_sim_ig_b200.utils import summarizers as bs
+    d, a, t1 = TASKS[task]
+    states, actions = synth_rollouts(seed, n, t1, d, a)
+    cf = bs.corr_factors(states.to(DEV), actions.to(DEV), use_state_diff=use_diff)
+    return states, actions, cf
+
+
+def _oracle_x(states, actions, use_diff=True):
+    from oracle import summarizers_np as osum
+    return np.asarray(osum.cross_correlation(states.numpy(), actions.numpy(), use_diff), np.float32)
+
+
+def _rel(got, ref):
+    ref = np.asarray(ref, np.float64)
+    return float(np.abs(np.asarray(got, np.float64) - ref).max() / (np.abs(ref).max() + 1e-30))
+
+
+@pytest.mark.parametrize('task', ['cartpole', 'ant', 'halfcheetah', 'shadowhand'])
+@pytest.mark.parametrize('use_diff', [True, False])
+def test_factors_reproduce_the_materialised_summary(task, use_diff):
+    from bayes_sim_ig_b200.utils import summarizers as bs
+    n = 37 if task != 'shadowhand' else 9
+    states, actions, cf = _factors(task, n, seed=3, use_diff=use_diff)
+    x_kernel = bs.cross_correlation(states.to(DEV), actions.to(DEV), use_state_diff=use_diff)
+    assert cf.shape == tuple(x_kernel.shape)
+    # the factored form expands to exactly what the summarizer kernel stores
+    assert torch.equal(cf.materialize(), x_kernel)
+    x_ref = _oracle_x(states, actions, use_diff)
+    got = cf.materialize().cpu().numpy()
+    assert np.array_equal(got[:, :-2], x_ref[:, :-2])          # product block bit-exact
+    assert _rel(got[:, -2:], x_ref[:, -2:]) < 2e-6
+    # time-major ingestion gives the same factors
+    cf_tm = bs.corr_factors(states.to(DEV).transpose(0, 1).contiguous(),
+                            actions.to(DEV).transpose(0, 1).contiguous(),
+                            use_state_diff=use_diff, time_major=True)
+    assert torch.equal(cf_tm.fac, cf.fac)
+
+
+def test_factors_flag_non_finite_inputs_and_overflow():
+    from bayes_sim_ig_b200.utils import summarizers as bs
+    d, a, t1 = TASKS['cartpole']
+    states, actions = synth_rollouts(0, 8, t1, d, a)
+    bad = states.clone()
+    bad[3, 2, 1] = float('nan')
+    with pytest.raises(AssertionError):
+        bs.corr_factors(bad.to(DEV), actions.to(DEV), use_state_diff=True)
+    big_s, big_a = states.clone(), actions.clone()
+    big_s[5, 1, 0] = 3e30
+    big_a[5, 4, 0] = 1e10                 # finite factors, the product overflows fp32
+    with pytest.raises(AssertionError):
+        bs.corr_factors(big_s.to(DEV), big_a.to(DEV), use_state_diff=False)
+
+
+FWD_CASES = [('cartpole', 100, 128, True), ('cartpole', 7, 20, False), ('ant', 100, 128, True),
+             ('halfcheetah', 200, 64, False), ('shadowhand', 100, 128, True),
+             ('shadowhand', 200, 128, False), ('ant', 300, 31, True)]
+
+
+@pytest.mark.parametrize('task,m,n_out,gather', FWD_CASES)
+def test_fused_forward_matches_oracle_summary_times_weight(task, m, n_out, gather):
+    lib = _lib()
+    n = m + 50 if gather else m
+    states, actions, cf = _factors(task, n, seed=m + n_out)
+    f = cf.shape[1]
+    g = torch.Generator('cpu').manual_seed(f + m)
+    w = (torch.randn(n_out, f, generator=g) / np.sqrt(f)).to(DEV)
+    b = torch.randn(n_out, generator=g).to(DEV)
+    rows = torch.randint(0, n, (m,), generator=g) if gather else None
+    rows_dev = None if rows is None else rows.to(DEV)
+    assert lib.load().bsig_corr_linear_applicable(min(m, 128), m, n_out, cf.s, cf.q) == 1
+    ws = torch.empty(lib.load().bsig_corr_linear_ws_bytes(m, n_out, cf.s, cf.q) + 256,
+                     dtype=torch.uint8, device=DEV)
+    x_ref = _oracle_x(states, actions).astype(np.float64)
+    if rows is not None:
+        x_ref = x_ref[rows.numpy()]
+    pre = x_ref @ w.double().cpu().numpy().T + b.double().cpu().numpy()
+    y = torch.empty(m, n_out, device=DEV)
+    for act in (0, 1):
+        y.fill_(float('nan'))
+        lib.call('bsig_corr_linear_fwd', cf.fac.data_ptr(), cf.fac.shape[1],
+                 None if rows_dev is None else rows_dev.data_ptr(), cf.s, cf.q, w.data_ptr(),
+                 b.data_ptr(), y.data_ptr(), m, n_out, act, ws.data_ptr(), ws.numel(),
+                 lib.stream_ptr(DEV))
+        ref = np.tanh(pre) if act else pre
+        err = _rel(y.cpu().numpy(), ref)
+        assert err < 2e-5 + 4e-8 * f, (task, m, n_out, act, err)
+
+
+WG_CASES = [('cartpole', 100, 128, True), ('cartpole', 5, 20, False), ('ant', 100, 128, True),
+            ('halfcheetah', 128, 64, False), ('shadowhand', 100, 128, True), ('ant', 33, 31, True)]
+
+
+@pytest.mark.parametrize('task,m,n_out,gather', WG_CASES)
+def test_fused_weight_gradient_matches_oracle(task, m, n_out, gather):
+    lib = _lib()
+    n = m + 20 if gather else m
+    states, actions, cf = _factors(task, n, seed=2 * m + n_out)
+    f = cf.shape[1]
+    g = torch.Generator('cpu').manual_seed(f + 3 * m)
+    dy = torch.randn(m, n_out, generator=g).to(DEV)
+    rows = torch.randint(0, n, (m,), generator=g) if gather else None
+    rows_dev = None if rows is None else rows.to(DEV)
+    dw = torch.full((n_out, f), float('nan'), device=DEV)
+    lib.call('bsig_corr_linear_wgrad', dy.data_ptr(), cf.fac.data_ptr(), cf.fac.shape[1],
+             None if rows_dev is None else rows_dev.data_ptr(), cf.s, cf.q, m, n_out,
+             dw.data_ptr(), None, None, None, 1, 0.0, 0.9, 0.999, 1e-8, 1.0, lib.stream_ptr(DEV))
+    x_ref = _oracle_x(states, actions).astype(np.float64)
+    if rows is not None:
+        x_ref = x_ref[rows.numpy()]
+    ref = dy.double().cpu().numpy().T @ x_ref
+    err = _rel(dw.cpu().numpy(), ref)
+    assert err < 2e-5 + 4e-8 * m, (task, m, n_out, err)
+
+
+@pytest.mark.parametrize('task,m,n_out', [('cartpole', 100, 128), ('ant', 100, 128),
+                                          ('shadowhand', 100, 128)])
+def test_fused_adam_epilogue_matches_oracle_adam(task, m, n_out):
+    """Three updates with the optimiser applied in the weight-gradient epilogue against the
+    oracle's torch.optim.Adam restatement fed with float64 gradients."""
+    from oracle import mdn_np
+    lib = _lib()
+    states, actions, cf = _factors(task, m + 10, seed=11)
+    f = cf.shape[1]
+    g = torch.Generator('cpu').manual_seed(f)
+    w0 = (torch.randn(n_out, f, generator=g) / np.sqrt(f))
+    w = w0.clone().to(DEV)
+    ea, es = torch.zeros_like(w), torch.zeros_like(w)
+    dw = torch.empty_like(w)
+    x_all = _oracle_x(states, actions).astype(np.float64)
+    params = {'w': w0.double().numpy().copy()}
+    m_ref = {'w': np.zeros_like(params['w'])}
+    v_ref = {'w': np.zeros_like(params['w'])}
+    lr = 1e-3
+    for step in range(1, 4):
+        dy = torch.randn(m, n_out, generator=g)
+        rows = torch.randint(0, m + 10, (m,), generator=g)
+        dy_dev, rows_dev = dy.to(DEV), rows.to(DEV)
+        lib.call('bsig_corr_linear_wgrad', dy_dev.data_ptr(), cf.fac.data_ptr(), cf.fac.shape[1],
+                 rows_dev.data_ptr(), cf.s, cf.q, m, n_out, dw.data_ptr(), w.data_ptr(),
+                 ea.data_ptr(), es.data_ptr(), step, lr, 0.9, 0.999, 1e-8, 1.0,
+                 lib.stream_ptr(DEV))
+        # (1) the gradient the epilogue consumed is the oracle's gradient ...
+        g_ref = dy.double().numpy().T @ x_all[rows.numpy()]
+        g_got = dw.cpu().numpy()
+        assert _rel(g_got, g_ref) < 2e-5 + 4e-8 * m
+        # (2) ... and the optimiser arithmetic on that gradient is torch.optim.Adam's.  (Feeding
+        # the oracle its OWN float64 gradient instead would test something else: Adam divides
+        # by sqrt(v), so a parameter whose gradient is far below the fp32 rounding of the sum
+        # moves by +-lr with the sign of the rounding error -- in 13.4 M entries some do.)
+        mdn_np.adam_step(params, {'w': g_got.astype(np.float64)}, m_ref, v_ref, step, lr)
+    assert np.abs(w.cpu().numpy() - params['w']).max() < 1e-6
+    assert _rel(ea.cpu().numpy(), m_ref['w']) < 1e-5
+    # (1 - beta2 is formed in fp32 from the fp32 beta2 of the C ABI, as in bsig_adam_step:
+    # 1.0f - 0.999f = 0.00100005, 4.7e-5 above torch's double 1 - 0.999; its effect on a
+    # parameter is < 3e-8 per step)
+    assert _rel(es.cpu().numpy(), v_ref['w']) < 1e-4
+
+
+def test_shapes_outside_the_envelope_are_refused():
+    lib = _lib()
+    assert lib.load().bsig_corr_linear_applicable(100, 200, 128, 1050, 100) == 1
+    assert lib.load().bsig_corr_linear_applicable(256, 256, 128, 1050, 100) == 0   # batch > 128
+    assert lib.load().bsig_corr_linear_applicable(100, 100, 256, 1050, 100) == 0   # n_out > 128
+    assert lib.load().bsig_corr_linear_applicable(100, 100, 128, 4096, 512) == 0   # F >= 2^20
+
+
+def _oracle_training(sd0, x, y_norm, idx, noise_train, noise_test, n_train, p, k, lr):
+    """models/mdnn.py:217-241 in float64 on the materialised oracle summary."""
+    from oracle import mdn_np
+    params = {name: np.asarray(v, np.float64).copy() for name, v in sd0.items()}
+    m_ref = {name: np.zeros_like(v) for name, v in params.items()}
+    v_ref = {name: np.zeros_like(v) for name, v in params.items()}
+    x_tr, y_tr, x_te, y_te = x[:n_train], y_norm[:n_train], x[n_train:], y_norm[n_train:]
+    train, test = [], []
+    for step in range(idx.shape[0]):
+        rows = idx[step]
+        loss, grads = mdn_np.mdnn_loss_and_grads(params, x_tr[rows], y_tr[rows], noise_train[step],
+                                                 p, k)
+        mdn_np.adam_step(params, grads, m_ref, v_ref, step + 1, lr)
+        w, mu, ld, low, _ = mdn_np.mdnn_forward(params, x_te, noise_test[step], p, k)
+        train.append(float(loss))
+        test.append(float(mdn_np.mdn_loss(w, mu, ld, low, y_te)))
+    return params, train, test
+
+
+@pytest.mark.parametrize('task,hidden', [('ant', (128, 64)), ('shadowhand', (128, 128)),
+                                         ('halfcheetah', (40,))])
+def test_training_on_factored_summaries_matches_oracle(task, hidden):
+    """MDNN.run_training fed with CorrFactors (fused first layer: generated operand tiles,
+    Adam in the weight-gradient epilogue) against the float64 oracle of the reference loop on
+    the materialised summary: same minibatch rows and eps-noise, three updates, every loss.
+    Parameters: Adam moves an entry whose gradient is below the rounding of the fp32 sum by
+    +-lr with the sign of that rounding, so the first-layer weight is compared by the share of
+    entries off by more than 2e-5 (< 0.1 %) and by the hard bound 2*lr per update; all other
+    tensors by the 2e-5 max-norm bound of tests/test_gpu_mdn.py."""
+    from bayes_sim_ig.models.mdnn import MDNN
+    from bayes_sim_ig_b200.models.train_engine import run_training_captured
+    n, b, n_up, p, k, lr = 140, 100, 3, 5, 4, 1e-3
+    states, actions, cf = _factors(task, n, seed=21)
+    f = cf.shape[1]
+    rs = np.random.RandomState(5)
+    lows, highs = np.full(p, -1.0), np.full(p, 3.0)
+    y_raw = (lows + (highs - lows) * rs.rand(n, p)).astype(np.float32)
+    torch.manual_seed(3)
+    model = MDNN(f, p, lows, highs, k, False, hidden, torch.nn.Tanh, lr, device=DEV)
+    sd0 = {name: v.detach().cpu().numpy().copy() for name, v in model.state_dict().items()}
+    n_train = int(n * 0.8)
+    n_test = n - n_train
+    idx = rs.randint(0, n_train, (n_up, b))
+    noise_train = rs.rand(n_up, b, p, k).astype(np.float32)
+    noise_test = rs.rand(n_up, n_test, p, k).astype(np.float32)
+    inj = dict(idx=idx, noise_train=noise_train, noise_test=noise_test)
+    logs = run_training_captured(model, cf, torch.from_numpy(y_raw).to(DEV), n_up, b, 0.2,
+                                 use_graph=True, injected=inj)
+    plan = list(model._plans.values())[-1]
+    assert plan.corr is not None and plan.corr_adam          # the fused path is what ran
+    x = _oracle_x(states, actions).astype(np.float64)
+    y_norm = (y_raw.astype(np.float64) - lows) / (highs - lows)
+    params, train, test = _oracle_training(sd0, x, y_norm, idx, noise_train, noise_test, n_train,
+                                           p, k, lr)
+    np.testing.assert_allclose(logs['train_loss'][0], train[0], rtol=1e-5)
+    np.testing.assert_allclose(logs['train_loss'], train, rtol=1e-4)
+    np.testing.assert_allclose(logs['test_loss'], test, rtol=1e-4)
+    for name, ref in params.items():
+        diff = np.abs(model.state_dict()[name].cpu().numpy() - ref)
+        if name == 'net.fcon0.weight':
+            assert diff.max() <= 2 * lr * n_up + 1e-6
+            assert (diff > 2e-5).mean() < 1e-3, (name, (diff > 2e-5).mean())
+        else:
+            assert diff.max() <= 2e-5, (name, diff.max())
+
+
+def test_bayessim_uses_the_fused_first_layer_and_agrees_with_the_materialised_path(monkeypatch):
+    """BayesSim.run_training (reference bayes_sim.py:91-114) on Ant-shaped rollouts with
+    summary_corrdiff: the factored path (default for wide summaries) and the materialised path
+    (BSIG_FUSED_CORR=0) see the same random draws and must produce the same training curve."""
+    import contextlib
+    import io
+    from bayes_sim_ig.bayes_sim import BayesSim
+    d, a, t1 = TASKS['ant']
+    n, p = 400, 6
+    states, actions = synth_rollouts(8, n, t1, d, a, device=DEV)
+    rs = np.random.RandomState(1)
+    lows, highs = np.zeros(p), np.full(p, 2.0)
+    params = torch.from_numpy((2.0 * rs.rand(n, p)).astype(np.float32)).to(DEV)
+    cfg = {'modelClass': 'MDNN', 'summarizerFxn': 'summary_corrdiff', 'trainTrajLen': t1 - 1,
+           'components': 5, 'hiddenLayers': [128, 128], 'lr': 1e-4}
+    curves = {}
+    for fused in ('1', '0'):
+        monkeypatch.setenv('BSIG_FUSED_CORR', fused)
+        torch.manual_seed(0)
+        np.random.seed(0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            bsim = BayesSim(cfg, d, a, p, lows, highs, prior=None, proposal=None, device=DEV)
+            logs = bsim.run_training(params, states, actions)
+        plan = list(bsim.model._plans.values())[-1]
+        assert (plan.corr is not None) == (fused == '1')
+        curves[fused] = logs
+    np.testing.assert_allclose(curves['1']['train_loss'], curves['0']['train_loss'], rtol=2e-3)
+    np.testing.assert_allclose(curves['1']['test_loss'], curves['0']['test_loss'], rtol=2e-3)

@@ -21,6 +21,8 @@
 // the TF32x3 split recovers the fp32 mantissas of both operands, accumulation is fp32 in TMEM.
 #include <cuda.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -155,13 +157,20 @@ struct FwdArgs {
   int stages;              // shared-memory / tensor-memory ring depth (<= FWD_MAX_STAGES)
   int qp, npp;             // odd pitches of the staged af (wrap-extended by 32) / sf rows
   float* partial;          // [splits][M][N]
+  long long* prof;         // BSIG_CORR_PROF (profiling only): clock64 marks of CTA 0
+  int dbg;                 // BSIG_CORR_DBG (profiling only): 1 no x math, 2 no W split, 4 no MMA, 8 no W copy
 };
+
+#define CORR_MARK(slot)                                                          \
+  do {                                                                           \
+    if (g.prof != nullptr && blockIdx.x == 0 && lane == 0) g.prof[slot] = clock64(); \
+  } while (0)
 
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 corr_fwd_kernel(FwdArgs g, FastDiv divQ) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~(uintptr_t)1023);
+  // (offset arithmetic on the array keeps the shared address space: LDS / STS, not generic)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ uint64_t full_bar[FWD_MAX_STAGES], conv_bar[FWD_MAX_STAGES], empty_bar[FWD_MAX_STAGES];
   __shared__ uint64_t tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
@@ -169,6 +178,7 @@ corr_fwd_kernel(FwdArgs g, FastDiv divQ) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (g.M + BM - 1) / BM;
   const int num_items = m_tiles * g.splits;
+  if (warp == 0) CORR_MARK(0);
   auto tile_b = [&](int s) { return smem + (size_t)s * 2 * TILE_BYTES; };
   auto tile_blo = [&](int s) { return tile_b(s) + TILE_BYTES; };
   float* af_s = reinterpret_cast<float*>(smem + (size_t)STAGES * 2 * TILE_BYTES);   // [128][qp]
@@ -198,6 +208,7 @@ corr_fwd_kernel(FwdArgs g, FastDiv divQ) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_slot;
+  if (warp == 0) CORR_MARK(1);                       // set-up done
 
   if (warp < 4) {
     // ------------------------------------------------ producers: W tiles by 8-byte cp.async
@@ -210,20 +221,21 @@ corr_fwd_kernel(FwdArgs g, FastDiv divQ) {
     const uint32_t c0 = (uint32_t)((pc >> 1) ^ h);          // 16-byte chunk before the row swizzle
     const uint32_t dst_lane = (uint32_t)(warp * 32 + h) * 128u + (uint32_t)((pc & 1) << 3);
     const float* src_lane = g.w + (int64_t)(warp * 32 + h) * g.F + 2 * pc;
-    int it = 0;
+    int s = 0;
+    uint32_t ph = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const int split = item % g.splits;
       const int kb0 = split * g.kb_per_split, kb1 = min(g.num_kb, kb0 + g.kb_per_split);
-      for (int kb = kb0; kb < kb1; ++kb, ++it) {
-        const int s = it % STAGES;
+      for (int kb = kb0; kb < kb1; ++kb, ph ^= (++s == STAGES), s = (s == STAGES ? 0 : s)) {
         const int k0 = kb * BK;
         // warm L2 a few stages ahead: one 128-byte line per lane (row 32*warp + lane)
         if (kb + FWD_PREFETCH < kb1 && warp * 32 + lane < g.N)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(g.w + (int64_t)(warp * 32 + lane) * g.F +
                                                        k0 + FWD_PREFETCH * BK));
-        mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+        mbar_wait(&empty_bar[s], ph ^ 1);
         const uint32_t dst_base = smem_u32(tile_b(s)) + dst_lane;
         const bool k_ok = k0 + 2 * pc < g.F;
+        if (!(g.dbg & 8))
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const uint32_t dst = dst_base + (uint32_t)(2 * i) * 128u + ((c0 ^ (uint32_t)((2 * i) & 7)) << 4);
@@ -236,14 +248,17 @@ corr_fwd_kernel(FwdArgs g, FastDiv divQ) {
         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(
                          smem_u32(&full_bar[s]))
                      : "memory");
+        if (warp == 0 && kb == kb0) CORR_MARK(2);      // first stage issued
       }
     }
+    if (warp == 0) CORR_MARK(3);                     // all stages issued
   } else if (warp == 4) {
     // ------------------------------------------------ MMA issuer (A from tensor memory)
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
                              ((uint32_t)(BM >> 4) << 24);
-      int it = 0, tcount = 0;
+      int s = 0, tcount = 0;
+      uint32_t ph = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++tcount) {
         const int split = item % g.splits;
         const int kb0 = split * g.kb_per_split, kb1 = min(g.num_kb, kb0 + g.kb_per_split);
@@ -251,11 +266,12 @@ corr_fwd_kernel(FwdArgs g, FastDiv divQ) {
         mbar_wait(&tmem_empty_bar[buf], ((tcount >> 1) & 1) ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(&conv_bar[s], (it / STAGES) & 1);
+        for (int kb = kb0; kb < kb1; ++kb, ph ^= (++s == STAGES), s = (s == STAGES ? 0 : s)) {
+          mbar_wait(&conv_bar[s], ph);
+          if (kb == kb0) CORR_MARK(4);                 // first stage converted
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t b_hi = smem_u32(tile_b(s)), b_lo = smem_u32(tile_blo(s));
+          if (!(g.dbg & 4))
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {
             const uint32_t a_tm = tmem_base + 256u + (uint32_t)(s * 64 + k * 8);
@@ -267,6 +283,7 @@ corr_fwd_kernel(FwdArgs g, FastDiv divQ) {
           umma_commit(&empty_bar[s]);
         }
         umma_commit(&tmem_full_bar[buf]);
+        CORR_MARK(5);                                  // last MMA issued
       }
     }
   } else if (warp < 13) {
@@ -276,7 +293,8 @@ corr_fwd_kernel(FwdArgs g, FastDiv divQ) {
     const int half = (warp - 5) >> 2;           // K columns [16*half, 16*half + 16) of a block
     const int m = (warp & 3) * 32 + lane;       // row of the tile = TMEM lane of this thread
     const uint32_t SQ = (uint32_t)(g.F - 2);
-    int it = 0;
+    int s = 0;
+    uint32_t ph = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const int mt = item / g.splits, split = item - mt * g.splits;
       const int kb0 = split * g.kb_per_split, kb1 = min(g.num_kb, kb0 + g.kb_per_split);
@@ -289,47 +307,69 @@ corr_fwd_kernel(FwdArgs g, FastDiv divQ) {
       // of the K slice.  Thread pair (t, t+128) shares row t & 127; 4-byte cp.async each.
       asm volatile("bar.sync 1, 256;" ::: "memory");     // previous item fully generated
       {
-        const int r = t & 127, part = t >> 7;
-        const bool row_ok = m0 + r < g.M;
-        const int64_t src = row_ok ? (g.rows ? __ldg(g.rows + m0 + r) : (int64_t)(m0 + r)) : 0;
-        const float* frow = g.fac + src * g.ldf;
-        const uint32_t a_dst = smem_u32(af_s + r * g.qp), s_dst = smem_u32(sf_s + r * g.npp);
-        const int sz = row_ok ? 4 : 0;           // rows past the batch: zero fill
+        // generator warp gw copies rows gw, gw+8, ... (16 rows): lanes run along the feature
+        // index, so every 4-byte cp.async instruction reads one 128-byte line of a factor row;
+        // the 16 source-row indices are fetched by 16 lanes at once (one load latency)
+        const int gw = warp - 5;
         const int qx = g.Q + 32;
-        for (int q = part; q < qx; q += 2) {
-          int qs = q;
-          while (qs >= g.Q) qs -= g.Q;
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(a_dst + 4u * q),
-                       "l"(frow + g.S + qs), "r"(sz)
+        int64_t my_src = -1;
+        if (lane < 16 && m0 + gw + 8 * lane < g.M)
+          my_src = g.rows ? __ldg(g.rows + m0 + gw + 8 * lane) : (int64_t)(m0 + gw + 8 * lane);
+        // (pointer-increment loops: this warp is a single chain of dependent instructions, every
+        // instruction of address arithmetic costs ~5 cycles)
+        const int n_full = g.Q >> 5;                       // whole 32-float groups of af
+        const int q_tail = (n_full << 5) + lane;
+        const int ext_src = lane < g.Q ? lane : 0;         // (Q < 32: extension unused)
+#pragma unroll 2
+        for (int u = 0; u < 16; ++u) {
+          const int64_t src = __shfl_sync(0xffffffffu, my_src, u);
+          const int r = gw + 8 * u;
+          const int sz = src >= 0 ? 4 : 0;               // rows past the batch: zero fill
+          const float* frow = g.fac + (src >= 0 ? src : 0) * g.ldf;
+          const float* ap = frow + g.S + lane;
+          uint32_t ad = smem_u32(af_s + r * g.qp) + 4u * lane;
+          for (int i = 0; i < n_full; ++i, ap += 32, ad += 128u)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(ad), "l"(ap), "r"(sz)
+                         : "memory");
+          if (q_tail < g.Q)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(ad), "l"(ap), "r"(sz)
+                         : "memory");
+          // [Q, Q+32): the first entries again; then mean, std
+          const uint32_t xd = smem_u32(af_s + r * g.qp + g.Q) + 4u * lane;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(xd),
+                       "l"(frow + g.S + ext_src), "r"(sz)
                        : "memory");
+          if (lane < 2)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(xd + 128u),
+                         "l"(frow + g.S + g.Q + lane), "r"(sz)
+                         : "memory");
+          const float* sp = frow + p_base + lane;
+          uint32_t sd_ = smem_u32(sf_s + r * g.npp) + 4u * lane;
+          for (int c = lane; c < np; c += 32, sp += 32, sd_ += 128u)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sd_), "l"(sp), "r"(sz)
+                         : "memory");
         }
-        for (int c = part; c < np; c += 2)
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(s_dst + 4u * c),
-                       "l"(frow + p_base + c), "r"(sz)
-                       : "memory");
-      }
-      float mu = 0.f, sd = 0.f;
-      if (m0 + m < g.M) {
-        const int64_t src = g.rows ? __ldg(g.rows + m0 + m) : (int64_t)(m0 + m);
-        mu = __ldg(g.fac + src * g.ldf + g.S + g.Q);
-        sd = __ldg(g.fac + src * g.ldf + g.S + g.Q + 1);
       }
       asm volatile("cp.async.wait_all;" ::: "memory");
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (warp == 5) CORR_MARK(6);                   // factors staged
       const float* afr = af_s + m * g.qp;
+      const float mu = afr[g.Q + 32], sd = afr[g.Q + 33];
       const float* sfr = sf_s + m * g.npp;
-      for (int kb = kb0; kb < kb1; ++kb, ++it) {
-        const int s = it % STAGES;
+      for (int kb = kb0; kb < kb1; ++kb, ph ^= (++s == STAGES), s = (s == STAGES ? 0 : s)) {
         // the x tile does not depend on the W data, but its TMEM slot is only free once the
         // MMAs of the previous round have retired -- which is what let the producers refill
         // the stage, i.e. what full_bar certifies
-        mbar_wait(&full_bar[s], (it / STAGES) & 1);
+        mbar_wait(&full_bar[s], ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t k0 = (uint32_t)kb * BK + 16u * (uint32_t)half;
         const uint32_t pcur = fdiv(k0, divQ);
         const uint32_t q0 = k0 - pcur * (uint32_t)g.Q;
         uint32_t hi[16], lo[16];
-        if (g.Q >= 16 && k0 + 16 <= SQ) {
+        if (g.dbg & 1) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) hi[i] = lo[i] = 0u;
+        } else if (g.Q >= 32 && k0 + 16 <= SQ) {
           // common case: 16 products from at most two state features, no wrap in af
           const uint32_t n1 = (uint32_t)g.Q - q0;          // elements left in feature row pcur
           const float sv0 = sfr[pcur - p_base];
@@ -372,6 +412,7 @@ corr_fwd_kernel(FwdArgs g, FastDiv divQ) {
         // W tile: hi in place, lo beside it
         float4* b = reinterpret_cast<float4*>(tile_b(s));
         float4* blo = reinterpret_cast<float4*>(tile_blo(s));
+        if (!(g.dbg & 2))
 #pragma unroll
         for (int u = 0; u < TILE_BYTES / 16 / 256; ++u) {
           const int idx = t + 256 * u;
@@ -398,10 +439,13 @@ corr_fwd_kernel(FwdArgs g, FastDiv divQ) {
       const int mt = item / g.splits, split = item - mt * g.splits;
       const int buf = tcount & 1;
       mbar_wait(&tmem_full_bar[buf], (tcount >> 1) & 1);
+      if (warp == 13) CORR_MARK(7);                  // accumulator complete
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int row = mt * BM + qd * 32 + lane;
       const bool row_ok = row < g.M;
-      float* prow = g.partial + ((int64_t)split * g.M + (row_ok ? row : 0)) * g.N;
+      // partial sums are stored TRANSPOSED, [split][j][m]: the lanes of a warp hold 32
+      // consecutive rows m, so every store instruction writes one 128-byte line
+      float* pcol = g.partial + (int64_t)split * g.N * g.M + (row_ok ? row : 0);
 #pragma unroll 1
       for (int cb = 0; cb < BN / 32; ++cb) {
         if (cb * 32 >= g.N) break;
@@ -411,29 +455,72 @@ corr_fwd_kernel(FwdArgs g, FastDiv divQ) {
         BSIG_TMEM_LD32(r, taddr);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (!row_ok) continue;
+        float* pp = pcol + (int64_t)(cb * 32) * g.M;
+        if (cb * 32 + 32 <= g.N) {                       // full block: no per-element predicate
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const int j = cb * 32 + c;
-          if (j < g.N) prow[j] = __uint_as_float(r[c]);
+          for (int c = 0; c < 32; ++c, pp += g.M) *pp = __uint_as_float(r[c]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c, pp += g.M)
+            if (cb * 32 + c < g.N) *pp = __uint_as_float(r[c]);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(&tmem_empty_bar[buf]);
+      if (warp == 13) CORR_MARK(8);                  // partials stored
     }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (warp == 0) CORR_MARK(9);
   if (warp == 4) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512)
                  : "memory");
   }
 }
 
+// y[m][j] = act( sum_s partial[s][j][m] + b[j] ): fixed-order, four threads per element each
+// summing a quarter of the splits (eight loads in flight), combined through shared memory in
+// quarter order -- deterministic, and 4x the memory-level parallelism of one thread per element.
+__global__ void __launch_bounds__(256)
+corr_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ bias,
+                   float* __restrict__ y, int M, int N, int splits, int act) {
+  __shared__ float part[4][64];
+  const int el = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  const int64_t total = (int64_t)M * N;
+  const int64_t e = (int64_t)blockIdx.x * 64 + el;            // e = j * M + m
+  const int per = (splits + 3) / 4;
+  const int s0 = grp * per, s1 = min(splits, s0 + per);
+  float acc = 0.f;
+  if (e < total) {
+    int sidx = s0;
+    for (; sidx + 8 <= s1; sidx += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcg(partial + (int64_t)(sidx + u) * total + e);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc += v[u];
+    }
+    for (; sidx < s1; ++sidx) acc += __ldcg(partial + (int64_t)sidx * total + e);
+  }
+  part[grp][el] = acc;
+  __syncthreads();
+  if (grp == 0 && e < total) {
+    const float sum = ((part[0][el] + part[1][el]) + part[2][el]) + part[3][el];
+    const int j = (int)(e / M), m = (int)(e - (int64_t)j * M);
+    float v = sum + (bias != nullptr ? __ldg(bias + j) : 0.f);
+    if (act) v = tanhf(v);
+    y[(int64_t)m * N + j] = v;
+  }
+}
+
 // ------------------------------------------------------------------ weight gradient (+ Adam)
 constexpr int WG_TN = 64;                         // k columns per output tile
-constexpr int WG_EPI_WARPS = 16;
-constexpr int WG_THREADS = (5 + WG_EPI_WARPS) * 32;   // warp0 MMA, 1-4 generate, 5-20 epilogue
+constexpr int WG_EPI_WARPS = 8;
+// warp 0 MMA, warps 1-2 generate, warp 3 idle, warps 4-11 epilogue: 12 warps, because registers
+// are allocated to warps in groups of four and the epilogue wants ~150 of them per thread
+constexpr int WG_THREADS = (4 + WG_EPI_WARPS) * 32;
 constexpr int WG_STAGE_BYTES = 2 * 4 * WG_TN * 128;   // hi + lo, four [64 x 32] sub-tiles = 64 KB
 constexpr int WG_EP = 65;                         // pitch of the epilogue staging tile
 
@@ -446,7 +533,7 @@ struct WgradArgs {
   int M, N;                // batch rows (<= 128), n_out (<= 128)
   int KP;                  // M rounded up to 8
   int NP;                  // pitch of the transposed factor rows in shared memory
-  int np_max;              // sf columns a CTA can need
+  int npt;                 // sf columns one tile of WG_TN summary columns can touch
   int num_tiles;
   float* dw;               // nullable: store the gradient [N][F]
   float* w;                // Adam in the epilogue when exp_avg != nullptr
@@ -455,33 +542,33 @@ struct WgradArgs {
   float one_minus_b1, b2, one_minus_b2, step_size, inv_bc2_sqrt, eps, gscale;
 };
 
-__global__ void __launch_bounds__(WG_THREADS, 1) corr_wgrad_kernel(WgradArgs g, FastDiv divQ) {
+__global__ void __maxnreg__(168) corr_wgrad_kernel(WgradArgs g, FastDiv divQ) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~(uintptr_t)1023);
-  __shared__ uint64_t b_full[2], b_empty[2], acc_full[2], acc_empty[2];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t b_full[2], b_empty[2], acc_full[2], acc_empty[2], sf_full[2];
   __shared__ uint32_t tmem_base_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* stage_b = smem;                                               // 2 x 64 KB
   float* ep_s = reinterpret_cast<float*>(smem + 2 * WG_STAGE_BYTES);      // [128][65]
   float* afT = ep_s + 128 * WG_EP;                                        // [Q][NP]
-  float* sfT = afT + (size_t)g.Q * g.NP;                                  // [np_max][NP]
-  float* mu_s = sfT + (size_t)g.np_max * g.NP;                            // [128]
+  float* sfc = afT + (size_t)g.Q * g.NP;                                  // [2][npt][NP]
+  float* mu_s = sfc + (size_t)2 * g.npt * g.NP;                           // [128]
   float* sd_s = mu_s + 128;                                               // [128]
+  int64_t* src_s = reinterpret_cast<int64_t*>(sd_s + 128);                // [128] factor row of n
 
-  // contiguous tile range of this CTA (its sf columns are contiguous too)
-  const int t_begin = (int)(((int64_t)blockIdx.x * g.num_tiles) / gridDim.x);
-  const int t_end = (int)(((int64_t)(blockIdx.x + 1) * g.num_tiles) / gridDim.x);
+  // tiles are dealt round-robin: at any moment the CTAs work on NEIGHBOURING 256-byte segments
+  // of every weight / moment row (148 x 256 B = 37 KB contiguous per row), which is what keeps
+  // the DRAM pages open; a contiguous range per CTA scatters 57 k concurrent segments over as
+  // many pages (measured: 3.7 TB/s)
   const uint32_t SQ = (uint32_t)(g.F - 2);
-  const uint32_t k_first = (uint32_t)t_begin * WG_TN;
-  const uint32_t p_base = min(fdiv(min(k_first, SQ - 1), divQ), (uint32_t)g.S - 1);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&b_full[i], 128);
+      mbar_init(&b_full[i], 64);
       mbar_init(&b_empty[i], 1);
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], WG_EPI_WARPS * 32);
+      mbar_init(&sf_full[i], 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -498,10 +585,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) corr_wgrad_kernel(WgradArgs g, 
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_slot;
 
-  if (warp >= 1 && warp <= 4) {
-    // ---- one-off: dy^T -> tensor memory (lane = output j, column = batch row n), transposed
-    //      factor rows -> shared memory
-    const int t = threadIdx.x - 32;              // 0..127
+  if (warp >= 4 && warp < 8) {
+    // ---- one-off (epilogue warps 4-7, one per TMEM lane quadrant): dy^T -> tensor memory
+    //      (lane = output j, column = batch row n)
     const int j = (warp & 3) * 32 + lane;        // TMEM lane of this thread
     const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     for (int n0 = 0; n0 < g.KP; n0 += 32) {
@@ -527,36 +613,43 @@ __global__ void __launch_bounds__(WG_THREADS, 1) corr_wgrad_kernel(WgradArgs g, 
       }
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    // thread t stages batch row t (transposed: [feature][row]) with 4-byte cp.async
-    if (t < g.KP) {
-      const bool row_ok = t < g.M;
-      const int64_t src = row_ok ? (g.rows ? __ldg(g.rows + t) : (int64_t)t) : 0;
-      const float* frow = g.fac + src * g.ldf;
-      const int sz = row_ok ? 4 : 0;
-      const uint32_t a_dst = smem_u32(afT + t), s_dst = smem_u32(sfT + t);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  } else if (warp >= 8) {
+    // ---- one-off (epilogue warps 8-11): warp gw stages batch rows gw, gw+4, ... transposed
+    //      ([feature][row]); lanes run along the feature index so that every 4-byte cp.async
+    //      instruction reads one line
+    const int t = threadIdx.x - 8 * 32;          // 0..127
+    {
+      const int gw = warp - 8;
       const uint32_t pitch = 4u * (uint32_t)g.NP;
-      for (int q = 0; q < g.Q; ++q)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(a_dst + pitch * q),
-                     "l"(frow + g.S + q), "r"(sz)
-                     : "memory");
-      for (int c = 0; c < g.np_max; ++c) {
-        const bool ok = row_ok && p_base + c < (uint32_t)g.S;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(s_dst + pitch * c),
-                     "l"(ok ? frow + p_base + c : g.fac), "r"(ok ? 4 : 0)
-                     : "memory");
+      // lane u holds the source row of batch row gw + 4u (KP <= 128: 32 rows per warp)
+      int64_t my_src = -1;
+      if (gw + 4 * lane < g.M) my_src = g.rows ? __ldg(g.rows + gw + 4 * lane) : (int64_t)(gw + 4 * lane);
+      const int n_rows = (g.KP - gw + 3) >> 2;
+      for (int u = 0; u < n_rows; ++u) {
+        const int64_t src = __shfl_sync(0xffffffffu, my_src, u);
+        const int n = gw + 4 * u;
+        const int sz = src >= 0 ? 4 : 0;
+        const float* frow = g.fac + (src >= 0 ? src : 0) * g.ldf;
+        const float* ap = frow + g.S + lane;
+        uint32_t ad = smem_u32(afT + n) + pitch * lane;
+        for (int q = lane; q < g.Q; q += 32, ap += 32, ad += 32u * pitch)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(ad), "l"(ap), "r"(sz)
+                       : "memory");
+        if (lane == 0) src_s[n] = src;             // (-1: row of the zero padding)
+        if (lane < 2)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(
+                           smem_u32((lane == 0 ? mu_s : sd_s) + n)),
+                       "l"(frow + g.S + g.Q + lane), "r"(sz)
+                       : "memory");
       }
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(mu_s + t)),
-                   "l"(frow + g.S + g.Q), "r"(sz)
-                   : "memory");
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(sd_s + t)),
-                   "l"(frow + g.S + g.Q + 1), "r"(sz)
-                   : "memory");
-    } else {
-      mu_s[t] = 0.f;
-      sd_s[t] = 0.f;
+      if (t >= g.KP) {
+        mu_s[t] = 0.f;
+        sd_s[t] = 0.f;
+        src_s[t] = -1;
+      }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -568,7 +661,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) corr_wgrad_kernel(WgradArgs g, 
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(WG_TN >> 3) << 17) |
                              ((uint32_t)(128 >> 4) << 24);
       int it = 0;
-      for (int tile = t_begin; tile < t_end; ++tile, ++it) {
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
         const int s = it & 1;
         const uint32_t par = (it >> 1) & 1;
         mbar_wait(&acc_empty[s], par ^ 1);
@@ -588,14 +681,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) corr_wgrad_kernel(WgradArgs g, 
         umma_commit(&acc_full[s]);
       }
     }
-  } else if (warp <= 4) {
+  } else if (warp <= 2) {
     // ------------------------------------------------ generators: x^T tiles, K-major, SW128
-    const int t = threadIdx.x - 32;              // 0..127
-    const int r = t & (WG_TN - 1);               // k row of the tile owned by this thread
+    const int r = threadIdx.x - 32;              // 0..63: k row of the tile owned by this thread
     int it = 0;
-    for (int tile = t_begin; tile < t_end; ++tile, ++it) {
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
       const int s = it & 1;
       mbar_wait(&b_empty[s], ((it >> 1) & 1) ^ 1);
+      mbar_wait(&sf_full[s], (it >> 1) & 1);
+      const uint32_t p_base = min(fdiv(min((uint32_t)tile * WG_TN, SQ - 1), divQ), (uint32_t)g.S - 1);
+      const float* sfT = sfc + (size_t)s * g.npt * g.NP;
       uint8_t* hi_base = stage_b + (size_t)s * WG_STAGE_BYTES;
       uint8_t* lo_base = hi_base + WG_STAGE_BYTES / 2;
       const uint32_t k = (uint32_t)tile * WG_TN + (uint32_t)r;
@@ -606,7 +701,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) corr_wgrad_kernel(WgradArgs g, 
       const float* afp = afT + (size_t)(prod ? qk : 0) * g.NP;
       const float* tailp = k == SQ ? mu_s : sd_s;
       const bool tail = (k == SQ) || (k == SQ + 1);
-      for (int c = t >> 6; c < n_chunks; c += 2) {
+      for (int c = 0; c < n_chunks; ++c) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (prod) {
           const float4 a = *reinterpret_cast<const float4*>(afp + 4 * c);
@@ -629,76 +724,130 @@ __global__ void __launch_bounds__(WG_THREADS, 1) corr_wgrad_kernel(WgradArgs g, 
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(&b_full[s]);
     }
-  } else {
-    // ------------------------------------------------ epilogue: Adam / gradient store
-    // 16 warps: four per TMEM lane quadrant, each drains 16 of the 64 accumulator columns into
-    // the staging tile; then warp ew owns rows ew, ew+16, ... (8 rows) and lane l the column
-    // pair 2l: every row is one coalesced 256-byte access per array.  The HBM stream (read and
-    // write W, exp_avg, exp_avg_sq: 24 B per parameter) is the whole cost of the kernel, so it
-    // is kept in flight across everything else: the lines of tile t+1 are prefetched into L2
-    // while tile t is processed, and the 24 loads of a thread are issued BEFORE it waits for
-    // the accumulator and the staging barriers.
-    const int ew = warp - 5;                      // 0..15
-    const int qd = warp & 3;                      // TMEM lane quadrant
-    const int part = ew >> 2;                     // which 16 of the 64 accumulator columns
-    const int et = threadIdx.x - 5 * 32;          // 0..511
-    const bool adam = g.exp_avg != nullptr;
-    auto prefetch_tile = [&](int tile) {
-      // 128 rows x 3 arrays x 256 B (8-byte aligned: up to three 128-byte lines each)
-      if (!adam) return;
-      const int j = et >> 2, sub = et & 3;        // 4 threads per row
-      if (j >= g.N || sub == 3) return;
-      const float* base = sub == 0 ? g.w : (sub == 1 ? g.exp_avg : g.exp_avg_sq);
-      const int64_t e0 = (int64_t)j * g.F + (int64_t)tile * WG_TN;
-      const int64_t e1 = min(e0 + WG_TN, (int64_t)(j + 1) * g.F);
-      const char* p0 = reinterpret_cast<const char*>(base + e0);
-      const char* p1 = reinterpret_cast<const char*>(base + e1) - 1;
-      for (const char* q = reinterpret_cast<const char*>((uintptr_t)p0 & ~(uintptr_t)127); q <= p1;
-           q += 128)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
-    };
-    if (t_begin < t_end) prefetch_tile(t_begin);
+  } else if (warp == 3) {
+    // ------------------------------------------------ loader: the (at most npt) state-feature
+    // columns a tile touches, [column][batch row], straight from the L2-resident factor rows;
+    // runs up to two tiles ahead of the generators (its buffer is free as soon as they have
+    // finished the tile that used it: their own arrival on b_full)
     int it = 0;
-    for (int tile = t_begin; tile < t_end; ++tile, ++it) {
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
       const int s = it & 1;
-      if (tile + 1 < t_end) prefetch_tile(tile + 1);
-      const int64_t kcol = (int64_t)tile * WG_TN + 2 * lane;
-      const bool col_ok = kcol < g.F;
-      float2 pw[8], pm[8], pv[8];
-      if (adam && col_ok) {
+      if (it >= 2) mbar_wait(&b_full[s], ((it >> 1) & 1) ^ 1);
+      const uint32_t p_base = min(fdiv(min((uint32_t)tile * WG_TN, SQ - 1), divQ), (uint32_t)g.S - 1);
+      float* dst = sfc + (size_t)s * g.npt * g.NP;
+      // eight loads in flight per lane (the shared-memory stores would otherwise serialise
+      // them: the compiler must assume dst aliases src_s)
+      const int per_col = (g.KP + 31) >> 5, total = g.npt * per_col;
+      for (int e0 = 0; e0 < total; e0 += 8) {
+        float v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          const int j = ew + 16 * u;
-          if (j < g.N) {
-            const int64_t e = (int64_t)j * g.F + kcol;
-            pw[u] = *reinterpret_cast<const float2*>(g.w + e);
-            pm[u] = *reinterpret_cast<const float2*>(g.exp_avg + e);
-            pv[u] = *reinterpret_cast<const float2*>(g.exp_avg_sq + e);
+          const int e = e0 + u;
+          const int c = e / per_col, n = (e - c * per_col) * 32 + lane;
+          v[u] = 0.f;
+          if (e < total && n < g.KP && p_base + c < (uint32_t)g.S) {
+            const int64_t src = src_s[n];
+            if (src >= 0) v[u] = __ldg(g.fac + src * g.ldf + p_base + c);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = e0 + u;
+          const int c = e / per_col, n = (e - c * per_col) * 32 + lane;
+          if (e < total && n < g.KP) dst[c * g.NP + n] = v[u];
+        }
+      }
+      mbar_arrive(&sf_full[s]);
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------ epilogue: Adam / gradient store
+    // 8 warps: two per TMEM lane quadrant, each drains 32 of the 64 accumulator columns into
+    // the staging tile; then warp ew owns rows ew, ew+8, ... (16 rows) and lane l the column
+    // pair 2l: every row is one coalesced 256-byte access per array.  The HBM stream (read and
+    // write W, exp_avg, exp_avg_sq: 24 B per parameter) is the whole cost of the kernel: a
+    // thread issues the 48 loads of its 16 rows (96 registers -- the reason for only 13 warps
+    // per CTA) BEFORE it waits for the accumulator and the staging barriers, so ~100 KB per SM
+    // are in flight while the tensor core and the generators work on the next tile.
+    const int ew = warp - 4;                      // 0..7
+    const int qd = warp & 3;                      // TMEM lane quadrant
+    const int part = ew >> 2;                     // which 32 of the 64 accumulator columns
+    const bool adam = g.exp_avg != nullptr;
+    // L2 prefetch of a later tile's lines of W / exp_avg / exp_avg_sq (256 B per row and array,
+    // 8-byte aligned: up to three 128-byte lines; thread pair (2j, 2j+1) covers row j), so that
+    // the demand loads below find their lines in L2 instead of paying the DRAM latency
+    const int et = threadIdx.x - 4 * 32;          // 0..255
+    auto prefetch_tile = [&](int tile) {
+      const int j = et >> 1;
+      const int64_t k0 = (int64_t)tile * WG_TN;
+      if (!adam || tile >= g.num_tiles || j >= g.N || k0 >= g.F) return;
+      const int64_t e = (int64_t)j * g.F + k0;
+      const int64_t bytes = 4 * min((int64_t)WG_TN, (int64_t)g.F - k0);
+      if (et & 1) {
+        const char* p0 = reinterpret_cast<const char*>(g.exp_avg_sq + e);
+        for (const char* q = reinterpret_cast<const char*>((uintptr_t)p0 & ~(uintptr_t)127);
+             q < p0 + bytes; q += 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+      } else {
+        const char* p0 = reinterpret_cast<const char*>(g.w + e);
+        const char* p1 = reinterpret_cast<const char*>(g.exp_avg + e);
+        for (const char* q = reinterpret_cast<const char*>((uintptr_t)p0 & ~(uintptr_t)127);
+             q < p0 + bytes; q += 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+        for (const char* q = reinterpret_cast<const char*>((uintptr_t)p1 & ~(uintptr_t)127);
+             q < p1 + bytes; q += 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+      }
+    };
+    prefetch_tile(blockIdx.x);
+    prefetch_tile(blockIdx.x + gridDim.x);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+      const int s = it & 1;
+      prefetch_tile(tile + 2 * gridDim.x);
+      const int64_t kcol = (int64_t)tile * WG_TN + 2 * lane;
+      const bool col_ok = kcol < g.F;
+      float2 pw[16], pm[16], pv[16];
+      if (adam && col_ok) {
+        const float* wp = g.w + (int64_t)ew * g.F + kcol;
+        const float* mp = g.exp_avg + (int64_t)ew * g.F + kcol;
+        const float* vp = g.exp_avg_sq + (int64_t)ew * g.F + kcol;
+        const int64_t step8 = 8 * (int64_t)g.F;
+#pragma unroll
+        for (int u = 0; u < 16; ++u, wp += step8, mp += step8, vp += step8) {
+          if (ew + 8 * u < g.N) {
+            pw[u] = *reinterpret_cast<const float2*>(wp);
+            pm[u] = *reinterpret_cast<const float2*>(mp);
+            pv[u] = *reinterpret_cast<const float2*>(vp);
           }
         }
       }
       mbar_wait(&acc_full[s], (it >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      uint32_t r[16];
-      const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + 256u +
-                             (uint32_t)(s * WG_TN + part * 16);
-      BSIG_TMEM_LD16(r, taddr);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(&acc_empty[s]);
-      asm volatile("bar.sync 1, 512;" ::: "memory");    // previous tile's staging fully consumed
-      float* erow = ep_s + (qd * 32 + lane) * WG_EP + part * 16;
+      {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + 256u +
+                               (uint32_t)(s * WG_TN + part * 32);
+        BSIG_TMEM_LD32(r, taddr);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(&acc_empty[s]);
+        asm volatile("bar.sync 1, 256;" ::: "memory");    // previous tile's staging fully consumed
+        float* erow = ep_s + (qd * 32 + lane) * WG_EP + part * 32;
 #pragma unroll
-      for (int c = 0; c < 16; ++c) erow[c] = __uint_as_float(r[c]);
-      asm volatile("bar.sync 1, 512;" ::: "memory");
+        for (int c = 0; c < 32; ++c) erow[c] = __uint_as_float(r[c]);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (col_ok) {
+        const float* gs = ep_s + ew * WG_EP + 2 * lane;
         if (adam) {
+          float* wp = g.w + (int64_t)ew * g.F + kcol;
+          float* mp = g.exp_avg + (int64_t)ew * g.F + kcol;
+          float* vp = g.exp_avg_sq + (int64_t)ew * g.F + kcol;
+          float* dp = g.dw != nullptr ? g.dw + (int64_t)ew * g.F + kcol : nullptr;
+          const int64_t step8 = 8 * (int64_t)g.F;
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int j = ew + 16 * u;
-            if (j < g.N) {
-              const int64_t e = (int64_t)j * g.F + kcol;
-              const float* gs = ep_s + j * WG_EP + 2 * lane;
+          for (int u = 0; u < 16; ++u, gs += 8 * WG_EP, wp += step8, mp += step8, vp += step8) {
+            if (ew + 8 * u < g.N) {
               auto upd = [&](float& pp, float gg, float& mm, float& vv) {
                 gg *= g.gscale;
                 mm = mm + (gg - mm) * g.one_minus_b1;
@@ -709,17 +858,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) corr_wgrad_kernel(WgradArgs g, 
               const float g0 = gs[0], g1 = gs[1];
               upd(pw[u].x, g0, pm[u].x, pv[u].x);
               upd(pw[u].y, g1, pm[u].y, pv[u].y);
-              *reinterpret_cast<float2*>(g.w + e) = pw[u];
-              *reinterpret_cast<float2*>(g.exp_avg + e) = pm[u];
-              *reinterpret_cast<float2*>(g.exp_avg_sq + e) = pv[u];
-              if (g.dw != nullptr) *reinterpret_cast<float2*>(g.dw + e) = make_float2(g0, g1);
+              *reinterpret_cast<float2*>(wp) = pw[u];
+              *reinterpret_cast<float2*>(mp) = pm[u];
+              *reinterpret_cast<float2*>(vp) = pv[u];
+              if (dp != nullptr) *reinterpret_cast<float2*>(dp + u * step8) = make_float2(g0, g1);
             }
           }
         } else {
-          for (int j = ew; j < g.N; j += WG_EPI_WARPS) {
-            const float* gs = ep_s + j * WG_EP + 2 * lane;
-            *reinterpret_cast<float2*>(g.dw + (int64_t)j * g.F + kcol) = make_float2(gs[0], gs[1]);
-          }
+          float* dp = g.dw + (int64_t)ew * g.F + kcol;
+          const int64_t step8 = 8 * (int64_t)g.F;
+          for (int j = ew; j < g.N; j += WG_EPI_WARPS, gs += 8 * WG_EP, dp += step8)
+            *reinterpret_cast<float2*>(dp) = make_float2(gs[0], gs[1]);
         }
       }
     }
@@ -749,7 +898,7 @@ static FwdPlan plan_fwd(int64_t m, int64_t n_out, int64_t s, int64_t q) {
   int64_t splits = std::max<int64_t>(1, std::min<int64_t>(p.num_kb, sm_count() / m_tiles));
   p.kb_per_split = (int)ceil_div(p.num_kb, splits);
   p.splits = (int)ceil_div(p.num_kb, p.kb_per_split);
-  p.qp = (int)((q + 32) | 1);
+  p.qp = (int)((q + 34) | 1);          // af + 32 wrap entries + mean, std
   const int64_t np = ((int64_t)p.kb_per_split * BK) / q + 2;
   p.npp = (int)(np | 1);
   const size_t factors = (size_t)BM * (p.qp + p.npp) * 4;
@@ -767,7 +916,7 @@ static FwdPlan plan_fwd(int64_t m, int64_t n_out, int64_t s, int64_t q) {
 
 struct WgPlan {
   bool ok;
-  int KP, NP, np_max, num_tiles, grid;
+  int KP, NP, npt, num_tiles, grid;
   size_t smem;
 };
 
@@ -779,10 +928,9 @@ static WgPlan plan_wgrad(int64_t m, int64_t n_out, int64_t s, int64_t q) {
   p.NP = p.KP + 4;
   p.num_tiles = (int)ceil_div(F, WG_TN);
   p.grid = (int)std::min<int64_t>(p.num_tiles, sm_count());
-  const int64_t tiles_per_cta = ceil_div(p.num_tiles, p.grid);
-  p.np_max = (int)((tiles_per_cta * WG_TN) / q + 2);
+  p.npt = (int)((WG_TN - 1) / q + 2);
   p.smem = (size_t)2 * WG_STAGE_BYTES + (size_t)128 * WG_EP * 4 +
-           (size_t)(q + p.np_max) * p.NP * 4 + 2 * 128 * 4 + 1024;
+           (size_t)(q + 2 * p.npt) * p.NP * 4 + 2 * 128 * 4 + 128 * 8 + 1024;
   p.ok = p.smem <= 225 * 1024;
   return p;
 }
@@ -854,6 +1002,14 @@ extern "C" int bsig_corr_linear_fwd(const float* fac, int64_t ldf, const int64_t
   g.M = (int)m; g.N = (int)n_out;
   g.splits = p.splits; g.kb_per_split = p.kb_per_split; g.num_kb = p.num_kb; g.stages = p.stages;
   g.qp = p.qp; g.npp = p.npp;
+  { const char* e = getenv("BSIG_CORR_DBG"); g.dbg = e ? atoi(e) : 0; }
+  static long long* prof_dev = nullptr;
+  g.prof = nullptr;
+  if (getenv("BSIG_CORR_PROF") != nullptr) {
+    if (prof_dev == nullptr) BSIG_CUDA(cudaMalloc(&prof_dev, 16 * sizeof(long long)));
+    BSIG_CUDA(cudaMemset(prof_dev, 0, 16 * sizeof(long long)));
+    g.prof = prof_dev;
+  }
   g.partial = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
   const int64_t items = ceil_div(m, BM) * p.splits;
   BSIG_CUDA(cudaFuncSetAttribute(corr_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -861,12 +1017,20 @@ extern "C" int bsig_corr_linear_fwd(const float* fac, int64_t ldf, const int64_t
   corr_fwd_kernel<<<(unsigned)std::min<int64_t>(items, sm_count()), FWD_THREADS, p.smem,
                     (cudaStream_t)stream>>>(g, mk_div((uint64_t)q));
   BSIG_LAUNCH_CHECK();
-  GemmArgs r2 = gemm_args_zero();
-  r2.C = y; r2.ldc = n_out; r2.M = (int)m; r2.N = (int)n_out; r2.K = (int)F;
-  r2.bias = b;
-  r2.epi = b == nullptr ? EPI_STORE : (act == BSIG_ACT_TANH ? EPI_BIAS_TANH : EPI_BIAS);
-  r2.partial = g.partial;
-  return gemm_splitk_reduce(r2, p.splits, (cudaStream_t)stream);
+  if (g.prof != nullptr) {
+    long long h[16];
+    BSIG_CUDA(cudaDeviceSynchronize());
+    BSIG_CUDA(cudaMemcpy(h, prof_dev, sizeof(h), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "corr_fwd CTA0 cycles since start: setup %lld  first-issue %lld  all-issued %lld  "
+            "staged %lld  first-converted %lld  last-mma %lld  acc-complete %lld  stored %lld  end %lld\n",
+            h[1] - h[0], h[2] - h[0], h[3] - h[0], h[6] - h[0], h[4] - h[0], h[5] - h[0], h[7] - h[0],
+            h[8] - h[0], h[9] - h[0]);
+  }
+  const int64_t total = m * n_out;
+  corr_reduce_kernel<<<(unsigned)ceil_div(total, 64), 256, 0, (cudaStream_t)stream>>>(
+      g.partial, b, y, (int)m, (int)n_out, p.splits, act == BSIG_ACT_TANH ? 1 : 0);
+  BSIG_LAUNCH_CHECK();
+  return 0;
 }
 
 extern "C" int bsig_corr_linear_wgrad(const float* dy, const float* fac, int64_t ldf,
@@ -887,7 +1051,7 @@ extern "C" int bsig_corr_linear_wgrad(const float* dy, const float* fac, int64_t
   WgradArgs g;
   g.dy = dy; g.fac = fac; g.ldf = ldf; g.rows = rows;
   g.S = (int)s; g.Q = (int)q; g.F = (int)(s * q + 2);
-  g.M = (int)m; g.N = (int)n_out; g.KP = p.KP; g.NP = p.NP; g.np_max = p.np_max;
+  g.M = (int)m; g.N = (int)n_out; g.KP = p.KP; g.NP = p.NP; g.npt = p.npt;
   g.num_tiles = p.num_tiles;
   g.dw = dw; g.w = w; g.exp_avg = exp_avg; g.exp_avg_sq = exp_avg_sq;
   const double bc1 = 1.0 - pow((double)beta1, (double)(adam ? step : 1));

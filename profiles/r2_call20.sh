@@ -1,0 +1,6 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_corr_layer.py tests/test_gpu_gemm.py -m gpu -q -x > gpurun_out/r2b_corr_tests.log 2>&1
+tail -5 gpurun_out/r2b_corr_tests.log
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2b_shadowhand_launches2.csv python profiles/shadowhand_step.py 4 > gpurun_out/r2b_sh.log 2>&1; tail -2 gpurun_out/r2b_sh.log
+python profiles/summarize_launches.py gpurun_out/r2b_shadowhand_launches2.csv 2>&1 | head -5
+timeout 600 python profiles/rooflines_only.py 2>&1 | grep rff

@@ -328,6 +328,9 @@ __device__ __forceinline__ float cluster_sum(cg::cluster_group& cluster, float* 
   return *bcast;
 }
 
+// (SFU transcendentals -- ex2 / lg2 / rcp.approx, <= 2 ulp -- as in the streaming kernel: the
+// minibatch step is a chain of dependent instructions and the full-precision expf / logf /
+// division sequences were a third of them)
 // Small-batch form (B*GW <= 8*512 lanes, i.e. the reference's minibatch of 100
 // and its 200-row test split): exp-sum, NLL forward/backward, eps-term fix-up and
 // the loss in ONE launch.  The CTAs form a single thread-block cluster; the three
@@ -438,7 +441,7 @@ __global__ void __launch_bounds__(512) nll_small_kernel(NllArgs a) {
   bool bad = false;
 #pragma unroll
   for (int ii = 0; ii < PLMAX; ++ii) {
-    e[ii] = expf(e[ii]);
+    e[ii] = xexp<true>(e[ii]);
     if (ok && ii * PS + ph < P) esum += e[ii];
   }
   esum = block_sum(esum, scratch);
@@ -450,7 +453,7 @@ __global__ void __launch_bounds__(512) nll_small_kernel(NllArgs a) {
   // ---- mixture weights: softmax -> clamp -> renormalise (every p-half computes
   // the same values; xor offsets < GW stay inside one p-half)
   float mx = group_max<GW>(zpi);
-  float soft = (zpi == -INFINITY) ? 0.f : expf(zpi - mx);
+  float soft = (zpi == -INFINITY) ? 0.f : xexp<true>(zpi - mx);
   const float sm = group_sum<GW>(soft);
   soft = soft / sm;
   float w = (k < K) ? fminf(fmaxf(soft, kMinWeight), 1.0f) : 0.f;
@@ -465,9 +468,9 @@ __global__ void __launch_bounds__(512) nll_small_kernel(NllArgs a) {
     if (ii * PS + ph < P) {
       const float ldv = e[ii] + nz[ii] * eps;
       bad |= ok && !(finite_f(ldv) && finite_f(zi[ii]));
-      zi[ii] = zi[ii] / ldv;               // z = (y - mu) / L_d
+      zi[ii] = xdiv<true>(zi[ii], ldv);    // z = (y - mu) / L_d
       quad += zi[ii] * zi[ii];
-      logdet += logf(ldv);
+      logdet += xlog<true>(ldv);
     }
   }
 #pragma unroll
@@ -478,16 +481,16 @@ __global__ void __launch_bounds__(512) nll_small_kernel(NllArgs a) {
   const float gj = -0.5f * ((float)P * kLog2Pi + quad) - logdet;
   bad |= ok && !(finite_f(gj) && finite_f(w));
   const float wc = fminf(fmaxf(w, kMinWeight), 1.0f);
-  const float rk = ok ? fminf(fmaxf(gj, -kLLLimit), kLLLimit) + logf(wc) : -INFINITY;
+  const float rk = ok ? fminf(fmaxf(gj, -kLLLimit), kLLLimit) + xlog<true>(wc) : -INFINITY;
   mx = group_max<GW>(rk);
-  const float se = group_sum<GW>(rk == -INFINITY ? 0.f : expf(rk - mx));
-  const float lse = mx + logf(se);
+  const float se = group_sum<GW>(rk == -INFINITY ? 0.f : xexp<true>(rk - mx));
+  const float lse = mx + xlog<true>(se);
   float loss_acc = (b < B && lane_s == 0) ? -lse : 0.f;
   if (bad) atomicOr(a.flag, 1);
 
   float s_acc = 0.f;
   if (BWD) {
-    const float coef = ok ? -expf(rk - lse) / (float)B : 0.f;
+    const float coef = ok ? -xexp<true>(rk - lse) / (float)B : 0.f;
     const bool in_w = (w >= kMinWeight) && (w <= 1.0f);
     const float dw = (ok && in_w) ? coef / wc : 0.f;
     const float t1 = group_sum<GW>(dw * w);
@@ -501,7 +504,7 @@ __global__ void __launch_bounds__(512) nll_small_kernel(NllArgs a) {
       const int i = ii * PS + ph;
       if (i < P) {
         const float ldv = e[ii] + nz[ii] * eps;
-        const float inv = 1.0f / ldv;
+        const float inv = xdiv<true>(1.0f, ldv);
         const float vi = zi[ii] * inv;
         const float dld = cg * (vi * zi[ii] - inv);
         if (ok) a.d_mu[bb * a.ldo_mu + i * K + k] = cg * vi;

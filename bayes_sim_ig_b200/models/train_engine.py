@@ -629,7 +629,18 @@ def run_training_captured(model, x_data, y_data, n_updates, batch_size, test_fra
             plan.replay_dp()
             _REPLAYED[0] += int(getattr(plan, 'launches_per_replay', 0))
         elif use_graph:
-            if plan.graph is None:
+            fresh = plan.graph is None
+            if dp and plan.p2p is not None:
+                # warm_up() runs one extra fused exchange (it advances the device-side epoch)
+                # and a barrier, and plan keys contain the RANK-LOCAL split sizes: with uneven
+                # shards one rank can meet a new shape while its peers replay a cached plan.
+                # The decision is therefore collective: if any rank warms up, all of them do.
+                need = torch.tensor([1 if fresh else 0], dtype=torch.int32, device=dev)
+                torch.distributed.all_reduce(need, op=torch.distributed.ReduceOp.MAX,
+                                             group=getattr(model, '_dp_group', None))
+                if int(need.item()) and not fresh:
+                    plan.warm_up()
+            if fresh:
                 plan.warm_up()
                 before = _lib.load().bsig_launch_count()
                 plan.capture()

@@ -380,6 +380,52 @@ def kernel_rooflines(dev, flush, peak_gbs, peak_src):
         _lib.call('bsig_adam_step', pr.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), cnt, 1,
                   1e-4, 0.9, 0.999, 1e-8, 1.0, st())
     entry('adam_13.5M', 28 * cnt, time_kernel(adam, flush), 'flat fp32 buffer of %d params' % cnt)
+    del pr, g, m, v
+    # fused cross-correlation -> first layer (csrc/corr_layer.cu) at the
+    # ShadowHand shape: minibatch 100, s = 1050, q = 100 (F = 105002), 128 hidden units.  The
+    # summary rows are generated inside the GEMMs; what has to move is the weight (forward:
+    # 4 B/param read) and weight + both Adam moments (weight gradient + optimiser: 24 B/param).
+    cs, cq, mb, nh0 = 1050, 100, 100, 128
+    fdim = cs * cq + 2
+    ldf = (cs + cq + 2 + 3) // 4 * 4
+    fac = torch.randn(800, ldf, device=dev)
+    rows = torch.randint(0, 800, (mb,), device=dev)
+    w0 = torch.randn(nh0, fdim, device=dev) / 300.0
+    b0 = torch.zeros(nh0, device=dev)
+    y0 = torch.empty(mb, nh0, device=dev)
+    dy0 = torch.randn(mb, nh0, device=dev)
+    ea, es = torch.zeros_like(w0), torch.zeros_like(w0)
+    wsc = torch.empty(_lib.load().bsig_corr_linear_ws_bytes(mb, nh0, cs, cq) + 256, dtype=torch.uint8,
+                      device=dev)
+    step_no = [0]
+
+    def warm_small():          # what the training step keeps L2-resident between kernels
+        fac.sum(); dy0.sum(); rows.sum()
+
+    def corr_fwd():
+        _lib.call('bsig_corr_linear_fwd', fac.data_ptr(), ldf, rows.data_ptr(), cs, cq, w0.data_ptr(),
+                  b0.data_ptr(), y0.data_ptr(), mb, nh0, 1, wsc.data_ptr(), wsc.numel(), st())
+
+    def corr_wgrad():
+        step_no[0] += 1
+        _lib.call('bsig_corr_linear_wgrad', dy0.data_ptr(), fac.data_ptr(), ldf, rows.data_ptr(), cs,
+                  cq, mb, nh0, None, w0.data_ptr(), ea.data_ptr(), es.data_ptr(), step_no[0], 1e-4,
+                  0.9, 0.999, 1e-8, 1.0, st())
+
+    def flush_keep_small():
+        flush()
+        warm_small()
+    shape = 'minibatch 100 of ShadowHand factors (s=1050, q=100, F=%d), 128 outputs' % fdim
+    traffic['corr_fused_first_layer_fwd'] = 56.2e6
+    traffic['corr_fused_first_layer_wgrad_adam'] = 278.7e6
+    entry('corr_fused_first_layer_fwd', 4 * (nh0 * fdim + mb * (cs + cq + 2) + mb * nh0),
+          time_kernel(corr_fwd, flush_keep_small), shape + ': generated x tiles (TMEM) x W by cp.async, '
+          'tcgen05 TF32x3 split-K + reduce (2 launches)')
+    entry('corr_fused_first_layer_wgrad_adam', 24 * nh0 * fdim + 4 * mb * (nh0 + cs + cq + 2),
+          time_kernel(corr_wgrad, flush_keep_small), shape + ': dW on tcgen05 from generated x^T tiles, '
+          'Adam of W / exp_avg / exp_avg_sq in the epilogue (1 launch, the gradient never reaches HBM)')
+    for key in ('corr_fused_first_layer_fwd', 'corr_fused_first_layer_wgrad_adam'):
+        out[key]['tflops'] = round(2.0 * mb * nh0 * fdim / (out[key]['ms'] * 1e-3) / 1e12, 2)
     return out
 
 
@@ -545,12 +591,31 @@ def extra_shadowhand(dev):
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
     n_par = int(bsim.model.flat_params.numel())
+    fused = any(getattr(pl, 'corr', None) is not None for pl in bsim.model._plans.values())
+    # the same call with the summary materialised ([1000, 105002] fp32 = 420 MB) and the generic
+    # tcgen05 layer GEMMs + flat Adam: what the fused first layer replaces
+    os.environ['BSIG_FUSED_CORR'] = '0'
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            bsim2 = BayesSim(cfg, task['D'], task['A'], task['P'], lows, highs, prior=None,
+                             proposal=None, device=str(dev))
+            bsim2.run_training(params, states, actions)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            bsim2.run_training(params, states, actions)
+            torch.cuda.synchronize()
+            dt_mat = time.perf_counter() - t0
+        del bsim2
+    finally:
+        os.environ.pop('BSIG_FUSED_CORR', None)
     res = {'shadowhand_corrdiff_mdnn_1k': {
         'config': 'configs[3] (one GPU, one reference-sized call): ShadowHand-shaped 1000 '
                   'trajectories, summary_corrdiff(F=105002) + MDNN[128,128] K=10, 100 Adam updates x '
                   'minibatch 100 + 6 test evals',
         'fit_trajectories_per_s': n / dt, 'seconds': dt, 'parameters': n_par,
-        'ms_per_update': 1e3 * dt / 100, 'final_test_loss': logs['test_loss'][-1]}}
+        'ms_per_update': 1e3 * dt / 100, 'final_test_loss': logs['test_loss'][-1],
+        'fused_corr_first_layer': bool(fused),
+        'ms_per_update_materialised_summary': 1e3 * dt_mat / 100}}
     del bsim, states, actions, params
     torch.cuda.empty_cache()
     return res

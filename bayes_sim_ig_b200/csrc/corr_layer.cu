@@ -848,12 +848,18 @@ __global__ void __maxnreg__(168) corr_wgrad_kernel(WgradArgs g, FastDiv divQ) {
 #pragma unroll
           for (int u = 0; u < 16; ++u, gs += 8 * WG_EP, wp += step8, mp += step8, vp += step8) {
             if (ew + 8 * u < g.N) {
+              // (SFU square root and reciprocal, <= 2 ulp each: the epilogue is instruction-
+              // bound -- 16 rows x 2 elements per thread and tile -- and the IEEE sequences of
+              // sqrtf and the division were half of its instructions; the difference to
+              // bsig_adam_step's arithmetic is ~2e-7 of an lr-sized step)
               auto upd = [&](float& pp, float gg, float& mm, float& vv) {
                 gg *= g.gscale;
                 mm = mm + (gg - mm) * g.one_minus_b1;
                 vv = vv * g.b2 + g.one_minus_b2 * gg * gg;
-                const float denom = sqrtf(vv) * g.inv_bc2_sqrt + g.eps;
-                pp = pp - g.step_size * (mm / denom);
+                float sq;
+                asm("sqrt.approx.f32 %0, %1;" : "=f"(sq) : "f"(vv));
+                const float denom = sq * g.inv_bc2_sqrt + g.eps;
+                pp = pp - g.step_size * __fdividef(mm, denom);
               };
               const float g0 = gs[0], g1 = gs[1];
               upd(pw[u].x, g0, pm[u].x, pv[u].x);

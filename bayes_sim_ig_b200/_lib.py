@@ -52,6 +52,8 @@ SIGNATURES = {
     'bsig_corr_linear_ws_bytes': (_i64, [_i64] * 4),
     'bsig_corr_linear_fwd': (_int, [_c_ptr, _i64, _c_ptr, _i64, _i64, _c_ptr, _c_ptr, _c_ptr, _i64,
                                     _i64, _int, _c_ptr, _i64, _c_ptr]),
+    'bsig_corr_rff_features': (_int, [_c_ptr, _i64, _c_ptr, _i64, _i64, _c_ptr, _c_ptr, _i64, _i64,
+                                      _f32, _c_ptr, _i64, _c_ptr]),
     'bsig_corr_linear_wgrad': (_int, [_c_ptr, _c_ptr, _i64, _c_ptr, _i64, _i64, _i64, _i64,
                                       _c_ptr, _c_ptr, _c_ptr, _c_ptr, _i64, _f32, _f32, _f32,
                                       _f32, _f32, _c_ptr]),

@@ -94,9 +94,10 @@ class BayesSim(object):
 
     def _training_summaries(self, states, actions):
         name = self.summarizer_fxn.__name__
+        width = getattr(self.model, 'raw_input_dim', self.model.input_dim)
         fused = (name in ('summary_corr', 'summary_corrdiff', 'cross_correlation') and
-                 type(self.model) is MDNN and self.model.net is not None and
-                 self.model.input_dim >= self.FUSED_CORR_MIN_WIDTH and
+                 ((type(self.model) is MDNN and self.model.net is not None) or
+                  type(self.model) is MDRFF) and width >= self.FUSED_CORR_MIN_WIDTH and
                  os.environ.get('BSIG_FUSED_CORR', '1') != '0')
         if not fused:
             return self.summarizer_fxn(states, actions)

@@ -483,9 +483,11 @@ corr_fwd_kernel(FwdArgs g, FastDiv divQ) {
 // y[m][j] = act( sum_s partial[s][j][m] + b[j] ): fixed-order, four threads per element each
 // summing a quarter of the splits (eight loads in flight), combined through shared memory in
 // quarter order -- deterministic, and 4x the memory-level parallelism of one thread per element.
+// act: 0 none, 1 tanh, 2 random Fourier features: y[m][j] = scale cos(sum), y[m][N + j] =
+// scale sin(sum) (models/rff.py:128-132; full-precision sincosf, as the SIMT engine).
 __global__ void __launch_bounds__(256)
 corr_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ bias,
-                   float* __restrict__ y, int M, int N, int splits, int act) {
+                   float* __restrict__ y, int M, int N, int splits, int act, float scale) {
   __shared__ float part[4][64];
   const int el = threadIdx.x & 63, grp = threadIdx.x >> 6;
   const int64_t total = (int64_t)M * N;
@@ -510,8 +512,15 @@ corr_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ 
     const float sum = ((part[0][el] + part[1][el]) + part[2][el]) + part[3][el];
     const int j = (int)(e / M), m = (int)(e - (int64_t)j * M);
     float v = sum + (bias != nullptr ? __ldg(bias + j) : 0.f);
-    if (act) v = tanhf(v);
-    y[(int64_t)m * N + j] = v;
+    if (act == 2) {
+      float sn, co;
+      sincosf(v, &sn, &co);
+      y[(int64_t)m * 2 * N + j] = scale * co;
+      y[(int64_t)m * 2 * N + N + j] = scale * sn;
+    } else {
+      if (act == 1) v = tanhf(v);
+      y[(int64_t)m * N + j] = v;
+    }
   }
 }
 
@@ -989,16 +998,15 @@ extern "C" int64_t bsig_corr_linear_ws_bytes(int64_t m, int64_t n_out, int64_t s
   return (int64_t)p.splits * m * n_out * 4 + 1024;
 }
 
-extern "C" int bsig_corr_linear_fwd(const float* fac, int64_t ldf, const int64_t* rows, int64_t s,
-                                    int64_t q, const float* w, const float* b, float* y, int64_t m,
-                                    int64_t n_out, int act, void* ws, int64_t ws_bytes,
-                                    void* stream) {
+static int corr_fwd_impl(const float* fac, int64_t ldf, const int64_t* rows, int64_t s, int64_t q,
+                         const float* w, const float* b, float* y, int64_t m, int64_t n_out,
+                         int act, float scale, void* ws, int64_t ws_bytes, void* stream) {
   using namespace corr;
   const FwdPlan p = plan_fwd(m, n_out, s, q);
   BSIG_REQUIRE(p.ok, "corr_linear_fwd: shape outside the fused kernel's envelope "
                "(n_out <= 128, s*q+2 < 2^20, factors must fit shared memory)");
-  BSIG_REQUIRE(act == BSIG_ACT_NONE || act == BSIG_ACT_TANH, "corr_linear_fwd: unknown activation");
-  BSIG_REQUIRE(!(b == nullptr && act == BSIG_ACT_TANH), "corr_linear_fwd: tanh needs a bias");
+  BSIG_REQUIRE(act == 0 || act == 1 || act == 2, "corr_linear_fwd: unknown activation");
+  BSIG_REQUIRE(!(b == nullptr && act == 1), "corr_linear_fwd: tanh needs a bias");
   BSIG_REQUIRE((reinterpret_cast<uintptr_t>(w) & 7) == 0, "corr_linear_fwd: weight must be 8-byte aligned");
   BSIG_REQUIRE(ws != nullptr && ws_bytes >= bsig_corr_linear_ws_bytes(m, n_out, s, q),
                "corr_linear_fwd: workspace too small");
@@ -1034,9 +1042,26 @@ extern "C" int bsig_corr_linear_fwd(const float* fac, int64_t ldf, const int64_t
   }
   const int64_t total = m * n_out;
   corr_reduce_kernel<<<(unsigned)ceil_div(total, 64), 256, 0, (cudaStream_t)stream>>>(
-      g.partial, b, y, (int)m, (int)n_out, p.splits, act == BSIG_ACT_TANH ? 1 : 0);
+      g.partial, b, y, (int)m, (int)n_out, p.splits, act, scale);
   BSIG_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int bsig_corr_linear_fwd(const float* fac, int64_t ldf, const int64_t* rows, int64_t s,
+                                    int64_t q, const float* w, const float* b, float* y, int64_t m,
+                                    int64_t n_out, int act, void* ws, int64_t ws_bytes,
+                                    void* stream) {
+  BSIG_REQUIRE(act == BSIG_ACT_NONE || act == BSIG_ACT_TANH, "corr_linear_fwd: unknown activation");
+  return corr_fwd_impl(fac, ldf, rows, s, q, w, b, y, m, n_out, act == BSIG_ACT_TANH ? 1 : 0, 1.f, ws,
+                       ws_bytes, stream);
+}
+
+extern "C" int bsig_corr_rff_features(const float* fac, int64_t ldf, const int64_t* rows, int64_t s,
+                                      int64_t q, const float* coeff, float* out, int64_t m,
+                                      int64_t nf_half, float scale, void* ws, int64_t ws_bytes,
+                                      void* stream) {
+  return corr_fwd_impl(fac, ldf, rows, s, q, coeff, nullptr, out, m, nf_half, 2, scale, ws, ws_bytes,
+                       stream);
 }
 
 extern "C" int bsig_corr_linear_wgrad(const float* dy, const float* fac, int64_t ldf,

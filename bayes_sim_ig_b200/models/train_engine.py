@@ -124,7 +124,7 @@ class TrainPlan(object):
         lib = _lib.load()
         rows_max = max(batch, n_test, 1)
         shapes = [(nh, model.head_in)] + list(zip(widths, [feat_dim] + widths[:-1]))
-        if self.rff is not None:
+        if self.rff is not None and corr is None:
             shapes.append((self.rff.freqs.shape[0], in_dim))
         ws_bytes = max(lib.bsig_linear_ws_bytes(rows, n_out, k_in)
                        for rows in (batch, rows_max) for n_out, k_in in shapes)
@@ -132,13 +132,14 @@ class TrainPlan(object):
         self.ws_mdn = torch.zeros(lib.bsig_mdn_ws_bytes(rows_max), dtype=torch.uint8, device=dev)
         self.corr_adam = False
         if corr is not None:
-            n0 = widths[0]
+            n0 = widths[0] if self.rff is None else int(self.rff.freqs.shape[0])
             self.ws_corr = torch.empty(int(lib.bsig_corr_linear_ws_bytes(rows_max, n0, corr[0],
                                                                          corr[1])) + 256,
                                        dtype=torch.uint8, device=dev)
             # single GPU: Adam of the first-layer weight runs in the weight-gradient epilogue
             # (the gradient never reaches HBM); the flat Adam pass then starts behind that weight
-            self.corr_adam = (data_parallel.world_of(model) == 1 and (n0 * in_dim) % 4 == 0)
+            self.corr_adam = (self.rff is None and data_parallel.world_of(model) == 1 and
+                              (n0 * in_dim) % 4 == 0)
         # weight-gradient GEMMs run on a side stream, concurrently with the dgrad chain,
         # when every GEMM of the step is a single-launch (workspace-free) kernel
         def single_launch(m_, n_, k_):
@@ -281,9 +282,15 @@ class TrainPlan(object):
         cur, ld = x, (x.shape[1] if ld is None else ld)
         if self.rff is not None:
             coeff = self.rff.coeff()
-            _lib.call('bsig_rff_features', cur.data_ptr(), ld, rows_p, coeff.data_ptr(),
-                      acts['feat'].data_ptr(), n_rows, self.rff.d, coeff.shape[0],
-                      float(self.rff.a), int(self.rff.gemm_engine), wsp, wsn, st)
+            if self.corr is not None:
+                cs, cq, cld = self.corr        # projection of the never-materialised summary
+                _lib.call('bsig_corr_rff_features', cur.data_ptr(), cld, rows_p, cs, cq,
+                          coeff.data_ptr(), acts['feat'].data_ptr(), n_rows, coeff.shape[0],
+                          float(self.rff.a), self.ws_corr.data_ptr(), self.ws_corr.numel(), st)
+            else:
+                _lib.call('bsig_rff_features', cur.data_ptr(), ld, rows_p, coeff.data_ptr(),
+                          acts['feat'].data_ptr(), n_rows, self.rff.d, coeff.shape[0],
+                          float(self.rff.a), int(self.rff.gemm_engine), wsp, wsn, st)
             cur, ld, rows_p = acts['feat'], acts['feat'].shape[1], None
         for li, lay in enumerate(layers):
             if li == 0 and self.corr is not None:
@@ -551,14 +558,21 @@ def _stage_inputs(plan, model, x_data, y_data):
 
 def _corr_layout(model, x_data, batch_size, n_test):
     """(s, q, ldf) when ``x_data`` is a CorrFactors object the fused first-layer kernels can
-    consume for this model (an MDNN trunk whose first layer is at most 128 wide, minibatch of at
-    most 128 rows, csrc/corr_layer.cu), else None."""
+    consume for this model (an MDNN trunk whose first layer is at most 128 wide, or an MDRFF
+    with at most 128 frequency rows; minibatch of at most 128 rows, csrc/corr_layer.cu), else
+    None."""
     if not hasattr(x_data, 'fac') or not hasattr(x_data, 'materialize'):
         return None
     trunk = model._trunk_layers()
-    if getattr(model, 'rff', None) is not None or not trunk:
+    rff = getattr(model, 'rff', None)
+    if rff is not None:
+        n0 = int(rff.freqs.shape[0])           # MDRFF: the projection x . (freqs / sigma)^T
+        if rff.d != x_data.shape[1] or not getattr(rff, 'to_features', None) == rff._to_cos_sin_features:
+            return None
+    elif trunk:
+        n0 = trunk[0].weight.shape[0]
+    else:
         return None
-    n0 = trunk[0].weight.shape[0]
     ok = _lib.load().bsig_corr_linear_applicable(batch_size, max(batch_size, n_test, 1), n0,
                                                  x_data.s, x_data.q)
     return (x_data.s, x_data.q, int(x_data.fac.shape[1])) if ok else None

@@ -112,6 +112,13 @@ int64_t bsig_corr_linear_ws_bytes(int64_t m, int64_t n_out, int64_t s, int64_t q
 int bsig_corr_linear_fwd(const float* fac, int64_t ldf, const int64_t* rows, int64_t s,
                          int64_t q, const float* w, const float* b, float* y, int64_t m,
                          int64_t n_out, int act, void* ws, int64_t ws_bytes, void* stream);
+/* Random Fourier features of the never-materialised summary (models/rff.py:128-132 on the output
+ * of summarizers.py:106-119, the MDRFF input of bayes_sim.py:108-113): out [m, 2*nf_half] =
+ * scale * [cos(x coeff^T) | sin(x coeff^T)], coeff [nf_half, s*q+2] = freqs / sigma, same
+ * kernels and workspace as bsig_corr_linear_fwd (nf_half <= 128). */
+int bsig_corr_rff_features(const float* fac, int64_t ldf, const int64_t* rows, int64_t s, int64_t q,
+                           const float* coeff, float* out, int64_t m, int64_t nf_half, float scale,
+                           void* ws, int64_t ws_bytes, void* stream);
 /* dw [n_out, s*q+2] = dy^T [n_out, m] x [m, s*q+2] (autograd of mdnn.py:108, weight part).
  * exp_avg != NULL: torch.optim.Adam (mdnn.py:203,234; same arithmetic as bsig_adam_step,
  * gradient scaled by grad_scale) is applied to w / exp_avg / exp_avg_sq in the epilogue and

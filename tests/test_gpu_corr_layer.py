@@ -290,3 +290,68 @@ def test_bayessim_uses_the_fused_first_layer_and_agrees_with_the_materialised_pa
         curves[fused] = logs
     np.testing.assert_allclose(curves['1']['train_loss'], curves['0']['train_loss'], rtol=2e-3)
     np.testing.assert_allclose(curves['1']['test_loss'], curves['0']['test_loss'], rtol=2e-3)
+
+
+@pytest.mark.parametrize('task,m,nf_half,gather', [('ant', 100, 100, True), ('cartpole', 64, 50, False),
+                                                   ('shadowhand', 100, 100, True)])
+def test_fused_rff_projection_matches_oracle_features(task, m, nf_half, gather):
+    """models/rff.py:128-132 on the never-materialised summary against the oracle's
+    rff_features(oracle summary): a * [cos(x (freqs/sigma)^T) | sin(.)].  The angle carries the
+    TF32x3 bound of the projection (2e-5 + 4e-8*F relative to its largest magnitude); cos / sin
+    turn an angle error d into at most a*d."""
+    from oracle import mdn_np
+    lib = _lib()
+    n = m + 30 if gather else m
+    states, actions, cf = _factors(task, n, seed=m + nf_half)
+    f = cf.shape[1]
+    g = torch.Generator('cpu').manual_seed(f + nf_half)
+    freqs = torch.randn(nf_half, f, generator=g)
+    x_ref = _oracle_x(states, actions).astype(np.float64)
+    sigma = float(4.0 * np.sqrt(f)) * float(np.abs(x_ref).mean() + 1e-3)   # angles of order one
+    coeff = (freqs / sigma).to(DEV)
+    rows = torch.randint(0, n, (m,), generator=g) if gather else None
+    rows_dev = None if rows is None else rows.to(DEV)
+    if rows is not None:
+        x_ref = x_ref[rows.numpy()]
+    ws = torch.empty(lib.load().bsig_corr_linear_ws_bytes(m, nf_half, cf.s, cf.q) + 256,
+                     dtype=torch.uint8, device=DEV)
+    out = torch.full((m, 2 * nf_half), float('nan'), device=DEV)
+    scale = float(np.sqrt(1.0 / nf_half))
+    lib.call('bsig_corr_rff_features', cf.fac.data_ptr(), cf.fac.shape[1],
+             None if rows_dev is None else rows_dev.data_ptr(), cf.s, cf.q, coeff.data_ptr(),
+             out.data_ptr(), m, nf_half, scale, ws.data_ptr(), ws.numel(), lib.stream_ptr(DEV))
+    ref = mdn_np.rff_features(x_ref, freqs.double().numpy(), np.full((1, f), sigma))
+    angle_max = float(np.abs(x_ref @ (freqs.double().numpy() / sigma).T).max())
+    tol = scale * (2e-5 + 4e-8 * f) * max(angle_max, 1.0) + 2e-7
+    assert np.abs(out.cpu().numpy() - ref).max() < tol, (np.abs(out.cpu().numpy() - ref).max(), tol)
+
+
+def test_bayessim_mdrff_on_factored_summaries_agrees_with_the_materialised_path(monkeypatch):
+    """BayesSim + MDRFF + summary_corrdiff on Ant-shaped rollouts (F = 11 802): the projection of
+    the factored summary (default) and of the materialised one (BSIG_FUSED_CORR=0) see the same
+    frequencies and random draws and must give the same training curve."""
+    import contextlib
+    import io
+    from bayes_sim_ig.bayes_sim import BayesSim
+    d, a, t1 = TASKS['ant']
+    n, p = 300, 4
+    states, actions = synth_rollouts(9, n, t1, d, a, device=DEV)
+    states = 0.05 * states                      # keep the RBF angles moderate
+    rs = np.random.RandomState(2)
+    lows, highs = np.zeros(p), np.full(p, 2.0)
+    params = torch.from_numpy((2.0 * rs.rand(n, p)).astype(np.float32)).to(DEV)
+    cfg = {'modelClass': 'MDRFF', 'summarizerFxn': 'summary_corrdiff', 'trainTrajLen': t1 - 1,
+           'components': 4, 'hiddenLayers': [], 'lr': 1e-3}
+    curves = {}
+    for fused in ('1', '0'):
+        monkeypatch.setenv('BSIG_FUSED_CORR', fused)
+        torch.manual_seed(0)
+        np.random.seed(0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            bsim = BayesSim(cfg, d, a, p, lows, highs, prior=None, proposal=None, device=DEV)
+            logs = bsim.run_training(params, states, actions)
+        plan = list(bsim.model._plans.values())[-1]
+        assert (plan.corr is not None) == (fused == '1')
+        curves[fused] = logs
+    np.testing.assert_allclose(curves['1']['train_loss'], curves['0']['train_loss'], rtol=2e-3)
+    np.testing.assert_allclose(curves['1']['test_loss'], curves['0']['test_loss'], rtol=2e-3)

@@ -270,15 +270,18 @@ corr_fwd_kernel(FwdArgs g, FastDiv divQ) {
           mbar_wait(&conv_bar[s], ph);
           if (kb == kb0) CORR_MARK(4);                 // first stage converted
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t b_hi = smem_u32(tile_b(s)), b_lo = smem_u32(tile_blo(s));
+          // descriptors once per stage (the issuing thread is one chain of dependent
+          // instructions); a K step = 32 bytes = +2 in the address field
+          const uint64_t db_hi = umma_desc(smem_u32(tile_b(s))), db_lo = umma_desc(smem_u32(tile_blo(s)));
+          const uint32_t a_tm0 = tmem_base + 256u + (uint32_t)(s * 64);
           if (!(g.dbg & 4))
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {
-            const uint32_t a_tm = tmem_base + 256u + (uint32_t)(s * 64 + k * 8);
+            const uint32_t a_tm = a_tm0 + (uint32_t)(k * 8);
             const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
-            umma_tf32_ts(d_tmem, a_tm, umma_desc(b_hi + k * 32), idesc, acc);
-            umma_tf32_ts(d_tmem, a_tm, umma_desc(b_lo + k * 32), idesc, 1u);
-            umma_tf32_ts(d_tmem, a_tm + 32u, umma_desc(b_hi + k * 32), idesc, 1u);
+            umma_tf32_ts(d_tmem, a_tm, db_hi + 2 * k, idesc, acc);
+            umma_tf32_ts(d_tmem, a_tm, db_lo + 2 * k, idesc, 1u);
+            umma_tf32_ts(d_tmem, a_tm + 32u, db_hi + 2 * k, idesc, 1u);
           }
           umma_commit(&empty_bar[s]);
         }
@@ -679,12 +682,14 @@ __global__ void __maxnreg__(168) corr_wgrad_kernel(WgradArgs g, FastDiv divQ) {
         const uint32_t d_tmem = tmem_base + 256u + (uint32_t)(s * WG_TN);
         const uint32_t b_hi = smem_u32(stage_b + (size_t)s * WG_STAGE_BYTES);
         const uint32_t b_lo = b_hi + WG_STAGE_BYTES / 2;
+        const uint64_t db_hi = umma_desc(b_hi), db_lo = umma_desc(b_lo);
         for (int ks = 0; ks < g.KP / 8; ++ks) {
-          const uint32_t off = (uint32_t)(ks >> 2) * (WG_TN * 128) + (uint32_t)(ks & 3) * 32;
+          // sub-tile (32 batch rows) = 8 KB = +512 descriptor units, K step inside it = +2
+          const uint64_t off = (uint64_t)((ks >> 2) * (WG_TN * 128 / 16) + (ks & 3) * 2);
           const uint32_t a_hi = tmem_base + (uint32_t)(ks * 8), a_lo = a_hi + 128u;
-          umma_tf32_ts(d_tmem, a_hi, umma_desc(b_hi + off), idesc, ks > 0 ? 1u : 0u);
-          umma_tf32_ts(d_tmem, a_hi, umma_desc(b_lo + off), idesc, 1u);
-          umma_tf32_ts(d_tmem, a_lo, umma_desc(b_hi + off), idesc, 1u);
+          umma_tf32_ts(d_tmem, a_hi, db_hi + off, idesc, ks > 0 ? 1u : 0u);
+          umma_tf32_ts(d_tmem, a_hi, db_lo + off, idesc, 1u);
+          umma_tf32_ts(d_tmem, a_lo, db_hi + off, idesc, 1u);
         }
         umma_commit(&b_empty[s]);
         umma_commit(&acc_full[s]);

@@ -68,8 +68,7 @@ template <bool X3>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                TcArgs g) {
-  constexpr int STAGES = X3 ? STAGES_X3 : STAGES_X1;
-  constexpr int TILES_PER_STAGE = X3 ? 4 : 2;      // A, B (+ A_lo, B_lo)
+  constexpr int MAX_STAGES = X3 ? STAGES_X3 + 1 : STAGES_X1;
   constexpr int EPI_WARPS = X3 ? 4 : 8;
   constexpr uint32_t TMEM_COLS = X3 ? 512 : 256;
   // X3 with a K-major A: the converter warps write hi / lo of A into tensor memory and the
@@ -77,10 +76,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   // bandwidth (128 B/clk: exactly what three SS MMAs per K step consume) was the limit of
   // the all-shared-memory form
   const bool a_ts = X3 && !g.a_mn;
+  // stage = A, B (+ A_lo, B_lo); with A in tensor memory the A_lo tile does not exist and the
+  // same 192 KB hold FOUR stages (the TF32x3 form is bound by the TMA -> convert -> MMA ->
+  // release latency chain, i.e. by the ring depth)
+  const int TILES_PER_STAGE = X3 ? (a_ts ? 3 : 4) : 2;
+  const int STAGES = X3 ? (a_ts ? STAGES_X3 + 1 : STAGES_X3) : STAGES_X1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // (offset arithmetic on the array keeps the shared address space: LDS / STS, not generic)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  __shared__ uint64_t full_bar[STAGES], conv_bar[STAGES], empty_bar[STAGES];
+  __shared__ uint64_t full_bar[MAX_STAGES], conv_bar[MAX_STAGES], empty_bar[MAX_STAGES];
   __shared__ uint64_t tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
 
@@ -94,7 +98,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   auto tile_a = [&](int s) { return smem + (size_t)s * TILES_PER_STAGE * TILE_BYTES; };
   auto tile_b = [&](int s) { return tile_a(s) + TILE_BYTES; };
   auto tile_alo = [&](int s) { return tile_a(s) + 2 * TILE_BYTES; };
-  auto tile_blo = [&](int s) { return tile_a(s) + 3 * TILE_BYTES; };
+  auto tile_blo = [&](int s) { return tile_a(s) + (TILES_PER_STAGE - 1) * TILE_BYTES; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -125,14 +129,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      int it = 0;
+      int s = 0;
+      uint32_t ph = 0;                         // ring position and phase (no division per stage)
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         const int tile = item / g.splits, split = item - tile * g.splits;
         const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
         const int kb0 = split * g.kb_per_split, kb1 = min(num_kb, kb0 + g.kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+        for (int kb = kb0; kb < kb1; ++kb, ph ^= (uint32_t)(++s == STAGES), s = (s == STAGES ? 0 : s)) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
           mbar_expect_tx(&full_bar[s], 2 * TILE_BYTES);
           if (!g.a_mn) {
             tma_load_2d(tile_a(s), &map_a, &full_bar[s], kb * BK, m0);
@@ -159,7 +163,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.a_mn & 1) << 15) |
                              ((uint32_t)(g.b_mn & 1) << 16) | ((uint32_t)(BN >> 3) << 17) |
                              ((uint32_t)(BM >> 4) << 24);
-      int it = 0, tcount = 0;
+      int s = 0, tcount = 0;
+      uint32_t ph = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++tcount) {
         const int split = item % g.splits;
         const int kb0 = split * g.kb_per_split, kb1 = min(num_kb, kb0 + g.kb_per_split);
@@ -167,38 +172,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_wait(&tmem_empty_bar[buf], ((tcount >> 1) & 1) ^ 1);   // epilogue drained it
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t parity = (it / STAGES) & 1;
+        for (int kb = kb0; kb < kb1; ++kb, ph ^= (uint32_t)(++s == STAGES), s = (s == STAGES ? 0 : s)) {
+          const uint32_t parity = ph;
           if (X3) mbar_wait(&conv_bar[s], parity);
           else mbar_wait(&full_bar[s], parity);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          // The issuing thread is ONE chain of dependent instructions (~5 cycles each): the four
+          // operand descriptors of a stage are built once, a K step only adds its offset to the
+          // address field (32 bytes along a K-major swizzled row = +2 descriptor units, one
+          // 1024-byte atom of an MN-major tile = +64; tile bases are 1024-byte aligned, so the
+          // 14-bit field never carries)
           const uint32_t a_hi = smem_u32(tile_a(s)), b_hi = smem_u32(tile_b(s));
+          const uint64_t a_step = g.a_mn ? 64u : 2u, b_step = g.b_mn ? 64u : 2u;
+          const uint64_t db_hi = g.b_mn ? umma_desc_mn(b_hi, MN_BOX) : umma_desc(b_hi);
+          if (a_ts) {
+            const uint32_t b_lo = smem_u32(tile_blo(s));
+            const uint64_t db_lo = umma_desc(b_lo);            // (a_ts implies X3; B may be MN-major)
+            const uint64_t db_lo2 = g.b_mn ? umma_desc_mn(b_lo, MN_BOX) : db_lo;
+            const uint32_t a_tm0 = tmem_base + 256u + (uint32_t)(s * 64);
 #pragma unroll
-          for (int k = 0; k < BK / 8; ++k) {
-            // one MMA = 8 reduction steps: 32 bytes along a K-major swizzled row, or one
-            // 8-row (1024-byte) atom of an MN-major tile
-            const uint32_t a_off = g.a_mn ? k * 1024 : k * 32;
-            const uint32_t b_off = g.b_mn ? k * 1024 : k * 32;
-            const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
-            auto da = [&](uint32_t base) {
-              return g.a_mn ? umma_desc_mn(base + a_off, MN_BOX) : umma_desc(base + a_off);
-            };
-            auto db = [&](uint32_t base) {
-              return g.b_mn ? umma_desc_mn(base + b_off, MN_BOX) : umma_desc(base + b_off);
-            };
-            if (a_ts) {
-              const uint32_t a_tm = tmem_base + 256u + (uint32_t)(s * 64 + k * 8);
-              const uint32_t b_lo = smem_u32(tile_blo(s));
-              umma_tf32_ts(d_tmem, a_tm, db(b_hi), idesc, acc);
-              umma_tf32_ts(d_tmem, a_tm, db(b_lo), idesc, 1u);
-              umma_tf32_ts(d_tmem, a_tm + 32u, db(b_hi), idesc, 1u);
-            } else {
-              umma_tf32(d_tmem, da(a_hi), db(b_hi), idesc, acc);
+            for (int k = 0; k < BK / 8; ++k) {
+              const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+              const uint32_t a_tm = a_tm0 + (uint32_t)(k * 8);
+              umma_tf32_ts(d_tmem, a_tm, db_hi + k * b_step, idesc, acc);
+              umma_tf32_ts(d_tmem, a_tm, db_lo2 + k * b_step, idesc, 1u);
+              umma_tf32_ts(d_tmem, a_tm + 32u, db_hi + k * b_step, idesc, 1u);
+            }
+          } else {
+            const uint64_t da_hi = g.a_mn ? umma_desc_mn(a_hi, MN_BOX) : umma_desc(a_hi);
+            uint64_t da_lo = 0, db_lo = 0;
+            if (X3) {
+              const uint32_t a_lo = smem_u32(tile_alo(s)), b_lo = smem_u32(tile_blo(s));
+              da_lo = g.a_mn ? umma_desc_mn(a_lo, MN_BOX) : umma_desc(a_lo);
+              db_lo = g.b_mn ? umma_desc_mn(b_lo, MN_BOX) : umma_desc(b_lo);
+            }
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k) {
+              const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+              umma_tf32(d_tmem, da_hi + k * a_step, db_hi + k * b_step, idesc, acc);
               if (X3) {
-                const uint32_t a_lo = smem_u32(tile_alo(s)), b_lo = smem_u32(tile_blo(s));
-                umma_tf32(d_tmem, da(a_hi), db(b_lo), idesc, 1u);
-                umma_tf32(d_tmem, da(a_lo), db(b_hi), idesc, 1u);
+                umma_tf32(d_tmem, da_hi + k * a_step, db_lo + k * b_step, idesc, 1u);
+                umma_tf32(d_tmem, da_lo + k * a_step, db_hi + k * b_step, idesc, 1u);
               }
             }
           }
@@ -210,13 +224,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (X3 && warp < 6) {
     // ------------------------------------------------- hi/lo converters (X3 only)
     const int t = threadIdx.x - 64;             // 0..127
-    int it = 0;
+    int s = 0;
+    uint32_t ph = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const int split = item % g.splits;
       const int kb0 = split * g.kb_per_split, kb1 = min(num_kb, kb0 + g.kb_per_split);
-      for (int kb = kb0; kb < kb1; ++kb, ++it) {
-        const int s = it % STAGES;
-        mbar_wait(&full_bar[s], (it / STAGES) & 1);
+      for (int kb = kb0; kb < kb1; ++kb, ph ^= (uint32_t)(++s == STAGES), s = (s == STAGES ? 0 : s)) {
+        mbar_wait(&full_bar[s], ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float4* a = reinterpret_cast<float4*>(tile_a(s));
         float4* b = reinterpret_cast<float4*>(tile_b(s));
@@ -538,7 +552,7 @@ int gemm_tc(const GemmArgs& g, bool x3, void* ws, int64_t ws_bytes, cudaStream_t
   t.partial = splits > 1 ? wsp : nullptr;
   const int64_t num_items = ceil_div(g.M, BM) * ceil_div(g.N, BN) * splits;
   const dim3 grid((unsigned)std::min<int64_t>(num_items, sm_count()));
-  const size_t smem = (size_t)(x3 ? STAGES_X3 * 4 : STAGES_X1 * 2) * TILE_BYTES + 1024;
+  const size_t smem = (size_t)(x3 ? STAGES_X3 * 4 : STAGES_X1 * 2) * TILE_BYTES + 1024;   // 192 KB either way
   if (x3) {
     BSIG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));

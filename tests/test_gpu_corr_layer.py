@@ -355,3 +355,49 @@ def test_bayessim_mdrff_on_factored_summaries_agrees_with_the_materialised_path(
         curves[fused] = logs
     np.testing.assert_allclose(curves['1']['train_loss'], curves['0']['train_loss'], rtol=2e-3)
     np.testing.assert_allclose(curves['1']['test_loss'], curves['0']['test_loss'], rtol=2e-3)
+
+
+def test_factored_path_edge_shapes():
+    """Short trajectories (T < window), a single-row minibatch, an odd first-layer width and an
+    empty held-out split: the fused path must agree with the materialised summary everywhere."""
+    from bayes_sim_ig.models.mdnn import MDNN
+    from bayes_sim_ig_b200.models.train_engine import run_training_captured
+    from bayes_sim_ig_b200.utils import summarizers as bs
+    lib = _lib()
+    # T = 3 < 10: window = 3 steps (reference summarizers.py:97-100 only chops longer ones)
+    states, actions = synth_rollouts(4, 12, 3, 6, 2)
+    cf = bs.corr_factors(states.to(DEV), actions.to(DEV), use_state_diff=True)
+    x = bs.summary_corrdiff(states.to(DEV), actions.to(DEV))
+    assert cf.s == 3 * 5 and cf.q == 3 * 2 and torch.equal(cf.materialize(), x)
+    # m = 1, n_out = 7 (odd), no gather
+    f = cf.shape[1]
+    g = torch.Generator('cpu').manual_seed(1)
+    w = torch.randn(7, f, generator=g).to(DEV)
+    b = torch.randn(7, generator=g).to(DEV)
+    y = torch.empty(1, 7, device=DEV)
+    ws = torch.empty(lib.load().bsig_corr_linear_ws_bytes(1, 7, cf.s, cf.q) + 256, dtype=torch.uint8,
+                     device=DEV)
+    lib.call('bsig_corr_linear_fwd', cf.fac.data_ptr(), cf.fac.shape[1], None, cf.s, cf.q, w.data_ptr(),
+             b.data_ptr(), y.data_ptr(), 1, 7, 0, ws.data_ptr(), ws.numel(), lib.stream_ptr(DEV))
+    ref = x[:1].double() @ w.double().T + b.double()
+    assert _rel(y.cpu().numpy(), ref.cpu().numpy()) < 2e-5
+    dy = torch.randn(1, 7, generator=g).to(DEV)
+    dw = torch.empty(7, f, device=DEV)
+    lib.call('bsig_corr_linear_wgrad', dy.data_ptr(), cf.fac.data_ptr(), cf.fac.shape[1], None, cf.s,
+             cf.q, 1, 7, dw.data_ptr(), None, None, None, 1, 0.0, 0.9, 0.999, 1e-8, 1.0,
+             lib.stream_ptr(DEV))
+    assert _rel(dw.cpu().numpy(), (dy.double().T @ x[:1].double()).cpu().numpy()) < 2e-5
+    # empty held-out split (test_frac = 0): nan test losses, same training losses as materialised
+    lows, highs = np.zeros(3), np.ones(3)
+    yv = torch.rand(12, 3, generator=g).to(DEV)
+    losses = []
+    for data in (cf, x):
+        torch.manual_seed(5)
+        model = MDNN(f, 3, lows, highs, 2, False, (16,), torch.nn.Tanh, 1e-3, device=DEV)
+        rs = np.random.RandomState(0)
+        inj = dict(idx=rs.randint(0, 12, (2, 5)), noise_train=rs.rand(2, 5, 3, 2).astype(np.float32),
+                   noise_test=None)
+        logs = run_training_captured(model, data, yv, 2, 5, test_frac=0.0, use_graph=True, injected=inj)
+        assert all(np.isnan(v) for v in logs['test_loss'])
+        losses.append(logs['train_loss'])
+    np.testing.assert_allclose(losses[0], losses[1], rtol=1e-4)

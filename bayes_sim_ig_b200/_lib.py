@@ -86,6 +86,7 @@ SIGNATURES = {
     'bsig_p2p_read': (_int, [_c_ptr, _c_ptr, _i64]),
     'bsig_p2p_free': (_int, [_c_ptr]),
     'bsig_p2p_set_timeout_ms': (_int, [_i64]),
+    'bsig_p2p_preload': (_int, []),
     'bsig_adam_allreduce_step': (_int, [_c_ptr, ctypes.POINTER(_c_ptr), ctypes.POINTER(_c_ptr),
                                         _c_ptr, _int, _int, _c_ptr, _c_ptr, _i64, _i64,
                                         _f32, _f32, _f32, _f32, _c_ptr]),

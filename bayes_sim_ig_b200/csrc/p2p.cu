@@ -230,3 +230,14 @@ extern "C" int bsig_adam_allreduce_step(float* param, const void* const* peer_gr
   BSIG_LAUNCH_CHECK();
   return 0;
 }
+
+// Loads adam_allreduce_kernel's code without launching it.  A kernel's FIRST launch loads its
+// module lazily, which is not allowed while a stream is capturing; the training engine's warm-up
+// therefore runs update 0 once eagerly -- for the exchange kernel that would mean a real
+// rendezvous with the peers (and an epoch that must stay in step on every rank), so it is
+// preloaded instead and the warm-up stays rank-local.
+extern "C" int bsig_p2p_preload(void) {
+  cudaFuncAttributes attr;
+  BSIG_CUDA(cudaFuncGetAttributes(&attr, bsig::adam_allreduce_kernel));
+  return 0;
+}

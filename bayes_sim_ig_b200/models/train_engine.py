@@ -484,19 +484,28 @@ class TrainPlan(object):
                 self._enqueue_rff_train_features(st)
             self._enqueue_segment(0, 1, st)
             self._enqueue_eval(0, st)
+        elif self.p2p is not None:
+            # Peer-memory exchange: the warm-up stays RANK-LOCAL.  Plan keys contain the
+            # rank-local split sizes, so with uneven shards one rank can build a new plan while
+            # its peers replay cached ones -- a rendezvous here (the exchange kernel advances a
+            # device-side epoch and waits for every peer) would hang or desynchronise them.
+            # The exchange kernel's code is loaded without launching it; update 0 runs with the
+            # plain local Adam on this rank's own gradient buffer (parity 0, which the graph's
+            # update 0 overwrites before it publishes anything) and is undone below.
+            _lib.call('bsig_p2p_preload')
+            self._enqueue_step(0, st)
+            _lib.call('bsig_adam_step', m.flat_params.data_ptr(), self.p2p.local_grads(0),
+                      self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), m.flat_params.numel(),
+                      1, float(m.lr), 0.9, 0.999, 1e-8, 1.0, st)
+            self._enqueue_eval(0, st)
         else:
             self._enqueue_step(0, st)
-            if self.p2p is None:
-                data_parallel.allreduce_gradients(m, self.grads)
+            data_parallel.allreduce_gradients(m, self.grads)
             self._enqueue_update(0, st)
         torch.cuda.synchronize(self.dev)
         m.flat_params.copy_(saved)
         self.loss_buf.copy_(saved_loss)
         self.flag.copy_(saved_flag)
-        if self.p2p is not None:
-            # the exchange used gradient buffer 0, which update 0 of the graph writes again:
-            # every rank must have finished reading it
-            torch.distributed.barrier(group=getattr(m, '_dp_group', None))
 
     def capture(self):
         graph = torch.cuda.CUDAGraph()
@@ -644,16 +653,6 @@ def run_training_captured(model, x_data, y_data, n_updates, batch_size, test_fra
             _REPLAYED[0] += int(getattr(plan, 'launches_per_replay', 0))
         elif use_graph:
             fresh = plan.graph is None
-            if dp and plan.p2p is not None:
-                # warm_up() runs one extra fused exchange (it advances the device-side epoch)
-                # and a barrier, and plan keys contain the RANK-LOCAL split sizes: with uneven
-                # shards one rank can meet a new shape while its peers replay a cached plan.
-                # The decision is therefore collective: if any rank warms up, all of them do.
-                need = torch.tensor([1 if fresh else 0], dtype=torch.int32, device=dev)
-                torch.distributed.all_reduce(need, op=torch.distributed.ReduceOp.MAX,
-                                             group=getattr(model, '_dp_group', None))
-                if int(need.item()) and not fresh:
-                    plan.warm_up()
             if fresh:
                 plan.warm_up()
                 before = _lib.load().bsig_launch_count()

@@ -248,6 +248,9 @@ int bsig_p2p_read(const void* dev_ptr, void* host_ptr, int64_t bytes);   /* Watc
  * BSIG_P2P_TIMEOUT_MS), store 1 + peer index in the sticky error word ctrl[2] (read it with
  * bsig_p2p_read(ctrl + 8 bytes, ...)) and let every later launch skip its wait. */
 int bsig_p2p_set_timeout_ms(int64_t ms);
+/* Load the exchange kernel's code (no launch): lets a CUDA-graph capture contain the kernel's
+ * first launch, so that the engine's pre-capture warm-up never has to rendezvous with peers. */
+int bsig_p2p_preload(void);
 /* blocking D2H copy */
 int bsig_p2p_free(void* ptr);
 int bsig_adam_allreduce_step(float* param, const void* const* peer_grads,

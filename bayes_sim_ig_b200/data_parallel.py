@@ -40,6 +40,10 @@ def enable(model, group=None):
         model._dp_world = 1
         return model
     model._ensure_flat()
+    world = dist.get_world_size(group)
+    if model.flat_params.numel() % (4 * world) != 0:
+        # equal 16-byte aligned shards for the sharded exchange of large models (train_engine)
+        model._flatten_parameters(model.flat_params.device, pad_multiple=4 * world)
     src = dist.get_global_rank(group, 0) if group else 0
     dist.broadcast(model.flat_params, src=src, group=group)
     rff = getattr(model, 'rff', None)

@@ -243,7 +243,7 @@ class MDNN(nn.Module):
             heads.append(self.Lower)
         return heads
 
-    def _flatten_parameters(self, dev):
+    def _flatten_parameters(self, dev, pad_multiple=4):
         """Move every parameter into one flat fp32 CUDA buffer, laid out as
         [trunk W,b ...][head weights pi|mu|Diag|Lower][head biases ...] so that the
         four heads form ONE [n_head, H] GEMM operand."""
@@ -253,7 +253,11 @@ class MDNN(nn.Module):
         order += [h.weight for h in self._head_layers()]
         order += [h.bias for h in self._head_layers()]
         total = sum(p.numel() for p in order)
-        padded = (total + 3) // 4 * 4
+        # (pad_multiple = 4 * world in data-parallel runs: equal, 16-byte aligned shards of the
+        # flat buffer for the reduce-scatter / sharded Adam / all-gather exchange)
+        pad_multiple = max(4, int(pad_multiple))
+        self._pad_multiple = pad_multiple
+        padded = (total + pad_multiple - 1) // pad_multiple * pad_multiple
         flat = torch.zeros(padded, dtype=torch.float32, device=dev)
         off = 0
         self._offsets = []
@@ -280,7 +284,7 @@ class MDNN(nn.Module):
     def _ensure_flat(self):
         if not self._params_are_flat():     # e.g. after module.to(...) / .data reassignment
             dev = self._param_order[0].device
-            self._flatten_parameters(_lib.require_cuda(dev))
+            self._flatten_parameters(_lib.require_cuda(dev), getattr(self, '_pad_multiple', 4))
             self._plans = {}
 
     def _head_weight_bias(self):

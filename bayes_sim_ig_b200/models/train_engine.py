@@ -516,26 +516,73 @@ class TrainPlan(object):
     # ---- data parallel: two graphs per step with the NCCL all-reduce launched between
     # them (collectives stay out of graph capture; 2 graph launches + 1 collective per
     # step keep the host far ahead of the ~50 us the device needs)
+    # Sharded exchange (ZeRO-1 style) whenever the flat buffer splits evenly: reduce-scatter of
+    # the gradients, Adam on this rank's 1/world slice only (a 13.5 M-parameter Adam pass is
+    # 74 us of HBM traffic: divided by the world size instead of replicated), all-gather of the
+    # updated weights -- the same bytes on the wire as the all-reduce it replaces.
+    # Default from 4 ranks up (measured on configs[3]: 0.428 vs 0.452 ms per update at 8 GPUs,
+    # 0.356 vs 0.347 at 2, where halving the Adam pass does not pay for the second collective);
+    # BSIG_DP_SHARDED=1 / 0 forces it on / off.
+    def _sharded(self):
+        world = data_parallel.world_of(self.model)
+        n = self.model.flat_params.numel()
+        want = os.environ.get('BSIG_DP_SHARDED', '1' if world >= 4 else '0') != '0'
+        return world > 1 and n % (4 * world) == 0 and want
+
+    def _enqueue_adam_shard(self, step, st):
+        m = self.model
+        world = data_parallel.world_of(m)
+        shard = m.flat_params.numel() // world
+        off = 4 * shard * torch.distributed.get_rank(getattr(m, '_dp_group', None))
+        _lib.call('bsig_adam_step', m.flat_params.data_ptr() + off, self.grads.data_ptr() + off,
+                  self.exp_avg.data_ptr() + off, self.exp_avg_sq.data_ptr() + off, shard,
+                  step + 1, float(m.lr), 0.9, 0.999, 1e-8, 1.0 / world, st)
+
     def capture_dp(self):
         self.dp_graphs = []
         pool = None
+        sharded = self._sharded()
         for step in range(self.n_updates):
-            pair = []
-            for half in (self._enqueue_step, self._enqueue_update):
+            halves = [self._enqueue_step]
+            if sharded:
+                halves += [self._enqueue_adam_shard, self._enqueue_eval]
+            else:
+                halves += [self._enqueue_update]
+            graphs = []
+            for half in halves:
+                if half == self._enqueue_eval and not (step in self.logs and self.n_test > 0):
+                    graphs.append(None)
+                    continue
                 g = torch.cuda.CUDAGraph()
                 with _quiet_gc(), torch.cuda.graph(g, pool=pool, capture_error_mode='relaxed'):
                     half(step, _lib.stream_ptr(self.dev))
                 pool = g.pool()
-                pair.append(g)
-            self.dp_graphs.append(pair)
+                graphs.append(g)
+            self.dp_graphs.append(graphs)
 
     def replay_dp(self):
         self.exp_avg.zero_()
         self.exp_avg_sq.zero_()
-        for fwd_bwd, update in self.dp_graphs:
+        m = self.model
+        if not self._sharded():
+            for fwd_bwd, update in self.dp_graphs:
+                fwd_bwd.replay()
+                data_parallel.allreduce_gradients(m, self.grads)
+                update.replay()
+            return
+        group = getattr(m, '_dp_group', None)
+        world = data_parallel.world_of(m)
+        rank = torch.distributed.get_rank(group)
+        shard = m.flat_params.numel() // world
+        g_mine = self.grads[rank * shard:(rank + 1) * shard]
+        p_mine = m.flat_params.data[rank * shard:(rank + 1) * shard]
+        for fwd_bwd, adam, evalg in self.dp_graphs:
             fwd_bwd.replay()
-            data_parallel.allreduce_gradients(self.model, self.grads)
-            update.replay()
+            torch.distributed.reduce_scatter_tensor(g_mine, self.grads, group=group)   # in place
+            adam.replay()
+            torch.distributed.all_gather_into_tensor(m.flat_params.data, p_mine, group=group)
+            if evalg is not None:
+                evalg.replay()
 
 
 def _stage_inputs(plan, model, x_data, y_data):

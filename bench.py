@@ -887,8 +887,12 @@ def multi_gpu_extras(world, rank, dev, flush, peak_gbs):
         'config': 'configs[3]: ShadowHand-shaped 1000 trajectories per GPU and call, '
                   'summary_corrdiff(F=105002) + MDNN[128,128] K=10 (13.5 M parameters), 100 Adam '
                   'updates x minibatch 100 per GPU + 6 test evals, data parallel',
-        'gradient_exchange': 'p2p' if plan.p2p is not None else
-                             'nccl all-reduce (54 MB) between two CUDA graphs per update',
+        'gradient_exchange': 'p2p' if plan.p2p is not None else (
+            'nccl reduce-scatter (54 MB) -> Adam on the owned 1/%d slice -> all-gather of the weights, '
+            'between CUDA graphs' % world if plan._sharded() else
+            'nccl all-reduce (54 MB) between two CUDA graphs per update'),
+        'first_layer': 'fused cross-correlation (dW stored for the exchange)'
+                       if getattr(plan, 'corr', None) is not None else 'materialised summary',
         'ms_per_call': ms, 'ms_per_update': ms / 100,
         'fit_trajectories_per_s': world * 1000 / (ms * 1e-3),
         'parameters': int(bsim.model.flat_params.numel())}

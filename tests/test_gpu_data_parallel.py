@@ -1,7 +1,8 @@
 """Two-GPU parity of data-parallel training: two ranks, each with half of
 the reference's recorded minibatch, must reproduce the reference's single-process
 parameters after three Adam updates -- through both exchange implementations
-(the fused peer-memory all-reduce + Adam kernel of csrc/p2p.cu, and NCCL).
+(the fused peer-memory all-reduce + Adam kernel of csrc/p2p.cu, NCCL all-reduce, and the
+sharded NCCL form: reduce-scatter -> Adam on the owned slice -> all-gather of the weights).
 
 Needs two CUDA devices: skipped on a one-GPU box (run with ``gpurun --gpus 2``)."""
 import os
@@ -34,9 +35,11 @@ def _worker(rank, world, port, outdir):
     g = Golden('mdn')
     out = {}
     for case in CASES:
-        for mode in ('p2p', 'nccl'):
+        for mode in ('p2p', 'nccl', 'nccl_sharded'):
             for use_graph in (True, False):
-                os.environ['BSIG_DP_EXCHANGE'] = mode
+                os.environ['BSIG_DP_EXCHANGE'] = 'p2p' if mode == 'p2p' else 'nccl'
+                # reduce-scatter -> Adam on the owned slice -> all-gather (default from 4 ranks up)
+                os.environ['BSIG_DP_SHARDED'] = '1' if mode == 'nccl_sharded' else '0'
                 model, (din, p, k, full, b) = test_gpu_mdn.build(g, case)
                 data_parallel.enable(model)
                 half = b // world
@@ -50,6 +53,7 @@ def _worker(rank, world, port, outdir):
                                              use_graph=use_graph, injected=inj)
                 plan = list(model._plans.values())[0]
                 assert (plan.p2p is not None) == (mode == 'p2p')
+                assert plan._sharded() == (mode == 'nccl_sharded')
                 tag = '%s.%s.%d.' % (case, mode, int(use_graph))
                 out[tag + 'flat'] = model.flat_params.detach().cpu().numpy()
                 out[tag + 'loss'] = np.asarray(logs['train_loss'])
@@ -69,7 +73,7 @@ def test_two_rank_training_matches_single_process_reference(golden, tmp_path):
     g = golden('mdn')
     for case in CASES:
         ref_losses = np.array([float(g['%s.step%d.loss' % (case, s)]) for s in range(3)])
-        for mode in ('p2p', 'nccl'):
+        for mode in ('p2p', 'nccl', 'nccl_sharded'):
             for use_graph in (1, 0):
                 tag = '%s.%s.%d.' % (case, mode, use_graph)
                 # replicas stay bit-identical
@@ -85,7 +89,8 @@ def test_two_rank_training_matches_single_process_reference(golden, tmp_path):
                     assert np.abs(got - ref).max() <= 3e-5, (tag, name)
         # the two exchange implementations differ only in summation order
         a, b = ranks[0][case + '.p2p.1.flat'], ranks[0][case + '.nccl.1.flat']
-        assert np.abs(a - b).max() <= 1e-6, case
+        c = ranks[0][case + '.nccl_sharded.1.flat']
+        assert np.abs(a - b).max() <= 1e-6 and np.abs(a - c).max() <= 1e-6, case
 
 
 def test_exchange_watchdog_reports_a_missing_peer():

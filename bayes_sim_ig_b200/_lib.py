@@ -66,6 +66,8 @@ SIGNATURES = {
                                  _c_ptr, _i64, _c_ptr]),
     'bsig_linear_wgrad': (_int, [_c_ptr, _c_ptr, _i64, _c_ptr, _c_ptr, _c_ptr, _i64, _i64, _i64,
                                  _int, _c_ptr, _i64, _c_ptr]),
+    'bsig_linear_wgrad_adam': (_int, [_c_ptr, _c_ptr, _i64, _c_ptr, _i64, _i64, _i64, _c_ptr, _c_ptr,
+                                      _c_ptr, _c_ptr, _i64, _i64, _f32, _f32, _f32, _f32, _c_ptr]),
     'bsig_linear_colsum': (_int, [_c_ptr, _c_ptr, _i64, _i64, _c_ptr]),
     'bsig_tanh_bwd': (_int, [_c_ptr, _c_ptr, _c_ptr, _i64, _c_ptr]),
     'bsig_rff_features': (_int, [_c_ptr, _i64, _c_ptr, _c_ptr, _c_ptr, _i64, _i64, _i64, _f32,

@@ -9,7 +9,9 @@ enum Epilogue {
   EPI_BIAS = 1,       // C = acc + bias[j]
   EPI_BIAS_TANH = 2,  // C = tanh(acc + bias[j])
   EPI_MUL_DTANH = 3,  // C = acc * (1 - aux[i,j]^2)
-  EPI_SINCOS = 4      // C[i,j] = scale*cos(acc), C[i,N+j] = scale*sin(acc)
+  EPI_SINCOS = 4,     // C[i,j] = scale*cos(acc), C[i,N+j] = scale*sin(acc)
+  EPI_ADAM = 5        // small engine, weight gradients: acc is the gradient of C[i,j] = a
+                      // PARAMETER; Adam is applied to it (and to the rest of the model) in place
 };
 
 struct GemmArgs {
@@ -28,6 +30,12 @@ struct GemmArgs {
   int64_t ld_aux;
   float scale;
   float* rowsum;             // optional: rowsum[i] = sum_r A(i,r) (small engine only)
+  // EPI_ADAM: C = the layer's weight inside the flat parameter buffer ad_p (at offset 0), its
+  // bias at ad_b_off; ad_m / ad_v the flat Adam moments, ad_g the flat gradient buffer of
+  // every OTHER parameter [ad_tail_off, ad_tail_off + ad_tail_cnt)
+  float* ad_p; float* ad_m; float* ad_v; const float* ad_g;
+  int64_t ad_b_off, ad_tail_off, ad_tail_cnt;
+  float ad_ob1, ad_b2, ad_ob2, ad_step, ad_ibc2, ad_eps;
   // filled by the launcher
   int k_per_split;
   float* partial;
@@ -39,6 +47,8 @@ inline GemmArgs gemm_args_zero() {
   g.a_si = g.a_sr = g.b_sr = g.b_sj = g.ldc = 0;
   g.a_rows = g.b_rows = nullptr; g.epi = EPI_STORE; g.bias = g.aux = nullptr;
   g.ld_aux = 0; g.scale = 1.f; g.rowsum = nullptr; g.k_per_split = 0; g.partial = nullptr;
+  g.ad_p = g.ad_m = g.ad_v = nullptr; g.ad_g = nullptr; g.ad_b_off = g.ad_tail_off = g.ad_tail_cnt = 0;
+  g.ad_ob1 = g.ad_b2 = g.ad_ob2 = g.ad_step = g.ad_ibc2 = g.ad_eps = 0.f;
   return g;
 }
 

@@ -25,6 +25,28 @@ constexpr int SBM = 32, SBN = 32, SBK = 64;   // SBK = reduction steps per pass
 constexpr int APITCH = SBM + 1;               // conflict-free transposing stores
 constexpr int BPITCH = SBN + 4;               // float4-aligned rows
 
+// torch.optim.Adam on one element: the arithmetic of adam_kernel (optim.cu), bit for bit.
+__device__ __forceinline__ void adam_elem(const GemmArgs& g, float& pp, float gg, float& mm, float& vv) {
+  mm = mm + (gg - mm) * g.ad_ob1;
+  vv = vv * g.ad_b2 + g.ad_ob2 * gg * gg;
+  const float denom = sqrtf(vv) * g.ad_ibc2 + g.ad_eps;
+  pp = pp - g.ad_step * (mm / denom);
+}
+// EPI_ADAM: the parameters this GEMM does not produce gradients for (every other layer: their
+// gradients are complete, the weight-gradient GEMM of the first layer is the last kernel of the
+// backward pass) are updated by the CTAs that have nothing else left to do.
+__device__ __forceinline__ void adam_tail(const GemmArgs& g, int64_t worker, int64_t n_workers) {
+  float* p = g.ad_p + g.ad_tail_off;
+  float* m = g.ad_m + g.ad_tail_off;
+  float* v = g.ad_v + g.ad_tail_off;
+  const float* gr = g.ad_g + g.ad_tail_off;
+  for (int64_t i = worker; i < g.ad_tail_cnt; i += n_workers) {
+    float pp = p[i], mm = m[i], vv = v[i];
+    adam_elem(g, pp, gr[i], mm, vv);
+    p[i] = pp; m[i] = mm; v[i] = vv;
+  }
+}
+
 // EPI: epilogue (compile-time, keeps tanhf / sincosf out of the other variants);
 // GATHER: 0 none, 1 rows of A gathered (a_rows), 2 reduction rows of B gathered.
 // All global loads are unconditional (indices clamped into range, out-of-range
@@ -147,8 +169,18 @@ __global__ void __launch_bounds__(256) gemm_small_kernel(GemmArgs g) {
       }
     }
     cluster.sync();     // peers keep their shared memory alive until rank 0 has read it
-    if (rank != 0) return;
+    if (rank != 0) {
+      if (EPI == EPI_ADAM) {
+        const int64_t tile = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
+        adam_tail(g, (tile * (S - 1) + (rank - 1)) * 256 + tid,
+                  (int64_t)gridDim.x * gridDim.y * (S - 1) * 256);
+      }
+      return;
+    }
   }
+  if (EPI == EPI_ADAM && S == 1)
+    adam_tail(g, ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 256 + tid,
+              (int64_t)gridDim.x * gridDim.y * 256);
 
   if (gi_out >= g.M) return;
   float* c = g.C + (int64_t)gi_out * g.ldc + gj_out;
@@ -156,7 +188,13 @@ __global__ void __launch_bounds__(256) gemm_small_kernel(GemmArgs g) {
   for (int v = 0; v < 4; ++v) {
     if (gj_out + v >= g.N) continue;
     const float a = acc[v];
-    if (EPI == EPI_STORE) c[v] = a;
+    if (EPI == EPI_ADAM) {
+      const int64_t e = (int64_t)gi_out * g.ldc + gj_out + v;
+      float pp = c[v], mm = g.ad_m[e], vv = g.ad_v[e];
+      adam_elem(g, pp, a, mm, vv);
+      c[v] = pp; g.ad_m[e] = mm; g.ad_v[e] = vv;
+    }
+    else if (EPI == EPI_STORE) c[v] = a;
     else if (EPI == EPI_BIAS) c[v] = a + ep4[v];
     else if (EPI == EPI_BIAS_TANH) c[v] = tanhf(a + ep4[v]);
     else if (EPI == EPI_MUL_DTANH) c[v] = a * (1.0f - ep4[v] * ep4[v]);
@@ -167,7 +205,16 @@ __global__ void __launch_bounds__(256) gemm_small_kernel(GemmArgs g) {
       c[v + g.N] = g.scale * sn;
     }
   }
-  if (want_rsum && tx == 0) g.rowsum[gi_out] = rs;
+  if (want_rsum && tx == 0) {
+    if (EPI == EPI_ADAM) {       // the bias gradient goes straight into the bias
+      const int64_t e = g.ad_b_off + gi_out;
+      float pp = g.ad_p[e], mm = g.ad_m[e], vv = g.ad_v[e];
+      adam_elem(g, pp, rs, mm, vv);
+      g.ad_p[e] = pp; g.ad_m[e] = mm; g.ad_v[e] = vv;
+    } else {
+      g.rowsum[gi_out] = rs;
+    }
+  }
 }
 
 template <int EPI, int GATHER>
@@ -234,6 +281,7 @@ int gemm_small(GemmArgs g, cudaStream_t st) {
     case EPI_BIAS_TANH: return launch_small_g<EPI_BIAS_TANH>(g, grid, S, st);
     case EPI_MUL_DTANH: return launch_small_g<EPI_MUL_DTANH>(g, grid, S, st);
     case EPI_SINCOS: return launch_small_g<EPI_SINCOS>(g, grid, S, st);
+    case EPI_ADAM: return launch_small_g<EPI_ADAM>(g, grid, S, st);
   }
   set_error("gemm_small: unknown epilogue %d", g.epi);
   return 1;

@@ -101,3 +101,35 @@ extern "C" int bsig_linear_colsum(const float* dy, float* db, int64_t m, int64_t
   BSIG_REQUIRE(m >= 1 && n >= 1, "linear_colsum: empty problem");
   return colsum(dy, db, m, n, nullptr, 0, (cudaStream_t)stream);
 }
+
+// Last kernel of a single-GPU backward pass: dW = dy^T x of the FIRST layer (weight at the start
+// of the flat parameter buffer, bias right behind it) with torch.optim.Adam applied in the
+// epilogue -- to that weight and bias from the accumulators, and to every other parameter from
+// the flat gradient buffer by the CTAs of the launch that have nothing else left to do.  One
+// launch instead of weight gradient + Adam on the critical path of an update.
+extern "C" int bsig_linear_wgrad_adam(const float* dy, const float* x, int64_t ldx,
+                                      const int64_t* x_rows, int64_t m, int64_t n, int64_t k,
+                                      float* param, const float* grad, float* exp_avg,
+                                      float* exp_avg_sq, int64_t n_params, int64_t step, float lr,
+                                      float beta1, float beta2, float eps, void* stream) {
+  BSIG_REQUIRE(m >= 1 && n >= 1 && k >= 1 && step >= 1, "linear_wgrad_adam: bad sizes");
+  BSIG_REQUIRE(n_params >= n * k + n, "linear_wgrad_adam: parameter buffer smaller than the layer");
+  GemmArgs g = gemm_args_zero();
+  g.A = dy; g.a_si = 1; g.a_sr = n;         // A(i,r) = dy[r,i]
+  g.B = x; g.b_sr = ldx; g.b_sj = 1; g.b_rows = x_rows;
+  g.C = param; g.ldc = k; g.M = (int)n; g.N = (int)k; g.K = (int)m;
+  g.epi = EPI_ADAM;
+  g.rowsum = param;                          // (non-null: request the row sums = bias gradient)
+  BSIG_REQUIRE(gemm_small_applicable(g), "linear_wgrad_adam: layer too large for the fused form");
+  g.ad_p = param; g.ad_m = exp_avg; g.ad_v = exp_avg_sq; g.ad_g = grad;
+  g.ad_b_off = n * k;
+  g.ad_tail_off = n * k + n;
+  g.ad_tail_cnt = n_params - g.ad_tail_off;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  g.ad_ob1 = 1.0f - beta1; g.ad_b2 = beta2; g.ad_ob2 = 1.0f - beta2;
+  g.ad_step = (float)((double)lr / bc1);
+  g.ad_ibc2 = (float)(1.0 / sqrt(bc2));
+  g.ad_eps = eps;
+  return gemm_small(g, (cudaStream_t)stream);
+}

@@ -167,7 +167,18 @@ class TrainPlan(object):
                                  self.p2p is None and batch <= 128 and
                                  data_parallel.world_of(model) == 1 and
                                  os.environ.get('BSIG_FUSED_WGRAD', '0') == '1')
+        # single GPU, minibatch-sized layers: Adam rides in the epilogue of the LAST backward
+        # kernel (the first layer's weight-gradient GEMM: by then every other gradient is
+        # complete and nothing reads the old weights any more), which also updates all other
+        # parameters with its idle CTAs -- one launch less on the critical path of an update.
+        # BSIG_FUSED_L0_ADAM=0 restores the separate Adam launch.
+        self.fused_l0_adam = (corr is None and self.rff is None and len(trunk) >= 1 and
+                              self.p2p is None and data_parallel.world_of(model) == 1 and
+                              self.fork_wgrad and not self.fused_wgrad_adam and
+                              os.environ.get('BSIG_FUSED_L0_ADAM', '1') != '0')
         self._setup_persistent()
+        if self.persistent:
+            self.fused_l0_adam = False
 
     # ------------------------------------------------- persistent cluster kernel (default)
     def _setup_persistent(self):
@@ -363,6 +374,18 @@ class TrainPlan(object):
                 self._enqueue_corr_wgrad(step, lay, rows, st)
                 dcur, nxt = self.dh[li], lay
                 continue
+            if li == 0 and self.fused_l0_adam:
+                # (side stream, in order behind the other weight gradients; dgrad of layer 1,
+                # the last reader of any weight, precedes it through wait_stream)
+                side.wait_stream(main)
+                _lib.call('bsig_linear_wgrad_adam', self.dh[0].data_ptr(),
+                          self.x_train_buf.data_ptr(), self.x_ld, rows.data_ptr(), b, lay['n'],
+                          lay['k'], m.flat_params.data_ptr(), self.grads.data_ptr(),
+                          self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                          m.flat_params.numel(), step + 1, float(m.lr), 0.9, 0.999, 1e-8,
+                          side.cuda_stream)
+                dcur, nxt = self.dh[li], lay
+                continue
             if li > 0:
                 xin, xld, xrows = self.tr['h'][li - 1], layers[li - 1]['n'], None
             elif self.rff is not None:
@@ -418,6 +441,8 @@ class TrainPlan(object):
                       m.flat_params.data_ptr(), self.exp_avg.data_ptr(),
                       self.exp_avg_sq.data_ptr(), self.batch, step + 1, float(m.lr), 0.9, 0.999,
                       1e-8, st)
+        elif self.fused_l0_adam:
+            pass                                # applied by bsig_linear_wgrad_adam in _enqueue_step
         elif self.p2p is not None:
             # one kernel: all-reduce over NVLink peer memory (1/world folded in) + Adam
             self.p2p.adam_allreduce(m, self.exp_avg, self.exp_avg_sq, step, step + 1, st)

@@ -162,6 +162,15 @@ int bsig_linear_fwd(const float* x, int64_t ldx, const int64_t* x_rows,
 int bsig_linear_dgrad(const float* dy, const float* w, const float* h_prev, float* dx,
                       int64_t m, int64_t n, int64_t k, int act_prev, int engine,
                       void* ws, int64_t ws_bytes, void* stream);
+/* The last kernel of a single-GPU backward pass: weight gradient of the FIRST layer (weight
+ * [n,k] at param[0], bias [n] at param[n*k]; x optionally row-gathered) with torch.optim.Adam
+ * (mdnn.py:203,234; arithmetic of bsig_adam_step) applied in its epilogue, and Adam of all other
+ * parameters param[n*k+n : n_params] from grad[...] by the otherwise idle CTAs of the launch.
+ * Only for layers the small engine takes (n*k <= 128 K, m <= 8192). */
+int bsig_linear_wgrad_adam(const float* dy, const float* x, int64_t ldx, const int64_t* x_rows,
+                           int64_t m, int64_t n, int64_t k, float* param, const float* grad,
+                           float* exp_avg, float* exp_avg_sq, int64_t n_params, int64_t step,
+                           float lr, float beta1, float beta2, float eps, void* stream);
 /* db [n] = colsum(dy [m,n]): the bias gradient alone (autograd of mdnn.py:108-119), for layers
  * whose weight gradient is formed by bsig_corr_linear_wgrad. */
 int bsig_linear_colsum(const float* dy, float* db, int64_t m, int64_t n, void* stream);

@@ -529,9 +529,8 @@ corr_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ 
 
 // ------------------------------------------------------------------ weight gradient (+ Adam)
 constexpr int WG_TN = 64;                         // k columns per output tile
-constexpr int WG_EPI_WARPS = 8;
-// warp 0 MMA, warps 1-2 generate, warp 3 idle, warps 4-11 epilogue: 12 warps, because registers
-// are allocated to warps in groups of four and the epilogue wants ~150 of them per thread
+constexpr int WG_EPI_WARPS = 16;
+// warp 0 MMA, warps 1-2 generate, warp 3 loads state-feature columns, warps 4-19 epilogue
 constexpr int WG_THREADS = (4 + WG_EPI_WARPS) * 32;
 constexpr int WG_STAGE_BYTES = 2 * 4 * WG_TN * 128;   // hi + lo, four [64 x 32] sub-tiles = 64 KB
 constexpr int WG_EP = 65;                         // pitch of the epilogue staging tile
@@ -554,7 +553,7 @@ struct WgradArgs {
   float one_minus_b1, b2, one_minus_b2, step_size, inv_bc2_sqrt, eps, gscale;
 };
 
-__global__ void __maxnreg__(168) corr_wgrad_kernel(WgradArgs g, FastDiv divQ) {
+__global__ void __launch_bounds__(WG_THREADS, 1) corr_wgrad_kernel(WgradArgs g, FastDiv divQ) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ uint64_t b_full[2], b_empty[2], acc_full[2], acc_empty[2], sf_full[2];
@@ -626,7 +625,7 @@ __global__ void __maxnreg__(168) corr_wgrad_kernel(WgradArgs g, FastDiv divQ) {
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  } else if (warp >= 8) {
+  } else if (warp >= 8 && warp < 12) {
     // ---- one-off (epilogue warps 8-11): warp gw stages batch rows gw, gw+4, ... transposed
     //      ([feature][row]); lanes run along the feature index so that every 4-byte cp.async
     //      instruction reads one line
@@ -775,122 +774,94 @@ __global__ void __maxnreg__(168) corr_wgrad_kernel(WgradArgs g, FastDiv divQ) {
     }
   } else if (warp >= 4) {
     // ------------------------------------------------ epilogue: Adam / gradient store
-    // 8 warps: two per TMEM lane quadrant, each drains 32 of the 64 accumulator columns into
-    // the staging tile; then warp ew owns rows ew, ew+8, ... (16 rows) and lane l the column
+    // 16 warps: four per TMEM lane quadrant, each drains 16 of the 64 accumulator columns into
+    // the staging tile; then warp ew owns rows ew, ew+16, ... (8 rows) and lane l the column
     // pair 2l: every row is one coalesced 256-byte access per array.  The HBM stream (read and
-    // write W, exp_avg, exp_avg_sq: 24 B per parameter) is the whole cost of the kernel: a
-    // thread issues the 48 loads of its 16 rows (96 registers -- the reason for only 13 warps
-    // per CTA) BEFORE it waits for the accumulator and the staging barriers, so ~100 KB per SM
-    // are in flight while the tensor core and the generators work on the next tile.
-    const int ew = warp - 4;                      // 0..7
+    // write W, exp_avg, exp_avg_sq: 24 B per parameter) is the whole cost of the kernel.
+    const int ew = warp - 4;                      // 0..15
     const int qd = warp & 3;                      // TMEM lane quadrant
-    const int part = ew >> 2;                     // which 32 of the 64 accumulator columns
+    const int part = ew >> 2;                     // which 16 of the 64 accumulator columns
     const bool adam = g.exp_avg != nullptr;
-    // L2 prefetch of a later tile's lines of W / exp_avg / exp_avg_sq (256 B per row and array,
-    // 8-byte aligned: up to three 128-byte lines; thread pair (2j, 2j+1) covers row j), so that
-    // the demand loads below find their lines in L2 instead of paying the DRAM latency
-    const int et = threadIdx.x - 4 * 32;          // 0..255
-    auto prefetch_tile = [&](int tile) {
-      const int j = et >> 1;
-      const int64_t k0 = (int64_t)tile * WG_TN;
-      if (!adam || tile >= g.num_tiles || j >= g.N || k0 >= g.F) return;
-      const int64_t e = (int64_t)j * g.F + k0;
-      const int64_t bytes = 4 * min((int64_t)WG_TN, (int64_t)g.F - k0);
-      if (et & 1) {
-        const char* p0 = reinterpret_cast<const char*>(g.exp_avg_sq + e);
-        for (const char* q = reinterpret_cast<const char*>((uintptr_t)p0 & ~(uintptr_t)127);
-             q < p0 + bytes; q += 128)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
-      } else {
-        const char* p0 = reinterpret_cast<const char*>(g.w + e);
-        const char* p1 = reinterpret_cast<const char*>(g.exp_avg + e);
-        for (const char* q = reinterpret_cast<const char*>((uintptr_t)p0 & ~(uintptr_t)127);
-             q < p0 + bytes; q += 128)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
-        for (const char* q = reinterpret_cast<const char*>((uintptr_t)p1 & ~(uintptr_t)127);
-             q < p1 + bytes; q += 128)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+    // Software pipeline over (tile, sub-batch of 4 rows): the loads of the NEXT sub-batch are in
+    // flight while Adam runs on the current one (two register sets of 4 rows x 3 arrays), across
+    // tile boundaries as well -- without it the kernel alternated between a phase that saturates
+    // HBM (loads of tile t + stores of tile t-1) and a phase that leaves it idle (the
+    // arithmetic), 4.5 + 2.8 us per tile.
+    struct RowSet {
+      float2 w[4], m[4], v[4];
+    };
+    const int64_t step8 = 16 * (int64_t)g.F;      // row stride of a warp: 16 rows
+    auto issue = [&](RowSet& rs, int tile, int q) {
+      const int64_t kcol = (int64_t)tile * WG_TN + 2 * lane;
+      if (!adam || kcol >= g.F) return;
+      const int64_t e0 = (int64_t)(ew + 64 * q) * g.F + kcol;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (ew + 16 * (4 * q + u) < g.N) {
+          rs.w[u] = *reinterpret_cast<const float2*>(g.w + e0 + u * step8);
+          rs.m[u] = *reinterpret_cast<const float2*>(g.exp_avg + e0 + u * step8);
+          rs.v[u] = *reinterpret_cast<const float2*>(g.exp_avg_sq + e0 + u * step8);
+        }
       }
     };
-    prefetch_tile(blockIdx.x);
-    prefetch_tile(blockIdx.x + gridDim.x);
+    // (SFU square root and reciprocal, <= 2 ulp each: the IEEE sequences of sqrtf and the
+    // division were half of the epilogue's instructions; the difference to bsig_adam_step's
+    // arithmetic is ~2e-7 of an lr-sized step)
+    auto upd = [&](float& pp, float gg, float& mm, float& vv) {
+      gg *= g.gscale;
+      mm = mm + (gg - mm) * g.one_minus_b1;
+      vv = vv * g.b2 + g.one_minus_b2 * gg * gg;
+      float sq;
+      asm("sqrt.approx.f32 %0, %1;" : "=f"(sq) : "f"(vv));
+      const float denom = sq * g.inv_bc2_sqrt + g.eps;
+      pp = pp - g.step_size * __fdividef(mm, denom);
+    };
+    auto apply = [&](RowSet& rs, int tile, int q) {
+      const int64_t kcol = (int64_t)tile * WG_TN + 2 * lane;
+      if (kcol >= g.F) return;
+      const int64_t e0 = (int64_t)(ew + 64 * q) * g.F + kcol;
+      const float* gs = ep_s + (ew + 64 * q) * WG_EP + 2 * lane;
+#pragma unroll
+      for (int u = 0; u < 4; ++u, gs += 16 * WG_EP) {
+        if (ew + 16 * (4 * q + u) < g.N) {
+          const float g0 = gs[0], g1 = gs[1];
+          const int64_t e = e0 + u * step8;
+          if (adam) {
+            upd(rs.w[u].x, g0, rs.m[u].x, rs.v[u].x);
+            upd(rs.w[u].y, g1, rs.m[u].y, rs.v[u].y);
+            *reinterpret_cast<float2*>(g.w + e) = rs.w[u];
+            *reinterpret_cast<float2*>(g.exp_avg + e) = rs.m[u];
+            *reinterpret_cast<float2*>(g.exp_avg_sq + e) = rs.v[u];
+          }
+          if (g.dw != nullptr) *reinterpret_cast<float2*>(g.dw + e) = make_float2(g0, g1);
+        }
+      }
+    };
+    RowSet ra, rb;
+    if ((int)blockIdx.x < g.num_tiles) issue(ra, blockIdx.x, 0);
     int it = 0;
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
       const int s = it & 1;
-      prefetch_tile(tile + 2 * gridDim.x);
-      const int64_t kcol = (int64_t)tile * WG_TN + 2 * lane;
-      const bool col_ok = kcol < g.F;
-      float2 pw[16], pm[16], pv[16];
-      if (adam && col_ok) {
-        const float* wp = g.w + (int64_t)ew * g.F + kcol;
-        const float* mp = g.exp_avg + (int64_t)ew * g.F + kcol;
-        const float* vp = g.exp_avg_sq + (int64_t)ew * g.F + kcol;
-        const int64_t step8 = 8 * (int64_t)g.F;
-#pragma unroll
-        for (int u = 0; u < 16; ++u, wp += step8, mp += step8, vp += step8) {
-          if (ew + 8 * u < g.N) {
-            pw[u] = *reinterpret_cast<const float2*>(wp);
-            pm[u] = *reinterpret_cast<const float2*>(mp);
-            pv[u] = *reinterpret_cast<const float2*>(vp);
-          }
-        }
-      }
       mbar_wait(&acc_full[s], (it >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       {
-        uint32_t r[32];
+        uint32_t r[16];
         const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + 256u +
-                               (uint32_t)(s * WG_TN + part * 32);
-        BSIG_TMEM_LD32(r, taddr);
+                               (uint32_t)(s * WG_TN + part * 16);
+        BSIG_TMEM_LD16(r, taddr);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         mbar_arrive(&acc_empty[s]);
-        asm volatile("bar.sync 1, 256;" ::: "memory");    // previous tile's staging fully consumed
-        float* erow = ep_s + (qd * 32 + lane) * WG_EP + part * 32;
+        asm volatile("bar.sync 1, 512;" ::: "memory");    // previous tile's staging fully consumed
+        float* erow = ep_s + (qd * 32 + lane) * WG_EP + part * 16;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) erow[c] = __uint_as_float(r[c]);
+        for (int c = 0; c < 16; ++c) erow[c] = __uint_as_float(r[c]);
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (col_ok) {
-        const float* gs = ep_s + ew * WG_EP + 2 * lane;
-        if (adam) {
-          float* wp = g.w + (int64_t)ew * g.F + kcol;
-          float* mp = g.exp_avg + (int64_t)ew * g.F + kcol;
-          float* vp = g.exp_avg_sq + (int64_t)ew * g.F + kcol;
-          float* dp = g.dw != nullptr ? g.dw + (int64_t)ew * g.F + kcol : nullptr;
-          const int64_t step8 = 8 * (int64_t)g.F;
-#pragma unroll
-          for (int u = 0; u < 16; ++u, gs += 8 * WG_EP, wp += step8, mp += step8, vp += step8) {
-            if (ew + 8 * u < g.N) {
-              // (SFU square root and reciprocal, <= 2 ulp each: the epilogue is instruction-
-              // bound -- 16 rows x 2 elements per thread and tile -- and the IEEE sequences of
-              // sqrtf and the division were half of its instructions; the difference to
-              // bsig_adam_step's arithmetic is ~2e-7 of an lr-sized step)
-              auto upd = [&](float& pp, float gg, float& mm, float& vv) {
-                gg *= g.gscale;
-                mm = mm + (gg - mm) * g.one_minus_b1;
-                vv = vv * g.b2 + g.one_minus_b2 * gg * gg;
-                float sq;
-                asm("sqrt.approx.f32 %0, %1;" : "=f"(sq) : "f"(vv));
-                const float denom = sq * g.inv_bc2_sqrt + g.eps;
-                pp = pp - g.step_size * __fdividef(mm, denom);
-              };
-              const float g0 = gs[0], g1 = gs[1];
-              upd(pw[u].x, g0, pm[u].x, pv[u].x);
-              upd(pw[u].y, g1, pm[u].y, pv[u].y);
-              *reinterpret_cast<float2*>(wp) = pw[u];
-              *reinterpret_cast<float2*>(mp) = pm[u];
-              *reinterpret_cast<float2*>(vp) = pv[u];
-              if (dp != nullptr) *reinterpret_cast<float2*>(dp + u * step8) = make_float2(g0, g1);
-            }
-          }
-        } else {
-          float* dp = g.dw + (int64_t)ew * g.F + kcol;
-          const int64_t step8 = 8 * (int64_t)g.F;
-          for (int j = ew; j < g.N; j += WG_EPI_WARPS, gs += 8 * WG_EP, dp += step8)
-            *reinterpret_cast<float2*>(dp) = make_float2(gs[0], gs[1]);
-        }
-      }
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      issue(rb, tile, 1);
+      apply(ra, tile, 0);
+      if (tile + (int)gridDim.x < g.num_tiles) issue(ra, tile + gridDim.x, 0);
+      apply(rb, tile, 1);
     }
   }
 

@@ -530,8 +530,8 @@ corr_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ 
 // ------------------------------------------------------------------ weight gradient (+ Adam)
 constexpr int WG_TN = 64;                         // k columns per output tile
 constexpr int WG_EPI_WARPS = 16;
-// warp 0 MMA, warps 1-2 generate, warp 3 loads state-feature columns, warps 4-19 epilogue
-constexpr int WG_THREADS = (4 + WG_EPI_WARPS) * 32;
+// warp 0 MMA, warps 1-4 generate, warp 5 loads state-feature columns, warps 6-21 epilogue
+constexpr int WG_THREADS = (6 + WG_EPI_WARPS) * 32;
 constexpr int WG_STAGE_BYTES = 2 * 4 * WG_TN * 128;   // hi + lo, four [64 x 32] sub-tiles = 64 KB
 constexpr int WG_EP = 65;                         // pitch of the epilogue staging tile
 
@@ -575,7 +575,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) corr_wgrad_kernel(WgradArgs g, 
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&b_full[i], 64);
+      mbar_init(&b_full[i], 128);
       mbar_init(&b_empty[i], 1);
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], WG_EPI_WARPS * 32);
@@ -596,8 +596,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) corr_wgrad_kernel(WgradArgs g, 
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_slot;
 
-  if (warp >= 4 && warp < 8) {
-    // ---- one-off (epilogue warps 4-7, one per TMEM lane quadrant): dy^T -> tensor memory
+  if (warp >= 6 && warp < 10) {
+    // ---- one-off (epilogue warps 6-9, one per TMEM lane quadrant): dy^T -> tensor memory
     //      (lane = output j, column = batch row n)
     const int j = (warp & 3) * 32 + lane;        // TMEM lane of this thread
     const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
@@ -625,13 +625,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) corr_wgrad_kernel(WgradArgs g, 
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  } else if (warp >= 8 && warp < 12) {
-    // ---- one-off (epilogue warps 8-11): warp gw stages batch rows gw, gw+4, ... transposed
+  } else if (warp >= 10 && warp < 14) {
+    // ---- one-off (epilogue warps 10-13): warp gw stages batch rows gw, gw+4, ... transposed
     //      ([feature][row]); lanes run along the feature index so that every 4-byte cp.async
     //      instruction reads one line
-    const int t = threadIdx.x - 8 * 32;          // 0..127
+    const int t = threadIdx.x - 10 * 32;         // 0..127
     {
-      const int gw = warp - 8;
+      const int gw = warp - 10;
       const uint32_t pitch = 4u * (uint32_t)g.NP;
       // lane u holds the source row of batch row gw + 4u (KP <= 128: 32 rows per warp)
       int64_t my_src = -1;
@@ -694,9 +694,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) corr_wgrad_kernel(WgradArgs g, 
         umma_commit(&acc_full[s]);
       }
     }
-  } else if (warp <= 2) {
+  } else if (warp <= 4) {
     // ------------------------------------------------ generators: x^T tiles, K-major, SW128
-    const int r = threadIdx.x - 32;              // 0..63: k row of the tile owned by this thread
+    const int t = threadIdx.x - 32;              // 0..127
+    const int r = t & (WG_TN - 1);               // k row of the tile owned by this thread
     int it = 0;
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
       const int s = it & 1;
@@ -714,7 +715,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) corr_wgrad_kernel(WgradArgs g, 
       const float* afp = afT + (size_t)(prod ? qk : 0) * g.NP;
       const float* tailp = k == SQ ? mu_s : sd_s;
       const bool tail = (k == SQ) || (k == SQ + 1);
-      for (int c = 0; c < n_chunks; ++c) {
+      for (int c = t >> 6; c < n_chunks; c += 2) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (prod) {
           const float4 a = *reinterpret_cast<const float4*>(afp + 4 * c);
@@ -737,7 +738,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) corr_wgrad_kernel(WgradArgs g, 
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(&b_full[s]);
     }
-  } else if (warp == 3) {
+  } else if (warp == 5) {
     // ------------------------------------------------ loader: the (at most npt) state-feature
     // columns a tile touches, [column][batch row], straight from the L2-resident factor rows;
     // runs up to two tiles ahead of the generators (its buffer is free as soon as they have
@@ -772,13 +773,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) corr_wgrad_kernel(WgradArgs g, 
       }
       mbar_arrive(&sf_full[s]);
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 6) {
     // ------------------------------------------------ epilogue: Adam / gradient store
     // 16 warps: four per TMEM lane quadrant, each drains 16 of the 64 accumulator columns into
     // the staging tile; then warp ew owns rows ew, ew+16, ... (8 rows) and lane l the column
     // pair 2l: every row is one coalesced 256-byte access per array.  The HBM stream (read and
     // write W, exp_avg, exp_avg_sq: 24 B per parameter) is the whole cost of the kernel.
-    const int ew = warp - 4;                      // 0..15
+    const int ew = warp - 6;                      // 0..15
     const int qd = warp & 3;                      // TMEM lane quadrant
     const int part = ew >> 2;                     // which 16 of the 64 accumulator columns
     const bool adam = g.exp_avg != nullptr;

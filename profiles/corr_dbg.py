@@ -44,8 +44,10 @@ dy = torch.randn(m, n_out, device=dev)
 ea, es = torch.zeros_like(w), torch.zeros_like(w)
 for dbg in (0,):
     ts = []
-    for rep in range(6):
+    for rep in range(7):
         flush.add_(1.0)
+        if rep == 6:
+            os.environ['BSIG_CORR_PROF'] = '1'
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         _lib.call('bsig_corr_linear_wgrad', dy.data_ptr(), fac.data_ptr(), ldf, rows.data_ptr(), s, q,

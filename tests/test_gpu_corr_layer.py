@@ -401,3 +401,34 @@ def test_factored_path_edge_shapes():
         assert all(np.isnan(v) for v in logs['test_loss'])
         losses.append(logs['train_loss'])
     np.testing.assert_allclose(losses[0], losses[1], rtol=1e-4)
+
+
+def test_shapes_outside_the_envelope_fall_back_to_the_materialised_summary():
+    """A minibatch of more than 128 rows (or a first layer wider than 128) is outside the fused
+    kernels' envelope: MDNN.run_training must materialise the CorrFactors object and train on the
+    generic path, with the same losses as when it is handed the summary tensor."""
+    from bayes_sim_ig.models.mdnn import MDNN
+    from bayes_sim_ig_b200.models.train_engine import run_training_captured
+    from bayes_sim_ig_b200.utils import summarizers as bs
+    states, actions = synth_rollouts(6, 200, 21, 4, 1)
+    cf = bs.corr_factors(states.to(DEV), actions.to(DEV), use_state_diff=True)
+    x = cf.materialize()
+    lows, highs = np.zeros(2), np.ones(2)
+    g = torch.Generator('cpu').manual_seed(2)
+    yv = torch.rand(200, 2, generator=g).to(DEV)
+    rs = np.random.RandomState(3)
+    inj = dict(idx=rs.randint(0, 160, (2, 130)), noise_train=rs.rand(2, 130, 2, 3).astype(np.float32),
+               noise_test=rs.rand(2, 40, 2, 3).astype(np.float32))
+    curves = []
+    for data, hidden in ((cf, (16,)), (x, (16,)), (cf, (130,)), (x, (130,))):
+        torch.manual_seed(7)
+        batch = 130 if hidden == (16,) else 64
+        inj_b = dict(idx=inj['idx'][:, :batch], noise_train=inj['noise_train'][:, :batch],
+                     noise_test=inj['noise_test'])
+        model = MDNN(x.shape[1], 2, lows, highs, 3, False, hidden, torch.nn.Tanh, 1e-3, device=DEV)
+        logs = run_training_captured(model, data, yv, 2, batch, 0.2, use_graph=True, injected=inj_b)
+        plan = list(model._plans.values())[-1]
+        assert plan.corr is None
+        curves.append(logs['train_loss'] + logs['test_loss'])
+    np.testing.assert_allclose(curves[0], curves[1], rtol=1e-6)
+    np.testing.assert_allclose(curves[2], curves[3], rtol=1e-6)

@@ -293,6 +293,7 @@ class TrainPlan(object):
         cur, ld = x, (x.shape[1] if ld is None else ld)
         if self.rff is not None:
             coeff = self.rff.coeff()
+            self._coeff_ref = coeff        # the captured graph holds this tensor's address
             if self.corr is not None:
                 cs, cq, cld = self.corr        # projection of the never-materialised summary
                 _lib.call('bsig_corr_rff_features', cur.data_ptr(), cld, rows_p, cs, cq,
@@ -724,6 +725,11 @@ def run_training_captured(model, x_data, y_data, n_updates, batch_size, test_fra
             plan.replay_dp()
             _REPLAYED[0] += int(getattr(plan, 'launches_per_replay', 0))
         elif use_graph:
+            if (plan.graph is not None and plan.rff is not None and
+                    plan.rff.coeff() is not getattr(plan, '_coeff_ref', None)):
+                # freqs / sigma were edited since the capture: the cached coefficient tensor
+                # the graph points at has been replaced (RFF.coeff) -> record the call again
+                plan.graph = None
             fresh = plan.graph is None
             if fresh:
                 plan.warm_up()

@@ -258,3 +258,28 @@ def test_streaming_nll_without_gather_and_with_misaligned_rows():
         assert rel_err(dz.cpu(), ref_dz) < GRAD_RTOL
     # same per-sample formulas in both kernels (SFU vs full-precision transcendentals)
     assert rel_err(outs[0][1].cpu(), outs[1][1].cpu()) < 1e-5
+
+
+def test_graph_replay_follows_an_edited_rff_bandwidth(golden):
+    """The captured training graph points at the cached `freqs / sigma` tensor of the RFF.  Editing
+    sigma (or freqs) replaces that tensor; the next run_training call must notice and record the
+    call again instead of replaying against the old (freed) coefficients."""
+    from bayes_sim_ig_b200.models.train_engine import run_training_captured
+    g = golden('mdn')
+    case = 'rff'
+    x = torch.from_numpy(g[case + '.x']).to(DEV)
+    y_raw = torch.from_numpy(g[case + '.y_raw']).to(DEV)
+    model, (din, p, k, full, b) = build(g, case)
+    noise = np.stack([g['%s.step%d.noise' % (case, s)] for s in range(3)])
+    inj = dict(idx=np.tile(np.arange(b), (3, 1)), noise_train=noise, noise_test=None)
+    init = {name: v.clone() for name, v in model.state_dict().items()}
+    first = run_training_captured(model, x, y_raw, 3, b, test_frac=0.0, use_graph=True, injected=inj)
+    model.load_state_dict(init)
+    model.rff.sigma.mul_(2.0)                      # in place: bumps the tensor version
+    edited = run_training_captured(model, x, y_raw, 3, b, test_frac=0.0, use_graph=True, injected=inj)
+    # reference for the edited bandwidth: a fresh model, no graph
+    ref_model, _ = build(g, case)
+    ref_model.rff.sigma = ref_model.rff.sigma * 2.0
+    ref = run_training_captured(ref_model, x, y_raw, 3, b, test_frac=0.0, use_graph=False, injected=inj)
+    assert abs(edited['train_loss'][0] - first['train_loss'][0]) > 1e-4      # it did change
+    np.testing.assert_allclose(edited['train_loss'], ref['train_loss'], rtol=1e-6)

@@ -525,8 +525,10 @@ class TrainPlan(object):
                       1, float(m.lr), 0.9, 0.999, 1e-8, 1.0, st)
             self._enqueue_eval(0, st)
         else:
+            # (NCCL data parallel as well: no collective here -- the warm-up only has to launch
+            # every kernel of the graphs once, its result is undone below, and a collective
+            # would have to be matched by peers that may be replaying cached plans)
             self._enqueue_step(0, st)
-            data_parallel.allreduce_gradients(m, self.grads)
             self._enqueue_update(0, st)
         torch.cuda.synchronize(self.dev)
         m.flat_params.copy_(saved)

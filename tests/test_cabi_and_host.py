@@ -316,3 +316,59 @@ def test_packed_lane_group_reduction_scheme_for_every_width():
             np.testing.assert_allclose(tot[g * k:(g + 1) * k], grp.sum(), rtol=1e-12, atol=1e-12)
             assert len(set(tot[g * k:(g + 1) * k].tolist())) == 1      # identical bits per group
             np.testing.assert_array_equal(mx[g * k:(g + 1) * k], grp.max())
+
+
+def test_corr_factors_object_expands_to_the_oracle_summary():
+    """Host side of the fused first layer: a CorrFactors object built from
+    the oracle's own factors must expand (materialize) to the oracle's cross-correlation summary
+    (reference summarizers.py:106-119), report its shape, support the row slicing run_training's
+    ordered 80/20 split uses, and refuse column indexing."""
+    import torch
+    from oracle import summarizers_np as osum
+    from bayes_sim_ig_b200.utils.summarizers import CorrFactors
+    rs = np.random.RandomState(0)
+    n, t1, d, a = 9, 12, 5, 2
+    states = rs.randn(n, t1, d).astype(np.float32)
+    actions = rs.rand(n, t1, a).astype(np.float32)
+    ref = osum.cross_correlation(states, actions, use_state_diff=True)
+    w = 10
+    sf = (states[:, :w, 1:] - states[:, :w, :-1]).reshape(n, -1)
+    af = actions[:, :w, :].reshape(n, -1)
+    s, q = sf.shape[1], af.shape[1]
+    ldf = (s + q + 2 + 3) // 4 * 4
+    fac = np.zeros((n, ldf), np.float32)
+    fac[:, :s], fac[:, s:s + q] = sf, af
+    fac[:, s + q:s + q + 2] = ref[:, -2:]
+    cf = CorrFactors(torch.from_numpy(fac), s, q)
+    assert cf.shape == ref.shape and len(cf) == n
+    assert np.array_equal(cf.materialize().numpy(), ref)
+    head, tail = cf[:7], cf[7:]
+    assert head.shape == (7, ref.shape[1]) and tail.shape == (2, ref.shape[1])
+    assert np.array_equal(tail.materialize().numpy(), ref[7:])
+    with pytest.raises(TypeError):
+        cf[:, :3]
+
+
+def test_sharded_exchange_arithmetic_matches_allreduce_then_adam():
+    """The sharded data-parallel exchange (reduce-scatter -> Adam on the owned slice -> all-gather
+    of the weights, train_engine.replay_dp) restated with numpy: for any world size that divides
+    the padded buffer it must give the parameters of all-reduce + full Adam (oracle adam_step)."""
+    from oracle import mdn_np
+    rs = np.random.RandomState(1)
+    for world in (2, 4, 8):
+        n = 4 * world * 13
+        p0 = rs.randn(n)
+        grads = [rs.randn(n) for _ in range(world)]
+        full = {'p': p0.copy()}
+        m, v = {'p': np.zeros(n)}, {'p': np.zeros(n)}
+        mdn_np.adam_step(full, {'p': sum(grads) / world}, m, v, 1, 1e-3)
+        shard = n // world
+        out = np.empty(n)
+        for r in range(world):                       # what rank r computes and all-gathers
+            sl = slice(r * shard, (r + 1) * shard)
+            g_r = sum(g[sl] for g in grads) / world  # its slice of the reduce-scatter
+            pr = {'p': p0[sl].copy()}
+            mr, vr = {'p': np.zeros(shard)}, {'p': np.zeros(shard)}
+            mdn_np.adam_step(pr, {'p': g_r}, mr, vr, 1, 1e-3)
+            out[sl] = pr['p']
+        assert np.allclose(out, full['p'], rtol=0, atol=1e-15)

@@ -32,7 +32,8 @@ def _rel(got, ref):
 
 
 SHAPES = [(300, 100, 680), (128, 128, 128), (1000, 270, 128), (65, 20, 36), (257, 128, 100),
-          (100, 128, 302), (4096, 128, 1292), (100, 128, 11804)]
+          (100, 128, 302), (4096, 128, 1292), (100, 128, 11804),
+          (38001, 128, 160)]     # >= 148 tiles of 256 rows: the plain TF32 engine's two-accumulator form
 
 
 @pytest.mark.parametrize('engine', [SIMT, TC_TF32, TC_X3])
@@ -56,7 +57,8 @@ def test_linear_forward_engines(engine, shape):
 
 
 @pytest.mark.parametrize('engine', [SIMT, TC_TF32, TC_X3])
-@pytest.mark.parametrize('shape', [(300, 100, 680), (4099, 100, 1292), (70, 10, 40), (512, 100, 52)])
+@pytest.mark.parametrize('shape', [(300, 100, 680), (4099, 100, 1292), (70, 10, 40), (512, 100, 52),
+                                   (40003, 100, 300)])
 def test_rff_features_engines(engine, shape):
     lib = _lib()
     m, nf, d = shape

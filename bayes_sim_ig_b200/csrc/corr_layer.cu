@@ -884,7 +884,9 @@ struct FwdPlan {
 static FwdPlan plan_fwd(int64_t m, int64_t n_out, int64_t s, int64_t q) {
   FwdPlan p = {};
   const int64_t F = s * q + 2;
-  if (m < 1 || n_out < 1 || n_out > 128 || s < 1 || q < 1 || F >= (1 << 20)) return p;
+  // (F odd -- Humanoid: 5*107 x 5*21 + 2 -- leaves the rows of W only 4-byte aligned: the 8-byte
+  // copies / float2 accesses of these kernels need an even F)
+  if (m < 1 || n_out < 1 || n_out > 128 || s < 1 || q < 1 || F >= (1 << 20) || (F & 1)) return p;
   const int64_t m_tiles = ceil_div(m, BM);
   p.num_kb = (int)ceil_div(F, BK);
   int64_t splits = std::max<int64_t>(1, std::min<int64_t>(p.num_kb, sm_count() / m_tiles));
@@ -915,7 +917,7 @@ struct WgPlan {
 static WgPlan plan_wgrad(int64_t m, int64_t n_out, int64_t s, int64_t q) {
   WgPlan p = {};
   const int64_t F = s * q + 2;
-  if (m < 1 || m > 128 || n_out < 1 || n_out > 128 || s < 1 || q < 1 || F >= (1 << 20)) return p;
+  if (m < 1 || m > 128 || n_out < 1 || n_out > 128 || s < 1 || q < 1 || F >= (1 << 20) || (F & 1)) return p;
   p.KP = (int)(ceil_div(m, 8) * 8);
   p.NP = p.KP + 4;
   p.num_tiles = (int)ceil_div(F, WG_TN);
@@ -981,7 +983,7 @@ static int corr_fwd_impl(const float* fac, int64_t ldf, const int64_t* rows, int
   using namespace corr;
   const FwdPlan p = plan_fwd(m, n_out, s, q);
   BSIG_REQUIRE(p.ok, "corr_linear_fwd: shape outside the fused kernel's envelope "
-               "(n_out <= 128, s*q+2 < 2^20, factors must fit shared memory)");
+               "(n_out <= 128, s*q+2 even and < 2^20, factors must fit shared memory)");
   BSIG_REQUIRE(act == 0 || act == 1 || act == 2, "corr_linear_fwd: unknown activation");
   BSIG_REQUIRE(!(b == nullptr && act == 1), "corr_linear_fwd: tanh needs a bias");
   BSIG_REQUIRE((reinterpret_cast<uintptr_t>(w) & 7) == 0, "corr_linear_fwd: weight must be 8-byte aligned");
@@ -1049,7 +1051,7 @@ extern "C" int bsig_corr_linear_wgrad(const float* dy, const float* fac, int64_t
   using namespace corr;
   const WgPlan p = plan_wgrad(m, n_out, s, q);
   BSIG_REQUIRE(p.ok, "corr_linear_wgrad: shape outside the fused kernel's envelope "
-               "(batch <= 128, n_out <= 128, s*q+2 < 2^20, factors must fit shared memory)");
+               "(batch <= 128, n_out <= 128, s*q+2 even and < 2^20, factors must fit shared memory)");
   const bool adam = exp_avg != nullptr;
   BSIG_REQUIRE(adam || dw != nullptr, "corr_linear_wgrad: nothing to do (no dw, no Adam state)");
   BSIG_REQUIRE(!adam || (w != nullptr && exp_avg_sq != nullptr && step >= 1),

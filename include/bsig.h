@@ -101,7 +101,7 @@ int bsig_corr_factors(const float* states, const float* actions, float* fac, int
                       void* stream);
 /* 1 if the fused first-layer kernels take this shape (minibatch `batch` <= 128 rows for the
  * weight gradient, forward passes of up to rows_max rows, n_out <= 128,
- * s*q + 2 < 2^20, factor rows within shared memory), else 0: the caller then materialises the
+ * s*q + 2 even and < 2^20, factor rows within shared memory), else 0: the caller then materialises the
  * summary and uses bsig_linear_*. */
 int bsig_corr_linear_applicable(int64_t batch, int64_t rows_max, int64_t n_out, int64_t s,
                                 int64_t q);

@@ -194,6 +194,8 @@ def test_shapes_outside_the_envelope_are_refused():
     assert lib.load().bsig_corr_linear_applicable(256, 256, 128, 1050, 100) == 0   # batch > 128
     assert lib.load().bsig_corr_linear_applicable(100, 100, 256, 1050, 100) == 0   # n_out > 128
     assert lib.load().bsig_corr_linear_applicable(100, 100, 128, 4096, 512) == 0   # F >= 2^20
+    # Humanoid: 5*107 x 5*21 + 2 is odd -> rows of W only 4-byte aligned -> materialised path
+    assert lib.load().bsig_corr_linear_applicable(100, 100, 128, 535, 105) == 0
 
 
 def _oracle_training(sd0, x, y_norm, idx, noise_train, noise_test, n_train, p, k, lr):
@@ -432,3 +434,28 @@ def test_shapes_outside_the_envelope_fall_back_to_the_materialised_summary():
         curves.append(logs['train_loss'] + logs['test_loss'])
     np.testing.assert_allclose(curves[0], curves[1], rtol=1e-6)
     np.testing.assert_allclose(curves[2], curves[3], rtol=1e-6)
+
+
+def test_humanoid_shaped_summaries_with_an_odd_width_take_the_materialised_path():
+    """Humanoid (D = 108, A = 21): s*q + 2 = 535*105 + 2 is odd, the rows of the first-layer weight
+    are only 4-byte aligned, outside the fused kernels' envelope.  BayesSim.run_training must fall
+    back to the materialised summary (bit-identical to the summarizer's tensor) and train."""
+    import contextlib
+    import io
+    from bayes_sim_ig.bayes_sim import BayesSim
+    from bayes_sim_ig_b200.utils import summarizers as bs
+    d, a, t1, n, p = 108, 21, 11, 120, 3
+    states, actions = synth_rollouts(12, n, t1, d, a, device=DEV)
+    cf = bs.corr_factors(states, actions, use_state_diff=True)
+    assert cf.shape[1] % 2 == 1
+    assert torch.equal(cf.materialize(), bs.summary_corrdiff(states, actions))
+    rs = np.random.RandomState(4)
+    params = torch.from_numpy(rs.rand(n, p).astype(np.float32)).to(DEV)
+    cfg = {'modelClass': 'MDNN', 'summarizerFxn': 'summary_corrdiff', 'trainTrajLen': t1 - 1,
+           'components': 3, 'hiddenLayers': [32], 'lr': 1e-4}
+    with contextlib.redirect_stdout(io.StringIO()):
+        bsim = BayesSim(cfg, d, a, p, np.zeros(p), np.ones(p), prior=None, proposal=None, device=DEV)
+        logs = bsim.run_training(params, states, actions)
+    plan = list(bsim.model._plans.values())[-1]
+    assert plan.corr is None
+    assert np.isfinite(logs['train_loss']).all() and np.isfinite(logs['test_loss']).all()

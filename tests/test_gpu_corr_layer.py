@@ -459,3 +459,72 @@ def test_humanoid_shaped_summaries_with_an_odd_width_take_the_materialised_path(
     plan = list(bsim.model._plans.values())[-1]
     assert plan.corr is None
     assert np.isfinite(logs['train_loss']).all() and np.isfinite(logs['test_loss']).all()
+
+
+@pytest.mark.parametrize('seed', list(range(24)))
+def test_fused_kernels_on_random_shapes(seed):
+    """Randomised sweep over (D, A, T, minibatch, first-layer width, gather): forward, random
+    Fourier projection, weight gradient and Adam epilogue against float64 torch arithmetic on the
+    expanded factors (whose equality with the oracle summary is pinned above).  Shapes outside
+    the envelope (odd width, > 128 rows / outputs) must be refused by the applicability query and
+    by the kernels themselves."""
+    from bayes_sim_ig_b200.utils import summarizers as bs
+    lib = _lib()
+    rs = np.random.RandomState(1000 + seed)
+    d = int(rs.choice([2, 3, 4, 7, 12, 23, 52, 61]))
+    a = int(rs.choice([1, 2, 3, 6, 8]))
+    t1 = int(rs.choice([2, 3, 6, 11, 15]))
+    m = int(rs.choice([1, 2, 7, 31, 64, 100, 128]))
+    n_out = int(rs.choice([1, 2, 5, 16, 33, 64, 127, 128]))
+    gather = bool(rs.randint(2))
+    n = m + int(rs.randint(0, 9))
+    states, actions = synth_rollouts(seed, n, t1, d, a, device=DEV)
+    cf = bs.corr_factors(states, actions, use_state_diff=bool(rs.randint(2)))
+    f = cf.shape[1]
+    ok = lib.load().bsig_corr_linear_applicable(m, m, n_out, cf.s, cf.q)
+    g = torch.Generator('cpu').manual_seed(seed)
+    w = (torch.randn(n_out, f, generator=g) / np.sqrt(f)).to(DEV)
+    b = torch.randn(n_out, generator=g).to(DEV)
+    dy = torch.randn(m, n_out, generator=g).to(DEV)
+    rows = torch.randint(0, n, (m,), generator=g).to(DEV) if gather else None
+    rows_p = None if rows is None else rows.data_ptr()
+    y = torch.empty(m, n_out, device=DEV)
+    ws = torch.empty(max(int(lib.load().bsig_corr_linear_ws_bytes(m, n_out, cf.s, cf.q)), 0) + 256,
+                     dtype=torch.uint8, device=DEV)
+    args_fwd = (cf.fac.data_ptr(), cf.fac.shape[1], rows_p, cf.s, cf.q, w.data_ptr(), b.data_ptr(),
+                y.data_ptr(), m, n_out, 1, ws.data_ptr(), ws.numel(), lib.stream_ptr(DEV))
+    if not ok:
+        assert f % 2 == 1                          # the only way these sizes leave the envelope
+        with pytest.raises(lib.BsigError):
+            lib.call('bsig_corr_linear_fwd', *args_fwd)
+        return
+    x = cf.materialize().double()
+    x = x[rows] if rows is not None else x[:m]
+    tol = 2e-5 + 4e-8 * f
+    lib.call('bsig_corr_linear_fwd', *args_fwd)
+    ref = torch.tanh(x @ w.double().T + b.double())
+    assert _rel(y.cpu().numpy(), ref.cpu().numpy()) < tol, ('fwd', d, a, t1, m, n_out)
+    if n_out <= 128 and 2 * n_out <= 256:
+        out = torch.empty(m, 2 * n_out, device=DEV)
+        lib.call('bsig_corr_rff_features', cf.fac.data_ptr(), cf.fac.shape[1], rows_p, cf.s, cf.q,
+                 w.data_ptr(), out.data_ptr(), m, n_out, 0.5, ws.data_ptr(), ws.numel(),
+                 lib.stream_ptr(DEV))
+        ang = x @ w.double().T
+        ref2 = 0.5 * torch.cat([torch.cos(ang), torch.sin(ang)], dim=1)
+        assert float((out.double() - ref2).abs().max()) < 0.5 * tol * max(float(ang.abs().max()), 1.0) + 2e-7
+    wv, ea, es = w.clone(), torch.rand_like(w) * 0.01, torch.rand_like(w) * 1e-4
+    w0, ea0, es0 = wv.double().clone(), ea.double().clone(), es.double().clone()
+    dw = torch.empty_like(w)
+    lib.call('bsig_corr_linear_wgrad', dy.data_ptr(), cf.fac.data_ptr(), cf.fac.shape[1], rows_p, cf.s,
+             cf.q, m, n_out, dw.data_ptr(), wv.data_ptr(), ea.data_ptr(), es.data_ptr(), 3, 1e-3, 0.9,
+             0.999, 1e-8, 1.0, lib.stream_ptr(DEV))
+    g_ref = dy.double().T @ x
+    assert _rel(dw.cpu().numpy(), g_ref.cpu().numpy()) < 2e-5 + 4e-8 * m, ('wgrad', d, a, t1, m, n_out)
+    gk = dw.double()                               # Adam arithmetic on the kernel's own gradient
+    m_ref = 0.9 * ea0 + 0.1 * gk
+    v_ref = 0.999 * es0 + 0.001 * gk * gk
+    denom = v_ref.sqrt() / np.sqrt(1 - 0.999 ** 3) + 1e-8
+    p_ref = w0 - (1e-3 / (1 - 0.9 ** 3)) * m_ref / denom
+    assert float((wv.double() - p_ref).abs().max()) < 1e-6
+    assert _rel(ea.cpu().numpy(), m_ref.cpu().numpy()) < 1e-5
+    assert _rel(es.cpu().numpy(), v_ref.cpu().numpy()) < 1e-4

@@ -148,3 +148,38 @@ def test_dgrad_wgrad_gather_on_tensor_cores(engine, shape):
              y.data_ptr(), m, n, k, 1, engine, ws.data_ptr(), ws.numel(), st)
     ref = torch.tanh(xg @ w.double().T + b.double())
     assert _rel(y, ref) < tol_for(engine, k), ('fwd', _rel(y, ref))
+
+
+@pytest.mark.parametrize('shape', [(100, 128, 302), (100, 24, 30), (16, 16, 1), (37, 130, 65), (128, 7, 9)])
+def test_weight_gradient_with_adam_epilogue_is_bit_identical_to_the_two_kernel_form(shape):
+    """bsig_linear_wgrad_adam (last backward kernel of a single-GPU update: first-layer weight
+    gradient with Adam of the WHOLE flat parameter buffer in its epilogue) against
+    bsig_linear_wgrad + bsig_adam_step on the same buffers: same arithmetic, same parameters bit for bit."""
+    lib = _lib()
+    m, n, k = shape
+    g = torch.Generator('cpu').manual_seed(m * 7 + n * 3 + k)
+    tail = 1000 + (m % 3)                              # parameters of the other layers
+    n_params = n * k + n + tail
+    flat = torch.randn(n_params, generator=g).to(DEV)
+    grads = torch.randn(n_params, generator=g).to(DEV)
+    ea = (0.01 * torch.randn(n_params, generator=g)).to(DEV)
+    es = (1e-4 * torch.rand(n_params, generator=g)).to(DEV)
+    x = torch.randn(m + 11, k, generator=g).to(DEV)
+    rows = torch.randint(0, m + 11, (m,), generator=g).to(DEV)
+    dy = torch.randn(m, n, generator=g).to(DEV)
+    ws = _ws(m, n, k)
+    # reference: separate weight gradient (+ bias gradient) into the flat gradient buffer, then Adam
+    p_ref, g_ref, m_ref, v_ref = flat.clone(), grads.clone(), ea.clone(), es.clone()
+    lib.call('bsig_linear_wgrad', dy.data_ptr(), x.data_ptr(), k, rows.data_ptr(), g_ref.data_ptr(),
+             g_ref.data_ptr() + 4 * n * k, m, n, k, SIMT, ws.data_ptr(), ws.numel(), lib.stream_ptr(DEV))
+    # (bsig_adam_step wants 16-byte aligned buffers: clones are)
+    lib.call('bsig_adam_step', p_ref.data_ptr(), g_ref.data_ptr(), m_ref.data_ptr(), v_ref.data_ptr(),
+             n_params, 5, 1e-3, 0.9, 0.999, 1e-8, 1.0, lib.stream_ptr(DEV))
+    p, mm, vv = flat.clone(), ea.clone(), es.clone()
+    lib.call('bsig_linear_wgrad_adam', dy.data_ptr(), x.data_ptr(), k, rows.data_ptr(), m, n, k,
+             p.data_ptr(), grads.data_ptr(), mm.data_ptr(), vv.data_ptr(), n_params, 5, 1e-3, 0.9,
+             0.999, 1e-8, lib.stream_ptr(DEV))
+    # (the second moment may differ in its last bit: the compiler contracts v*b2 + (1-b2)*g*g into
+    # different fma shapes in the two kernels)
+    assert torch.equal(p, p_ref) and torch.equal(mm, m_ref)
+    assert torch.allclose(vv, v_ref, rtol=3e-7, atol=0.0)

@@ -782,7 +782,9 @@ def dp_parity_check(world, rank, dev):
             logs1 = run_training_captured(single, torch.from_numpy(x).to(dev),
                                           torch.from_numpy(y).to(dev), n_upd, n_rows, 0.0,
                                           injected=inj1)
-            err = float((single.flat_params - model.flat_params).abs().max().item())
+            # (data_parallel.enable pads the flat buffer to 4 * world floats: compare the parameters)
+            npar = int(single.n_params)
+            err = float((single.flat_params[:npar] - model.flat_params[:npar]).abs().max().item())
             lerr = float(np.abs(np.asarray(logs1['train_loss']) - loss.cpu().numpy()).max())
             out['max_abs_param_diff_vs_single_process'] = err
             out['max_abs_loss_diff_vs_single_process'] = lerr

@@ -22,7 +22,7 @@ namespace cg = cooperative_groups;
 namespace bsig {
 
 constexpr int SBM = 32, SBN = 32, SBK = 64;   // SBK = reduction steps per pass
-constexpr int APITCH = SBM + 1;               // conflict-free transposing stores
+constexpr int APITCH = SBM + 4;               // float4-aligned rows
 constexpr int BPITCH = SBN + 4;               // float4-aligned rows
 
 // torch.optim.Adam on one element: the arithmetic of adam_kernel (optim.cu), bit for bit.
@@ -53,12 +53,16 @@ __device__ __forceinline__ void adam_tail(const GemmArgs& g, int64_t worker, int
 // lanes zeroed by a select) so the 16 requests of a pass issue back to back.
 template <int EPI, int GATHER>
 __global__ void __launch_bounds__(256) gemm_small_kernel(GemmArgs g) {
-  __shared__ float As[SBK][APITCH];
+  __shared__ __align__(16) float As[SBK][APITCH];
   __shared__ __align__(16) float Bs[SBK][BPITCH];
+  __shared__ __align__(16) float red[4][SBM][BPITCH];   // the four reduction quarters of this CTA
   __shared__ float part[SBM][SBN + 1];     // this CTA's partial tile (cluster reduce)
   __shared__ float rsum[SBM];              // partial row sums of A
   const int tid = threadIdx.x;
-  const int tx = tid & 7, ty = tid >> 3;   // row ty, cols tx*4..+3
+  const int tx = tid & 7, ty = tid >> 3;   // epilogue: row ty, cols tx*4..+3
+  // inner product: 4x4 outputs per thread (rows 4*my.., cols 4*mx..), the 64 steps of a pass
+  // split over four groups of two warps -- two 16-byte shared loads feed 16 FMAs
+  const int kg = tid >> 6, mx = tid & 7, my = (tid >> 3) & 7;
   const int i0 = blockIdx.y * SBM, j0 = blockIdx.x * SBN;
   const int S = gridDim.z, rank = blockIdx.z;
   const int r_begin = rank * g.k_per_split;
@@ -77,9 +81,12 @@ __global__ void __launch_bounds__(256) gemm_small_kernel(GemmArgs g) {
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const int e = tid + 256 * q;
-    if (a_r_contig) { a_r[q] = e & 63; a_i[q] = e >> 6; }
+    // reduction index contiguous in memory: 8 lanes walk one 32-byte sector, 4 sectors a warp,
+    // so that the transposing stores (pitch 36) hit 32 different banks
+    const int r_c = (tid & 7) | (((tid >> 5) & 7) << 3), i_c = ((tid >> 3) & 3) | (q << 2);
+    if (a_r_contig) { a_r[q] = r_c; a_i[q] = i_c; }
     else            { a_i[q] = e & 31; a_r[q] = e >> 5; }
-    if (b_r_contig) { b_r[q] = e & 63; b_j[q] = e >> 6; }
+    if (b_r_contig) { b_r[q] = r_c; b_j[q] = i_c; }
     else            { b_j[q] = e & 31; b_r[q] = e >> 5; }
     const int gj = j0 + b_j[q];
     b_ok[q] = gj < g.N;
@@ -108,7 +115,11 @@ __global__ void __launch_bounds__(256) gemm_small_kernel(GemmArgs g) {
       ep4[v] = __ldg(g.aux + (int64_t)gi_c * g.ld_aux + min(gj_out + v, g.N - 1));
   }
 
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc4[4][4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) acc4[u][v] = 0.f;
   float rs = 0.f;
   for (int r0 = r_begin; r0 < r_end; r0 += SBK) {
     float ra[8], rb[8];
@@ -130,16 +141,46 @@ __global__ void __launch_bounds__(256) gemm_small_kernel(GemmArgs g) {
       Bs[b_r[q]][b_j[q]] = (b_ok[q] && r0 + b_r[q] < r_end) ? rb[q] : 0.f;
     }
     __syncthreads();
-#pragma unroll 16
-    for (int kk = 0; kk < SBK; ++kk) {
-      const float av = As[kk][ty];
-      const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-      acc[0] = fmaf(av, bv.x, acc[0]);
-      acc[1] = fmaf(av, bv.y, acc[1]);
-      acc[2] = fmaf(av, bv.z, acc[2]);
-      acc[3] = fmaf(av, bv.w, acc[3]);
-      rs += av;
+#pragma unroll
+    for (int s = 0; s < SBK / 4; ++s) {
+      const int kk = kg * (SBK / 4) + s;
+      const float4 av = *reinterpret_cast<const float4*>(&As[kk][my * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][mx * 4]);
+      const float a4[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc4[u][0] = fmaf(a4[u], bv.x, acc4[u][0]);
+        acc4[u][1] = fmaf(a4[u], bv.y, acc4[u][1]);
+        acc4[u][2] = fmaf(a4[u], bv.z, acc4[u][2]);
+        acc4[u][3] = fmaf(a4[u], bv.w, acc4[u][3]);
+      }
     }
+    if (want_rsum) {       // row sums of A: 8 lanes per row, 8 steps each
+#pragma unroll
+      for (int j = 0; j < 8; ++j) rs += As[j * 8 + tx][ty];
+    }
+  }
+  // the four reduction quarters meet in shared memory, in a fixed order
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    *reinterpret_cast<float4*>(&red[kg][my * 4 + u][mx * 4]) =
+        make_float4(acc4[u][0], acc4[u][1], acc4[u][2], acc4[u][3]);
+  __syncthreads();
+  float acc[4];
+  {
+    const float4 r0 = *reinterpret_cast<const float4*>(&red[0][ty][tx * 4]);
+    const float4 r1 = *reinterpret_cast<const float4*>(&red[1][ty][tx * 4]);
+    const float4 r2 = *reinterpret_cast<const float4*>(&red[2][ty][tx * 4]);
+    const float4 r3 = *reinterpret_cast<const float4*>(&red[3][ty][tx * 4]);
+    acc[0] = (r0.x + r1.x) + (r2.x + r3.x);
+    acc[1] = (r0.y + r1.y) + (r2.y + r3.y);
+    acc[2] = (r0.z + r1.z) + (r2.z + r3.z);
+    acc[3] = (r0.w + r1.w) + (r2.w + r3.w);
+  }
+  if (want_rsum) {
+    rs += __shfl_xor_sync(0xffffffffu, rs, 1);
+    rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+    rs += __shfl_xor_sync(0xffffffffu, rs, 4);
   }
 
   if (S > 1) {

@@ -209,8 +209,11 @@ __global__ void __launch_bounds__(256) gemm_small_kernel(GemmArgs g) {
         }
       }
     }
-    cluster.sync();     // peers keep their shared memory alive until rank 0 has read it
+    // peers keep their shared memory alive until rank 0 has read it; rank 0 only announces that
+    // it has (its loads are consumed above) and goes on to the epilogue without waiting
+    auto token = cluster.barrier_arrive();
     if (rank != 0) {
+      cluster.barrier_wait(std::move(token));
       if (EPI == EPI_ADAM) {
         const int64_t tile = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
         adam_tail(g, (tile * (S - 1) + (rank - 1)) * 256 + tid,

@@ -96,6 +96,31 @@ __device__ __forceinline__ T block_sum(T v, T* scratch) {
   return scratch[32];
 }
 
+// Two sums at once (same fixed order per component as block_sum).
+__device__ __forceinline__ float2 block_sum2(float2 v, float2* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+    v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+  }
+  __syncthreads();
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    float2 t = lane < nw ? scratch[lane] : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      t.x += __shfl_xor_sync(0xffffffffu, t.x, o);
+      t.y += __shfl_xor_sync(0xffffffffu, t.y, o);
+    }
+    if (lane == 0) scratch[32] = t;
+  }
+  __syncthreads();
+  return scratch[32];
+}
+
 // Streaming (evict-first) 128-bit store: summaries are written once and read
 // much later, keep them out of the way of the L2-resident inputs.
 __device__ __forceinline__ void st_stream_f4(float* p, float4 v) {

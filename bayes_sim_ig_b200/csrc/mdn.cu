@@ -408,8 +408,13 @@ __global__ void __launch_bounds__(512) nll_cluster_kernel(NllArgs a) {
 template <int GW, int PS, int PLMAX, bool BWD>
 __global__ void __launch_bounds__(512) nll_small_kernel(NllArgs a) {
   __shared__ float scratch[33];
-  __shared__ float red[3], bc[3];
+  // batch-wide sums: every CTA PUSHES its partial into the inbox of every CTA of the cluster
+  // (remote stores before a release/acquire cluster barrier), then adds the NC values from its
+  // own shared memory in rank order -- no remote read latency, no barrier to keep a peer alive
+  __shared__ float inbox[3][8];
+  __shared__ float2 scratch2[33];
   cg::cluster_group cluster = cg::this_cluster();
+  auto started = cluster.barrier_arrive();     // a peer's shared memory exists once it got here
   constexpr int LPS = GW * PS;             // lanes per sample (<= 32)
   const int tid = threadIdx.x;
   const int NC = gridDim.x, rank = blockIdx.x;
@@ -445,13 +450,13 @@ __global__ void __launch_bounds__(512) nll_small_kernel(NllArgs a) {
     if (ok && ii * PS + ph < P) esum += e[ii];
   }
   esum = block_sum(esum, scratch);
-  if (tid == 0) red[0] = esum;
-  cluster.sync();
-  const float etot = cluster_sum(cluster, &red[0], NC, &bc[0]);
-  const float eps = kEpsNoise * (etot / (float)((int64_t)B * PK));
+  cluster.barrier_wait(std::move(started));
+  if (tid < NC) *cluster.map_shared_rank(&inbox[0][rank], tid) = esum;
+  auto pushed = cluster.barrier_arrive();
 
   // ---- mixture weights: softmax -> clamp -> renormalise (every p-half computes
-  // the same values; xor offsets < GW stay inside one p-half)
+  // the same values; xor offsets < GW stay inside one p-half); independent of eps, so it runs
+  // while the partial exp-sums cross the cluster
   float mx = group_max<GW>(zpi);
   float soft = (zpi == -INFINITY) ? 0.f : xexp<true>(zpi - mx);
   const float sm = group_sum<GW>(soft);
@@ -459,6 +464,11 @@ __global__ void __launch_bounds__(512) nll_small_kernel(NllArgs a) {
   float w = (k < K) ? fminf(fmaxf(soft, kMinWeight), 1.0f) : 0.f;
   const float csum = group_sum<GW>(w);
   w = w / csum;
+
+  cluster.barrier_wait(std::move(pushed));
+  float etot = 0.f;
+  for (int r = 0; r < NC; ++r) etot += inbox[0][r];
+  const float eps = kEpsNoise * (etot / (float)((int64_t)B * PK));
 
   // ---- log density of this component: partial sums over this lane's p, then
   // across the PS p-halves
@@ -513,14 +523,26 @@ __global__ void __launch_bounds__(512) nll_small_kernel(NllArgs a) {
       }
     }
   }
-  const float lsum = block_sum(loss_acc, scratch);
-  const float ssum = BWD ? block_sum(s_acc, scratch) : 0.f;
-  if (tid == 0) { red[1] = lsum; red[2] = ssum; }
+  float lsum, ssum = 0.f;
+  if (BWD) {               // both sums in one pass over the block
+    const float2 ls = block_sum2(make_float2(loss_acc, s_acc), scratch2);
+    lsum = ls.x; ssum = ls.y;
+  } else {
+    lsum = block_sum(loss_acc, scratch);
+  }
+  if (tid < NC) {
+    *cluster.map_shared_rank(&inbox[1][rank], tid) = lsum;
+    *cluster.map_shared_rank(&inbox[2][rank], tid) = ssum;
+  }
   cluster.sync();
-  const float ltot = cluster_sum(cluster, &red[1], NC, &bc[1]);
-  if (rank == 0 && tid == 0) a.loss[0] = ltot / (float)B;
+  if (rank == 0 && tid == 0) {
+    float ltot = 0.f;
+    for (int r = 0; r < NC; ++r) ltot += inbox[1][r];
+    a.loss[0] = ltot / (float)B;
+  }
   if (BWD) {
-    const float S = cluster_sum(cluster, &red[2], NC, &bc[2]);
+    float S = 0.f;
+    for (int r = 0; r < NC; ++r) S += inbox[2][r];
     const float c = kEpsNoise * S / (float)((int64_t)B * PK);
     if (ok) {
 #pragma unroll
@@ -530,7 +552,6 @@ __global__ void __launch_bounds__(512) nll_small_kernel(NllArgs a) {
       }
     }
   }
-  cluster.sync();       // keep red[] alive until every CTA has read it
 }
 
 // eps-term fix-up of the fused backward: dzd += exp(zd) * (1e-5/M) * S

@@ -40,10 +40,23 @@ __device__ __forceinline__ void adam_tail(const GemmArgs& g, int64_t worker, int
   float* m = g.ad_m + g.ad_tail_off;
   float* v = g.ad_v + g.ad_tail_off;
   const float* gr = g.ad_g + g.ad_tail_off;
-  for (int64_t i = worker; i < g.ad_tail_cnt; i += n_workers) {
-    float pp = p[i], mm = m[i], vv = v[i];
-    adam_elem(g, pp, gr[i], mm, vv);
-    p[i] = pp; m[i] = mm; v[i] = vv;
+  // four elements per round, every load requested before the first store (one round trip)
+  for (int64_t i0 = worker; i0 < g.ad_tail_cnt; i0 += 4 * n_workers) {
+    float pp[4], mm[4], vv[4], gg[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = i0 + u * n_workers;
+      const int64_t ic = i < g.ad_tail_cnt ? i : i0;
+      pp[u] = p[ic]; mm[u] = m[ic]; vv[u] = v[ic]; gg[u] = gr[ic];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = i0 + u * n_workers;
+      if (i < g.ad_tail_cnt) {
+        adam_elem(g, pp[u], gg[u], mm[u], vv[u]);
+        p[i] = pp[u]; m[i] = mm[u]; v[i] = vv[u];
+      }
+    }
   }
 }
 
@@ -213,12 +226,12 @@ __global__ void __launch_bounds__(256) gemm_small_kernel(GemmArgs g) {
     // it has (its loads are consumed above) and goes on to the epilogue without waiting
     auto token = cluster.barrier_arrive();
     if (rank != 0) {
-      cluster.barrier_wait(std::move(token));
-      if (EPI == EPI_ADAM) {
+      if (EPI == EPI_ADAM) {      // while rank 0 reads the partial tiles
         const int64_t tile = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
         adam_tail(g, (tile * (S - 1) + (rank - 1)) * 256 + tid,
                   (int64_t)gridDim.x * gridDim.y * (S - 1) * 256);
       }
+      cluster.barrier_wait(std::move(token));
       return;
     }
   }
@@ -228,16 +241,27 @@ __global__ void __launch_bounds__(256) gemm_small_kernel(GemmArgs g) {
 
   if (gi_out >= g.M) return;
   float* c = g.C + (int64_t)gi_out * g.ldc + gj_out;
+  if (EPI == EPI_ADAM) {         // all twelve loads before the first store
+    const int64_t e0 = (int64_t)gi_out * g.ldc + gj_out;
+    float pp[4], mm[4], vv[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int vc = gj_out + v < g.N ? v : 0;
+      pp[v] = c[vc]; mm[v] = g.ad_m[e0 + vc]; vv[v] = g.ad_v[e0 + vc];
+    }
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      if (gj_out + v < g.N) {
+        adam_elem(g, pp[v], acc[v], mm[v], vv[v]);
+        c[v] = pp[v]; g.ad_m[e0 + v] = mm[v]; g.ad_v[e0 + v] = vv[v];
+      }
+    }
+  }
 #pragma unroll
   for (int v = 0; v < 4; ++v) {
     if (gj_out + v >= g.N) continue;
     const float a = acc[v];
-    if (EPI == EPI_ADAM) {
-      const int64_t e = (int64_t)gi_out * g.ldc + gj_out + v;
-      float pp = c[v], mm = g.ad_m[e], vv = g.ad_v[e];
-      adam_elem(g, pp, a, mm, vv);
-      c[v] = pp; g.ad_m[e] = mm; g.ad_v[e] = vv;
-    }
+    if (EPI == EPI_ADAM) continue;
     else if (EPI == EPI_STORE) c[v] = a;
     else if (EPI == EPI_BIAS) c[v] = a + ep4[v];
     else if (EPI == EPI_BIAS_TANH) c[v] = tanhf(a + ep4[v]);

@@ -25,7 +25,7 @@ NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
     '-Xcompiler', '-fPIC',
     '-I', os.path.join(ROOT, 'include'), '-I', CSRC,
-]
+] + os.environ.get('BSIG_NVCC_EXTRA', '').split()     # instrumented builds (profiles/)
 
 
 def _nvcc():

@@ -25,6 +25,19 @@ constexpr int SBM = 32, SBN = 32, SBK = 64;   // SBK = reduction steps per pass
 constexpr int APITCH = SBM + 4;               // float4-aligned rows
 constexpr int BPITCH = SBN + 4;               // float4-aligned rows
 
+#ifdef BSIG_GS_PROF   // temporary instrumentation: %globaltimer marks of every CTA of the last launch
+__device__ unsigned long long gs_prof_buf[256 * 8];
+#define GS_MARK(i)                                                                      \
+  if (threadIdx.x == 0) {                                                               \
+    unsigned long long t_;                                                              \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                              \
+    const int c_ = ((blockIdx.y * gridDim.x + blockIdx.x) * gridDim.z + blockIdx.z);    \
+    if (c_ < 256) gs_prof_buf[c_ * 8 + (i)] = t_;                                       \
+  }
+#else
+#define GS_MARK(i)
+#endif
+
 // torch.optim.Adam on one element: the arithmetic of adam_kernel (optim.cu), bit for bit.
 __device__ __forceinline__ void adam_elem(const GemmArgs& g, float& pp, float gg, float& mm, float& vv) {
   mm = mm + (gg - mm) * g.ad_ob1;
@@ -60,18 +73,29 @@ __device__ __forceinline__ void adam_tail(const GemmArgs& g, int64_t worker, int
   }
 }
 
+// Shared memory of a CTA (dynamic, 65 KB): operand tiles of a pass, the four reduction quarters,
+// and -- used in rank 0 of a cluster only -- the partial tiles and row sums its peers push in.
+struct SmallSmem {
+  float As[SBK][APITCH];
+  float Bs[SBK][BPITCH];
+  float red[4][SBM][BPITCH];
+  float inbox[7][SBM][SBN];
+  float inbox_rs[7][SBM];
+};
+
 // EPI: epilogue (compile-time, keeps tanhf / sincosf out of the other variants);
 // GATHER: 0 none, 1 rows of A gathered (a_rows), 2 reduction rows of B gathered.
 // All global loads are unconditional (indices clamped into range, out-of-range
 // lanes zeroed by a select) so the 16 requests of a pass issue back to back.
 template <int EPI, int GATHER>
 __global__ void __launch_bounds__(256) gemm_small_kernel(GemmArgs g) {
-  __shared__ __align__(16) float As[SBK][APITCH];
-  __shared__ __align__(16) float Bs[SBK][BPITCH];
-  __shared__ __align__(16) float red[4][SBM][BPITCH];   // the four reduction quarters of this CTA
-  __shared__ float part[SBM][SBN + 1];     // this CTA's partial tile (cluster reduce)
-  __shared__ float rsum[SBM];              // partial row sums of A
+  extern __shared__ __align__(16) unsigned char gs_smem_raw[];
+  SmallSmem& sm = *reinterpret_cast<SmallSmem*>(gs_smem_raw);
+  auto& As = sm.As;
+  auto& Bs = sm.Bs;
+  auto& red = sm.red;
   const int tid = threadIdx.x;
+  GS_MARK(0)
   const int tx = tid & 7, ty = tid >> 3;   // epilogue: row ty, cols tx*4..+3
   // inner product: 4x4 outputs per thread (rows 4*my.., cols 4*mx..), the 64 steps of a pass
   // split over four groups of two warps -- two 16-byte shared loads feed 16 FMAs
@@ -81,6 +105,8 @@ __global__ void __launch_bounds__(256) gemm_small_kernel(GemmArgs g) {
   const int r_begin = rank * g.k_per_split;
   const int r_end = min(g.K, r_begin + g.k_per_split);
   const bool want_rsum = (g.rowsum != nullptr) && (blockIdx.x == 0);
+  // phase A of the cluster barrier: "my shared memory exists" (waited for before the first push)
+  if (S > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
   const int gi_out = i0 + ty, gj_out = j0 + tx * 4;
   const int gi_c = min(gi_out, g.M - 1);
 
@@ -116,6 +142,7 @@ __global__ void __launch_bounds__(256) gemm_small_kernel(GemmArgs g) {
   }
   // everything above is operand-independent set-up: it overlaps the previous kernel
   pdl_wait_then_release();
+  GS_MARK(1)
 
   // epilogue operands: requested now, consumed after the reduction
   float ep4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -154,6 +181,7 @@ __global__ void __launch_bounds__(256) gemm_small_kernel(GemmArgs g) {
       Bs[b_r[q]][b_j[q]] = (b_ok[q] && r0 + b_r[q] < r_end) ? rb[q] : 0.f;
     }
     __syncthreads();
+    GS_MARK(2)
 #pragma unroll
     for (int s = 0; s < SBK / 4; ++s) {
       const int kk = kg * (SBK / 4) + s;
@@ -196,44 +224,39 @@ __global__ void __launch_bounds__(256) gemm_small_kernel(GemmArgs g) {
     rs += __shfl_xor_sync(0xffffffffu, rs, 4);
   }
 
+  GS_MARK(3)
   if (S > 1) {
+    // split-K over the cluster: the peers PUSH their partial tiles into rank 0's shared memory
+    // (16-byte remote stores, released by the barrier arrival) and leave; rank 0 adds them from
+    // its own shared memory in rank order.  No remote read latency, nobody waits for rank 0.
     cg::cluster_group cluster = cg::this_cluster();
-#pragma unroll
-    for (int v = 0; v < 4; ++v) part[ty][tx * 4 + v] = acc[v];
-    if (tx == 0) rsum[ty] = rs;
-    cluster.sync();
-    if (rank == 0) {
-      float peer_acc[7][4], peer_rs[7];
-#pragma unroll
-      for (int peer = 1; peer < 8; ++peer) {
-        if (peer < S) {
-          const float* rp = cluster.map_shared_rank(&part[0][0], peer);
-#pragma unroll
-          for (int v = 0; v < 4; ++v) peer_acc[peer - 1][v] = rp[ty * (SBN + 1) + tx * 4 + v];
-          peer_rs[peer - 1] = (want_rsum && tx == 0) ? cluster.map_shared_rank(&rsum[0], peer)[ty] : 0.f;
-        }
-      }
-#pragma unroll
-      for (int peer = 1; peer < 8; ++peer) {
-        if (peer < S) {
-#pragma unroll
-          for (int v = 0; v < 4; ++v) acc[v] += peer_acc[peer - 1][v];
-          rs += peer_rs[peer - 1];
-        }
-      }
-    }
-    // peers keep their shared memory alive until rank 0 has read it; rank 0 only announces that
-    // it has (its loads are consumed above) and goes on to the epilogue without waiting
-    auto token = cluster.barrier_arrive();
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");            // phase A
     if (rank != 0) {
-      if (EPI == EPI_ADAM) {      // while rank 0 reads the partial tiles
+      SmallSmem* home = cluster.map_shared_rank(&sm, 0);
+      *reinterpret_cast<float4*>(&home->inbox[rank - 1][ty][tx * 4]) =
+          make_float4(acc[0], acc[1], acc[2], acc[3]);
+      if (want_rsum && tx == 0) home->inbox_rs[rank - 1][ty] = rs;
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");  // phase B
+      if (EPI == EPI_ADAM) {
         const int64_t tile = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
         adam_tail(g, (tile * (S - 1) + (rank - 1)) * 256 + tid,
                   (int64_t)gridDim.x * gridDim.y * (S - 1) * 256);
       }
-      cluster.barrier_wait(std::move(token));
+      GS_MARK(6)
       return;
     }
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");  // phase B
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    GS_MARK(4)
+#pragma unroll
+    for (int peer = 1; peer < 8; ++peer) {
+      if (peer < S) {
+        const float4 pv = *reinterpret_cast<const float4*>(&sm.inbox[peer - 1][ty][tx * 4]);
+        acc[0] += pv.x; acc[1] += pv.y; acc[2] += pv.z; acc[3] += pv.w;
+        if (want_rsum && tx == 0) rs += sm.inbox_rs[peer - 1][ty];
+      }
+    }
+    GS_MARK(5)
   }
   if (EPI == EPI_ADAM && S == 1)
     adam_tail(g, ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 256 + tid,
@@ -273,6 +296,7 @@ __global__ void __launch_bounds__(256) gemm_small_kernel(GemmArgs g) {
       c[v + g.N] = g.scale * sn;
     }
   }
+  GS_MARK(6)
   if (want_rsum && tx == 0) {
     if (EPI == EPI_ADAM) {       // the bias gradient goes straight into the bias
       const int64_t e = g.ad_b_off + gi_out;
@@ -290,8 +314,11 @@ static int launch_small(const GemmArgs& g, dim3 grid, int S, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(256);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = sizeof(SmallSmem);
   cfg.stream = st;
+  BSIG_CUDA(cudaFuncSetAttribute(gemm_small_kernel<EPI, GATHER>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(SmallSmem)));
   cudaLaunchAttribute attr[2];
   int na = 0;
   if (S > 1) {      // reduction split over a thread-block cluster
@@ -356,3 +383,9 @@ int gemm_small(GemmArgs g, cudaStream_t st) {
 }
 
 }  // namespace bsig
+
+#ifdef BSIG_GS_PROF
+extern "C" int dbg_gs_prof_read(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, bsig::gs_prof_buf, sizeof(unsigned long long) * 256 * 8);
+}
+#endif

@@ -140,6 +140,14 @@ __global__ void __launch_bounds__(256) gemm_small_kernel(GemmArgs g) {
     const int64_t row = (GATHER == 1) ? __ldg(g.a_rows + gi) : (int64_t)gi;
     a_ptr[q] = g.A + row * g.a_si;
   }
+  // (the same holds for gathered reduction rows: the first pass's indices are fetched here, so
+  // that the operand loads after the wait are one round trip, not two)
+  int64_t b_row0[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int rr = max(min(r_begin + b_r[q], r_end - 1), 0);
+    b_row0[q] = (GATHER == 2) ? __ldg(g.b_rows + rr) : (int64_t)rr;
+  }
   // everything above is operand-independent set-up: it overlaps the previous kernel
   pdl_wait_then_release();
   GS_MARK(1)
@@ -166,7 +174,8 @@ __global__ void __launch_bounds__(256) gemm_small_kernel(GemmArgs g) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const int rr = min(r0 + b_r[q], r_end - 1);
-      const int64_t row = (GATHER == 2) ? __ldg(g.b_rows + rr) : (int64_t)rr;
+      const int64_t row = (GATHER != 2) ? (int64_t)rr
+                          : (r0 == r_begin ? b_row0[q] : (int64_t)__ldg(g.b_rows + rr));
       rb[q] = __ldg(b_ptr[q] + row * g.b_sr);
     }
 #pragma unroll

@@ -405,15 +405,27 @@ __global__ void __launch_bounds__(512) nll_cluster_kernel(NllArgs a) {
 // A sample is owned by PS*GW lanes: lane = (ph, k), k < GW components, and the P
 // output dimensions are dealt round-robin over the PS "p-halves" (p = ii*PS + ph),
 // which divides the per-lane transcendental work by PS; PL = ceil(P / PS) <= PLMAX.
+#ifdef BSIG_NLL_PROF   // temporary instrumentation: %globaltimer marks of every CTA of the last launch
+__device__ unsigned long long nll_prof_buf[8 * 16];
+#define NLL_MARK(i)                                                        \
+  if (threadIdx.x == 0) {                                                  \
+    unsigned long long t_;                                                 \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                 \
+    nll_prof_buf[blockIdx.x * 16 + (i)] = t_;                              \
+  }
+#else
+#define NLL_MARK(i)
+#endif
 template <int GW, int PS, int PLMAX, bool BWD>
 __global__ void __launch_bounds__(512) nll_small_kernel(NllArgs a) {
   __shared__ float scratch[33];
   // batch-wide sums: every CTA PUSHES its partial into the inbox of every CTA of the cluster
   // (remote stores before a release/acquire cluster barrier), then adds the NC values from its
   // own shared memory in rank order -- no remote read latency, no barrier to keep a peer alive
-  __shared__ float inbox[3][8];
+  __shared__ float inbox[3][16];
   __shared__ float2 scratch2[33];
   cg::cluster_group cluster = cg::this_cluster();
+  NLL_MARK(0)
   auto started = cluster.barrier_arrive();     // a peer's shared memory exists once it got here
   constexpr int LPS = GW * PS;             // lanes per sample (<= 32)
   const int tid = threadIdx.x;
@@ -430,6 +442,7 @@ __global__ void __launch_bounds__(512) nll_small_kernel(NllArgs a) {
   // ---- all loads (the minibatch row index is constant during a training call)
   const int64_t yrow = (a.y_rows ? __ldg(a.y_rows + bb) : bb) * P;
   pdl_wait_then_release();
+  NLL_MARK(1)
   float zpi = ok ? __ldg(a.z_pi + bb * a.ld_pi + kk) : -INFINITY;
   float e[PLMAX], zi[PLMAX], nz[PLMAX];
 #pragma unroll
@@ -449,10 +462,13 @@ __global__ void __launch_bounds__(512) nll_small_kernel(NllArgs a) {
     e[ii] = xexp<true>(e[ii]);
     if (ok && ii * PS + ph < P) esum += e[ii];
   }
+  NLL_MARK(2)
   esum = block_sum(esum, scratch);
+  NLL_MARK(3)
   cluster.barrier_wait(std::move(started));
   if (tid < NC) *cluster.map_shared_rank(&inbox[0][rank], tid) = esum;
   auto pushed = cluster.barrier_arrive();
+  NLL_MARK(4)
 
   // ---- mixture weights: softmax -> clamp -> renormalise (every p-half computes
   // the same values; xor offsets < GW stay inside one p-half); independent of eps, so it runs
@@ -465,7 +481,9 @@ __global__ void __launch_bounds__(512) nll_small_kernel(NllArgs a) {
   const float csum = group_sum<GW>(w);
   w = w / csum;
 
+  NLL_MARK(5)
   cluster.barrier_wait(std::move(pushed));
+  NLL_MARK(6)
   float etot = 0.f;
   for (int r = 0; r < NC; ++r) etot += inbox[0][r];
   const float eps = kEpsNoise * (etot / (float)((int64_t)B * PK));
@@ -496,6 +514,7 @@ __global__ void __launch_bounds__(512) nll_small_kernel(NllArgs a) {
   const float se = group_sum<GW>(rk == -INFINITY ? 0.f : xexp<true>(rk - mx));
   const float lse = mx + xlog<true>(se);
   float loss_acc = (b < B && lane_s == 0) ? -lse : 0.f;
+  NLL_MARK(7)
   if (bad) atomicOr(a.flag, 1);
 
   float s_acc = 0.f;
@@ -523,6 +542,7 @@ __global__ void __launch_bounds__(512) nll_small_kernel(NllArgs a) {
       }
     }
   }
+  NLL_MARK(8)
   float lsum, ssum = 0.f;
   if (BWD) {               // both sums in one pass over the block
     const float2 ls = block_sum2(make_float2(loss_acc, s_acc), scratch2);
@@ -530,11 +550,13 @@ __global__ void __launch_bounds__(512) nll_small_kernel(NllArgs a) {
   } else {
     lsum = block_sum(loss_acc, scratch);
   }
+  NLL_MARK(9)
   if (tid < NC) {
     *cluster.map_shared_rank(&inbox[1][rank], tid) = lsum;
     *cluster.map_shared_rank(&inbox[2][rank], tid) = ssum;
   }
   cluster.sync();
+  NLL_MARK(10)
   if (rank == 0 && tid == 0) {
     float ltot = 0.f;
     for (int r = 0; r < NC; ++r) ltot += inbox[1][r];
@@ -552,6 +574,7 @@ __global__ void __launch_bounds__(512) nll_small_kernel(NllArgs a) {
       }
     }
   }
+  NLL_MARK(11)
 }
 
 // eps-term fix-up of the fused backward: dzd += exp(zd) * (1e-5/M) * S
@@ -782,6 +805,9 @@ static int launch_nll_small_t(const NllArgs& a, int nc, int tpb, cudaStream_t st
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = add_pdl_attr(attr, 1);
+  if (nc > 8)
+    BSIG_CUDA(cudaFuncSetAttribute(nll_small_kernel<GW, PS, PLMAX, BWD>,
+                                   cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   BSIG_CUDA(cudaLaunchKernelEx(&cfg, nll_small_kernel<GW, PS, PLMAX, BWD>, a));
   BSIG_LAUNCH_CHECK();
   return 0;
@@ -809,10 +835,12 @@ static int launch_nll_small(const NllArgs& a, bool bwd, cudaStream_t st) {
   int ps = 1;
   while (ps < 4 && gw * ps * 2 <= 32 && a.P >= 4 * ps) ps <<= 1;
   const int lps = gw * ps;
+  // the kernel is issue-bound per SM (16 warps of dependent chains): 256-thread CTAs over a
+  // cluster of up to 16 (non-portable size) halve every compute phase of the 100-row minibatch
   int tpb = 256;
-  if (ceil_div(a.B, tpb / lps) > 8) tpb = 512;
+  if (ceil_div(a.B, tpb / lps) > 16) tpb = 512;
   const int nc = (int)ceil_div(a.B, tpb / lps);
-  if (nc > 8) return -1;
+  if (nc > (tpb == 256 ? 16 : 8)) return -1;
 #define BSIG_NS(GWV, PSV) \
   if (gw == GWV && ps == PSV) return launch_nll_small_p<GWV, PSV>(a, bwd, nc, tpb, st);
   BSIG_NS(1, 1) BSIG_NS(1, 2) BSIG_NS(1, 4) BSIG_NS(2, 1) BSIG_NS(2, 2) BSIG_NS(2, 4)
@@ -1064,3 +1092,9 @@ extern "C" int bsig_mdn_nll_fused(const float* z, const float* noise, const floa
   }
   return 0;
 }
+
+#ifdef BSIG_NLL_PROF
+extern "C" int dbg_nll_prof_read(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, bsig::nll_prof_buf, sizeof(unsigned long long) * 8 * 16);
+}
+#endif

@@ -1,8 +1,5 @@
 mkdir -p gpurun_out
-for k in 128; do
-echo "== NOSPLIT_K=$k"
-BSIG_SMALL_GEMM_NOSPLIT_K=$k timeout 120 python profiles/gemm_latency.py 2>&1 | tail -8 | head -5
-BSIG_SMALL_GEMM_NOSPLIT_K=$k timeout 600 python bench.py --steps 5 --warmup 3 2>/dev/null | python -c "
+timeout 120 python profiles/gemm_latency.py 2>&1 | tail -8
+timeout 600 python bench.py --steps 5 --warmup 3 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('bench:', d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['us_per_launch'])"
-done

@@ -25,7 +25,9 @@ NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
     '-Xcompiler', '-fPIC',
     '-I', os.path.join(ROOT, 'include'), '-I', CSRC,
-] + os.environ.get('BSIG_NVCC_EXTRA', '').split()     # instrumented builds (profiles/)
+] + os.environ.get('BSIG_NVCC_EXTRA', '').split()
+# (BSIG_NVCC_EXTRA: instrumented builds for profiles/*_marks.py; the staleness check looks at
+# mtimes only, so touch the source -- and again before the clean rebuild)
 
 
 def _nvcc():

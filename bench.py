@@ -500,7 +500,7 @@ def dominant_kernel_roofline(dev, peak_gbs, peak_src):
             'traffic': 15000,
             'us_per_launch': round(us_per_launch, 2), 'algorithmic_bytes': int(algo / 8),
             'peak_source': peak_src,
-            'note': 'dominant kernel of the step (8 of 10 launches per Adam update); minibatch-100 '
+            'note': 'dominant kernel of the step (8 of 9 launches per Adam update); minibatch-100 '
                     'layer GEMMs with L2-resident operands are latency-bound, not bandwidth-bound: '
                     'see `rooflines` for the HBM-bound kernels at sizes that exceed L2'}
 
